@@ -1,0 +1,85 @@
+"""pytest config: registers the `gpu` marker and puts the repo roots on sys.path."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "clifford-vae_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def pytest_collection_modifyitems(config, items):
+    import torch
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for it in items:
+        if "gpu" in it.keywords:
+            it.add_marker(skip)
+
+
+class Golden:
+    """npz of 'case/key' arrays -> {case: {key: array}}."""
+
+    def __init__(self, fname):
+        z = np.load(os.path.join(GOLDEN, fname))
+        self.cases = {}
+        for k in z.files:
+            if "/" in k:
+                c, key = k.split("/", 1)
+                self.cases.setdefault(c, {})[key] = z[k]
+            else:
+                self.cases[k] = z[k]
+
+    def __getitem__(self, c):
+        return self.cases[c]
+
+    def names(self, prefix=""):
+        return [c for c in self.cases if c.startswith(prefix)]
+
+
+@pytest.fixture(scope="session")
+def golden_clifford():
+    return Golden("clifford.npz")
+
+
+@pytest.fixture(scope="session")
+def golden_ps():
+    return Golden("powerspherical.npz")
+
+
+@pytest.fixture(scope="session")
+def golden_vmf():
+    return Golden("vmf.npz")
+
+
+@pytest.fixture(scope="session")
+def golden_vsa():
+    return Golden("vsa.npz")
+
+
+@pytest.fixture(scope="session")
+def golden_special():
+    return Golden("special.npz")
+
+
+@pytest.fixture(scope="session")
+def golden_ks():
+    return Golden("ks_samples.npz")
+
+
+def rel_err(x, ref):
+    """max-norm relative error: max|x - ref| / max(max|ref|, tiny)."""
+    x = np.asarray(x, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    return float(np.max(np.abs(x - ref)) / max(np.max(np.abs(ref)), 1e-30)) if ref.size else 0.0
