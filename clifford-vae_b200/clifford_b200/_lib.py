@@ -1,0 +1,145 @@
+"""ctypes binding of libclifford_b200.so (C ABI in include/clifford_b200.h).
+
+There is no CPU fallback: a missing library, a CPU tensor or a non-B200 device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libclifford_b200.so")
+
+_lib = None
+_lock = threading.Lock()
+_inited_devices: set[int] = set()
+
+_f = C.c_void_p      # device pointers are passed as integers / None
+_ll = C.c_longlong
+_ull = C.c_ulonglong
+_i = C.c_int
+_fl = C.c_float
+_db = C.c_double
+
+_SIGNATURES = {
+    "cvb_version": ([], _i),
+    "cvb_last_error_string": ([], C.c_char_p),
+    "cvb_init": ([], _i),
+    "cvb_launch_count": ([], _ll),
+    "cvb_clifford_ps_rsample": ([_f, _f, _ll, _i, _ll, _f, _f, _ull, _ull, _f, _f, _f, _f, _f, _ll, _i, _f], _i),
+    "cvb_clifford_ps_rsample_backward": ([_f, _f, _f, _ll, _i, _ll, _f, _f, _f, _f, _f, _ll, _i, _f], _i),
+    "cvb_clifford_ps_log_prob": ([_f, _f, _f, _ll, _i, _ll, _f, _f, _f, _ll, _i, _f], _i),
+    "cvb_ps_entropy_kl": ([_f, _ll, _i, _ll, _i, _db, _i, _db, _f, _f, _f, _f], _i),
+    "cvb_clifford_phases_to_vector": ([_f, _fl, _ull, _ull, _f, _ll, _i, _f], _i),
+    "cvb_vsa_bind": ([_f, _f, _f, _ll, _ll, _ll, _i, _i, _f], _i),
+    "cvb_vsa_invert": ([_f, _f, _ll, _i, _f], _i),
+    "cvb_vsa_permute": ([_f, _f, _f, _ll, _i, _i, _f], _i),
+    "cvb_vsa_bundle_workspace_bytes": ([_ll, _i], _ll),
+    "cvb_vsa_bundle": ([_f, _f, _ll, _i, _fl, _f, _f], _i),
+    "cvb_vsa_cosine": ([_f, _f, _f, _ll, _ll, _ll, _i, _f], _i),
+    "cvb_vsa_cosine_backward": ([_f, _f, _f, _f, _f, _ll, _ll, _ll, _i, _f], _i),
+    "cvb_vsa_normalize": ([_f, _f, _ll, _i, _f], _i),
+    "cvb_vsa_normalize_backward": ([_f, _f, _f, _ll, _i, _f], _i),
+    "cvb_vsa_hrr_init": ([_f, _ll, _i, _ull, _ull, _f], _i),
+    "cvb_vsa_unitary_init": ([_f, _ll, _i, _fl, _ull, _ull, _f], _i),
+    "cvb_powerspherical_rsample": ([_f, _f, _ll, _f, _f, _ull, _ull, _f, _f, _ll, _i, _f], _i),
+    "cvb_powerspherical_rsample_backward": ([_f, _f, _f, _ll, _f, _f, _f, _ull, _ull, _f, _f, _ll, _i, _f], _i),
+    "cvb_powerspherical_log_prob": ([_f, _f, _f, _ll, _f, _f, _f, _ll, _i, _f], _i),
+    "cvb_ps_log_normalizer": ([_f, _ll, _db, _f, _f, _f], _i),
+    "cvb_sphere_uniform_rsample": ([_f, _ull, _ull, _f, _ll, _i, _fl, _f], _i),
+    "cvb_vmf_rsample": ([_f, _f, _ll, _f, _f, _i, _f, _ull, _ull, _f, _f, _ll, _i, _f], _i),
+    "cvb_vmf_rsample_backward": ([_f, _f, _f, _ll, _f, _f, _ull, _ull, _f, _f, _ll, _i, _f], _i),
+    "cvb_vmf_entropy_lognorm": ([_f, _ll, _i, _f, _f, _f, _f, _f], _i),
+    "cvb_philox_fill": ([_f, _ll, _ull, _ull, _f], _i),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+class CliffordB200Error(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise CliffordB200Error(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C clifford-vae_b200/csrc`). There is no CPU / PyTorch fallback for this path.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (argtypes, restype) in _SIGNATURES.items():
+            fn = getattr(lib, name)   # AttributeError if the .so does not export a declared symbol
+            fn.argtypes = argtypes
+            fn.restype = restype
+        _lib = lib
+    return _lib
+
+
+def ensure_device(device: torch.device) -> None:
+    """cvb_init() on `device` (per-device twiddle table); refuses anything but CUDA."""
+    if device.type != "cuda":
+        raise CliffordB200Error(
+            f"clifford_b200 ops run only on a CUDA (sm_100a) device, got a tensor on '{device}'. "
+            "There is deliberately no CPU fallback; move the tensors to the GPU.")
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx in _inited_devices:
+        return
+    lib = load()
+    with torch.cuda.device(idx):
+        rc = lib.cvb_init()
+    if rc != 0:
+        raise CliffordB200Error(f"cvb_init failed on cuda:{idx}: {lib.cvb_last_error_string().decode()}")
+    _inited_devices.add(idx)
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().cvb_last_error_string().decode()
+        if rc == 1:
+            raise ValueError(f"{what}: {msg}")
+        if rc == 2:
+            raise NotImplementedError(f"{what}: {msg}")
+        raise CliffordB200Error(f"{what}: {msg}")
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count() -> int:
+    return int(load().cvb_launch_count())
+
+
+# ---- Philox (seed, offset) bookkeeping ---------------------------------------------------------
+_rng_seed = None
+_rng_offset = 0
+
+
+def next_rng(n_calls: int = 1):
+    """(seed, offset) for the next kernel that draws on the device.
+
+    The seed follows torch's global generator (torch.manual_seed) xor the distributed rank, so DDP
+    ranks draw disjoint streams; the offset counts launches since the seed last changed.
+    """
+    global _rng_seed, _rng_offset
+    seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        seed ^= (torch.distributed.get_rank() * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+    if seed != _rng_seed:
+        _rng_seed, _rng_offset = seed, 0
+    off = _rng_offset
+    _rng_offset += n_calls
+    return seed, off

@@ -1,0 +1,235 @@
+"""torch.distributions-style classes with the reference's names, constructor signatures, attributes
+and KL registrations (reference dists/clifford.py), backed by the sm_100a kernels.
+
+These are re-exported as ``dists.clifford`` so the reference's model files
+(mnist/mlp_vae.py:11-16, cnn/models.py:8-15) import them unchanged.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict
+
+import torch
+from torch.distributions import Distribution, constraints
+from torch.distributions.kl import register_kl
+from torch.distributions.utils import broadcast_all
+
+from . import ops
+
+_LOG_2PI = math.log(2 * math.pi)
+
+
+def _numel(shape) -> int:
+    n = 1
+    for s in shape:
+        n *= int(s)
+    return n
+
+
+class HypersphericalUniform(Distribution):
+    """Uniform distribution on S^(dim-1) in R^dim (reference dists/clifford.py:85-121)."""
+
+    arg_constraints: Dict[str, constraints.Constraint] = {}
+    has_rsample = True
+
+    def __init__(self, dim, device="cpu", dtype=torch.float32, validate_args=None):
+        self.dim = dim
+        self.device, self.dtype = device, dtype
+        super().__init__(batch_shape=torch.Size(), event_shape=torch.Size([dim]), validate_args=validate_args)
+
+    def rsample(self, sample_shape=torch.Size()):
+        shape = tuple(sample_shape) + tuple(self.event_shape)
+        rows = _numel(shape[:-1])
+        z = ops.sphere_uniform_rsample(rows, self.dim, self.device, 1e-7)
+        return z.reshape(shape).to(self.dtype)
+
+    def _log_density(self):
+        return math.lgamma(self.dim / 2) - (math.log(2) + (self.dim / 2) * math.log(math.pi))
+
+    def log_prob(self, value):
+        if self.dim <= 0:
+            return torch.tensor(float("-inf"), device=self.device, dtype=self.dtype)
+        return torch.full_like(value[..., 0], self._log_density())
+
+    def entropy(self):
+        if self.dim <= 0:
+            return torch.tensor(float("inf"), device=self.device, dtype=self.dtype)
+        return torch.full((1,), -self._log_density(), device=self.device, dtype=self.dtype)
+
+
+class PowerSpherical(Distribution):
+    """Power spherical distribution on S^(D-1) (reference dists/clifford.py:162-212).
+
+    loc (..., D) unit vectors, scale (...,) concentrations.  rsample / log_prob / entropy run as
+    fused row kernels (Beta draw + tangent normal + T-transform + Householder in one pass).
+    """
+
+    arg_constraints: Dict[str, constraints.Constraint] = {}
+    has_rsample = True
+
+    def __init__(self, loc, scale, validate_args=None):
+        self.loc, self.scale = loc, scale
+        self.dim = loc.shape[-1]
+        super().__init__(batch_shape=scale.shape, event_shape=torch.Size([self.dim]), validate_args=False)
+
+    def _flat(self):
+        D = self.dim
+        loc2 = self.loc.expand(tuple(self.batch_shape) + (D,)).reshape(-1, D)
+        return loc2, self.scale.reshape(-1)
+
+    def rsample(self, sample_shape=torch.Size(), _base_draws=None):
+        sample_shape = torch.Size(sample_shape)
+        loc2, kap = self._flat()
+        n = _numel(sample_shape)
+        z = ops.PowerSphericalRsample.apply(loc2, kap, n, _base_draws)
+        return z.reshape(tuple(sample_shape) + tuple(self.batch_shape) + (self.dim,)).to(self.loc.dtype)
+
+    def sample(self, sample_shape=torch.Size()):
+        with torch.no_grad():
+            return self.rsample(sample_shape)
+
+    def log_normalizer(self):
+        # log C(kappa) = -((a+b) ln 2 + lgamma(a) - lgamma(a+b) + b ln pi) evaluated on the device
+        return ops.PSLogNormalizer.apply(self.scale, self.dim)
+
+    def log_prob(self, value):
+        loc2, kap = self._flat()
+        D = self.dim
+        lead = torch.broadcast_shapes(value.shape[:-1], tuple(self.batch_shape))
+        v2 = value.expand(tuple(lead) + (D,)).reshape(-1, D)
+        lp = ops.PowerSphericalLogProb.apply(v2, loc2, kap)
+        return lp.reshape(lead).to(self.loc.dtype)
+
+    def entropy(self):
+        ent = ops.PSEntropy.apply(self.scale, 1, (self.dim - 1) / 2, False)
+        return ent.reshape(self.scale.shape).to(self.loc.dtype)
+
+
+class CliffordTorusUniform(Distribution):
+    """Uniform distribution on the Clifford torus (S^1)^d (reference dists/clifford.py:215-242)."""
+
+    arg_constraints: Dict[str, constraints.Constraint] = {}
+    has_rsample = True
+
+    def __init__(self, dim, device="cpu", dtype=torch.float32, validate_args=None):
+        self.dim = dim
+        self.device, self.dtype = device, dtype
+        super().__init__(event_shape=torch.Size([2 * self.dim]), validate_args=validate_args)
+
+    def rsample(self, sample_shape=torch.Size(), _base_draws=None):
+        sample_shape = tuple(sample_shape)
+        rows = _numel(sample_shape)
+        z = ops.clifford_phases_to_vector(_base_draws, 2 * math.pi, rows, self.dim, self.device)
+        return z.reshape(sample_shape + (2 * self.dim,)).to(self.dtype)
+
+    def log_prob(self, value):
+        return -torch.ones_like(value[..., 0]) * self.entropy()
+
+    def entropy(self):
+        return (self.dim - 1) * _LOG_2PI
+
+
+class CliffordTorusDistribution(Distribution):
+    """Product of von Mises distributions on the torus (reference dists/clifford.py:245-278).
+
+    Kept for the isinstance / KL-registry relations.  The reference's own ``rsample`` raises an
+    AssertionError for generic angles (its Hermitian-symmetry assert at :274 uses the wrong flip), so
+    no driver uses it; here it raises NotImplementedError.  ``entropy`` is evaluated with
+    torch.special.i0e/i1e (off the hot path).
+    """
+
+    arg_constraints: Dict[str, constraints.Constraint] = {}
+    has_rsample = True
+
+    def __init__(self, loc, concentration, validate_args=None):
+        self._raw_concentration = concentration
+        self.loc, self.concentration = broadcast_all(loc, concentration)
+        self.orig_dim = loc.shape[-1]
+        super().__init__(batch_shape=loc.shape[:-1], event_shape=torch.Size([2 * self.orig_dim]),
+                         validate_args=validate_args)
+
+    def rsample(self, sample_shape=torch.Size()):
+        raise NotImplementedError(
+            "CliffordTorusDistribution (von Mises) sampling is unusable in the reference (AssertionError at "
+            "dists/clifford.py:274); use CliffordPowerSphericalDistribution")
+
+    def entropy(self):
+        k = self.concentration
+        eps = 1e-7
+        log_i0 = torch.log(torch.special.i0e(k) + eps) + k
+        log_i1 = torch.log(torch.special.i1e(k) + eps) + k
+        ent = _LOG_2PI + log_i0 - k * torch.exp(log_i1 - log_i0)
+        return ent[..., 1:].sum(-1)
+
+
+class CliffordPowerSphericalDistribution(CliffordTorusDistribution):
+    """Clifford-torus distribution with a power-spherical phase on every circle
+    (reference dists/clifford.py:281-322).
+
+    ``rsample`` is ONE fused kernel: Beta/sign draws (device Philox, or injected through the private
+    ``_base_draws=(tprime, g)`` test hook) -> phases -> Hermitian phasors -> C2R inverse FFT, with the
+    row entropy / dH/dkappa produced in the same pass and cached for ``entropy()`` / ``kl_divergence``
+    (the reference evaluates the entropy twice per step, mnist/mlp_vae.py:126-129).
+    """
+
+    arg_constraints = {"loc": constraints.real, "concentration": constraints.positive}
+    has_rsample = True
+
+    def __init__(self, loc, concentration, validate_args=None, normalize_ifft: bool = False):
+        super().__init__(loc, concentration, validate_args=validate_args)
+        self.normalize_ifft = normalize_ifft
+        self.dtype = loc.dtype
+        self._fused_entropy = None
+        d = self.orig_dim
+        conc = self.concentration
+        # one concentration per row (every reference driver) vs a full (.., d) tensor
+        raw = self._raw_concentration
+        if torch.is_tensor(raw) and raw.dim() >= 1 and raw.shape[-1] == 1 and d != 1:
+            self._kappa = raw.expand(tuple(self.batch_shape) + (1,))
+        elif conc.stride(-1) == 0 or d == 1:
+            self._kappa = conc[..., :1]
+        else:
+            self._kappa = conc
+
+    def _flat(self):
+        d = self.orig_dim
+        return self.loc.reshape(-1, d), self._kappa.reshape(-1, self._kappa.shape[-1])
+
+    def rsample(self, sample_shape=torch.Size(), _base_draws=None) -> torch.Tensor:
+        sample_shape = torch.Size(sample_shape)
+        loc2, kap2 = self._flat()
+        n = _numel(sample_shape)
+        z, ent = ops.CliffordPSRsample.apply(loc2, kap2, n, _base_draws, True)
+        if ent.numel():
+            self._fused_entropy = ent.reshape(self.batch_shape)
+        return z.reshape(tuple(sample_shape) + tuple(self.batch_shape) + (2 * self.orig_dim,)).to(self.dtype)
+
+    def log_prob(self, value):
+        loc2, kap2 = self._flat()
+        n = 2 * self.orig_dim
+        lead = torch.broadcast_shapes(value.shape[:-1], tuple(self.batch_shape))
+        v2 = value.expand(tuple(lead) + (n,)).reshape(-1, n)
+        lp = ops.CliffordPSLogProb.apply(v2, loc2, kap2)
+        return lp.reshape(lead).to(self.dtype)
+
+    def entropy(self):
+        if self._fused_entropy is not None:
+            return self._fused_entropy.to(self.dtype)
+        _, kap2 = self._flat()
+        ent = ops.PSEntropy.apply(kap2, self.orig_dim, 0.5, True)
+        return ent.reshape(self.batch_shape).to(self.dtype)
+
+
+@register_kl(CliffordPowerSphericalDistribution, CliffordTorusUniform)
+def _kl_ps_uniform(p, q):
+    return -p.entropy() + q.entropy()
+
+
+@register_kl(CliffordTorusDistribution, CliffordTorusUniform)
+def _kl_vm_uniform(p, q):
+    return -p.entropy() + q.entropy()
+
+
+@register_kl(PowerSpherical, HypersphericalUniform)
+def _kl_powerspherical_uniform(p, q):
+    return -p.entropy() + q.entropy()

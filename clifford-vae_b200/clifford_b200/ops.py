@@ -1,0 +1,590 @@
+"""torch.autograd.Function wrappers over the C ABI (include/clifford_b200.h).
+
+Everything here is plumbing: shape flattening, output allocation with torch (device memory and
+streams are torch's), saving tensors for backward.  The arithmetic lives in the CUDA kernels.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import _lib
+from ._lib import check, ptr, stream_ptr
+
+BIND_MUL, BIND_MUL_CONJ, BIND_DIV, BIND_DIV_CONJ, BIND_NEG_MUL_CONJ = range(5)
+
+
+def _launch(name, *args):
+    """Call a C-ABI launcher on the device of its first tensor pointer's owner (set by _prep/_dev)."""
+    lib = _lib.load()
+    dev = _CUR_DEV[0]
+    if dev is not None and dev.index is not None and dev.index != torch.cuda.current_device():
+        with torch.cuda.device(dev):
+            rc = getattr(lib, name)(*args, torch.cuda.current_stream().cuda_stream)
+    else:
+        rc = getattr(lib, name)(*args, stream_ptr())
+    check(rc, name)
+
+
+_CUR_DEV = [None]
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    """contiguous fp32 view/copy of t (the kernels compute in fp32)."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _prep(*tensors):
+    dev = tensors[0].device
+    _lib.ensure_device(dev)
+    _CUR_DEV[0] = dev
+    for t in tensors[1:]:
+        if t is not None and t.device != dev:
+            raise _lib.CliffordB200Error(f"tensors on different devices: {dev} vs {t.device}")
+    return _lib.load(), dev
+
+
+def _kappa_layout(kappa: torch.Tensor, d: int):
+    """kappa is (B, 1) [row scalar] or (B, d). Returns (tensor, row_stride, el_stride)."""
+    if kappa.shape[-1] == 1:
+        k = _f32c(kappa.reshape(-1))
+        return k, 1, 0
+    k = _f32c(kappa.reshape(-1, d))
+    return k, d, 1
+
+
+# =================================================================================================
+# Clifford torus
+# =================================================================================================
+class CliffordPSRsample(torch.autograd.Function):
+    """z, entropy = f(loc (B,d), kappa (B,1)|(B,d)); rows = n_samples * B.
+
+    draws: None (device Philox) or (tprime, g) each (n_samples*B, d) -- parity mode.
+    Returns (z (rows, 2d), entropy (B,) or None-like empty when kappa is per element).
+    """
+
+    @staticmethod
+    def forward(ctx, loc, kappa, n_samples, draws, want_entropy):
+        lib, dev = _prep(loc, kappa)
+        B, d = loc.shape
+        rows = B * n_samples
+        loc_c = _f32c(loc)
+        kap_c, krs, kes = _kappa_layout(kappa, d)
+        z = torch.empty(rows, 2 * d, device=dev, dtype=torch.float32)
+        need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        fused_ent = bool(want_entropy) and kes == 0 and n_samples == 1
+        ent = torch.empty(B, device=dev, dtype=torch.float32) if fused_ent else None
+        dent = torch.empty(B, device=dev, dtype=torch.float32) if fused_ent else None
+        if draws is None:
+            tp = g = None
+            tp_signed = torch.empty(rows, d, device=dev, dtype=torch.float32) if need_grad else None
+            seed, off = _lib.next_rng()
+        else:
+            tp, g = (_f32c(t.reshape(rows, d)) for t in draws)
+            tp_signed = None
+            seed, off = 0, 0
+        _launch("cvb_clifford_ps_rsample", ptr(loc_c), ptr(kap_c), krs, kes, B, ptr(tp), ptr(g), seed, off, ptr(z),
+                                          ptr(tp_signed), ptr(ent), None, ptr(dent), rows, d)
+        ctx.save_for_backward(loc_c, kap_c, tp, g, tp_signed, dent)
+        ctx.meta = (B, d, rows, n_samples, krs, kes, tuple(kappa.shape))
+        if ent is None:
+            ent = z.new_empty(0)
+        return z, ent
+
+    @staticmethod
+    def backward(ctx, grad_z, grad_ent):
+        loc_c, kap_c, tp, g, tp_signed, dent = ctx.saved_tensors
+        B, d, rows, n_samples, krs, kes, kshape = ctx.meta
+        lib = _lib.load()
+        dloc = dkap = None
+        if grad_z is not None:
+            gz = _f32c(grad_z)
+            dloc_rows = torch.empty(rows, d, device=gz.device, dtype=torch.float32)
+            dk_rows = torch.empty((rows,) if kes == 0 else (rows, d), device=gz.device, dtype=torch.float32)
+            _launch("cvb_clifford_ps_rsample_backward", ptr(gz), ptr(loc_c), ptr(kap_c), krs, kes, B, ptr(tp), ptr(g),
+                                                       ptr(tp_signed), ptr(dloc_rows), ptr(dk_rows), rows, d)
+            if n_samples > 1:
+                dloc_rows = dloc_rows.view(n_samples, B, d).sum(0)
+                dk_rows = dk_rows.view(n_samples, B, -1).sum(0) if kes else dk_rows.view(n_samples, B).sum(0)
+            dloc = dloc_rows
+            dkap = dk_rows.reshape(kshape)
+        if dent is not None and grad_ent is not None and grad_ent.numel():
+            de = (grad_ent * dent).reshape(kshape)
+            dkap = de if dkap is None else dkap + de
+        if dloc is None and ctx.needs_input_grad[0]:
+            dloc = torch.zeros_like(loc_c)
+        return dloc, dkap, None, None, None
+
+
+class PSEntropy(torch.autograd.Function):
+    """Power-spherical entropy per row.  torus=True: sum over circles k>=1 of kappa (B,1)|(B,d)
+    (dists/clifford.py:318-322).  torus=False: one D-dim PowerSpherical per row, kappa (B,)."""
+
+    @staticmethod
+    def forward(ctx, kappa, d, half_dm1, torus):
+        lib, dev = _prep(kappa)
+        if torus:
+            kap_c, krs, kes = _kappa_layout(kappa, d)
+            B = kap_c.shape[0]
+        else:
+            kap_c, krs, kes = _f32c(kappa.reshape(-1)), 1, 0
+            B = kap_c.shape[0]
+        ent = torch.empty(B, device=dev, dtype=torch.float32)
+        dent = torch.empty((B,) if kes == 0 else (B, d), device=dev, dtype=torch.float32)
+        _launch("cvb_ps_entropy_kl", ptr(kap_c), krs, kes, B, d, float(half_dm1), 1 if torus else 0, 0.0, ptr(ent),
+                                    None, ptr(dent))
+        ctx.save_for_backward(dent)
+        ctx.kshape = tuple(kappa.shape)
+        ctx.kes = kes
+        return ent
+
+    @staticmethod
+    def backward(ctx, grad):
+        (dent,) = ctx.saved_tensors
+        g = grad.reshape(-1)
+        dk = g * dent if ctx.kes == 0 else g[:, None] * dent
+        return dk.reshape(ctx.kshape), None, None, None
+
+
+class CliffordPSLogProb(torch.autograd.Function):
+    """log_prob (rows,) of value (rows, 2d) under (loc (B,d), kappa (B,1)|(B,d)); rows = S*B."""
+
+    @staticmethod
+    def forward(ctx, value, loc, kappa):
+        lib, dev = _prep(value, loc, kappa)
+        B, d = loc.shape
+        rows = value.shape[0]
+        val_c, loc_c = _f32c(value), _f32c(loc)
+        kap_c, krs, kes = _kappa_layout(kappa, d)
+        lp = torch.empty(rows, device=dev, dtype=torch.float32)
+        need = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        if ctx.needs_input_grad[0]:
+            raise NotImplementedError(
+                "clifford log_prob: gradient with respect to `value` is not implemented (the reference only "
+                "evaluates log_prob under no_grad, mnist/mlp_vae.py:181); detach the value")
+        dl = torch.empty(rows, d, device=dev, dtype=torch.float32) if need else None
+        dk = torch.empty((rows,) if kes == 0 else (rows, d), device=dev, dtype=torch.float32) if need else None
+        _launch("cvb_clifford_ps_log_prob", ptr(val_c), ptr(loc_c), ptr(kap_c), krs, kes, B, ptr(lp), ptr(dl), ptr(dk),
+                                           rows, d)
+        ctx.save_for_backward(dl, dk)
+        ctx.meta = (B, d, rows, kes, tuple(kappa.shape))
+        return lp
+
+    @staticmethod
+    def backward(ctx, grad):
+        dl, dk = ctx.saved_tensors
+        B, d, rows, kes, kshape = ctx.meta
+        S = rows // B
+        g = grad.reshape(rows)
+        dloc = (g[:, None] * dl).view(S, B, d).sum(0)
+        dkap = (g * dk).view(S, B).sum(0) if kes == 0 else (g[:, None] * dk).view(S, B, d).sum(0)
+        return None, dloc, dkap.reshape(kshape)
+
+
+def clifford_phases_to_vector(phases, scale, rows, d, device):
+    """phases (rows, d) * scale -> (rows, 2d); phases None draws U[0,1) on the device."""
+    _lib.ensure_device(torch.device(device))
+    lib = _lib.load()
+    z = torch.empty(rows, 2 * d, device=device, dtype=torch.float32)
+    _CUR_DEV[0] = z.device
+    if phases is None:
+        seed, off = _lib.next_rng()
+        ph = None
+    else:
+        ph, seed, off = _f32c(phases.reshape(rows, d)), 0, 0
+    with torch.cuda.device(z.device):
+        _launch("cvb_clifford_phases_to_vector", ptr(ph), float(scale), seed, off, ptr(z), rows, d)
+    return z
+
+
+# =================================================================================================
+# VSA
+# =================================================================================================
+def _bind_raw(a2, b2, rows, d, mode):
+    lib = _lib.load()
+    out = torch.empty(rows, d, device=a2.device, dtype=torch.float32)
+    _launch("cvb_vsa_bind", ptr(a2), ptr(b2), ptr(out), rows, a2.shape[0], b2.shape[0], d, mode)
+    return out
+
+
+def _flatten_pair(a, b):
+    """Broadcast leading dims of a, b (..., d). Returns (a2 (Ra,d), b2 (Rb,d), rows, out_shape) where
+    each operand is either fully expanded or a single broadcast row (Rx == 1) -- the kernel indexes
+    operand rows modulo Rx."""
+    d = a.shape[-1]
+    if b.shape[-1] != d:
+        raise ValueError(f"last dims differ: {a.shape} vs {b.shape}")
+    lead = torch.broadcast_shapes(a.shape[:-1], b.shape[:-1])
+    rows = int(math.prod(lead)) if len(lead) else 1
+
+    def flat(x):
+        if x.shape[:-1] == lead:
+            return _f32c(x).reshape(rows, d)
+        if x.numel() == d:
+            return _f32c(x).reshape(1, d)
+        return _f32c(x.expand(*lead, d)).reshape(rows, d)
+
+    return flat(a), flat(b), rows, tuple(lead) + (d,)
+
+
+def _reduce_to(grad_rows, shape, out_shape):
+    """Sum a (rows, d) gradient of the broadcast result back to an operand of `shape`."""
+    g = grad_rows.reshape(out_shape)
+    return g.sum_to_size(shape) if tuple(shape) != tuple(out_shape) else g
+
+
+class Bind(torch.autograd.Function):
+    """mode MUL: bind (utils/vsa.py:43-46); MUL_CONJ: unbind 'inv' (vsa.py:56-64); DIV: unbind 'deconv'."""
+
+    @staticmethod
+    def forward(ctx, a, b, mode):
+        _prep(a, b)
+        a2, b2, rows, out_shape = _flatten_pair(a, b)
+        out = _bind_raw(a2, b2, rows, a.shape[-1], mode)
+        ctx.save_for_backward(a2, b2, out if mode == BIND_DIV else None)
+        ctx.meta = (mode, rows, out_shape, tuple(a.shape), tuple(b.shape))
+        return out.reshape(out_shape)
+
+    @staticmethod
+    def backward(ctx, grad):
+        a2, b2, out = ctx.saved_tensors
+        mode, rows, out_shape, ashape, bshape = ctx.meta
+        d = out_shape[-1]
+        g = _f32c(grad).reshape(rows, d)
+        da = db = None
+        if mode == BIND_MUL:          # d/da = bind(g, invert(b)), d/db = bind(g, invert(a))
+            if ctx.needs_input_grad[0]:
+                da = _bind_raw(g, b2, rows, d, BIND_MUL_CONJ)
+            if ctx.needs_input_grad[1]:
+                db = _bind_raw(g, a2, rows, d, BIND_MUL_CONJ)
+        elif mode == BIND_MUL_CONJ:   # out = irfft(A conj B): d/da = bind(g, b), d/db = irfft(A conj G)
+            if ctx.needs_input_grad[0]:
+                da = _bind_raw(g, b2, rows, d, BIND_MUL)
+            if ctx.needs_input_grad[1]:
+                db = _bind_raw(a2, g, rows, d, BIND_MUL_CONJ)
+        else:                         # DIV: d/da = irfft(G / conj(B+eps)), d/db = -irfft(dA conj OUT)
+            da_rows = _bind_raw(g, b2, rows, d, BIND_DIV_CONJ)
+            if ctx.needs_input_grad[0]:
+                da = da_rows
+            if ctx.needs_input_grad[1]:
+                db = _bind_raw(da_rows, out, rows, d, BIND_NEG_MUL_CONJ)
+        if da is not None:
+            da = _reduce_to(da, ashape, out_shape)
+        if db is not None:
+            db = _reduce_to(db, bshape, out_shape)
+        return da, db, None
+
+
+def invert(a):
+    lib, dev = _prep(a)
+    d = a.shape[-1]
+    a2 = _f32c(a).reshape(-1, d)
+    out = torch.empty_like(a2)
+    _launch("cvb_vsa_invert", ptr(a2), ptr(out), a2.shape[0], d)
+    return out.reshape(a.shape)
+
+
+class Invert(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a):
+        return invert(a)
+
+    @staticmethod
+    def backward(ctx, grad):
+        return invert(grad)   # the index reversal is an involutive permutation
+
+
+def permute(v, perm, inverse):
+    lib, dev = _prep(v, perm)
+    d = v.shape[-1]
+    if perm.numel() != d:
+        raise ValueError("permutation length must equal the vector dimension")
+    v2 = _f32c(v).reshape(-1, d)
+    pm = perm.to(torch.int64).contiguous()
+    out = torch.empty_like(v2)
+    _launch("cvb_vsa_permute", ptr(v2), ptr(pm), ptr(out), v2.shape[0], d, 1 if inverse else 0)
+    return out.reshape(v.shape)
+
+
+class Permute(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, v, perm, inverse):
+        ctx.save_for_backward(perm)
+        ctx.inverse = inverse
+        return permute(v, perm, inverse)
+
+    @staticmethod
+    def backward(ctx, grad):
+        (perm,) = ctx.saved_tensors
+        return permute(grad, perm, not ctx.inverse), None, None
+
+
+class Bundle(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, vectors, scale):
+        lib, dev = _prep(vectors)
+        k = vectors.shape[0]
+        inner = tuple(vectors.shape[1:])
+        d = int(math.prod(inner)) if inner else 1
+        v2 = _f32c(vectors).reshape(k, d)
+        out = torch.empty(d, device=dev, dtype=torch.float32)
+        ws = torch.empty(max(int(lib.cvb_vsa_bundle_workspace_bytes(k, d)) // 4, 1), device=dev, dtype=torch.float32)
+        _launch("cvb_vsa_bundle", ptr(v2), ptr(out), k, d, float(scale), ptr(ws))
+        ctx.meta = (tuple(vectors.shape), float(scale))
+        return out.reshape(inner)
+
+    @staticmethod
+    def backward(ctx, grad):
+        shape, scale = ctx.meta
+        return (grad * scale).unsqueeze(0).expand(shape), None
+
+
+class Cosine(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        lib, dev = _prep(a, b)
+        a2, b2, rows, out_shape = _flatten_pair(a, b)
+        d = out_shape[-1]
+        out = torch.empty(rows, device=dev, dtype=torch.float32)
+        _launch("cvb_vsa_cosine", ptr(a2), ptr(b2), ptr(out), rows, a2.shape[0], b2.shape[0], d)
+        ctx.save_for_backward(a2, b2)
+        ctx.meta = (rows, out_shape, tuple(a.shape), tuple(b.shape))
+        return out.reshape(out_shape[:-1])
+
+    @staticmethod
+    def backward(ctx, grad):
+        a2, b2 = ctx.saved_tensors
+        rows, out_shape, ashape, bshape = ctx.meta
+        d = out_shape[-1]
+        lib = _lib.load()
+        g = _f32c(grad).reshape(rows)
+        da = torch.empty(rows, d, device=g.device, dtype=torch.float32) if ctx.needs_input_grad[0] else None
+        db = torch.empty(rows, d, device=g.device, dtype=torch.float32) if ctx.needs_input_grad[1] else None
+        _launch("cvb_vsa_cosine_backward", ptr(a2), ptr(b2), ptr(g), ptr(da), ptr(db), rows, a2.shape[0], b2.shape[0], d)
+        if da is not None:
+            da = _reduce_to(da, ashape, out_shape)
+        if db is not None:
+            db = _reduce_to(db, bshape, out_shape)
+        return da, db
+
+
+class Normalize(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        lib, dev = _prep(x)
+        d = x.shape[-1]
+        x2 = _f32c(x).reshape(-1, d)
+        out = torch.empty_like(x2)
+        _launch("cvb_vsa_normalize", ptr(x2), ptr(out), x2.shape[0], d)
+        ctx.save_for_backward(x2)
+        ctx.shape = tuple(x.shape)
+        return out.reshape(x.shape)
+
+    @staticmethod
+    def backward(ctx, grad):
+        (x2,) = ctx.saved_tensors
+        lib = _lib.load()
+        g = _f32c(grad).reshape(x2.shape)
+        dx = torch.empty_like(x2)
+        _launch("cvb_vsa_normalize_backward", ptr(x2), ptr(g), ptr(dx), x2.shape[0], x2.shape[1])
+        return dx.reshape(ctx.shape)
+
+
+def hrr_init(n, d, device):
+    dev = torch.device(device)
+    _lib.ensure_device(dev)
+    lib = _lib.load()
+    out = torch.empty(n, d, device=dev, dtype=torch.float32)
+    _CUR_DEV[0] = out.device
+    seed, off = _lib.next_rng()
+    with torch.cuda.device(out.device):
+        _launch("cvb_vsa_hrr_init", ptr(out), n, d, seed, off)
+    return out
+
+
+def unitary_init(n, d, device, eps):
+    dev = torch.device(device)
+    _lib.ensure_device(dev)
+    lib = _lib.load()
+    out = torch.empty(n, d, device=dev, dtype=torch.float32)
+    _CUR_DEV[0] = out.device
+    seed, off = _lib.next_rng()
+    with torch.cuda.device(out.device):
+        _launch("cvb_vsa_unitary_init", ptr(out), n, d, float(eps), seed, off)
+    return out
+
+
+# =================================================================================================
+# D-dimensional PowerSpherical / vMF / uniform sphere
+# =================================================================================================
+def sphere_uniform_rsample(rows, D, device, norm_eps, gnoise=None):
+    dev = torch.device(device)
+    _lib.ensure_device(dev)
+    z = torch.empty(rows, D, device=dev, dtype=torch.float32)
+    _CUR_DEV[0] = z.device
+    if gnoise is None:
+        seed, off = _lib.next_rng()
+        g = None
+    else:
+        g, seed, off = _f32c(gnoise.reshape(rows, D)), 0, 0
+    _launch("cvb_sphere_uniform_rsample", ptr(g), seed, off, ptr(z), rows, D, float(norm_eps))
+    return z
+
+
+class PowerSphericalRsample(torch.autograd.Function):
+    """z (n*B, D) = PowerSpherical(loc (B,D), kappa (B,)).rsample; draws None or (tprime (rows,), g (rows, D-1))."""
+
+    @staticmethod
+    def forward(ctx, loc, kappa, n_samples, draws):
+        lib, dev = _prep(loc, kappa)
+        B, D = loc.shape
+        rows = B * n_samples
+        loc_c, kap_c = _f32c(loc), _f32c(kappa.reshape(-1))
+        z = torch.empty(rows, D, device=dev, dtype=torch.float32)
+        if draws is None:
+            tp = g = None
+            save = torch.empty(rows, 2, device=dev, dtype=torch.float32)
+            seed, off = _lib.next_rng()
+        else:
+            tp = _f32c(draws[0].reshape(rows))
+            g = _f32c(draws[1].reshape(rows, D - 1))
+            save, seed, off = None, 0, 0
+        _launch("cvb_powerspherical_rsample", ptr(loc_c), ptr(kap_c), B, ptr(tp), ptr(g), seed, off, ptr(z), ptr(save),
+                rows, D)
+        ctx.save_for_backward(loc_c, kap_c, tp, g, save)
+        ctx.meta = (B, D, rows, n_samples, seed, off, tuple(kappa.shape))
+        return z
+
+    @staticmethod
+    def backward(ctx, grad_z):
+        loc_c, kap_c, tp, g, save = ctx.saved_tensors
+        B, D, rows, n_samples, seed, off, kshape = ctx.meta
+        gz = _f32c(grad_z).reshape(rows, D)
+        _CUR_DEV[0] = gz.device
+        dloc = torch.empty(rows, D, device=gz.device, dtype=torch.float32)
+        dk = torch.empty(rows, device=gz.device, dtype=torch.float32)
+        _launch("cvb_powerspherical_rsample_backward", ptr(gz), ptr(loc_c), ptr(kap_c), B, ptr(tp), ptr(g), ptr(save),
+                seed, off, ptr(dloc), ptr(dk), rows, D)
+        if n_samples > 1:
+            dloc = dloc.view(n_samples, B, D).sum(0)
+            dk = dk.view(n_samples, B).sum(0)
+        return dloc, dk.reshape(kshape), None, None
+
+
+class PowerSphericalLogProb(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, value, loc, kappa):
+        lib, dev = _prep(value, loc, kappa)
+        B, D = loc.shape
+        rows = value.shape[0]
+        val_c, loc_c, kap_c = _f32c(value), _f32c(loc), _f32c(kappa.reshape(-1))
+        lp = torch.empty(rows, device=dev, dtype=torch.float32)
+        need = any(ctx.needs_input_grad)
+        coef = torch.empty(rows, device=dev, dtype=torch.float32) if need else None
+        dk = torch.empty(rows, device=dev, dtype=torch.float32) if need else None
+        _launch("cvb_powerspherical_log_prob", ptr(val_c), ptr(loc_c), ptr(kap_c), B, ptr(lp), ptr(coef), ptr(dk),
+                rows, D)
+        ctx.save_for_backward(val_c, loc_c, coef, dk)
+        ctx.meta = (B, D, rows, tuple(kappa.shape))
+        return lp
+
+    @staticmethod
+    def backward(ctx, grad):
+        val_c, loc_c, coef, dk = ctx.saved_tensors
+        B, D, rows, kshape = ctx.meta
+        S = rows // B
+        w = (grad.reshape(rows) * coef)[:, None]
+        dval = w * loc_c.repeat(S, 1) if ctx.needs_input_grad[0] else None
+        dloc = (w * val_c).view(S, B, D).sum(0) if ctx.needs_input_grad[1] else None
+        dkap = (grad.reshape(rows) * dk).view(S, B).sum(0).reshape(kshape) if ctx.needs_input_grad[2] else None
+        return dval, dloc, dkap
+
+
+class PSLogNormalizer(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, kappa, dim):
+        lib, dev = _prep(kappa)
+        k = _f32c(kappa.reshape(-1))
+        ln = torch.empty_like(k)
+        dln = torch.empty_like(k)
+        _launch("cvb_ps_log_normalizer", ptr(k), k.numel(), (dim - 1) / 2, ptr(ln), ptr(dln))
+        ctx.save_for_backward(dln)
+        ctx.kshape = tuple(kappa.shape)
+        return ln.reshape(kappa.shape)
+
+    @staticmethod
+    def backward(ctx, grad):
+        (dln,) = ctx.saved_tensors
+        return (grad.reshape(-1) * dln).reshape(ctx.kshape), None
+
+
+class VMFRsample(torch.autograd.Function):
+    """z (rows, D) = VonMisesFisher(loc (B,D), kappa (B,1)).rsample.
+    draws: None or (e_rounds (R, rows) f64 | None for D == 3, u_rounds (R, rows) f64, g (rows, D))."""
+
+    @staticmethod
+    def forward(ctx, loc, kappa, n_samples, draws):
+        lib, dev = _prep(loc, kappa)
+        B, D = loc.shape
+        rows = B * n_samples
+        loc_c, kap_c = _f32c(loc), _f32c(kappa.reshape(-1))
+        z = torch.empty(rows, D, device=dev, dtype=torch.float32)
+        save = torch.empty(rows, 2, device=dev, dtype=torch.float32)
+        if draws is None:
+            e = u = g = None
+            R = 0
+            seed, off = _lib.next_rng()
+        else:
+            e, u, g = draws
+            u = u.to(torch.float64).reshape(-1, rows).contiguous()
+            e = None if e is None else e.to(torch.float64).reshape(-1, rows).contiguous()
+            R = u.shape[0]
+            g = _f32c(g.reshape(rows, D))
+            seed, off = 0, 0
+        _launch("cvb_vmf_rsample", ptr(loc_c), ptr(kap_c), B, ptr(e), ptr(u), R, ptr(g), seed, off, ptr(z), ptr(save),
+                rows, D)
+        ctx.save_for_backward(loc_c, kap_c, g, save)
+        ctx.meta = (B, D, rows, n_samples, seed, off, tuple(kappa.shape))
+        return z
+
+    @staticmethod
+    def backward(ctx, grad_z):
+        loc_c, kap_c, g, save = ctx.saved_tensors
+        B, D, rows, n_samples, seed, off, kshape = ctx.meta
+        gz = _f32c(grad_z).reshape(rows, D)
+        _CUR_DEV[0] = gz.device
+        dloc = torch.empty(rows, D, device=gz.device, dtype=torch.float32)
+        dk = torch.empty(rows, device=gz.device, dtype=torch.float32)
+        _launch("cvb_vmf_rsample_backward", ptr(gz), ptr(loc_c), ptr(kap_c), B, ptr(g), ptr(save), seed, off, ptr(dloc),
+                ptr(dk), rows, D)
+        if n_samples > 1:
+            dloc = dloc.view(n_samples, B, D).sum(0)
+            dk = dk.view(n_samples, B).sum(0)
+        return dloc, dk.reshape(kshape), None, None
+
+
+class VMFEntropyLogNorm(torch.autograd.Function):
+    """(entropy, log_norm) per row of kappa (B,1) for sphere dimension D."""
+
+    @staticmethod
+    def forward(ctx, kappa, D):
+        lib, dev = _prep(kappa)
+        k = _f32c(kappa.reshape(-1))
+        ent, ln, dent, dln = (torch.empty_like(k) for _ in range(4))
+        _launch("cvb_vmf_entropy_lognorm", ptr(k), k.numel(), D, ptr(ent), ptr(ln), ptr(dent), ptr(dln))
+        ctx.save_for_backward(dent, dln)
+        ctx.kshape = tuple(kappa.shape)
+        return ent, ln
+
+    @staticmethod
+    def backward(ctx, g_ent, g_ln):
+        dent, dln = ctx.saved_tensors
+        out = torch.zeros_like(dent)
+        if g_ent is not None:
+            out = out + g_ent.reshape(-1) * dent
+        if g_ln is not None:
+            out = out + g_ln.reshape(-1) * dln
+        return out.reshape(ctx.kshape), None

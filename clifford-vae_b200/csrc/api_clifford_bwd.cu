@@ -1,0 +1,82 @@
+// C ABI entry points for the Clifford-torus kernels (include/clifford_b200.h).
+#include "launch.cuh"
+#include "clifford_kernels.cuh"
+#include "../../include/clifford_b200.h"
+
+using namespace cvb;
+
+namespace {
+
+constexpr size_t kGenericSmemLimit = 200 * 1024;
+
+template <int LOG2N, bool ROWK>
+int launch_bwd_fast(const CliffordBwdParams& p, cudaStream_t st) {
+  using Pl = FftPlan<LOG2N>;
+  const cplx* tw = device_twiddles();
+  if (!tw) return kCudaError;
+  const size_t smem = sizeof(cplx) * Pl::XCH * Pl::GROUPS + sizeof(float) * 32 * Pl::GROUPS;
+  auto kern = clifford_bwd_kernel<LOG2N, ROWK>;
+  int grid = 0;
+  const long long work = (p.rows + Pl::GROUPS - 1) / Pl::GROUPS;
+  if (int rc = persistent_grid(kern, Pl::THREADS, smem, work, &grid)) return rc;
+  kern<<<grid, Pl::THREADS, smem, st>>>(p, tw);
+  return check_launch("clifford_bwd_kernel");
+}
+
+template <bool ROWK>
+int dispatch_bwd(const CliffordBwdParams& p, cudaStream_t st) {
+  const bool fast = is_pow2(p.d) && p.d >= 16 && p.d <= 8192 && aligned(p.grad_z, 8);
+  if (fast) {
+    switch (ilog2(p.d)) {
+#define CVB_CASE(L) case L: return launch_bwd_fast<L, ROWK>(p, st);
+      CVB_CASE(4) CVB_CASE(5) CVB_CASE(6) CVB_CASE(7) CVB_CASE(8) CVB_CASE(9) CVB_CASE(10) CVB_CASE(11) CVB_CASE(12)
+      CVB_CASE(13)
+#undef CVB_CASE
+    }
+  }
+  const int n = 2 * p.d;
+  const size_t smem = sizeof(cplx) * n + sizeof(float) * (n + 32);
+  CVB_REQUIRE(smem <= kGenericSmemLimit, kUnsupported, "clifford backward: d=%d too large for the direct-DFT path", p.d);
+  auto kern = clifford_bwd_generic_kernel<ROWK>;
+  int grid = 0;
+  if (int rc = persistent_grid(kern, kGenericThreads, smem, p.rows, &grid)) return rc;
+  kern<<<grid, kGenericThreads, smem, st>>>(p);
+  return check_launch("clifford_bwd_generic_kernel");
+}
+
+}  // namespace
+
+extern "C" {
+
+int cvb_clifford_ps_rsample_backward(const float* grad_z, const float* loc, const float* kappa,
+                                     long long kappa_row_stride, int kappa_el_stride, long long loc_rows,
+                                     const float* tprime, const float* gnoise, const float* tp_signed, float* dloc,
+                                     float* dkappa, long long rows, int d, void* stream) {
+  CVB_REQUIRE(grad_z && loc && kappa && dloc && dkappa, kBadArgument, "cvb_clifford_ps_rsample_backward: null pointer");
+  CVB_REQUIRE(rows > 0 && d >= 1 && loc_rows > 0, kBadArgument, "cvb_clifford_ps_rsample_backward: bad sizes");
+  CVB_REQUIRE(tp_signed || (tprime && gnoise), kBadArgument, "cvb_clifford_ps_rsample_backward: need tp_signed or (tprime, gnoise)");
+  CliffordBwdParams p{};
+  p.grad_z = grad_z; p.loc = loc; p.kappa = kappa; p.kappa_row_stride = kappa_row_stride;
+  p.kappa_el_stride = kappa_el_stride; p.loc_rows = (int)loc_rows; p.tprime = tprime; p.gnoise = gnoise;
+  p.tp_signed = tp_signed; p.dloc = dloc; p.dkappa = dkappa; p.rows = rows; p.d = d;
+  cudaStream_t st = (cudaStream_t)stream;
+  return kappa_el_stride == 0 ? dispatch_bwd<true>(p, st) : dispatch_bwd<false>(p, st);
+}
+
+int cvb_ps_entropy_kl(const float* kappa, long long kappa_row_stride, int kappa_el_stride, long long rows, int d,
+                      double half_dm1, int torus, double prior_entropy, float* entropy, float* kl, float* dentropy,
+                      void* stream) {
+  CVB_REQUIRE(kappa && rows > 0 && d >= 1, kBadArgument, "cvb_ps_entropy_kl: bad arguments");
+  EntropyParams p{};
+  p.kappa = kappa; p.kappa_row_stride = kappa_row_stride; p.kappa_el_stride = kappa_el_stride; p.entropy = entropy;
+  p.kl = kl; p.dentropy = dentropy; p.rows = rows; p.d = d; p.half_dm1 = half_dm1; p.skip_first = torus ? 1 : 0;
+  p.prior_entropy = prior_entropy;
+  long long warps = rows;
+  int blocks = (int)((warps * 32 + 255) / 256);
+  const int cap = sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  ps_entropy_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p);
+  return check_launch("ps_entropy_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,91 @@
+// C ABI entry points for the Clifford-torus kernels (include/clifford_b200.h).
+#include "launch.cuh"
+#include "clifford_kernels.cuh"
+#include "../../include/clifford_b200.h"
+
+using namespace cvb;
+
+namespace {
+
+constexpr size_t kGenericSmemLimit = 200 * 1024;
+
+template <int LOG2N, int MODE, bool ROWK>
+int launch_fwd_fast(const CliffordFwdParams& p, cudaStream_t st) {
+  using Pl = FftPlan<LOG2N>;
+  const cplx* tw = device_twiddles();
+  if (!tw) return kCudaError;
+  const size_t smem = sizeof(cplx) * Pl::XCH * Pl::GROUPS;
+  auto kern = clifford_fwd_kernel<LOG2N, MODE, ROWK>;
+  int grid = 0;
+  const long long work = (p.rows + Pl::GROUPS - 1) / Pl::GROUPS;
+  if (int rc = persistent_grid(kern, Pl::THREADS, smem, work, &grid)) return rc;
+  kern<<<grid, Pl::THREADS, smem, st>>>(p, tw);
+  return check_launch("clifford_fwd_kernel");
+}
+
+template <int MODE, bool ROWK>
+int dispatch_fwd(const CliffordFwdParams& p, cudaStream_t st) {
+  const bool fast = is_pow2(p.d) && p.d >= 16 && p.d <= 8192 && p.n == 2 * p.d && aligned(p.z, 8);
+  if (fast) {
+    switch (ilog2(p.d)) {
+#define CVB_CASE(L) case L: return launch_fwd_fast<L, MODE, ROWK>(p, st);
+      CVB_CASE(4) CVB_CASE(5) CVB_CASE(6) CVB_CASE(7) CVB_CASE(8) CVB_CASE(9) CVB_CASE(10) CVB_CASE(11) CVB_CASE(12)
+      CVB_CASE(13)
+#undef CVB_CASE
+    }
+  }
+  const int nph = (p.n - 1) / 2;
+  const size_t smem = sizeof(cplx) * ((size_t)p.n + nph + 1);
+  CVB_REQUIRE(smem <= kGenericSmemLimit, kUnsupported, "clifford rsample: length n=%d too large for the direct-DFT path", p.n);
+  auto kern = clifford_fwd_generic_kernel<MODE, ROWK>;
+  int grid = 0;
+  if (int rc = persistent_grid(kern, kGenericThreads, smem, p.rows, &grid)) return rc;
+  kern<<<grid, kGenericThreads, smem, st>>>(p);
+  return check_launch("clifford_fwd_generic_kernel");
+}
+
+}  // namespace
+
+extern "C" {
+
+int cvb_clifford_ps_rsample(const float* loc, const float* kappa, long long kappa_row_stride, int kappa_el_stride,
+                            long long loc_rows, const float* tprime, const float* gnoise, unsigned long long seed,
+                            unsigned long long offset, float* z, float* tp_signed, float* entropy, float* kl,
+                            float* dentropy, long long rows, int d, void* stream) {
+  CVB_REQUIRE(loc && kappa && z, kBadArgument, "cvb_clifford_ps_rsample: null pointer");
+  CVB_REQUIRE(rows > 0 && d >= 1 && loc_rows > 0, kBadArgument, "cvb_clifford_ps_rsample: rows=%lld d=%d loc_rows=%lld", rows, d, loc_rows);
+  CVB_REQUIRE((tprime == nullptr) == (gnoise == nullptr), kBadArgument, "cvb_clifford_ps_rsample: give both tprime and gnoise or neither");
+  CVB_REQUIRE(kappa_el_stride == 0 || (!entropy && !kl && !dentropy), kBadArgument,
+              "cvb_clifford_ps_rsample: fused entropy/kl needs one concentration per row; use cvb_ps_entropy_kl");
+  CliffordFwdParams p{};
+  p.loc = loc; p.kappa = kappa; p.kappa_row_stride = kappa_row_stride; p.kappa_el_stride = kappa_el_stride;
+  p.loc_rows = (int)loc_rows; p.tprime = tprime; p.gnoise = gnoise; p.z = z; p.tp_signed = tp_signed;
+  p.entropy = entropy; p.kl = kl; p.dentropy = dentropy; p.rows = rows; p.d = d; p.n = 2 * d;
+  p.key = make_key(seed, offset, 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool rowk = kappa_el_stride == 0;
+  if (tprime) return rowk ? dispatch_fwd<kPsInjected, true>(p, st) : dispatch_fwd<kPsInjected, false>(p, st);
+  return rowk ? dispatch_fwd<kPsRng, true>(p, st) : dispatch_fwd<kPsRng, false>(p, st);
+}
+
+int cvb_clifford_phases_to_vector(const float* phases, float phase_scale, unsigned long long seed,
+                                  unsigned long long offset, float* z, long long rows, int d, void* stream) {
+  CVB_REQUIRE(z && rows > 0 && d >= 1, kBadArgument, "cvb_clifford_phases_to_vector: bad arguments");
+  CliffordFwdParams p{};
+  p.loc_rows = 1; p.phases = phases; p.phase_scale = phase_scale; p.z = z; p.rows = rows; p.d = d; p.n = 2 * d;
+  p.key = make_key(seed, offset, 1);
+  cudaStream_t st = (cudaStream_t)stream;
+  return phases ? dispatch_fwd<kPhases, true>(p, st) : dispatch_fwd<kUniformRng, true>(p, st);
+}
+
+// used by api_vsa.cu
+int cvb_internal_unitary(float* out, long long n, int d, float eps, unsigned long long seed, unsigned long long offset,
+                         void* stream) {
+  CliffordFwdParams p{};
+  // n = d output samples, (d-1)/2 free phases at bins 1..; p.d is only the per-row pitch of the RNG index
+  p.loc_rows = 1; p.phase_scale = eps; p.z = out; p.rows = n; p.n = d; p.d = (d & 1) ? (d + 1) / 2 : d / 2;
+  p.key = make_key(seed, offset, 2);
+  return dispatch_fwd<kUnitaryRng, true>(p, (cudaStream_t)stream);
+}
+
+}  // extern "C"

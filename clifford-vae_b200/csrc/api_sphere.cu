@@ -1,0 +1,116 @@
+// C ABI entry points for the D-dimensional PowerSpherical / vMF / uniform-sphere kernels.
+#include "launch.cuh"
+#include "sphere_kernels.cuh"
+#include "../../include/clifford_b200.h"
+
+using namespace cvb;
+
+namespace {
+inline int row_warp_grid(long long rows) {
+  long long b = (rows * 32 + 255) / 256;
+  const long long cap = (long long)sm_count() * 8;
+  return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+}  // namespace
+
+extern "C" {
+
+int cvb_powerspherical_rsample(const float* loc, const float* kappa, long long loc_rows, const float* tprime,
+                               const float* gnoise, unsigned long long seed, unsigned long long offset, float* z,
+                               float* save, long long rows, int D, void* stream) {
+  CVB_REQUIRE(loc && kappa && z && rows > 0 && loc_rows > 0 && D >= 2, kBadArgument, "cvb_powerspherical_rsample: bad arguments");
+  CVB_REQUIRE((tprime == nullptr) == (gnoise == nullptr), kBadArgument, "cvb_powerspherical_rsample: give both tprime and gnoise or neither");
+  SphereParams p{};
+  p.loc = loc; p.kappa = kappa; p.loc_rows = loc_rows; p.tprime = tprime; p.gnoise = gnoise; p.g_pitch = D - 1;
+  p.g_off = 0; p.z = z; p.save = save; p.rows = rows; p.D = D; p.norm_eps = 1e-7f; p.clamp_eps = 1e-7f;
+  p.house_eps = 1e-7f; p.key = make_key(seed, offset, 0);
+  sphere_rsample_kernel<kFamilyPS><<<row_warp_grid(rows), 256, 0, (cudaStream_t)stream>>>(p);
+  return check_launch("sphere_rsample_kernel<PS>");
+}
+
+int cvb_powerspherical_rsample_backward(const float* grad_z, const float* loc, const float* kappa, long long loc_rows,
+                                        const float* tprime, const float* gnoise, const float* save,
+                                        unsigned long long seed, unsigned long long offset, float* dloc, float* dkappa,
+                                        long long rows, int D, void* stream) {
+  CVB_REQUIRE(grad_z && loc && kappa && dloc && dkappa && rows > 0 && loc_rows > 0 && D >= 2, kBadArgument,
+              "cvb_powerspherical_rsample_backward: bad arguments");
+  CVB_REQUIRE((tprime && gnoise) || (save && !tprime && !gnoise), kBadArgument,
+              "cvb_powerspherical_rsample_backward: need (tprime, gnoise) or save");
+  SphereParams p{};
+  p.loc = loc; p.kappa = kappa; p.loc_rows = loc_rows; p.tprime = tprime; p.gnoise = gnoise; p.g_pitch = D - 1;
+  p.g_off = 0; p.save = const_cast<float*>(save); p.grad_z = grad_z; p.dloc = dloc; p.dkappa = dkappa; p.rows = rows;
+  p.D = D; p.norm_eps = 1e-7f; p.clamp_eps = 1e-7f; p.house_eps = 1e-7f; p.key = make_key(seed, offset, 0);
+  sphere_rsample_bwd_kernel<kFamilyPS><<<row_warp_grid(rows), 256, 0, (cudaStream_t)stream>>>(p);
+  return check_launch("sphere_rsample_bwd_kernel<PS>");
+}
+
+int cvb_powerspherical_log_prob(const float* value, const float* loc, const float* kappa, long long loc_rows,
+                                float* log_prob, float* coef, float* dlp_dkappa, long long rows, int D, void* stream) {
+  CVB_REQUIRE(value && loc && kappa && log_prob && rows > 0 && loc_rows > 0 && D >= 2, kBadArgument,
+              "cvb_powerspherical_log_prob: bad arguments");
+  CVB_REQUIRE((coef == nullptr) == (dlp_dkappa == nullptr), kBadArgument, "cvb_powerspherical_log_prob: give both coef and dlp_dkappa or neither");
+  SphereLogProbParams p{value, loc, kappa, loc_rows, log_prob, coef, dlp_dkappa, rows, D};
+  powerspherical_log_prob_kernel<<<row_warp_grid(rows), 256, 0, (cudaStream_t)stream>>>(p);
+  return check_launch("powerspherical_log_prob_kernel");
+}
+
+int cvb_ps_log_normalizer(const float* kappa, long long rows, double half_dm1, float* log_norm, float* dlog_norm,
+                          void* stream) {
+  CVB_REQUIRE(kappa && log_norm && rows > 0, kBadArgument, "cvb_ps_log_normalizer: bad arguments");
+  int blocks = (int)((rows + 127) / 128);
+  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+  ps_log_normalizer_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(kappa, rows, half_dm1, log_norm, dlog_norm);
+  return check_launch("ps_log_normalizer_kernel");
+}
+
+int cvb_sphere_uniform_rsample(const float* gnoise, unsigned long long seed, unsigned long long offset, float* z,
+                               long long rows, int D, float norm_eps, void* stream) {
+  CVB_REQUIRE(z && rows > 0 && D >= 1, kBadArgument, "cvb_sphere_uniform_rsample: bad arguments");
+  SphereParams p{};
+  p.gnoise = gnoise; p.g_pitch = D; p.g_off = 0; p.z = z; p.rows = rows; p.D = D; p.norm_eps = norm_eps;
+  p.loc_rows = 1; p.key = make_key(seed, offset, 0);
+  sphere_rsample_kernel<kFamilyUniform><<<row_warp_grid(rows), 256, 0, (cudaStream_t)stream>>>(p);
+  return check_launch("sphere_rsample_kernel<Uniform>");
+}
+
+int cvb_vmf_rsample(const float* loc, const float* kappa, long long loc_rows, const double* e_rounds,
+                    const double* u_rounds, int n_rounds, const float* gnoise, unsigned long long seed,
+                    unsigned long long offset, float* z, float* save, long long rows, int D, void* stream) {
+  CVB_REQUIRE(loc && kappa && z && rows > 0 && loc_rows > 0 && D >= 2, kBadArgument, "cvb_vmf_rsample: bad arguments");
+  const bool injected = gnoise != nullptr;
+  if (injected) {
+    CVB_REQUIRE(u_rounds && n_rounds >= 1 && (D == 3 || e_rounds), kBadArgument, "cvb_vmf_rsample: injected mode needs e_rounds/u_rounds");
+  } else {
+    CVB_REQUIRE(!e_rounds && !u_rounds, kBadArgument, "cvb_vmf_rsample: give all injected draws or none");
+  }
+  SphereParams p{};
+  p.loc = loc; p.kappa = kappa; p.loc_rows = loc_rows; p.e_rounds = e_rounds; p.u_rounds = u_rounds;
+  p.n_rounds = n_rounds; p.gnoise = gnoise; p.g_pitch = D; p.g_off = 1; p.z = z; p.save = save; p.rows = rows; p.D = D;
+  p.norm_eps = 0.0f; p.clamp_eps = 1e-10f; p.house_eps = 1e-5f; p.key = make_key(seed, offset, 0);
+  sphere_rsample_kernel<kFamilyVMF><<<row_warp_grid(rows), 256, 0, (cudaStream_t)stream>>>(p);
+  return check_launch("sphere_rsample_kernel<VMF>");
+}
+
+int cvb_vmf_rsample_backward(const float* grad_z, const float* loc, const float* kappa, long long loc_rows,
+                             const float* gnoise, const float* save, unsigned long long seed, unsigned long long offset,
+                             float* dloc, float* dkappa, long long rows, int D, void* stream) {
+  CVB_REQUIRE(grad_z && loc && kappa && save && dloc && dkappa && rows > 0 && loc_rows > 0 && D >= 2, kBadArgument,
+              "cvb_vmf_rsample_backward: bad arguments");
+  SphereParams p{};
+  p.loc = loc; p.kappa = kappa; p.loc_rows = loc_rows; p.gnoise = gnoise; p.g_pitch = D; p.g_off = 1;
+  p.save = const_cast<float*>(save); p.grad_z = grad_z; p.dloc = dloc; p.dkappa = dkappa; p.rows = rows; p.D = D;
+  p.norm_eps = 0.0f; p.clamp_eps = 1e-10f; p.house_eps = 1e-5f; p.key = make_key(seed, offset, 0);
+  sphere_rsample_bwd_kernel<kFamilyVMF><<<row_warp_grid(rows), 256, 0, (cudaStream_t)stream>>>(p);
+  return check_launch("sphere_rsample_bwd_kernel<VMF>");
+}
+
+int cvb_vmf_entropy_lognorm(const float* kappa, long long rows, int D, float* entropy, float* log_norm, float* dentropy,
+                            float* dlog_norm, void* stream) {
+  CVB_REQUIRE(kappa && rows > 0 && D >= 2, kBadArgument, "cvb_vmf_entropy_lognorm: bad arguments");
+  int blocks = (int)((rows + 127) / 128);
+  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+  vmf_entropy_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(kappa, rows, D, entropy, log_norm, dentropy, dlog_norm);
+  return check_launch("vmf_entropy_kernel");
+}
+
+}  // extern "C"

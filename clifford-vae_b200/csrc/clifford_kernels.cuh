@@ -1,0 +1,535 @@
+// Fused Clifford-torus kernels: sample -> Hermitian phasors -> C2R iFFT -> z, with the row
+// entropy / KL in the same pass; backward (R2C FFT of grad_z -> dloc, dkappa); log_prob (R2C FFT
+// -> angle -> power-spherical log density).  Power-of-two d uses the register/shared-memory FFT
+// engine (fft_core.cuh); any other d uses the direct-DFT kernels at the bottom (same element
+// math, O(d^2) per row) so every length the reference accepts runs on the device.
+//
+// Reference semantics: dists/clifford.py:281-327 (CliffordPowerSphericalDistribution),
+// :215-242 (CliffordTorusUniform), utils/vsa.py:15-36 (unitary_init); closed forms in
+// SURVEY.md section 8(a).
+#pragma once
+#include "fft_core.cuh"
+#include "rng.cuh"
+#include "special.cuh"
+
+namespace cvb {
+
+enum CliffordMode : int {
+  kPsInjected = 0,   // t' and g supplied (parity mode)
+  kPsRng = 1,        // Philox on device
+  kPhases = 2,       // theta = phase_scale * phases[row, k]   (uniform prior with injected u; unitary init)
+  kUniformRng = 3,   // theta = 2 pi U
+  kUnitaryRng = 4,   // theta = sign * pi * (eps + a (1 - 2 eps))   (utils/vsa.py:15-36)
+};
+
+struct CliffordFwdParams {
+  const float* loc;        // (loc_rows, d)
+  const float* kappa;      // element (r, k) at kappa[r * kappa_row_stride + k * kappa_el_stride]
+  long long kappa_row_stride;
+  int kappa_el_stride;     // 0: one concentration per row
+  int loc_rows;            // rows are (sample, batch) flattened: row r uses loc/kappa row r % loc_rows
+  const float* tprime;     // (rows, d) injected Beta draws           [kPsInjected]
+  const float* gnoise;     // (rows, d) injected N(0,1) sign draws    [kPsInjected]
+  const float* phases;     // (rows, d)                               [kPhases]
+  float phase_scale;       //                                         [kPhases]; eps for kUnitaryRng
+  float* z;                // (rows, n) out
+  float* tp_signed;        // (rows, d) out, optional: copysign(t', s) saved for backward [kPsRng]
+  float* entropy;          // (rows) out, optional (row-scalar kappa only)
+  float* kl;               // (rows) out, optional (row-scalar kappa only)
+  float* dentropy;         // (rows) out, optional: d entropy / d kappa (row-scalar kappa only)
+  long long rows;
+  int d;                   // phases per row (row pitch of loc / draws / phases)
+  int n;                   // output length: 2d for the torus; any n >= 2 with d = n/2 rounded down... see generic kernel
+  PhiloxKey key;
+};
+
+constexpr float kEps = 1e-7f;
+
+__device__ __forceinline__ float sign_from_normal(float g) { return g / (fabsf(g) + kEps); }
+
+// Pieces of phi = atan2(s sqrt(max(1 - t^2, eps)), t), t = 2 t' - 1   (clifford.py:44-48,:300)
+struct CirclePhase {
+  float c, s;        // cos phi, sin phi
+  float dphi_dt;     // d phi / d t
+};
+__device__ __forceinline__ CirclePhase circle_phase(float tp, float sgn) {
+  const float t = 2.0f * tp - 1.0f;
+  const float om = fmaf(-t, t, 1.0f);
+  const float sq = sqrtf(fmaxf(om, kEps));
+  const float y1 = sgn * sq;
+  const float r2 = fmaf(t, t, y1 * y1);
+  const float rinv = rsqrtf(r2);
+  CirclePhase o;
+  o.c = t * rinv;
+  o.s = y1 * rinv;
+  const float dy1 = (om > kEps) ? (-sgn * t / sq) : 0.0f;
+  o.dphi_dt = (t * dy1 - y1) / r2;
+  return o;
+}
+
+// e^{i theta_k} for bin k (1 <= k <= d-1) of `row`
+template <int MODE, bool ROWK>
+__device__ __forceinline__ cplx clifford_phasor(const CliffordFwdParams& p, long long row, long long prow, int k,
+                                                GammaMT& gm) {
+  const long long idx = row * p.d + k;
+  if (MODE == kPsInjected || MODE == kPsRng) {
+    float tp, s;
+    if (MODE == kPsInjected) {
+      tp = ldg_stream1(p.tprime + idx);
+      s = sign_from_normal(ldg_stream1(p.gnoise + idx));
+    } else {
+      if (!ROWK) gm = GammaMT(0.5f + (__ldg(p.kappa + prow * p.kappa_row_stride + (long long)k * p.kappa_el_stride) + kEps));
+      tp = beta_half_draw(gm, p.key, (uint64_t)idx, s);
+      if (p.tp_signed) stg_stream1(p.tp_signed + idx, copysignf(tp, s));
+    }
+    const CirclePhase ph = circle_phase(tp, s);
+    float sl, cl;
+    sincosf(ldg_stream1(p.loc + prow * p.d + k), &sl, &cl);
+    return make_float2(fmaf(cl, ph.c, -sl * ph.s), fmaf(sl, ph.c, cl * ph.s));
+  }
+  float th;
+  if (MODE == kPhases) {
+    th = p.phase_scale * ldg_stream1(p.phases + idx);
+  } else {
+    const uint4 r = philox_draw(p.key, (uint64_t)idx, 0);
+    if (MODE == kUniformRng) {
+      th = 6.283185307179586f * u01_open1(r.x);
+    } else {
+      const float a = u01_open1(r.x);
+      const float sg = (r.y & 0x80000000u) ? -1.0f : 1.0f;
+      th = sg * 3.14159265358979f * (p.phase_scale + a * (1.0f - 2.0f * p.phase_scale));
+    }
+  }
+  cplx x;
+  sincosf(th, &x.y, &x.x);
+  return x;
+}
+
+__device__ __forceinline__ void clifford_row_entropy(const CliffordFwdParams& p, long long row, float kap_row) {
+  const PsConsts c = ps_consts((double)kap_row, 0.5);
+  const double ent = (double)(p.d - 1) * c.entropy;
+  if (p.entropy) p.entropy[row] = (float)ent;
+  if (p.kl) p.kl[row] = (float)((double)(p.d - 1) * 1.83787706640934548356 - ent);
+  if (p.dentropy) p.dentropy[row] = (float)((double)(p.d - 1) * c.dentropy);
+}
+
+template <int LOG2N, int MODE, bool ROWK>
+__global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS)
+clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw) {
+  using Pl = FftPlan<LOG2N>;
+  constexpr int d = Pl::N, T = Pl::T, E = Pl::E, G = Pl::GROUPS;
+  extern __shared__ cplx smem[];
+  const int group = threadIdx.x / T, t = threadIdx.x % T;
+  cplx* xch = smem + group * Pl::XCH;
+  constexpr bool PS = (MODE == kPsInjected || MODE == kPsRng);
+
+  for (long long base = (long long)blockIdx.x * G; base < p.rows; base += (long long)gridDim.x * G) {
+    const long long row = base + group;
+    const bool valid = row < p.rows;
+    const long long prow = valid ? (row % p.loc_rows) : 0;
+    cplx v[E];
+    float kap_row = 1.0f;
+    if (PS && valid) kap_row = __ldg(p.kappa + prow * p.kappa_row_stride);
+    GammaMT gm(0.5f + (kap_row + kEps));
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int k = t + e * T;
+      v[e] = (valid && k != 0) ? clifford_phasor<MODE, ROWK>(p, row, prow, k, gm) : make_float2(1.0f, 0.0f);
+    }
+    c2r_pretangle<LOG2N>(v, 1.0f, xch, t, tw);
+    fft_run<LOG2N, true>(v, xch, t, tw);
+    if (valid) {
+      float2* zr = reinterpret_cast<float2*>(p.z + row * (2LL * d));
+#pragma unroll
+      for (int e = 0; e < E; ++e) stg_stream2(zr + t + e * T, v[e]);
+      if (PS && ROWK && t == 0 && (p.entropy || p.kl || p.dentropy)) clifford_row_entropy(p, row, kap_row);
+    }
+  }
+}
+
+// ---- backward of rsample ---------------------------------------------------------------------
+struct CliffordBwdParams {
+  const float* grad_z;     // (rows, 2d)
+  const float* loc;
+  const float* kappa;
+  long long kappa_row_stride;
+  int kappa_el_stride;
+  int loc_rows;
+  const float* tprime;     // injected draws (rows, d), or null when tp_signed is given
+  const float* gnoise;
+  const float* tp_signed;  // saved by the RNG forward
+  float* dloc;             // (rows, d) out
+  float* dkappa;           // ROWK: (rows) row sums; else (rows, d)
+  long long rows;
+  int d;
+};
+
+// Element k of the backward: returns dL/dtheta_k, accumulates / stores dL/dkappa_k.
+template <bool ROWK>
+__device__ __forceinline__ float clifford_bwd_element(const CliffordBwdParams& p, long long row, long long prow, int k,
+                                                      cplx Gk, BetaGradConsts& bc, float inv_d, float& dk) {
+  const long long idx = row * p.d + k;
+  float tp, s;
+  if (p.tp_signed) {
+    const float ts = ldg_stream1(p.tp_signed + idx);
+    tp = fabsf(ts);
+    s = (ts < 0.f) ? -1.0f : 1.0f;
+  } else {
+    tp = ldg_stream1(p.tprime + idx);
+    s = sign_from_normal(ldg_stream1(p.gnoise + idx));
+  }
+  const CirclePhase ph = circle_phase(tp, s);       // identical arithmetic to the forward
+  float sl, cl;
+  sincosf(ldg_stream1(p.loc + prow * p.d + k), &sl, &cl);
+  const cplx x = make_float2(fmaf(cl, ph.c, -sl * ph.s), fmaf(sl, ph.c, cl * ph.s));
+  // dL/dtheta_k = -(2/n) Im(X_k conj(G_k)), 2/n = 1/d
+  const float dth = -inv_d * (x.y * Gk.x - x.x * Gk.y);
+  if (!ROWK) bc = BetaGradConsts(0.5f + (__ldg(p.kappa + prow * p.kappa_row_stride + (long long)k * p.kappa_el_stride) + kEps), 0.5f);
+  const float dtp = dirichlet_grad_one(tp, bc) * (1.0f - tp);
+  dk = dth * ph.dphi_dt * 2.0f * dtp;
+  stg_stream1(p.dloc + idx, dth);
+  if (!ROWK) stg_stream1(p.dkappa + idx, dk);
+  return dth;
+}
+
+template <int LOG2N, bool ROWK>
+__global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS)
+clifford_bwd_kernel(const CliffordBwdParams p, const cplx* __restrict__ tw) {
+  using Pl = FftPlan<LOG2N>;
+  constexpr int d = Pl::N, T = Pl::T, E = Pl::E, G = Pl::GROUPS;
+  extern __shared__ cplx smem[];
+  const int group = threadIdx.x / T, t = threadIdx.x % T;
+  cplx* xch = smem + group * Pl::XCH;
+  float* scratch = reinterpret_cast<float*>(smem + G * Pl::XCH) + group * 32;
+
+  for (long long base = (long long)blockIdx.x * G; base < p.rows; base += (long long)gridDim.x * G) {
+    const long long row = base + group;
+    const bool valid = row < p.rows;
+    const long long prow = valid ? (row % p.loc_rows) : 0;
+    cplx v[E];
+    const float2* gz = reinterpret_cast<const float2*>(p.grad_z + (valid ? row : 0) * (2LL * d));
+#pragma unroll
+    for (int e = 0; e < E; ++e) v[e] = valid ? ldg_stream2(gz + t + e * T) : make_float2(0.f, 0.f);
+    fft_run<LOG2N, false>(v, xch, t, tw);
+    r2c_untangle<LOG2N>(v, xch, t, tw);        // v[e] = G[k]
+
+    const float kap_row = valid ? __ldg(p.kappa + prow * p.kappa_row_stride) : 1.0f;
+    BetaGradConsts bc(0.5f + (kap_row + kEps), 0.5f);
+    float dk_sum = 0.f;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int k = t + e * T;
+      float dk = 0.f;
+      if (valid && k != 0) {
+        clifford_bwd_element<ROWK>(p, row, prow, k, v[e], bc, 1.0f / (float)d, dk);
+      } else if (valid) {
+        stg_stream1(p.dloc + row * d, 0.0f);
+        if (!ROWK) stg_stream1(p.dkappa + row * d, 0.0f);
+      }
+      dk_sum += dk;
+    }
+    if (ROWK) {
+      const float tot = group_sum<T>(dk_sum, scratch, t);
+      if (valid && t == 0) p.dkappa[row] = tot;
+    }
+  }
+}
+
+// ---- log_prob ----------------------------------------------------------------------------------
+struct CliffordLogProbParams {
+  const float* value;      // (rows, 2d)
+  const float* loc;
+  const float* kappa;
+  long long kappa_row_stride;
+  int kappa_el_stride;
+  int loc_rows;
+  float* log_prob;         // (rows) out
+  float* dlp_dloc;         // optional (rows, d): d log_prob / d loc_k
+  float* dlp_dkappa;       // optional; ROWK: (rows), else (rows, d)
+  long long rows;
+  int d;
+};
+
+template <bool ROWK>
+__device__ __forceinline__ void clifford_lp_element(const CliffordLogProbParams& p, long long row, long long prow, int k,
+                                                    cplx Fk, float kap, float logc, float dlogc, float& acc,
+                                                    float& dk_acc) {
+  if (!ROWK) {
+    kap = __ldg(p.kappa + prow * p.kappa_row_stride + (long long)k * p.kappa_el_stride);
+    const PsConsts c = ps_consts((double)kap, 0.5);
+    logc = (float)c.log_norm;
+    dlogc = (float)c.dlog_norm;
+  }
+  // unit vector of the bin's angle; angle(0) = 0 like torch.angle
+  const float mag2 = fmaf(Fk.x, Fk.x, Fk.y * Fk.y);
+  float ca = 1.0f, sa = 0.0f;
+  if (mag2 > 0.f) {
+    const float ri = rsqrtf(mag2);
+    ca = Fk.x * ri;
+    sa = Fk.y * ri;
+  }
+  float sl, cl;
+  sincosf(ldg_stream1(p.loc + prow * p.d + k), &sl, &cl);
+  const float dot_raw = fmaf(cl, ca, sl * sa);
+  const float dot = fminf(fmaxf(dot_raw, -1.0f + kEps), 1.0f - kEps);
+  const float l1p = log1pf(dot);
+  acc += logc + kap * l1p;
+  if (p.dlp_dloc) {
+    // d dot / d loc = -sin(loc) cos(a) + cos(loc) sin(a); zero where the clamp is active
+    const bool inside = (dot_raw >= -1.0f + kEps) && (dot_raw <= 1.0f - kEps);
+    const float ddot = inside ? fmaf(cl, sa, -sl * ca) : 0.0f;
+    stg_stream1(p.dlp_dloc + row * p.d + k, kap * ddot / (1.0f + dot));
+    const float dkv = dlogc + l1p;
+    if (ROWK) dk_acc += dkv; else stg_stream1(p.dlp_dkappa + row * p.d + k, dkv);
+  }
+}
+
+template <int LOG2N, bool ROWK>
+__global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS)
+clifford_log_prob_kernel(const CliffordLogProbParams p, const cplx* __restrict__ tw) {
+  using Pl = FftPlan<LOG2N>;
+  constexpr int d = Pl::N, T = Pl::T, E = Pl::E, G = Pl::GROUPS;
+  extern __shared__ cplx smem[];
+  const int group = threadIdx.x / T, t = threadIdx.x % T;
+  cplx* xch = smem + group * Pl::XCH;
+  float* scratch = reinterpret_cast<float*>(smem + G * Pl::XCH) + group * 32;
+
+  for (long long base = (long long)blockIdx.x * G; base < p.rows; base += (long long)gridDim.x * G) {
+    const long long row = base + group;
+    const bool valid = row < p.rows;
+    const long long prow = valid ? (row % p.loc_rows) : 0;
+    cplx v[E];
+    const float2* vz = reinterpret_cast<const float2*>(p.value + (valid ? row : 0) * (2LL * d));
+#pragma unroll
+    for (int e = 0; e < E; ++e) v[e] = valid ? ldg_stream2(vz + t + e * T) : make_float2(1.f, 0.f);
+    fft_run<LOG2N, false>(v, xch, t, tw);
+    r2c_untangle<LOG2N>(v, xch, t, tw);        // v[e] = F[k], k = 0..d-1
+
+    const float kap_row = valid ? __ldg(p.kappa + prow * p.kappa_row_stride) : 1.0f;
+    float logc = 0.f, dlogc = 0.f;
+    if (ROWK) {
+      const PsConsts c = ps_consts((double)kap_row, 0.5);
+      logc = (float)c.log_norm;
+      dlogc = (float)c.dlog_norm;
+    }
+    float acc = 0.f, dk_acc = 0.f;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      if (valid) clifford_lp_element<ROWK>(p, row, prow, t + e * T, v[e], kap_row, logc, dlogc, acc, dk_acc);
+    }
+    const float tot = group_sum<T>(acc, scratch, t);
+    float dk_tot = 0.f;
+    if (ROWK && p.dlp_dloc) dk_tot = group_sum<T>(dk_acc, scratch, t);
+    if (valid && t == 0) {
+      p.log_prob[row] = tot;
+      if (ROWK && p.dlp_dkappa) p.dlp_dkappa[row] = dk_tot;
+    }
+  }
+}
+
+// =================================================================================================
+// Direct-DFT kernels for lengths the FFT engine does not cover (non power of two, d < 16,
+// d > 8192).  One CTA per row (grid-stride), O(n^2) work per row; twiddles from an exact
+// (index-reduced) shared-memory table.  Same element functions as the fast kernels.
+// =================================================================================================
+constexpr int kGenericThreads = 256;
+
+__device__ __forceinline__ float block_sum_256(float v, float* scratch) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kGenericThreads / 32; ++i) s += scratch[i];
+  return s;
+}
+
+// tw[m] = (cos(2 pi m / n), sin(2 pi m / n)), m in [0, n)
+__device__ __forceinline__ void fill_twiddles(cplx* tw, int n) {
+  for (int m = threadIdx.x; m < n; m += blockDim.x) {
+    double s, c;
+    sincospi(2.0 * (double)m / (double)n, &s, &c);
+    tw[m] = make_float2((float)c, (float)s);
+  }
+}
+
+// Output length n (any n >= 2), nph = (n-1)/2 free phases at bins 1..nph; DC = 1 and, for even n,
+// Nyquist = 1.  For the torus n = 2d and nph = d-1.
+// smem: tw[n] cplx, X[nph+1] cplx
+template <int MODE, bool ROWK>
+__global__ void __launch_bounds__(kGenericThreads)
+clifford_fwd_generic_kernel(const CliffordFwdParams p) {
+  extern __shared__ cplx smem[];
+  const int n = p.n, nph = (n - 1) / 2;
+  cplx* tw = smem;
+  cplx* X = smem + n;
+  constexpr bool PS = (MODE == kPsInjected || MODE == kPsRng);
+  fill_twiddles(tw, n);
+  for (long long row = blockIdx.x; row < p.rows; row += gridDim.x) {
+    const long long prow = row % p.loc_rows;
+    float kap_row = 1.0f;
+    if (PS) kap_row = __ldg(p.kappa + prow * p.kappa_row_stride);
+    GammaMT gm(0.5f + (kap_row + kEps));
+    __syncthreads();
+    for (int k = 1 + threadIdx.x; k <= nph; k += blockDim.x) X[k] = clifford_phasor<MODE, ROWK>(p, row, prow, k, gm);
+    __syncthreads();
+    const float inv_n = 1.0f / (float)n;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+      double acc = 0.0;
+      int m = 0;
+      for (int k = 1; k <= nph; ++k) {
+        m += j;
+        if (m >= n) m -= n;
+        const cplx w = tw[m], x = X[k];
+        acc += (double)(x.x * w.x - x.y * w.y);      // Re(X_k e^{+2 pi i jk/n})
+      }
+      float base = 1.0f;
+      if ((n & 1) == 0) base += (j & 1) ? -1.0f : 1.0f;
+      p.z[row * n + j] = inv_n * (base + 2.0f * (float)acc);
+    }
+    if (PS && ROWK && threadIdx.x == 0 && (p.entropy || p.kl || p.dentropy)) clifford_row_entropy(p, row, kap_row);
+  }
+}
+
+// smem: tw[n] cplx, g[n] float, scratch[32] float
+template <bool ROWK>
+__global__ void __launch_bounds__(kGenericThreads)
+clifford_bwd_generic_kernel(const CliffordBwdParams p) {
+  extern __shared__ cplx smem[];
+  const int d = p.d, n = 2 * d;
+  cplx* tw = smem;
+  float* g = reinterpret_cast<float*>(smem + n);
+  float* scratch = g + n;
+  fill_twiddles(tw, n);
+  for (long long row = blockIdx.x; row < p.rows; row += gridDim.x) {
+    const long long prow = row % p.loc_rows;
+    __syncthreads();
+    for (int j = threadIdx.x; j < n; j += blockDim.x) g[j] = p.grad_z[row * n + j];
+    __syncthreads();
+    const float kap_row = __ldg(p.kappa + prow * p.kappa_row_stride);
+    BetaGradConsts bc(0.5f + (kap_row + kEps), 0.5f);
+    float dk_sum = 0.f;
+    for (int k = threadIdx.x; k < d; k += blockDim.x) {
+      if (k == 0) {
+        p.dloc[row * d] = 0.f;
+        if (!ROWK) p.dkappa[row * d] = 0.f;
+        continue;
+      }
+      double gr = 0.0, gi = 0.0;
+      int m = 0;
+      for (int j = 0; j < n; ++j) {            // G_k = sum_j g_j e^{-2 pi i jk/n}
+        const cplx w = tw[m];
+        gr += (double)(g[j] * w.x);
+        gi -= (double)(g[j] * w.y);
+        m += k;
+        if (m >= n) m -= n;
+      }
+      float dk = 0.f;
+      clifford_bwd_element<ROWK>(p, row, prow, k, make_float2((float)gr, (float)gi), bc, 1.0f / (float)d, dk);
+      dk_sum += dk;
+    }
+    if (ROWK) {
+      const float tot = block_sum_256(dk_sum, scratch);
+      if (threadIdx.x == 0) p.dkappa[row] = tot;
+    }
+  }
+}
+
+template <bool ROWK>
+__global__ void __launch_bounds__(kGenericThreads)
+clifford_log_prob_generic_kernel(const CliffordLogProbParams p) {
+  extern __shared__ cplx smem[];
+  const int d = p.d, n = 2 * d;
+  cplx* tw = smem;
+  float* g = reinterpret_cast<float*>(smem + n);
+  float* scratch = g + n;
+  fill_twiddles(tw, n);
+  for (long long row = blockIdx.x; row < p.rows; row += gridDim.x) {
+    const long long prow = row % p.loc_rows;
+    __syncthreads();
+    for (int j = threadIdx.x; j < n; j += blockDim.x) g[j] = p.value[row * n + j];
+    __syncthreads();
+    const float kap_row = __ldg(p.kappa + prow * p.kappa_row_stride);
+    float logc = 0.f, dlogc = 0.f;
+    if (ROWK) {
+      const PsConsts c = ps_consts((double)kap_row, 0.5);
+      logc = (float)c.log_norm;
+      dlogc = (float)c.dlog_norm;
+    }
+    float acc = 0.f, dk_acc = 0.f;
+    for (int k = threadIdx.x; k < d; k += blockDim.x) {
+      double fr = 0.0, fi = 0.0;
+      int m = 0;
+      for (int j = 0; j < n; ++j) {
+        const cplx w = tw[m];
+        fr += (double)(g[j] * w.x);
+        fi -= (double)(g[j] * w.y);
+        m += k;
+        if (m >= n) m -= n;
+      }
+      if (k == 0) fi = 0.0;
+      clifford_lp_element<ROWK>(p, row, prow, k, make_float2((float)fr, (float)fi), kap_row, logc, dlogc, acc, dk_acc);
+    }
+    const float tot = block_sum_256(acc, scratch);
+    float dk_tot = 0.f;
+    if (ROWK && p.dlp_dloc) dk_tot = block_sum_256(dk_acc, scratch);
+    if (threadIdx.x == 0) {
+      p.log_prob[row] = tot;
+      if (ROWK && p.dlp_dkappa) p.dlp_dkappa[row] = dk_tot;
+    }
+  }
+}
+
+// Row entropy / KL for an arbitrary (rows, d) concentration tensor (strided): sum over k >= 1.
+// One warp per row.  Also the elementwise derivative dH/dkappa when requested.
+struct EntropyParams {
+  const float* kappa;
+  long long kappa_row_stride;
+  int kappa_el_stride;
+  float* entropy;      // (rows) optional
+  float* kl;           // (rows) optional
+  float* dentropy;     // optional; el_stride == 0: (rows) = (d-1) H'(kappa); else (rows, d) with [.,0] = 0
+  long long rows;
+  int d;
+  double half_dm1;     // (sphere dim - 1)/2 : 0.5 for the torus circles
+  int skip_first;      // 1: torus (sum over k >= 1, kl adds (d-1) ln 2 pi); 0: plain per-row PowerSpherical
+  double prior_entropy;   // added to -H for kl when skip_first == 0
+};
+
+static __global__ void ps_entropy_kernel(const EntropyParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long row = warp; row < p.rows; row += nwarps) {
+    const float* kr = p.kappa + row * p.kappa_row_stride;
+    if (p.kappa_el_stride == 0 || !p.skip_first) {
+      if (lane == 0) {
+        const PsConsts c = ps_consts((double)kr[0], p.half_dm1);
+        const double mult = p.skip_first ? (double)(p.d - 1) : 1.0;
+        const double ent = mult * c.entropy;
+        if (p.entropy) p.entropy[row] = (float)ent;
+        if (p.kl) p.kl[row] = (float)((p.skip_first ? mult * 1.83787706640934548356 : p.prior_entropy) - ent);
+        if (p.dentropy) p.dentropy[row] = (float)(mult * c.dentropy);
+      }
+    } else {
+      double acc = 0.0;
+      for (int k = lane; k < p.d; k += 32) {
+        if (k == 0) {
+          if (p.dentropy) p.dentropy[row * p.d] = 0.f;
+          continue;
+        }
+        const PsConsts c = ps_consts((double)kr[(long long)k * p.kappa_el_stride], p.half_dm1);
+        acc += c.entropy;
+        if (p.dentropy) p.dentropy[row * p.d + k] = (float)c.dentropy;
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) {
+        if (p.entropy) p.entropy[row] = (float)acc;
+        if (p.kl) p.kl[row] = (float)((double)(p.d - 1) * 1.83787706640934548356 - acc);
+      }
+    }
+  }
+}
+
+}  // namespace cvb

@@ -1,0 +1,78 @@
+// Shared device/host helpers for the clifford_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cmath>
+
+#ifndef __CUDA_ARCH__
+#define CVB_HOST_PASS 1
+#endif
+
+namespace cvb {
+
+// ---- status codes returned through the C ABI (include/clifford_b200.h) -------------------
+enum Status : int {
+  kOk = 0,
+  kBadArgument = 1,      // null pointer, non-positive size, misaligned row
+  kUnsupported = 2,      // shape outside what the kernels implement
+  kCudaError = 3,        // a CUDA runtime call failed (see cvb_last_error_string)
+};
+
+typedef float2 cplx;
+
+__device__ __forceinline__ cplx cmul(cplx a, cplx b) {
+  return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+// a * conj(b)
+__device__ __forceinline__ cplx cmulc(cplx a, cplx b) {
+  return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
+}
+__device__ __forceinline__ cplx cadd(cplx a, cplx b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ cplx csub(cplx a, cplx b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ cplx cconj(cplx a) { return make_float2(a.x, -a.y); }
+__device__ __forceinline__ cplx cscale(cplx a, float s) { return make_float2(a.x * s, a.y * s); }
+// multiply by +i / -i
+__device__ __forceinline__ cplx cmul_i(cplx a) { return make_float2(-a.y, a.x); }
+__device__ __forceinline__ cplx cmul_mi(cplx a) { return make_float2(a.y, -a.x); }
+
+// Shared-memory exchange buffers hold complex values as float2 with one pad slot every 16
+// entries: stride-R (R = 2..16) writes of the first Stockham pass and the contiguous reads of
+// the next pass are then both conflict-free for 64-bit accesses (DESIGN.md "smem layout").
+__host__ __device__ __forceinline__ constexpr int pad16(int i) { return i + (i >> 4); }
+
+// Twiddle table: g_twiddle[m] = exp(-2*pi*i*m / kTwiddleCircle), m in [0, kTwiddleCircle/2).
+// Filled once per device in double precision on the host (api.cu: ensure_device_tables()).
+constexpr int kTwiddleCircleLog2 = 14;
+constexpr int kTwiddleCircle = 1 << kTwiddleCircleLog2;     // supports real lengths up to 16384
+constexpr int kTwiddleEntries = kTwiddleCircle / 2;
+
+// streaming (read-once / write-once) global accesses: keep them out of L1
+__device__ __forceinline__ float2 ldg_stream2(const float2* p) {
+  float2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float ldg_stream1(const float* p) {
+  float r;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_stream2(float2* p, float2 v) {
+  asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ void stg_stream1(float* p, float v) {
+  asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace cvb

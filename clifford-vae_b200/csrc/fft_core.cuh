@@ -1,0 +1,248 @@
+// Batched power-of-two FFT engine: register-resident Stockham passes with shared-memory
+// exchanges, plus the half-length real-FFT (R2C / C2R) untangling steps.
+//
+// One FFT of N = 2^LOG2N complex points is owned by T = N/E consecutive threads ("a group");
+// thread t of the group holds the E points {t + e*T}.  Every pass applies radix-R butterflies
+// (R <= E, E/R butterflies per thread) entirely in registers; between passes the group
+// transposes through its padded shared-memory exchange buffer.  The ownership pattern
+// {t + e*T} is the same at the input of every pass and at the final output, so callers load
+// and store global memory with consecutive threads touching consecutive float2 (coalesced).
+//
+// All functions that touch the exchange buffer call __syncthreads(): every thread of the CTA
+// must call them the same number of times (callers keep loop trip counts CTA-uniform).
+#pragma once
+#include "common.cuh"
+
+namespace cvb {
+
+template <int LOG2N>
+struct FftPlan {
+  static_assert(LOG2N >= 4 && LOG2N <= 13, "fast path covers N = 16 .. 8192 complex points");
+  static constexpr int N = 1 << LOG2N;
+  static constexpr int LOGE = (LOG2N >= 8) ? 4 : (LOG2N >= 6 ? 3 : 2);
+  static constexpr int E = 1 << LOGE;              // points per thread
+  static constexpr int T = N / E;                  // threads per FFT
+  static constexpr int LOGT = LOG2N - LOGE;
+  static constexpr int XCH = pad16(N) + 2;         // float2 slots in one exchange buffer (index N usable)
+  static constexpr int THREADS = (T >= 128) ? T : 128;   // CTA size
+  static constexpr int GROUPS = THREADS / T;       // FFTs processed side by side in one CTA
+};
+
+// ---- small in-register DFTs (natural order in, natural order out) ---------------------------
+template <bool INV>
+__device__ __forceinline__ void dft2(cplx& a, cplx& b) {
+  cplx t = a;
+  a = cadd(t, b);
+  b = csub(t, b);
+}
+
+template <bool INV>
+__device__ __forceinline__ void dft4(cplx& a0, cplx& a1, cplx& a2, cplx& a3) {
+  cplx s0 = cadd(a0, a2), d0 = csub(a0, a2);
+  cplx s1 = cadd(a1, a3), d1 = csub(a1, a3);
+  cplx r = INV ? cmul_i(d1) : cmul_mi(d1);   // (-i)^1 * d1 forward, (+i) * d1 inverse
+  a0 = cadd(s0, s1);
+  a2 = csub(s0, s1);
+  a1 = cadd(d0, r);
+  a3 = csub(d0, r);
+}
+
+// z * exp(-+ i*phi) with (c, s) = (cos phi, sin phi): forward uses exp(-i phi)
+template <bool INV>
+__device__ __forceinline__ cplx rot(cplx z, float c, float s) {
+  return INV ? make_float2(fmaf(z.x, c, -z.y * s), fmaf(z.x, s, z.y * c))
+             : make_float2(fmaf(z.x, c, z.y * s), fmaf(z.y, c, -z.x * s));
+}
+
+template <int R, bool INV>
+struct Dft;
+
+template <bool INV>
+struct Dft<2, INV> {
+  static __device__ __forceinline__ void run(cplx (&u)[2]) { dft2<INV>(u[0], u[1]); }
+};
+template <bool INV>
+struct Dft<4, INV> {
+  static __device__ __forceinline__ void run(cplx (&u)[4]) { dft4<INV>(u[0], u[1], u[2], u[3]); }
+};
+template <bool INV>
+struct Dft<8, INV> {
+  static __device__ __forceinline__ void run(cplx (&u)[8]) {
+    constexpr float h = 0.70710678118654752440f;
+    dft4<INV>(u[0], u[2], u[4], u[6]);     // even samples -> E[k] in u[0],u[2],u[4],u[6]
+    dft4<INV>(u[1], u[3], u[5], u[7]);     // odd samples  -> O[k] in u[1],u[3],u[5],u[7]
+    cplx o0 = u[1];
+    cplx o1 = rot<INV>(u[3], h, h);
+    cplx o2 = INV ? cmul_i(u[5]) : cmul_mi(u[5]);
+    cplx o3 = rot<INV>(u[7], -h, h);
+    cplx e0 = u[0], e1 = u[2], e2 = u[4], e3 = u[6];
+    u[0] = cadd(e0, o0); u[4] = csub(e0, o0);
+    u[1] = cadd(e1, o1); u[5] = csub(e1, o1);
+    u[2] = cadd(e2, o2); u[6] = csub(e2, o2);
+    u[3] = cadd(e3, o3); u[7] = csub(e3, o3);
+  }
+};
+template <bool INV>
+struct Dft<16, INV> {
+  static __device__ __forceinline__ void run(cplx (&u)[16]) {
+    constexpr float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f;
+    constexpr float h = 0.70710678118654752440f;
+    // stage 1: for each n1, DFT-4 over n2 of x[n1 + 4 n2]  -> Y[n1][k2] left at slot n1 + 4 k2
+#pragma unroll
+    for (int n1 = 0; n1 < 4; ++n1) dft4<INV>(u[n1], u[n1 + 4], u[n1 + 8], u[n1 + 12]);
+    // stage 2: Y[n1][k2] *= W16^(n1 k2)
+    u[5] = rot<INV>(u[5], c1, s1);                       // m = 1
+    u[6] = rot<INV>(u[6], h, h);                         // m = 2
+    u[7] = rot<INV>(u[7], s1, c1);                       // m = 3
+    u[9] = rot<INV>(u[9], h, h);                         // m = 2
+    u[10] = INV ? cmul_i(u[10]) : cmul_mi(u[10]);        // m = 4
+    u[11] = rot<INV>(u[11], -h, h);                      // m = 6
+    u[13] = rot<INV>(u[13], s1, c1);                     // m = 3
+    u[14] = rot<INV>(u[14], -h, h);                      // m = 6
+    u[15] = rot<INV>(u[15], -c1, -s1);                   // m = 9
+    // stage 3: for each k2, DFT-4 over n1 -> X[4 k1 + k2] left at slot k1 + 4 k2
+#pragma unroll
+    for (int k2 = 0; k2 < 4; ++k2) dft4<INV>(u[4 * k2], u[4 * k2 + 1], u[4 * k2 + 2], u[4 * k2 + 3]);
+    // 4x4 register transpose (renaming only after unrolling)
+    cplx t;
+#define CVB_SWAP(a, b) t = u[a]; u[a] = u[b]; u[b] = t;
+    CVB_SWAP(1, 4) CVB_SWAP(2, 8) CVB_SWAP(3, 12) CVB_SWAP(6, 9) CVB_SWAP(7, 13) CVB_SWAP(11, 14)
+#undef CVB_SWAP
+  }
+};
+
+// u[r] *= w1^r, r = 1..R-1 (powers built by squaring / one extra multiply: depth <= 2 log2 R)
+template <int R>
+__device__ __forceinline__ void apply_twiddle_powers(cplx (&u)[R], cplx w1) {
+  cplx w[R];
+  w[1] = w1;
+#pragma unroll
+  for (int i = 2; i < R; ++i) {
+    if (i & 1) {
+      w[i] = cmul(w[i - 1], w1);
+    } else {
+      cplx h = w[i >> 1];
+      w[i] = make_float2(fmaf(h.x, h.x, -h.y * h.y), 2.0f * h.x * h.y);
+    }
+  }
+#pragma unroll
+  for (int i = 1; i < R; ++i) u[i] = cmul(u[i], w[i]);
+}
+
+template <int LOG2N, int P, bool INV>
+__device__ __forceinline__ void fft_pass(cplx (&v)[FftPlan<LOG2N>::E], cplx* xch, const int t,
+                                         const cplx* __restrict__ tw) {
+  using Pl = FftPlan<LOG2N>;
+  constexpr int LOGNS = P * Pl::LOGE;
+  constexpr int LOGR = (LOG2N - LOGNS) < Pl::LOGE ? (LOG2N - LOGNS) : Pl::LOGE;
+  constexpr int R = 1 << LOGR, Q = Pl::E / R, NS = 1 << LOGNS;
+  constexpr bool LAST = (LOGNS + LOGR == LOG2N);
+  if (!LAST) __syncthreads();               // earlier readers of xch are done
+#pragma unroll
+  for (int q = 0; q < Q; ++q) {
+    cplx u[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) u[r] = v[q + r * Q];
+    const int j = t + q * Pl::T;
+    const int k = j & (NS - 1);
+    if (P > 0) {
+      cplx w1 = __ldg(&tw[k << (kTwiddleCircleLog2 - LOGNS - LOGR)]);   // exp(-2 pi i k / (NS R))
+      if (INV) w1.y = -w1.y;
+      apply_twiddle_powers<R>(u, w1);
+    }
+    Dft<R, INV>::run(u);
+    if (LAST) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) v[q + r * Q] = u[r];
+    } else {
+      const int j0 = ((j - k) << LOGR) + k;
+#pragma unroll
+      for (int r = 0; r < R; ++r) xch[pad16(j0 + r * NS)] = u[r];
+    }
+  }
+  if constexpr (!LAST) {
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < Pl::E; ++e) v[e] = xch[pad16(t + e * Pl::T)];
+    fft_pass<LOG2N, P + 1, INV>(v, xch, t, tw);
+  }
+}
+
+// In: v[e] = x[t + e T].  Out: v[e] = X[t + e T], X[k] = sum_j x[j] exp(-+ 2 pi i j k / N) (unnormalised).
+template <int LOG2N, bool INV>
+__device__ __forceinline__ void fft_run(cplx (&v)[FftPlan<LOG2N>::E], cplx* xch, int t,
+                                        const cplx* __restrict__ tw) {
+  fft_pass<LOG2N, 0, INV>(v, xch, t, tw);
+}
+
+// R2C untangle.  In: v = Z = FFT_N(z), z[m] = x[2m] + i x[2m+1] of a real row of length n = 2N.
+// Out: v[e] = X[k], k = t + e T, the first N bins of the length-n real FFT; returns X[N] (real,
+// meaningful on the thread with t == 0 only).
+template <int LOG2N>
+__device__ __forceinline__ float r2c_untangle(cplx (&v)[FftPlan<LOG2N>::E], cplx* xch, int t,
+                                              const cplx* __restrict__ tw) {
+  using Pl = FftPlan<LOG2N>;
+  constexpr int N = Pl::N;
+  __syncthreads();
+#pragma unroll
+  for (int e = 0; e < Pl::E; ++e) xch[pad16(t + e * Pl::T)] = v[e];
+  __syncthreads();
+  const float nyq = v[0].x - v[0].y;      // for t == 0: Re Z0 - Im Z0
+#pragma unroll
+  for (int e = 0; e < Pl::E; ++e) {
+    const int k = t + e * Pl::T;
+    const cplx z = v[e];
+    const cplx zp = cconj(xch[pad16((N - k) & (N - 1))]);
+    const cplx w = __ldg(&tw[k << (kTwiddleCircleLog2 - LOG2N - 1)]);   // exp(-2 pi i k / n)
+    const cplx s = cadd(z, zp), d = csub(z, zp);
+    const cplx wd = cmul_mi(cmul(w, d));                                 // -i w (z - zp)
+    v[e] = make_float2(0.5f * (s.x + wd.x), 0.5f * (s.y + wd.y));
+  }
+  return nyq;
+}
+
+// C2R pre-processing.  In: v[e] = X[k] (k = t + e T, bins 0..N-1 of a Hermitian half spectrum),
+// x_nyq = X[N] (real; only the value passed by t == 0 is used).  Out: v = Z such that the
+// unnormalised inverse FFT_N(Z)[m] = (x[2m], x[2m+1]) with x = irfft(X, n = 2N) (1/n included).
+template <int LOG2N>
+__device__ __forceinline__ void c2r_pretangle(cplx (&v)[FftPlan<LOG2N>::E], float x_nyq, cplx* xch, int t,
+                                              const cplx* __restrict__ tw) {
+  using Pl = FftPlan<LOG2N>;
+  constexpr int N = Pl::N;
+  constexpr float scale = 1.0f / (2.0f * N);
+  __syncthreads();
+#pragma unroll
+  for (int e = 0; e < Pl::E; ++e) xch[pad16(t + e * Pl::T)] = v[e];
+  if (t == 0) xch[pad16(N)] = make_float2(x_nyq, 0.0f);
+  __syncthreads();
+#pragma unroll
+  for (int e = 0; e < Pl::E; ++e) {
+    const int k = t + e * Pl::T;
+    const cplx x = v[e];
+    const cplx xp = cconj(xch[pad16(N - k)]);
+    const cplx w = cconj(__ldg(&tw[k << (kTwiddleCircleLog2 - LOG2N - 1)]));   // exp(+2 pi i k / n)
+    const cplx s = cadd(x, xp), d = csub(x, xp);
+    const cplx wd = cmul_i(cmul(w, d));                                       // +i w (x - xp)
+    v[e] = make_float2(scale * (s.x + wd.x), scale * (s.y + wd.y));
+  }
+}
+
+// sum over the T threads of a group; scratch: >= 32 floats per group; uses __syncthreads when T > 32
+template <int T>
+__device__ __forceinline__ float group_sum(float val, float* scratch, int t) {
+  constexpr int W = T < 32 ? T : 32;
+#pragma unroll
+  for (int o = W / 2; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+  if constexpr (T > 32) {
+    __syncthreads();
+    if ((t & 31) == 0) scratch[t >> 5] = val;
+    __syncthreads();
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < T / 32; ++i) s += scratch[i];
+    val = s;
+  }
+  return val;
+}
+
+}  // namespace cvb

@@ -1,0 +1,83 @@
+// Host-side launch plumbing shared by the api_*.cu translation units.
+#pragma once
+#include <cstdio>
+#include <atomic>
+#include "common.cuh"
+#include "rng.cuh"
+
+namespace cvb {
+
+void set_last_error(const char* fmt, ...);
+// Device twiddle table for the current device (nullptr + error set if cvb_init() was not called).
+const cplx* device_twiddles();
+int sm_count();
+extern std::atomic<long long> g_launch_count;
+
+#define CVB_REQUIRE(cond, code, ...)          \
+  do {                                        \
+    if (!(cond)) {                            \
+      ::cvb::set_last_error(__VA_ARGS__);     \
+      return code;                            \
+    }                                         \
+  } while (0)
+
+#define CVB_CUDA(call)                                                                   \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess) {                                                             \
+      ::cvb::set_last_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      return ::cvb::kCudaError;                                                          \
+    }                                                                                    \
+  } while (0)
+
+inline int check_launch(const char* what) {
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_last_error("launch of %s failed: %s", what, cudaGetErrorString(e));
+    return kCudaError;
+  }
+  return kOk;
+}
+
+// Persistent grid: min(work CTAs, SMs x resident CTAs per SM).  Opts in to > 48 KB dynamic smem.
+// The occupancy answer is cached per kernel (one device per process is the deployment model).
+int cached_ctas_per_sm(const void* kernel, int threads, size_t smem, bool* found);
+void store_ctas_per_sm(const void* kernel, int per_sm);
+
+template <typename Kernel>
+inline int persistent_grid(Kernel kernel, int threads, size_t smem, long long work_ctas, int* grid_out) {
+  bool found = false;
+  int per_sm = cached_ctas_per_sm(reinterpret_cast<const void*>(kernel), threads, smem, &found);
+  if (!found) {
+    if (smem > 48 * 1024)
+      CVB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+    store_ctas_per_sm(reinterpret_cast<const void*>(kernel), per_sm);
+  }
+  if (per_sm < 1) {
+    set_last_error("kernel does not fit on an SM (threads=%d smem=%zu)", threads, smem);
+    return kUnsupported;
+  }
+  long long g = (long long)sm_count() * per_sm;
+  if (g > work_ctas) g = work_ctas;
+  if (g < 1) g = 1;
+  *grid_out = (int)g;
+  return kOk;
+}
+
+inline PhiloxKey make_key(unsigned long long seed, unsigned long long offset, uint32_t stream_id) {
+  PhiloxKey k;
+  k.k0 = (uint32_t)seed;
+  k.k1 = (uint32_t)(seed >> 32);
+  k.offset = (uint32_t)offset ^ (uint32_t)((offset >> 32) * 0x9E3779B9u);
+  k.stream = stream_id;
+  return k;
+}
+
+inline bool is_pow2(long long x) { return x > 0 && (x & (x - 1)) == 0; }
+inline int ilog2(long long x) { int l = 0; while ((1LL << l) < x) ++l; return l; }
+inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+}  // namespace cvb

@@ -1,0 +1,136 @@
+// Counter-based on-device RNG: Philox4x32-10 (Salmon et al., SC'11) plus the draws the latent
+// samplers need.  Every draw is addressed by (seed, call offset, element index, attempt), so
+// kernels are reproducible, need no RNG state in memory, and ranks stay disjoint by seed.
+#pragma once
+#include "common.cuh"
+
+namespace cvb {
+
+struct PhiloxKey {
+  uint32_t k0, k1;     // seed
+  uint32_t offset;     // per-call offset (host increments it for every launch that draws)
+  uint32_t stream;     // which variate family inside a call (0 = gamma proposals, 1 = normals ...)
+};
+
+__host__ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+#ifdef __CUDA_ARCH__
+    const uint32_t hi0 = __umulhi(M0, c.x), hi1 = __umulhi(M1, c.z);
+#else
+    const uint32_t hi0 = (uint32_t)(((uint64_t)M0 * c.x) >> 32), hi1 = (uint32_t)(((uint64_t)M1 * c.z) >> 32);
+#endif
+    const uint32_t lo0 = M0 * c.x, lo1 = M1 * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
+    k0 += W0;
+    k1 += W1;
+  }
+  return c;
+}
+
+// counter layout: (element lo, element hi, attempt | stream << 24, call offset)
+__device__ __forceinline__ uint4 philox_draw(const PhiloxKey& key, uint64_t elem, uint32_t attempt) {
+  return philox4x32_10(make_uint4((uint32_t)elem, (uint32_t)(elem >> 32), attempt | (key.stream << 24), key.offset),
+                       key.k0, key.k1);
+}
+
+// uniform in (0, 1]: never 0, so logs are finite
+__device__ __forceinline__ float u01_open0(uint32_t x) { return fmaf((float)(x >> 8), 0x1p-24f, 0x1p-24f); }
+// uniform in [0, 1)
+__device__ __forceinline__ float u01_open1(uint32_t x) { return (float)(x >> 8) * 0x1p-24f; }
+__device__ __forceinline__ double u01_double(uint32_t hi, uint32_t lo) {
+  // 53-bit uniform in (0,1)
+  const uint64_t m = ((uint64_t)hi << 21) ^ (lo >> 11);
+  return ((double)(m & ((1ull << 53) - 1)) + 0.5) * 0x1p-53;
+}
+
+// Box-Muller: two independent N(0,1) from two 32-bit words
+__device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
+  const float u = u01_open0(a);
+  const float r = sqrtf(-2.0f * __logf(u));
+  float s, c;
+  __sincosf(6.283185307179586f * u01_open1(b), &s, &c);
+  return make_float2(r * c, r * s);
+}
+__device__ __forceinline__ double2 box_muller_double(uint4 r) {
+  const double u = u01_double(r.x, r.y), v = u01_double(r.z, r.w);
+  const double rad = sqrt(-2.0 * log(u));
+  double s, c;
+  sincospi(2.0 * v, &s, &c);
+  return make_double2(rad * c, rad * s);
+}
+
+// Marsaglia-Tsang (2000) constants for Gamma(alpha), alpha > 0: boosts alpha < 1.
+struct GammaMT {
+  float d, c, inv_alpha;   // inv_alpha > 0 only when the alpha+1 boost is active
+  __device__ __forceinline__ explicit GammaMT(float alpha) {
+    inv_alpha = 0.f;
+    if (alpha < 1.0f) { inv_alpha = 1.0f / alpha; alpha += 1.0f; }
+    d = alpha - 0.333333333333f;
+    c = rsqrtf(9.0f * d);
+  }
+};
+
+// One Marsaglia-Tsang attempt from proposal normal x and uniform u (0,1]; returns accepted flag.
+__device__ __forceinline__ bool gamma_mt_attempt(const GammaMT& g, float x, float u, float& out) {
+  const float y = fmaf(g.c, x, 1.0f);
+  if (y <= 0.f) return false;
+  const float v = y * y * y;
+  const float xx = x * x;
+  const bool ok = (u < 1.0f - 0.0331f * xx * xx) || (__logf(u) < 0.5f * xx + g.d * (1.0f - v + __logf(v)));
+  out = g.d * v;
+  return ok;
+}
+
+// t' ~ Beta(alpha, 1/2) as X/(X+Y), X ~ Gamma(alpha), Y ~ Gamma(1/2) = N^2/2.  Returns t' and the
+// sign of the normal that produced Y (an independent fair sign, used as the circle's sign draw).
+__device__ __forceinline__ float beta_half_draw(const GammaMT& g, const PhiloxKey& key, uint64_t elem, float& sign) {
+  uint4 r = philox_draw(key, elem, 0);
+  float2 nn = box_muller(r.x, r.y);
+  const float y = 0.5f * nn.y * nn.y;
+  sign = (nn.y < 0.f) ? -1.0f : 1.0f;
+  float boost = 1.0f;
+  if (g.inv_alpha > 0.f) boost = __powf(u01_open0(r.w), g.inv_alpha);
+  float x;
+  bool ok = gamma_mt_attempt(g, nn.x, u01_open0(r.z), x);
+  uint32_t attempt = 1;
+  while (!ok) {
+    r = philox_draw(key, elem, attempt++);
+    nn = box_muller(r.x, r.y);
+    ok = gamma_mt_attempt(g, nn.x, u01_open0(r.z), x);
+    if (!ok) ok = gamma_mt_attempt(g, nn.y, u01_open0(r.w), x);
+  }
+  x *= boost;
+  const float tp = x / (x + y);
+  // keep t' inside [FLT_MIN, 1 - 2^-24] like torch's _sample_dirichlet clamp
+  return fminf(fmaxf(tp, 1.17549435e-38f), 1.0f - 5.9604645e-8f);
+}
+
+// Gamma(alpha) in double for alpha >= 1 (Marsaglia-Tsang), used by the per-row Beta draws of the
+// D-dimensional samplers (alpha ~ D/2, one draw per row, so cost is irrelevant).
+__device__ inline double gamma_mt_double(double alpha, const PhiloxKey& key, uint64_t elem, uint32_t& attempt) {
+  double boost = 1.0;
+  if (alpha < 1.0) {
+    uint4 r = philox_draw(key, elem, attempt++);
+    boost = pow(u01_double(r.x, r.y), 1.0 / alpha);
+    alpha += 1.0;
+  }
+  const double d = alpha - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+  for (;;) {
+    const uint4 r1 = philox_draw(key, elem, attempt++);
+    const uint4 r2 = philox_draw(key, elem, attempt++);
+    const double2 nn = box_muller_double(r1);
+    const double x = nn.x, y = 1.0 + c * x;
+    if (y <= 0.0) continue;
+    const double v = y * y * y, u = u01_double(r2.x, r2.y);
+    if (log(u) < 0.5 * x * x + d * (1.0 - v + log(v))) return boost * d * v;
+  }
+}
+__device__ inline double beta_draw_double(double a, double b, const PhiloxKey& key, uint64_t elem, uint32_t& attempt) {
+  const double x = gamma_mt_double(a, key, elem, attempt);
+  const double y = gamma_mt_double(b, key, elem, attempt);
+  return x / (x + y);
+}
+
+}  // namespace cvb

@@ -1,0 +1,240 @@
+// Special functions used by the latent distributions: digamma / trigamma, the power-spherical
+// normaliser and entropy, ATen's piecewise reparameterised Beta gradient (dirichlet_grad_one),
+// and log I_v(x) e^{-x} for the von Mises-Fisher normaliser.
+//
+// The reparameterised-gradient routine restates the arithmetic of PyTorch 2.11
+// (torch/include/ATen/native/Distributions.h:374-511, BSD-3) because parity with the
+// reference's `Beta.rsample` backward (reference dists/clifford.py:124-134 ->
+// torch/distributions/dirichlet.py:16-19) requires the same piecewise approximation and the
+// same coefficient table; the code below is an independent implementation of those formulas.
+#pragma once
+#include "common.cuh"
+
+namespace cvb {
+
+// ---- digamma / trigamma (recurrence to x >= 10, then the asymptotic series) -----------------
+__device__ __forceinline__ double digamma_d(double x) {
+  // x > 0 on every call site (alpha, beta > 0)
+  double r = 0.0;
+  while (x < 10.0) { r -= 1.0 / x; x += 1.0; }
+  const double z = 1.0 / (x * x);
+  // Bernoulli series: 1/12 z - 1/120 z^2 + 1/252 z^3 - 1/240 z^4 + 1/132 z^5 - 691/32760 z^6 + 1/12 z^7
+  const double y = z * (8.33333333333333333333e-2 + z * (-8.33333333333333333333e-3 + z * (3.96825396825396825397e-3 +
+                   z * (-4.16666666666666666667e-3 + z * (7.57575757575757575758e-3 + z * (-2.10927960927960927961e-2 +
+                   z * 8.33333333333333333333e-2))))));
+  return r + log(x) - 0.5 / x - y;
+}
+__device__ __forceinline__ double trigamma_d(double x) {
+  double r = 0.0;
+  while (x < 10.0) { r += 1.0 / (x * x); x += 1.0; }
+  const double z = 1.0 / (x * x);
+  // 1/x + 1/(2x^2) + sum B_2k / x^(2k+1)
+  const double s = 1.0 / x * (1.0 + 0.5 / x + z * (1.0 / 6 + z * (-1.0 / 30 + z * (1.0 / 42 + z * (-1.0 / 30 +
+                   z * (5.0 / 66 + z * (-691.0 / 2730 + z * (7.0 / 6))))))));
+  return r + s;
+}
+
+// ---- power-spherical normaliser / entropy for sphere dimension `dim` (reference clifford.py:187-212)
+// alpha = (dim-1)/2 + kappa + 1e-7, beta = (dim-1)/2.  fp64: evaluated once per row.
+struct PsConsts {
+  double log_norm;      // log C(kappa)
+  double entropy;       // H(kappa)
+  double dentropy;      // dH/dkappa
+  double dlog_norm;     // dlogC/dkappa
+};
+// lgamma, digamma, trigamma of one argument x > 0 with a shared upward recurrence to x >= 10 and
+// the Stirling / Bernoulli series there (abs error < 1e-12 for x >= 0.5).
+__device__ __forceinline__ void gamma_family(double x, double& lg, double& psi, double& psi1) {
+  double prod = 1.0, s1 = 0.0, s2 = 0.0;
+  while (x < 10.0) {
+    const double r = 1.0 / x;
+    prod *= x; s1 += r; s2 += r * r;
+    x += 1.0;
+  }
+  const double r = 1.0 / x, z = r * r, lx = log(x);
+  lg = (x - 0.5) * lx - x + 0.91893853320467274178 +
+       r * (1.0 / 12 + z * (-1.0 / 360 + z * (1.0 / 1260 + z * (-1.0 / 1680 + z * (1.0 / 1188 + z * (-691.0 / 360360)))))) - log(prod);
+  psi = lx - 0.5 * r - z * (1.0 / 12 + z * (-1.0 / 120 + z * (1.0 / 252 + z * (-1.0 / 240 + z * (1.0 / 132 + z * (-691.0 / 32760 + z / 12)))))) - s1;
+  psi1 = r * (1.0 + 0.5 * r + z * (1.0 / 6 + z * (-1.0 / 30 + z * (1.0 / 42 + z * (-1.0 / 30 + z * (5.0 / 66 + z * (-691.0 / 2730 + z * (7.0 / 6)))))))) + s2;
+}
+__device__ __forceinline__ PsConsts ps_consts(double kappa, double half_dm1) {
+  const double LOG2 = 0.69314718055994530942, LOGPI = 1.14472988584940017414;
+  const double s = kappa + 1e-7;
+  const double a = half_dm1 + s, b = half_dm1;
+  double lga, psa, p1a, lgt, pst, p1t;
+  gamma_family(a, lga, psa, p1a);
+  gamma_family(a + b, lgt, pst, p1t);
+  PsConsts c;
+  c.log_norm = -((a + b) * LOG2 + lga - lgt + b * LOGPI);
+  const double dpsi = psa - pst;
+  c.dlog_norm = -(LOG2 + dpsi);
+  c.entropy = -(c.log_norm + s * (LOG2 + dpsi));
+  c.dentropy = -s * (p1a - p1t);
+  return c;
+}
+
+// ---- reparameterised gradient of a Beta(alpha, beta) draw x wrt alpha, scaled by 1/(1-x) -----
+// Row constants (depend on alpha, beta only); hoisted out of the per-element loop.
+struct BetaGradConsts {
+  float alpha, beta, total;
+  float psi_alpha, psi_total;
+  float log_alpha, log_total;
+  __device__ __forceinline__ BetaGradConsts(float a, float b) {
+    alpha = a; beta = b; total = a + b;
+    psi_alpha = (float)digamma_d((double)a);
+    psi_total = (float)digamma_d((double)total);
+    log_alpha = logf(a);
+    log_total = logf(total);
+  }
+};
+
+__device__ __constant__ float kDirichletGradCoef[2][3][3][4] = {
+    {{{1.003668233f, -0.01061107488f, -0.0657888334f, 0.01201642863f},
+      {0.6336835991f, -0.3557432599f, 0.05486251648f, -0.001465281033f},
+      {-0.03276231906f, 0.004474107445f, 0.002429354597f, -0.0001557569013f}},
+     {{0.221950385f, -0.3187676331f, 0.01799915743f, 0.01074823814f},
+      {-0.2951249643f, 0.06219954479f, 0.01535556598f, 0.001550077057f},
+      {0.02155310298f, 0.004170831599f, 0.001292462449f, 6.976601077e-05f}},
+     {{-0.05980841433f, 0.008441916499f, 0.01085618172f, 0.002319392565f},
+      {0.02911413504f, 0.01400243777f, -0.002721828457f, 0.000751041181f},
+      {0.005900514878f, -0.001936558688f, -9.495446725e-06f, 5.385558597e-05f}}},
+    {{{1.f, -0.02924021934f, -0.04438342661f, 0.007285809825f},
+      {0.6357567472f, -0.3473456711f, 0.05454656494f, -0.002407477521f},
+      {-0.03301322327f, 0.004845219414f, 0.00231480583f, -0.0002307248149f}},
+     {{0.5925320577f, -0.1757678135f, 0.01505928619f, 0.000564515273f},
+      {0.1014815858f, -0.06589186703f, 0.01272886114f, -0.0007316646956f},
+      {-0.007258481865f, 0.001096195486f, 0.0003934994223f, -4.12701925e-05f}},
+     {{0.06469649321f, -0.0236701437f, 0.002902096474f, -5.896963079e-05f},
+      {0.001925008108f, -0.002869809258f, 0.0008000589141f, -6.063713228e-05f},
+      {-0.0003477407336f, 6.959756487e-05f, 1.097287507e-05f, -1.650964693e-06f}}},
+};
+
+// Taylor series in x around 0 for d/dalpha (ATen _beta_grad_alpha_small)
+__device__ __forceinline__ float beta_grad_alpha_small(float x, float alpha, float beta, float psi_alpha,
+                                                       float psi_total) {
+  const float factor = psi_alpha - psi_total - logf(x);
+  float numer = 1.f;
+  float series = numer / alpha * (factor + 1.f / alpha);
+#pragma unroll
+  for (int i = 1; i <= 10; ++i) {
+    const float ci = (float)i;
+    numer *= (ci - beta) * x / ci;
+    const float denom = alpha + ci;
+    series += numer / denom * (factor + 1.f / denom);
+  }
+  const float r = x * powf(1.f - x, -beta) * series;
+  return isnan(r) ? 0.f : r;
+}
+// Taylor series in x around 0 for d/dbeta (ATen _beta_grad_beta_small)
+__device__ __forceinline__ float beta_grad_beta_small(float x, float alpha, float beta, float psi_beta,
+                                                      float psi_total) {
+  const float factor = psi_total - psi_beta;
+  float numer = 1.f, betas = 1.f, dbetas = 0.f, series = factor / alpha;
+#pragma unroll
+  for (int i = 1; i <= 8; ++i) {
+    const float ci = (float)i;
+    numer *= -x / ci;
+    dbetas = dbetas * (beta - ci) + betas;
+    betas = betas * (beta - ci);
+    series += numer / (alpha + ci) * (dbetas + factor * betas);
+  }
+  const float r = -powf(1.f - x, 1.f - beta) * series;
+  return isnan(r) ? 0.f : r;
+}
+// Rice saddle-point expansion for alpha, beta both large (ATen _beta_grad_alpha_mid), fp64
+__device__ __forceinline__ float beta_grad_alpha_mid(double x, double alpha, double beta) {
+  const double total = alpha + beta;
+  const double mean = alpha / total;
+  const double sd = sqrt(alpha * beta / (total + 1)) / total;
+  if (mean - 0.1 * sd <= x && x <= mean + 0.1 * sd) {
+    const double b2 = beta * beta;
+    const double poly = 47 * x * b2 * b2 + alpha * ((43 + 20 * (16 + 27 * beta) * x) * b2 * beta +
+                        alpha * (3 * (59 + 180 * beta - 90 * x) * b2 +
+                        alpha * ((453 + 1620 * beta * (1 - x) - 455 * x) * beta + alpha * (8 * (1 - x) * (135 * beta - 11)))));
+    const double pn = (1 + 12 * alpha) * (1 + 12 * beta) / (total * total);
+    const double pd = 12960 * alpha * alpha * alpha * beta * beta * (1 + 12 * total);
+    return (float)(pn / (1 - x) * poly / pd);
+  }
+  const double prefactor = -x / sqrt(2 * alpha * beta / total);
+  const double stirling = (1 + 1 / (12 * alpha) + 1 / (288 * alpha * alpha)) * (1 + 1 / (12 * beta) + 1 / (288 * beta * beta)) /
+                          (1 + 1 / (12 * total) + 1 / (288 * total * total));
+  const double t1n = 2 * (alpha * alpha) * (x - 1) + alpha * beta * (x - 1) - x * (beta * beta);
+  const double axbx = alpha * (x - 1) + beta * x;
+  const double t1d = sqrt(2 * alpha / beta) * pow(total, 1.5) * axbx * axbx;
+  const double term1 = t1n / t1d;
+  const double term2 = 0.5 * log(alpha / (total * x));
+  const double term3 = sqrt(8 * alpha * beta / total) / (beta * x + alpha * (x - 1));
+  const double t4b = beta * log(beta / (total * (1 - x))) + alpha * log(alpha / (total * x));
+  const double term4 = pow(t4b, -1.5);
+  const double t1234 = term1 + term2 * (term3 + (x < mean ? term4 : -term4));
+  return (float)(stirling * prefactor * t1234);
+}
+
+// -(d/dalpha cdf(x; alpha, beta)) / pdf(x; alpha, beta) / (1 - x)
+__device__ __forceinline__ float dirichlet_grad_one(float x, const BetaGradConsts& c) {
+  const float boundary = c.total * x * (1.f - x);
+  if (x <= 0.5f && boundary < 2.5f) return beta_grad_alpha_small(x, c.alpha, c.beta, c.psi_alpha, c.psi_total);
+  if (x >= 0.5f && boundary < 0.75f) return -beta_grad_beta_small(1.f - x, c.beta, c.alpha, c.psi_alpha, c.psi_total);
+  if (c.alpha > 6.f && c.beta > 6.f) return beta_grad_alpha_mid((double)x, (double)c.alpha, (double)c.beta);
+  const float u = logf(x);
+  const float a = c.log_alpha - u;
+  const float b = c.log_total - a;
+  const float pu[3] = {1.f, u, u * u};
+  const float pa[3] = {1.f, a, a * a};
+  float p = 0.f, q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const float ua = pu[i] * pa[j];
+      const float* c0 = kDirichletGradCoef[0][i][j];
+      const float* c1 = kDirichletGradCoef[1][i][j];
+      p += ua * (c0[0] + b * (c0[1] + b * (c0[2] + b * c0[3])));
+      q += ua * (c1[0] + b * (c1[1] + b * (c1[2] + b * c1[3])));
+    }
+  }
+  const float approx = x * (c.psi_total - c.psi_alpha) / c.beta;
+  return p / q * approx;
+}
+
+// ---- log(I_v(x) e^{-x}), v >= 0, x > 0, fp64 ------------------------------------------------
+// Ascending series (A&S 9.6.10) when it converges fast, the uniform Debye expansion in v
+// (A&S 9.7.7) for v >= 12, otherwise Hankel's large-argument expansion (A&S 9.7.1).
+__device__ inline double log_ive(double v, double x) {
+  if (x * x <= 80.0 * (v + 1.0) || (v < 12.0 && x <= 30.0)) {
+    const double q = 0.25 * x * x;
+    double term = 1.0, sum = 1.0;
+    for (int k = 1; k < 2000; ++k) {
+      term *= q / ((double)k * ((double)k + v));
+      sum += term;
+      if (term < 1e-17 * sum) break;
+    }
+    return v * log(0.5 * x) - lgamma(v + 1.0) + log(sum) - x;
+  }
+  if (v >= 12.0) {
+    const double t2 = x / v;
+    const double r = sqrt(1.0 + t2 * t2);
+    const double p = 1.0 / r, p2 = p * p;
+    const double eta = r + log(t2 / (1.0 + r));
+    const double u1 = p * (3.0 - 5.0 * p2) / 24.0;
+    const double u2 = p2 * (81.0 - 462.0 * p2 + 385.0 * p2 * p2) / 1152.0;
+    const double u3 = p * p2 * (30375.0 - 369603.0 * p2 + 765765.0 * p2 * p2 - 425425.0 * p2 * p2 * p2) / 414720.0;
+    const double u4 = p2 * p2 * (4465125.0 - 94121676.0 * p2 + 349922430.0 * p2 * p2 - 446185740.0 * p2 * p2 * p2 +
+                                 185910725.0 * p2 * p2 * p2 * p2) / 39813120.0;
+    const double iv = 1.0 / v;
+    const double ser = 1.0 + iv * (u1 + iv * (u2 + iv * (u3 + iv * u4)));
+    return v * eta - 0.5 * log(6.283185307179586477 * v) - 0.5 * log(r) + log(ser) - x;
+  }
+  const double mu = 4.0 * v * v;
+  double term = 1.0, sum = 1.0;
+  for (int k = 1; k < 40; ++k) {
+    const double nt = -term * (mu - (double)((2 * k - 1) * (2 * k - 1))) / ((double)k * 8.0 * x);
+    if (fabs(nt) > fabs(term)) break;
+    term = nt;
+    sum += term;
+    if (fabs(term) < 1e-17 * fabs(sum)) break;
+  }
+  return -0.5 * log(6.283185307179586477 * x) + log(sum);
+}
+
+}  // namespace cvb

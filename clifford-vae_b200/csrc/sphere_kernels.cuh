@@ -1,0 +1,365 @@
+// Row kernels for the D-dimensional samplers: PowerSpherical (reference dists/clifford.py:85-212),
+// von Mises-Fisher (reference vmf/hyperspherical_vae/distributions/von_mises_fisher.py:50-217) and
+// the uniform sphere prior.  Both samplers share one structure:
+//     y = [t, sqrt(max(1 - t^2, clamp_eps)) * g / (||g|| + norm_eps)],   z = y - 2 (y.u) u,
+//     u = (e1 - loc) / (||e1 - loc|| + house_eps)
+// and differ only in how the scalar t is drawn (Beta marginal vs Wood rejection) -- so one warp per
+// row makes one pass for the three reductions and one pass for the Householder reflection
+// (8D + 8 algorithmic bytes per row).
+#pragma once
+#include "common.cuh"
+#include "rng.cuh"
+#include "special.cuh"
+
+namespace cvb {
+
+enum SphereFamily : int { kFamilyPS = 0, kFamilyVMF = 1, kFamilyUniform = 2 };
+
+struct SphereParams {
+  const float* loc;          // (loc_rows, D)
+  const float* kappa;        // (loc_rows)
+  long long loc_rows;
+  const float* tprime;       // PS injected (rows)
+  const double* e_rounds;    // vMF injected proposals (n_rounds, rows)
+  const double* u_rounds;    // vMF injected uniforms  (n_rounds, rows); D == 3: row 0 is the closed-form uniform
+  int n_rounds;
+  const float* gnoise;       // injected normals; tangent component i (1..D-1) at gnoise[row*g_pitch + g_off + i - 1]
+  int g_pitch, g_off;
+  float* z;                  // fwd: (rows, D) out
+  float* save;               // (rows, 2): PS (t', 0) ; vMF (w, dw/dkappa).  fwd: out, bwd: in
+  const float* grad_z;       // bwd: (rows, D)
+  float* dloc;               // bwd: (rows, D) out
+  float* dkappa;             // bwd: (rows) out
+  long long rows;
+  int D;
+  float norm_eps, clamp_eps, house_eps;
+  PhiloxKey key;
+};
+
+// generic float Gamma(alpha) draw (Marsaglia-Tsang with the alpha < 1 boost), independent stream per elem
+__device__ __forceinline__ float gamma_draw_float(float alpha, const PhiloxKey& key, uint64_t elem) {
+  const GammaMT g(alpha);
+  uint32_t attempt = 0;
+  float boost = 1.0f, x = 0.f;
+  bool first = true;
+  for (;;) {
+    const uint4 r = philox_draw(key, elem, attempt++);
+    const float2 nn = box_muller(r.x, r.y);
+    if (first && g.inv_alpha > 0.f) boost = __powf(u01_open0(r.w), g.inv_alpha);
+    first = false;
+    if (gamma_mt_attempt(g, nn.x, u01_open0(r.z), x)) break;
+  }
+  return x * boost;
+}
+
+// tangent normal for component i (1 <= i <= D-1) of `row`
+__device__ __forceinline__ float tangent_normal(const SphereParams& p, long long row, int i) {
+  if (p.gnoise) return p.gnoise[row * p.g_pitch + p.g_off + i - 1];
+  PhiloxKey k = p.key;
+  k.stream = 7;
+  const uint4 r = philox_draw(k, (uint64_t)(row * (long long)((p.D + 3) / 4) + (i >> 2)), 0);
+  const int j = i & 3;
+  const float2 nn = (j < 2) ? box_muller(r.x, r.y) : box_muller(r.z, r.w);
+  return (j & 1) ? nn.y : nn.x;
+}
+
+struct WoodDraw { float w, dw_dkappa; };
+
+// Wood (1994) rejection sampler for the vMF mixture coordinate w, fp64 like the reference (:90-175);
+// m == 3 uses the closed form (:73-88).  Executed redundantly by every lane of the row's warp.
+__device__ __forceinline__ WoodDraw vmf_draw_w(const SphereParams& p, long long row, float kappa_f) {
+  const double kap = (double)kappa_f;
+  const int m = p.D;
+  WoodDraw o;
+  if (m == 3) {
+    double u;
+    if (p.u_rounds) u = p.u_rounds[row];
+    else { PhiloxKey k = p.key; k.stream = 5; const uint4 r = philox_draw(k, (uint64_t)row, 0); u = (double)u01_open1(r.x); u = fmin(fmax(u, 1e-12), 1.0 - 1e-12); }
+    const double a = log(u), b = log(1.0 - u) - 2.0 * kap;
+    const double mx = fmax(a, b);
+    const double L = mx + log(exp(a - mx) + exp(b - mx));
+    const double sb = exp(b - L);
+    o.w = (float)(1.0 + L / kap);
+    o.dw_dkappa = (float)(-2.0 * sb / kap - L / (kap * kap));
+    return o;
+  }
+  const double m1 = (double)(m - 1);
+  const double c = sqrt(4.0 * kap * kap + m1 * m1);
+  const double b_true = (-2.0 * kap + c) / m1;
+  const double b_app = m1 / (4.0 * kap);
+  const double s = fmin(fmax(kap - 10.0, 0.0), 1.0);
+  const double b = b_app * s + b_true * (1.0 - s);
+  const double a = (m1 + 2.0 * kap + c) / 4.0;
+  const double dd = (4.0 * a * b) / (1.0 + b) - m1 * log(m1);
+  const double ds = (kap > 10.0 && kap < 11.0) ? 1.0 : 0.0;
+  const double db = (-m1 / (4.0 * kap * kap)) * s + b_app * ds + ((-2.0 + 4.0 * kap / c) / m1) * (1.0 - s) - b_true * ds;
+  double e = 0.5;
+  bool ok = false;
+  if (p.e_rounds) {
+    for (int r = 0; r < p.n_rounds && !ok; ++r) {
+      e = p.e_rounds[(long long)r * p.rows + row];
+      const double u = p.u_rounds[(long long)r * p.rows + row];
+      const double t = (2.0 * a * b) / (1.0 - (1.0 - b) * e);
+      ok = (m1 * log(t) - t + dd) > log(u);
+    }
+  } else {
+    PhiloxKey k = p.key;
+    k.stream = 5;
+    const float h = 0.5f * (float)(m - 1);
+    for (uint32_t round = 0; !ok; ++round) {
+      const float x = gamma_draw_float(h, k, (uint64_t)(row * 64 + 2 * round));
+      const float y = gamma_draw_float(h, k, (uint64_t)(row * 64 + 2 * round + 1));
+      e = (double)x / ((double)x + (double)y);
+      PhiloxKey ku = p.key;
+      ku.stream = 6;
+      const uint4 r = philox_draw(ku, (uint64_t)row, round);
+      const double u = fmin(fmax(u01_double(r.x, r.y), 1e-20), 1.0 - 1e-20);
+      const double t = (2.0 * a * b) / (1.0 - (1.0 - b) * e);
+      ok = (m1 * log(t) - t + dd) > log(u);
+      if (round > 1000) ok = true;   // cannot happen for finite kappa; guards a hang
+    }
+  }
+  const double den = 1.0 - (1.0 - b) * e;
+  o.w = (float)((1.0 - (1.0 + b) * e) / den);
+  o.dw_dkappa = (float)(-2.0 * e * (1.0 - e) / (den * den) * db);
+  return o;
+}
+
+// One warp per row.  FAMILY kFamilyUniform: z = g / (||g|| + norm_eps) with D tangent components.
+template <int FAMILY>
+__global__ void __launch_bounds__(256)
+sphere_rsample_kernel(const SphereParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int D = p.D;
+  for (long long row = warp; row < p.rows; row += nwarps) {
+    float* zr = p.z + row * D;
+    if (FAMILY == kFamilyUniform) {
+      float ss = 0.f;
+      for (int i = lane; i < D; i += 32) {
+        const float g = tangent_normal(p, row, i + 1);
+        zr[i] = g;
+        ss += g * g;
+      }
+      ss = warp_sum(ss);
+      const float inv = 1.0f / (sqrtf(ss) + p.norm_eps);
+      for (int i = lane; i < D; i += 32) zr[i] *= inv;
+      continue;
+    }
+    const long long prow = row % p.loc_rows;
+    const float* lr = p.loc + prow * D;
+    const float kap = __ldg(p.kappa + prow);
+    // scalar coordinate t
+    float t, save0, save1 = 0.f;
+    if (FAMILY == kFamilyPS) {
+      float tp;
+      if (p.tprime) {
+        tp = p.tprime[row];
+      } else {
+        const float half = 0.5f * (float)(D - 1);
+        PhiloxKey k = p.key;
+        k.stream = 4;
+        // lanes 0 / 1 draw the two gammas side by side
+        const float al = (lane & 1) ? half : half + (kap + 1e-7f);
+        const float gm = gamma_draw_float(al, k, (uint64_t)(row * 2 + (lane & 1)));
+        const float x = __shfl_sync(0xffffffffu, gm, 0), y = __shfl_sync(0xffffffffu, gm, 1);
+        tp = fminf(fmaxf(x / (x + y), 1.17549435e-38f), 1.0f - 5.9604645e-8f);
+      }
+      t = 2.0f * tp - 1.0f;
+      save0 = tp;
+    } else {
+      const WoodDraw wd = vmf_draw_w(p, row, kap);
+      t = wd.w;
+      save0 = wd.w;
+      save1 = wd.dw_dkappa;
+    }
+    // pass 1: stash g in the output row; ||g||^2, ||u||^2, sum g u
+    float sgg = 0.f, suu = 0.f, sgu = 0.f;
+    for (int i = lane; i < D; i += 32) {
+      const float u = (i == 0 ? 1.0f : 0.0f) - lr[i];
+      suu += u * u;
+      if (i > 0) {
+        const float g = tangent_normal(p, row, i);
+        zr[i] = g;
+        sgg += g * g;
+        sgu += g * u;
+      }
+    }
+    sgg = warp_sum(sgg); suu = warp_sum(suu); sgu = warp_sum(sgu);
+    const float sq = sqrtf(fmaxf(1.0f - t * t, p.clamp_eps));
+    const float cg = sq / (sqrtf(sgg) + p.norm_eps);           // y_i = cg * g_i, i >= 1
+    const float un = sqrtf(suu);
+    const float iu = 1.0f / (un + p.house_eps);
+    const float u0 = 1.0f - lr[0];
+    const float ydotu = (t * u0 + cg * sgu) * iu;               // y . u_hat
+    // pass 2: z = y - 2 (y.u_hat) u_hat
+    for (int i = lane; i < D; i += 32) {
+      const float u = ((i == 0 ? 1.0f : 0.0f) - lr[i]) * iu;
+      const float y = (i == 0) ? t : cg * zr[i];
+      zr[i] = y - 2.0f * ydotu * u;
+    }
+    if (p.save && lane == 0) { p.save[2 * row] = save0; p.save[2 * row + 1] = save1; }
+  }
+}
+
+// Backward: grad_z -> dloc (rows, D), dkappa (rows).
+template <int FAMILY>
+__global__ void __launch_bounds__(256)
+sphere_rsample_bwd_kernel(const SphereParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int D = p.D;
+  for (long long row = warp; row < p.rows; row += nwarps) {
+    const long long prow = row % p.loc_rows;
+    const float* lr = p.loc + prow * D;
+    const float* gz = p.grad_z + row * D;
+    float* dl = p.dloc + row * D;
+    const float kap = __ldg(p.kappa + prow);
+    float t, tp = 0.f, dt_dk_direct = 0.f;
+    if (FAMILY == kFamilyPS) {
+      tp = p.tprime ? p.tprime[row] : p.save[2 * row];
+      t = 2.0f * tp - 1.0f;
+    } else {
+      t = p.save[2 * row];
+      dt_dk_direct = p.save[2 * row + 1];
+    }
+    // pass 1: five reductions; stash g in the dloc row
+    float sgg = 0.f, suu = 0.f, sgu = 0.f, sug = 0.f, szg = 0.f;
+    for (int i = lane; i < D; i += 32) {
+      const float u = (i == 0 ? 1.0f : 0.0f) - lr[i];
+      const float gzi = gz[i];
+      suu += u * u;
+      sug += u * gzi;
+      if (i > 0) {
+        const float g = tangent_normal(p, row, i);
+        dl[i] = g;
+        sgg += g * g;
+        sgu += g * u;
+        szg += gzi * g;
+      }
+    }
+    sgg = warp_sum(sgg); suu = warp_sum(suu); sgu = warp_sum(sgu); sug = warp_sum(sug); szg = warp_sum(szg);
+    const float om = 1.0f - t * t;
+    const float sq = sqrtf(fmaxf(om, p.clamp_eps));
+    const float ng = sqrtf(sgg) + p.norm_eps;
+    const float cg = sq / ng;
+    const float un = sqrtf(suu);
+    const float ne = un + p.house_eps;
+    const float u0 = 1.0f - lr[0];
+    const float a = sug / ne;                                   // grad_z . u_hat
+    const float b = (t * u0 + cg * sgu) / ne;                   // y . u_hat
+    // grad wrt y = H grad_z; scalar chain through t
+    const float gy0 = gz[0] - 2.0f * a * u0 / ne;
+    const float s_gv = (szg - 2.0f * a * sgu / ne) / ng;        // grad_y[1:] . v
+    const float dsq = (om > p.clamp_eps) ? (-t / sq) : 0.0f;
+    const float gt = gy0 + dsq * s_gv;
+    // dloc_i = -gu_i,  gu_i = -2 (a y_i + b gz_i)/ne + u_i 4ab / (un ne)
+    const float k2 = (un > 0.f) ? 4.0f * a * b / (un * ne) : 0.0f;
+    for (int i = lane; i < D; i += 32) {
+      const float u = (i == 0 ? 1.0f : 0.0f) - lr[i];
+      const float y = (i == 0) ? t : cg * dl[i];
+      dl[i] = 2.0f * (a * y + b * gz[i]) / ne - u * k2;
+    }
+    if (lane == 0) {
+      float dk;
+      if (FAMILY == kFamilyPS) {
+        const float half = 0.5f * (float)(D - 1);
+        const BetaGradConsts bc(half + (kap + 1e-7f), half);
+        dk = 2.0f * gt * dirichlet_grad_one(tp, bc) * (1.0f - tp);
+      } else {
+        dk = gt * dt_dk_direct;
+      }
+      p.dkappa[row] = dk;
+    }
+  }
+}
+
+// PowerSpherical.log_prob (clifford.py:198-202): lp = logC(kappa) + kappa log1p(clamp(loc . x)).
+// Optional outputs for the backward: coef (rows) = kappa / (1 + dot) inside the clamp else 0
+// (d lp / d loc = coef * value, d lp / d value = coef * loc) and dlp_dkappa (rows).
+struct SphereLogProbParams {
+  const float* value; const float* loc; const float* kappa; long long loc_rows;
+  float* log_prob; float* coef; float* dlp_dkappa; long long rows; int D;
+};
+static __global__ void __launch_bounds__(256) powerspherical_log_prob_kernel(const SphereLogProbParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long row = warp; row < p.rows; row += nwarps) {
+    const long long prow = row % p.loc_rows;
+    const float* lr = p.loc + prow * p.D;
+    const float* vr = p.value + row * p.D;
+    float dot = 0.f;
+    for (int i = lane; i < p.D; i += 32) dot += lr[i] * vr[i];
+    dot = warp_sum(dot);
+    if (lane == 0) {
+      const float kap = p.kappa[prow];
+      const PsConsts c = ps_consts((double)kap, 0.5 * (double)(p.D - 1));
+      const float dc = fminf(fmaxf(dot, -1.0f + 1e-7f), 1.0f - 1e-7f);
+      const float l1p = log1pf(dc);
+      p.log_prob[row] = (float)c.log_norm + kap * l1p;
+      if (p.coef) {
+        const bool inside = (dot >= -1.0f + 1e-7f) && (dot <= 1.0f - 1e-7f);
+        p.coef[row] = inside ? kap / (1.0f + dc) : 0.0f;
+        p.dlp_dkappa[row] = (float)c.dlog_norm + l1p;
+      }
+    }
+  }
+}
+
+// log C(kappa) and its derivative for a batch of concentrations (PowerSpherical.log_normalizer)
+static __global__ void ps_log_normalizer_kernel(const float* kappa, long long rows, double half_dm1, float* log_norm,
+                                                float* dlog_norm) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (long long)gridDim.x * blockDim.x) {
+    const PsConsts c = ps_consts((double)kappa[i], half_dm1);
+    log_norm[i] = (float)c.log_norm;
+    if (dlog_norm) dlog_norm[i] = (float)c.dlog_norm;
+  }
+}
+
+// vMF entropy (:183-191) / log-normaliser (:200-212) and kappa-derivatives, one thread per row, fp64.
+// Reproduces the reference's log(ive + 1e-20) (ive underflows to 0 for large orders) and its Bessel-
+// ratio bound ive_fraction_approx2 (ops/ive.py:63-79).
+__device__ __forceinline__ void bessel_ratio_bound(double v, double z, double a, double& B, double& dB) {
+  const double lam = v + (a - 1.0) / 2.0;
+  const double r = sqrt(fmax(lam * lam + z * z, 1e-20));
+  const double delta = (v - 0.5) + lam / (2.0 * r);
+  const double ddelta = -lam * z / (2.0 * r * r * r);
+  const double S = fmax(sqrt(delta * delta + z * z), 1e-20);
+  const double dS = (delta * ddelta + z) / S;
+  const double den = delta + S;
+  B = z / den;
+  dB = (den - z * (ddelta + dS)) / (den * den);
+}
+static __global__ void vmf_entropy_kernel(const float* kappa, long long rows, int D, float* entropy, float* log_norm,
+                                          float* dentropy, float* dlog_norm) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (long long)gridDim.x * blockDim.x) {
+    const double k = (double)kappa[i];
+    const double m2 = 0.5 * (double)D, v = m2 - 1.0;
+    const double live = log_ive(v, k);
+    const double ive = exp(live);
+    const double lval = log(ive + 1e-20);
+    const double ln = -(v * log(k) - m2 * 1.83787706640934548356 - (k + lval));
+    // d ive/dk = ive(v-1) - ive(v) (v + k)/k   (ops/ive.py:29-34)
+    double im1;   // ive(v - 1, k); orders below zero only occur for m = 2 (I_{-1} = I_1) and m = 3 (closed form)
+    if (v >= 1.0) im1 = exp(log_ive(v - 1.0, k));
+    else if (v == 0.0) im1 = exp(log_ive(1.0, k));
+    else im1 = sqrt(2.0 / (3.14159265358979323846 * k)) * 0.5 * (1.0 + exp(-2.0 * k));
+    const double dive = im1 - ive * (v + k) / k;
+    const double dlval = dive / (ive + 1e-20);
+    const double dln = -(v / k - (1.0 + dlval));
+    const float ln_f = (float)ln;
+    double B0, dB0, B2, dB2;
+    bessel_ratio_bound(m2, k, 0.0, B0, dB0);
+    bessel_ratio_bound(m2, k, 2.0, B2, dB2);
+    const double frac = 0.5 * (B0 + B2), dfrac = 0.5 * (dB0 + dB2);
+    if (log_norm) log_norm[i] = ln_f;
+    if (dlog_norm) dlog_norm[i] = (float)dln;
+    if (entropy) entropy[i] = (float)(-k * frac + (double)ln_f);
+    if (dentropy) dentropy[i] = (float)(-frac - k * dfrac + dln);
+  }
+}
+
+}  // namespace cvb

@@ -1,0 +1,287 @@
+// FFT-domain VSA kernels (power-of-two d): bind / unbind fused as R2C(a), R2C(b) ->
+// pointwise op -> C2R, one HBM round trip per vector pair (12 d bytes).
+// Reference semantics: utils/vsa.py:43-72.
+#pragma once
+#include "fft_core.cuh"
+
+namespace cvb {
+
+enum BindMode : int {
+  kBindMul = 0,       // irfft(A * B)              bind (vsa.py:43-46)
+  kBindMulConj = 1,   // irfft(A * conj(B))        unbind "inv"/"*" (bind with invert(b), vsa.py:56-64); bind backward
+  kBindDiv = 2,       // irfft(A / (B + 1e-12))    unbind "dagger"/"deconv" (vsa.py:65-70)
+  kBindDivConj = 3,   // irfft(A / conj(B + 1e-12))     d/d(ab) of the deconv unbind
+  kBindNegMulConj = 4,   // -irfft(A * conj(B))         d/db of the deconv unbind (A = grad_ab, B = out)
+};
+
+struct BindParams {
+  const float* a;      // row r at a + (r % a_rows) * d
+  const float* b;
+  float* out;          // (rows, d)
+  long long rows;
+  long long a_rows, b_rows;   // broadcasting: operand row = r % operand_rows
+};
+
+__device__ __forceinline__ cplx bind_op(int mode, cplx a, cplx b) {
+  if (mode == kBindMul) return cmul(a, b);
+  if (mode == kBindMulConj) return cmulc(a, b);
+  if (mode == kBindNegMulConj) { const cplx q = cmulc(a, b); return make_float2(-q.x, -q.y); }
+  // a / (b + eps) (or its conjugated denominator): complex division
+  const cplx be = make_float2(b.x + 1e-12f, mode == kBindDivConj ? -b.y : b.y);
+  const float inv = 1.0f / fmaf(be.x, be.x, be.y * be.y);
+  const cplx q = cmulc(a, be);
+  return make_float2(q.x * inv, q.y * inv);
+}
+
+// LOG2N is log2 of the COMPLEX half length: d = 2 * 2^LOG2N.
+template <int LOG2N, int MODE>
+__global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS)
+bind_kernel(const BindParams p, const cplx* __restrict__ tw) {
+  using Pl = FftPlan<LOG2N>;
+  constexpr int N = Pl::N, T = Pl::T, E = Pl::E, G = Pl::GROUPS;
+  extern __shared__ cplx smem[];
+  const int group = threadIdx.x / T, t = threadIdx.x % T;
+  cplx* xch = smem + group * Pl::XCH;
+
+  for (long long base = (long long)blockIdx.x * G; base < p.rows; base += (long long)gridDim.x * G) {
+    const long long row = base + group;
+    const bool valid = row < p.rows;
+    const float2* ar = reinterpret_cast<const float2*>(p.a + (valid ? row % p.a_rows : 0) * (2LL * N));
+    const float2* br = reinterpret_cast<const float2*>(p.b + (valid ? row % p.b_rows : 0) * (2LL * N));
+    cplx va[E], vb[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      va[e] = valid ? ldg_stream2(ar + t + e * T) : make_float2(0.f, 0.f);
+      vb[e] = valid ? ldg_stream2(br + t + e * T) : make_float2(1.f, 0.f);
+    }
+    fft_run<LOG2N, false>(va, xch, t, tw);
+    const float a_nyq = r2c_untangle<LOG2N>(va, xch, t, tw);
+    fft_run<LOG2N, false>(vb, xch, t, tw);
+    const float b_nyq = r2c_untangle<LOG2N>(vb, xch, t, tw);
+#pragma unroll
+    for (int e = 0; e < E; ++e) va[e] = bind_op(MODE, va[e], vb[e]);
+    float p_nyq;
+    if (MODE == kBindDiv || MODE == kBindDivConj) p_nyq = a_nyq / (b_nyq + 1e-12f);
+    else if (MODE == kBindNegMulConj) p_nyq = -a_nyq * b_nyq;
+    else p_nyq = a_nyq * b_nyq;
+    c2r_pretangle<LOG2N>(va, p_nyq, xch, t, tw);
+    fft_run<LOG2N, true>(va, xch, t, tw);
+    if (valid) {
+      float2* o = reinterpret_cast<float2*>(p.out + row * (2LL * N));
+#pragma unroll
+      for (int e = 0; e < E; ++e) stg_stream2(o + t + e * T, va[e]);
+    }
+  }
+}
+
+
+// ---- any-length bind (direct DFT, O(d^2) per pair): covers odd / non power-of-two d -----------
+// smem: tw[d] cplx, a[d], b[d] float, P[d/2+1] cplx
+template <int MODE>
+__global__ void __launch_bounds__(256)
+bind_generic_kernel(const BindParams p, int d) {
+  extern __shared__ cplx smem[];
+  cplx* tw = smem;
+  float* sa = reinterpret_cast<float*>(smem + d);
+  float* sb = sa + d;
+  cplx* P = reinterpret_cast<cplx*>(sb + d + (d & 1));
+  const int nh = d / 2;                     // bins 0..nh
+  for (int m = threadIdx.x; m < d; m += blockDim.x) {
+    double s, c;
+    sincospi(2.0 * (double)m / (double)d, &s, &c);
+    tw[m] = make_float2((float)c, (float)s);
+  }
+  for (long long row = blockIdx.x; row < p.rows; row += gridDim.x) {
+    const float* ar = p.a + (row % p.a_rows) * (long long)d;
+    const float* br = p.b + (row % p.b_rows) * (long long)d;
+    __syncthreads();
+    for (int j = threadIdx.x; j < d; j += blockDim.x) { sa[j] = ar[j]; sb[j] = br[j]; }
+    __syncthreads();
+    for (int k = threadIdx.x; k <= nh; k += blockDim.x) {
+      double are = 0, aim = 0, bre = 0, bim = 0;
+      int m = 0;
+      for (int j = 0; j < d; ++j) {
+        const cplx w = tw[m];
+        are += (double)(sa[j] * w.x); aim -= (double)(sa[j] * w.y);
+        bre += (double)(sb[j] * w.x); bim -= (double)(sb[j] * w.y);
+        m += k;
+        if (m >= d) m -= d;
+      }
+      if (k == 0 || 2 * k == d) { aim = 0; bim = 0; }
+      P[k] = bind_op(MODE, make_float2((float)are, (float)aim), make_float2((float)bre, (float)bim));
+    }
+    __syncthreads();
+    const float inv_d = 1.0f / (float)d;
+    const int kmax = (d - 1) / 2;
+    for (int j = threadIdx.x; j < d; j += blockDim.x) {
+      double acc = 0.0;
+      int m = 0;
+      for (int k = 1; k <= kmax; ++k) {
+        m += j;
+        if (m >= d) m -= d;
+        const cplx w = tw[m], x = P[k];
+        acc += (double)(x.x * w.x - x.y * w.y);
+      }
+      float base = P[0].x;
+      if ((d & 1) == 0) base += (j & 1) ? -P[nh].x : P[nh].x;
+      p.out[row * (long long)d + j] = inv_d * (base + 2.0f * (float)acc);
+    }
+  }
+}
+
+// ---- elementwise / reduction VSA helpers --------------------------------------------------------
+// invert (vsa.py:49-53): out[r, j] = a[r, (d - j) mod d]
+__global__ void invert_kernel(const float* __restrict__ a, float* __restrict__ out, long long rows, int d) {
+  const long long total = rows * d;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / d;
+    const int j = (int)(i - r * d);
+    out[i] = a[r * d + (j == 0 ? 0 : d - j)];
+  }
+}
+
+// permute (vsa.py:82-84): out[r, j] = v[r, perm[j]];  unpermute (:87-90): out[r, perm[j]] = v[r, j]
+__global__ void permute_kernel(const float* __restrict__ v, const long long* __restrict__ perm, float* __restrict__ out,
+                               long long rows, int d, int inverse) {
+  const long long total = rows * d;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / d;
+    const int j = (int)(i - r * d);
+    const long long pj = perm[j];
+    if (inverse) out[r * d + pj] = v[i];
+    else out[i] = v[r * d + pj];
+  }
+}
+
+// bundle (vsa.py:75-79), stage 1: partial column sums of a (k, d) stack over row chunks.
+// grid = (ceil(d / 128), chunks); partial[(chunk, j)].
+__global__ void __launch_bounds__(128)
+bundle_partial_kernel(const float* __restrict__ v, float* __restrict__ partial, long long k, int d,
+                      long long rows_per_chunk) {
+  const int j = blockIdx.x * 128 + threadIdx.x;
+  const long long r0 = (long long)blockIdx.y * rows_per_chunk;
+  long long r1 = r0 + rows_per_chunk;
+  if (r1 > k) r1 = k;
+  if (j >= d) return;
+  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+  long long r = r0;
+  for (; r + 3 < r1; r += 4) {
+    acc0 += ldg_stream1(v + r * d + j);
+    acc1 += ldg_stream1(v + (r + 1) * d + j);
+    acc2 += ldg_stream1(v + (r + 2) * d + j);
+    acc3 += ldg_stream1(v + (r + 3) * d + j);
+  }
+  for (; r < r1; ++r) acc0 += ldg_stream1(v + r * d + j);
+  partial[(long long)blockIdx.y * d + j] = (acc0 + acc1) + (acc2 + acc3);
+}
+// stage 2: out[j] = scale * sum_chunks partial
+__global__ void bundle_final_kernel(const float* __restrict__ partial, float* __restrict__ out, int chunks, int d,
+                                    float scale) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= d) return;
+  float acc = 0.f;
+  for (int c = 0; c < chunks; ++c) acc += partial[(long long)c * d + j];
+  out[j] = acc * scale;
+}
+
+// similarity (vsa.py:93-96): cosine with each norm clamped at 1e-8.  One warp per output row;
+// operand row = r % operand_rows (broadcast).  Optional backward outputs handled by cosine_bwd_kernel.
+__global__ void __launch_bounds__(256)
+cosine_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, long long rows,
+              long long a_rows, long long b_rows, int d) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long row = warp; row < rows; row += nwarps) {
+    const float* ar = a + (row % a_rows) * (long long)d;
+    const float* br = b + (row % b_rows) * (long long)d;
+    float ab = 0.f, aa = 0.f, bb = 0.f;
+    if ((d & 3) == 0) {
+      const float4* a4 = reinterpret_cast<const float4*>(ar);
+      const float4* b4 = reinterpret_cast<const float4*>(br);
+#pragma unroll 4
+      for (int i = lane; i < d / 4; i += 32) {
+        const float4 x = __ldg(a4 + i), y = __ldg(b4 + i);
+        ab += x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
+        aa += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+        bb += y.x * y.x + y.y * y.y + y.z * y.z + y.w * y.w;
+      }
+    } else {
+      for (int i = lane; i < d; i += 32) {
+        const float x = ar[i], y = br[i];
+        ab += x * y; aa += x * x; bb += y * y;
+      }
+    }
+    ab = warp_sum(ab); aa = warp_sum(aa); bb = warp_sum(bb);
+    if (lane == 0) out[row] = ab / (fmaxf(sqrtf(aa), 1e-8f) * fmaxf(sqrtf(bb), 1e-8f));
+  }
+}
+
+// d cos / d a = g (b / (|a||b|) - cos a / |a|^2), same for b; per expanded row (caller reduces broadcasts)
+__global__ void __launch_bounds__(256)
+cosine_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ gout,
+                  float* __restrict__ da, float* __restrict__ db, long long rows, long long a_rows, long long b_rows,
+                  int d) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long row = warp; row < rows; row += nwarps) {
+    const float* ar = a + (row % a_rows) * (long long)d;
+    const float* br = b + (row % b_rows) * (long long)d;
+    float ab = 0.f, aa = 0.f, bb = 0.f;
+    for (int i = lane; i < d; i += 32) {
+      const float x = ar[i], y = br[i];
+      ab += x * y; aa += x * x; bb += y * y;
+    }
+    ab = warp_sum(ab); aa = warp_sum(aa); bb = warp_sum(bb);
+    const float na = sqrtf(aa), nb = sqrtf(bb);
+    const float ca = fmaxf(na, 1e-8f), cb = fmaxf(nb, 1e-8f);
+    const float g = gout[row];
+    const float inv = 1.0f / (ca * cb);
+    const float cosv = ab * inv;
+    // derivative of the clamped norms: d max(|a|, eps) / da = a/|a| when |a| > eps else 0
+    const float ka = (na > 1e-8f) ? cosv / (ca * na) : 0.f;
+    const float kb = (nb > 1e-8f) ? cosv / (cb * nb) : 0.f;
+    for (int i = lane; i < d; i += 32) {
+      const float x = ar[i], y = br[i];
+      if (da) da[row * (long long)d + i] = g * (y * inv - ka * x);
+      if (db) db[row * (long long)d + i] = g * (x * inv - kb * y);
+    }
+  }
+}
+
+// normalize_vectors (vsa.py:39-40): x / max(||x||, 1e-12); backward dx = (g - y (y.g)) / max(||x||, eps)
+__global__ void __launch_bounds__(256)
+normalize_kernel(const float* __restrict__ x, float* __restrict__ out, long long rows, int d) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long row = warp; row < rows; row += nwarps) {
+    const float* xr = x + row * (long long)d;
+    float ss = 0.f;
+    for (int i = lane; i < d; i += 32) { const float v = xr[i]; ss += v * v; }
+    ss = warp_sum(ss);
+    const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+    for (int i = lane; i < d; i += 32) out[row * (long long)d + i] = xr[i] * inv;
+  }
+}
+__global__ void __launch_bounds__(256)
+normalize_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gout, float* __restrict__ dx,
+                     long long rows, int d) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long row = warp; row < rows; row += nwarps) {
+    const float* xr = x + row * (long long)d;
+    const float* gr = gout + row * (long long)d;
+    float ss = 0.f, xg = 0.f;
+    for (int i = lane; i < d; i += 32) { const float v = xr[i]; ss += v * v; xg += v * gr[i]; }
+    ss = warp_sum(ss); xg = warp_sum(xg);
+    const float nrm = sqrtf(ss);
+    const float inv = 1.0f / fmaxf(nrm, 1e-12f);
+    const float k = (nrm > 1e-12f) ? xg * inv * inv * inv : 0.f;     // (y.g)/max(|x|) * 1/|x|
+    for (int i = lane; i < d; i += 32) dx[row * (long long)d + i] = gr[i] * inv - k * xr[i];
+  }
+}
+
+}  // namespace cvb

@@ -1,0 +1,172 @@
+/* clifford_b200 -- C ABI of the B200-native latent hot path (sm_100a).
+ *
+ * This is the drop-in boundary: every entry point takes raw DEVICE pointers (fp32 unless noted),
+ * explicit sizes / strides, a Philox (seed, offset) pair or pointers to pre-drawn base variates, and
+ * a cudaStream_t passed as void*.  Nothing allocates, nothing synchronises, every call returns an
+ * int status (0 = ok; see cvb_status below; text via cvb_last_error_string()).
+ *
+ * The reference (momalekabid/clifford-vae) has no FFI of its own: its boundary is a set of Python
+ * symbols.  Each function below names the reference code it replaces; the
+ * Python classes/functions with the reference's names live in clifford-vae_b200/{dists,utils,
+ * hyperspherical_vae} and call these through ctypes.
+ *
+ * Row conventions: "rows" are flattened leading dims (sample_shape x batch).  Parameters that are
+ * shared across sample_shape are indexed with row % loc_rows.  A concentration tensor is addressed
+ * as kappa[(row % loc_rows) * kappa_row_stride + k * kappa_el_stride]; kappa_el_stride == 0 means one
+ * concentration per row (what every reference driver uses: mnist/mlp_vae.py:70,93, cnn/models.py:228).
+ */
+#ifndef CLIFFORD_B200_H_
+#define CLIFFORD_B200_H_
+
+#if defined(__GNUC__)
+#define CVB_API __attribute__((visibility("default")))
+#else
+#define CVB_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum cvb_status { CVB_OK = 0, CVB_BAD_ARGUMENT = 1, CVB_UNSUPPORTED = 2, CVB_CUDA_ERROR = 3 };
+
+/* bind modes (cvb_vsa_bind) */
+enum cvb_bind_mode {
+  CVB_BIND_MUL = 0,          /* irfft(A * B)            utils/vsa.py:43-46  bind                          */
+  CVB_BIND_MUL_CONJ = 1,     /* irfft(A * conj B)       utils/vsa.py:56-64  unbind "inv"/"*"; bind bwd    */
+  CVB_BIND_DIV = 2,          /* irfft(A / (B + 1e-12))  utils/vsa.py:65-70  unbind "dagger"/"deconv"      */
+  CVB_BIND_DIV_CONJ = 3,     /* irfft(A / conj(B+1e-12))  adjoint of DIV wrt its first operand            */
+  CVB_BIND_NEG_MUL_CONJ = 4  /* -irfft(A * conj B)        adjoint of DIV wrt its second operand           */
+};
+
+CVB_API int cvb_version(void);
+CVB_API const char* cvb_last_error_string(void);
+/* Build the per-device twiddle table on the CURRENT device.  Call once per device before any other
+ * entry point (and outside CUDA-graph capture); idempotent. */
+CVB_API int cvb_init(void);
+/* Number of kernels this library has launched since load (bench.py's gpu_launches claim). */
+CVB_API long long cvb_launch_count(void);
+
+/* ---- Clifford-torus power-spherical distribution: dists/clifford.py:281-327 ------------------- */
+
+/* CliffordPowerSphericalDistribution.rsample (dists/clifford.py:295-308) fused with entropy()/KL
+ * (:318-327, :241-242).  loc (loc_rows, d).  Base draws: pass tprime and gnoise (rows, d) to inject
+ * t' ~ Beta(1/2 + kappa + 1e-7, 1/2) and g ~ N(0,1) (parity mode), or both NULL to draw on the device
+ * with Philox4x32-10 keyed by (seed, offset).  Outputs: z (rows, 2d); optional tp_signed (rows, d)
+ * = copysign(t', sign) saved for the backward in RNG mode; optional entropy / kl / dentropy (rows)
+ * (dentropy = d entropy / d kappa), written only when kappa_el_stride == 0 (otherwise call
+ * cvb_ps_entropy_kl). */
+CVB_API int cvb_clifford_ps_rsample(const float* loc, const float* kappa, long long kappa_row_stride, int kappa_el_stride,
+                            long long loc_rows, const float* tprime, const float* gnoise,
+                            unsigned long long seed, unsigned long long offset, float* z, float* tp_signed,
+                            float* entropy, float* kl, float* dentropy, long long rows, int d, void* stream);
+
+/* Backward of the above (autograd through ifft / exp / atan2 / _Dirichlet_backward in the reference).
+ * Give either (tprime, gnoise) or tp_signed.  dloc (rows, d); dkappa (rows) when kappa_el_stride == 0,
+ * else (rows, d). */
+CVB_API int cvb_clifford_ps_rsample_backward(const float* grad_z, const float* loc, const float* kappa,
+                                     long long kappa_row_stride, int kappa_el_stride, long long loc_rows,
+                                     const float* tprime, const float* gnoise, const float* tp_signed, float* dloc,
+                                     float* dkappa, long long rows, int d, void* stream);
+
+/* CliffordPowerSphericalDistribution.log_prob (dists/clifford.py:310-316, :198-202).  value (rows, 2d)
+ * -> log_prob (rows).  Optional derivative outputs: dlp_dloc (rows, d), dlp_dkappa ((rows) or (rows, d)). */
+CVB_API int cvb_clifford_ps_log_prob(const float* value, const float* loc, const float* kappa, long long kappa_row_stride,
+                             int kappa_el_stride, long long loc_rows, float* log_prob, float* dlp_dloc,
+                             float* dlp_dkappa, long long rows, int d, void* stream);
+
+/* Power-spherical entropy / KL-to-uniform and dH/dkappa without sampling.
+ * torus != 0: dists/clifford.py:318-327 -- sum over circles k >= 1 of the dim-2 entropy, kl = -H + (d-1) ln 2pi.
+ * torus == 0: dists/clifford.py:204-212, :335-337 -- one (2*half_dm1+1)-dim PowerSpherical per row
+ *             (el_stride ignored), kl = -H + prior_entropy.
+ * dentropy: (rows) when kappa_el_stride == 0 or torus == 0, else (rows, d). */
+CVB_API int cvb_ps_entropy_kl(const float* kappa, long long kappa_row_stride, int kappa_el_stride, long long rows, int d,
+                      double half_dm1, int torus, double prior_entropy, float* entropy, float* kl, float* dentropy,
+                      void* stream);
+
+/* CliffordTorusUniform.rsample (dists/clifford.py:228-236) and the shared "phases -> real vector with
+ * unit-magnitude spectrum" map.  phases (rows, d) are multiplied by phase_scale (2*pi for uniform u);
+ * phases == NULL draws u on the device.  z (rows, 2d). */
+CVB_API int cvb_clifford_phases_to_vector(const float* phases, float phase_scale, unsigned long long seed,
+                                  unsigned long long offset, float* z, long long rows, int d, void* stream);
+
+/* ---- VSA / HRR ops: utils/vsa.py:9-96 ----------------------------------------------------------- */
+
+/* bind / unbind family: out[r] = irfft(op(rfft a[r % a_rows], rfft b[r % b_rows])), rows of length d. */
+CVB_API int cvb_vsa_bind(const float* a, const float* b, float* out, long long rows, long long a_rows, long long b_rows, int d,
+                 int mode, void* stream);
+/* invert (utils/vsa.py:49-53) */
+CVB_API int cvb_vsa_invert(const float* a, float* out, long long rows, int d, void* stream);
+/* permute_vector / unpermute_vector (utils/vsa.py:82-90); perm is int64 (d). */
+CVB_API int cvb_vsa_permute(const float* v, const long long* perm, float* out, long long rows, int d, int inverse, void* stream);
+/* bundle (utils/vsa.py:75-79): out (d) = scale * sum_k v[k]; workspace >= cvb_vsa_bundle_workspace_bytes. */
+CVB_API long long cvb_vsa_bundle_workspace_bytes(long long k, int d);
+CVB_API int cvb_vsa_bundle(const float* v, float* out, long long k, int d, float scale, void* workspace, void* stream);
+/* similarity (utils/vsa.py:93-96): cosine, norms clamped at 1e-8; rows broadcast by modulo. */
+CVB_API int cvb_vsa_cosine(const float* a, const float* b, float* out, long long rows, long long a_rows, long long b_rows, int d,
+                   void* stream);
+CVB_API int cvb_vsa_cosine_backward(const float* a, const float* b, const float* grad_out, float* da, float* db, long long rows,
+                            long long a_rows, long long b_rows, int d, void* stream);
+/* normalize_vectors (utils/vsa.py:39-40) */
+CVB_API int cvb_vsa_normalize(const float* x, float* out, long long rows, int d, void* stream);
+CVB_API int cvb_vsa_normalize_backward(const float* x, const float* grad_out, float* dx, long long rows, int d, void* stream);
+/* hrr_init (utils/vsa.py:9-12): N(0, 1/d) ; unitary_init (utils/vsa.py:15-36) */
+CVB_API int cvb_vsa_hrr_init(float* out, long long n, int d, unsigned long long seed, unsigned long long offset, void* stream);
+CVB_API int cvb_vsa_unitary_init(float* out, long long n, int d, float eps, unsigned long long seed, unsigned long long offset,
+                         void* stream);
+
+/* ---- D-dimensional PowerSpherical: dists/clifford.py:85-212, :335-337 -------------------------- */
+
+/* PowerSpherical.rsample (dists/clifford.py:152-185).  loc (loc_rows, D) unit rows, kappa (loc_rows).
+ * Inject tprime (rows) ~ Beta((D-1)/2 + kappa + 1e-7, (D-1)/2) and gnoise (rows, D-1) ~ N(0,1), or both
+ * NULL for device RNG (Philox (seed, offset)).  z (rows, D).  save (rows, 2) optional: (t', 0) for the
+ * backward in RNG mode. */
+CVB_API int cvb_powerspherical_rsample(const float* loc, const float* kappa, long long loc_rows, const float* tprime,
+                                       const float* gnoise, unsigned long long seed, unsigned long long offset,
+                                       float* z, float* save, long long rows, int D, void* stream);
+/* Backward: grad_z (rows, D) -> dloc (rows, D), dkappa (rows).  Injected mode: pass the same tprime /
+ * gnoise; RNG mode: pass save from the forward and the same (seed, offset) -- the tangent normals are
+ * replayed from the counter-based generator instead of being stored. */
+CVB_API int cvb_powerspherical_rsample_backward(const float* grad_z, const float* loc, const float* kappa,
+                                                long long loc_rows, const float* tprime, const float* gnoise,
+                                                const float* save, unsigned long long seed, unsigned long long offset,
+                                                float* dloc, float* dkappa, long long rows, int D, void* stream);
+/* PowerSpherical.log_prob (dists/clifford.py:198-202).  Optional backward helpers: coef (rows) with
+ * d lp/d loc = coef * value and d lp/d value = coef * loc, and dlp_dkappa (rows). */
+CVB_API int cvb_powerspherical_log_prob(const float* value, const float* loc, const float* kappa, long long loc_rows,
+                                        float* log_prob, float* coef, float* dlp_dkappa, long long rows, int D,
+                                        void* stream);
+/* PowerSpherical.log_normalizer (dists/clifford.py:187-196) and d/dkappa (optional), elementwise. */
+CVB_API int cvb_ps_log_normalizer(const float* kappa, long long rows, double half_dm1, float* log_norm,
+                                  float* dlog_norm, void* stream);
+/* HypersphericalUniform.rsample (dists/clifford.py:100-107): gnoise (rows, D) or NULL -> z = g/(||g||+eps). */
+CVB_API int cvb_sphere_uniform_rsample(const float* gnoise, unsigned long long seed, unsigned long long offset,
+                                       float* z, long long rows, int D, float norm_eps, void* stream);
+
+/* ---- von Mises-Fisher: vmf/hyperspherical_vae/distributions/von_mises_fisher.py:11-217 ---------- */
+
+/* VonMisesFisher.rsample (:50-181).  kappa (loc_rows).  Injected mode: e_rounds / u_rounds
+ * (n_rounds, rows) fp64 rejection proposals (e ~ Beta((m-1)/2,(m-1)/2), u ~ U(1e-20, 1-1e-20)); each row
+ * takes its first accepted round; for D == 3 u_rounds row 0 is the closed-form uniform (:73-88); gnoise
+ * (rows, D) normals whose column 0 is discarded (:59-65).  All NULL: device rejection loop.
+ * z (rows, D); save (rows, 2) = (w, dw/dkappa) for the backward. */
+CVB_API int cvb_vmf_rsample(const float* loc, const float* kappa, long long loc_rows, const double* e_rounds,
+                            const double* u_rounds, int n_rounds, const float* gnoise, unsigned long long seed,
+                            unsigned long long offset, float* z, float* save, long long rows, int D, void* stream);
+CVB_API int cvb_vmf_rsample_backward(const float* grad_z, const float* loc, const float* kappa, long long loc_rows,
+                                     const float* gnoise, const float* save, unsigned long long seed,
+                                     unsigned long long offset, float* dloc, float* dkappa, long long rows, int D,
+                                     void* stream);
+/* entropy (:183-191), log-normaliser (:200-212; device log I_v replaces scipy.special.ive on the host,
+ * ops/ive.py:9-34) and their kappa-derivatives; all (rows), any pointer may be NULL. */
+CVB_API int cvb_vmf_entropy_lognorm(const float* kappa, long long rows, int D, float* entropy, float* log_norm,
+                                    float* dentropy, float* dlog_norm, void* stream);
+
+/* ---- test hook: raw Philox4x32-10 words, out[4*i .. 4*i+3] = philox(counter = (i, 0, 0, offset)) --- */
+CVB_API int cvb_philox_fill(unsigned int* out, long long n_vec4, unsigned long long seed, unsigned long long offset,
+                    void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLIFFORD_B200_H_ */

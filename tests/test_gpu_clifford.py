@@ -1,0 +1,186 @@
+"""GPU parity: Clifford-torus kernels (through dists.clifford -> ctypes -> C ABI) vs the CPU oracle
+and the golden vectors generated from the reference.  Tolerances are max-norm relative errors:
+1e-5 on forward values (north_star), looser where the reference itself sums O(d) fp32 terms with
+cancellation (documented per assert)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+CLIFF = ["b4_d16_rowk", "b3_d8_fullk", "b2_d512_rowk", "b5_d5_rowk", "b3_d64_rowk_s2", "b6_d2048_rowk",
+         "b4_d20_rowk"]
+DEV = "cuda"
+
+
+def T(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def _dist(c):
+    from dists.clifford import CliffordPowerSphericalDistribution
+    loc = T(c["loc"]).requires_grad_()
+    kap = T(c["kappa"]).requires_grad_()
+    return CliffordPowerSphericalDistribution(loc, kap), loc, kap
+
+
+@pytest.mark.parametrize("name", CLIFF)
+def test_rsample_injected_matches_reference(golden_clifford, name):
+    c = golden_clifford[name]
+    q, loc, kap = _dist(c)
+    sshape = c["z"].shape[:-2]
+    z = q.rsample(torch.Size(sshape), _base_draws=(T(c["tprime"]), T(c["g"])))
+    assert z.shape == c["z"].shape
+    assert rel_err(z.detach().cpu(), c["z"]) < 1e-5
+    dloc, dkap = torch.autograd.grad((z * T(c["grad_z"])).sum(), [loc, kap])
+    assert rel_err(dloc.cpu(), c["dloc"]) < 2e-5
+    # d-term fp32 sum with cancellation in the reference itself
+    assert rel_err(dkap.cpu(), c["dkappa"]) < 3e-4
+
+
+@pytest.mark.parametrize("name", CLIFF)
+def test_entropy_kl_log_prob(golden_clifford, name):
+    from dists.clifford import CliffordTorusUniform
+    c = golden_clifford[name]
+    q, loc, kap = _dist(c)
+    d = loc.shape[-1]
+    p = CliffordTorusUniform(d, device=DEV)
+    ent = q.entropy()
+    kl = torch.distributions.kl.kl_divergence(q, p)
+    assert rel_err(ent.detach().cpu(), c["entropy"]) < 1e-5
+    scale = (d - 1) * math.log(2 * math.pi)      # kl = scale - entropy: compare on that scale
+    assert np.max(np.abs(kl.detach().cpu().numpy() - c["kl"])) < 1e-5 * scale
+    (dk,) = torch.autograd.grad((kl * T(c["grad_kl"])).sum(), [kap])
+    assert rel_err(dk.cpu(), c["dkappa_kl"]) < 2e-5
+    lpz = q.log_prob(T(c["z"]))
+    assert rel_err(lpz.detach().cpu(), c["log_prob_z"]) < 2e-5
+    lpv = q.log_prob(T(c["value"]))
+    assert rel_err(lpv.detach().cpu(), c["log_prob_value"]) < 1e-5
+    dl, dk2 = torch.autograd.grad((lpv * T(c["grad_lp"])).sum(), [loc, kap])
+    assert rel_err(dl.cpu(), c["dloc_lp"]) < 2e-5
+    assert rel_err(dk2.cpu(), c["dkappa_lp"]) < 2e-5
+    assert rel_err(p.log_prob(T(c["z"])).cpu(), c["prior_log_prob"]) < 1e-6
+
+
+def test_fused_entropy_cache_and_training_grads(golden_clifford):
+    """rsample caches the fused entropy; kl + entropy backward both reach kappa (mlp_vae.py:126-129)."""
+    from dists.clifford import CliffordPowerSphericalDistribution, CliffordTorusUniform
+    c = golden_clifford["b4_d16_rowk"]
+    loc = T(c["loc"]).requires_grad_()
+    kap = T(c["kappa"]).requires_grad_()
+    q = CliffordPowerSphericalDistribution(loc, kap)
+    z = q.rsample(_base_draws=(T(c["tprime"]), T(c["g"])))
+    assert q._fused_entropy is not None
+    kl = torch.distributions.kl.kl_divergence(q, CliffordTorusUniform(16, device=DEV))
+    loss = (z * T(c["grad_z"])).sum() + (kl * T(c["grad_kl"])).sum()
+    dloc, dkap = torch.autograd.grad(loss, [loc, kap])
+    assert rel_err(dloc.cpu(), c["dloc"]) < 2e-5
+    assert rel_err(dkap.cpu(), c["dkappa"] + c["dkappa_kl"]) < 3e-4
+    assert rel_err(q.entropy().detach().cpu(), c["entropy"]) < 1e-5
+
+
+def test_expanded_concentration_like_cnn_models(golden_clifford):
+    """cnn/models.py:228 passes params.expand_as(mu)."""
+    from dists.clifford import CliffordPowerSphericalDistribution
+    c = golden_clifford["b2_d512_rowk"]
+    loc = T(c["loc"]).requires_grad_()
+    kap = T(c["kappa"]).requires_grad_()
+    q = CliffordPowerSphericalDistribution(loc, kap.expand_as(loc))
+    z = q.rsample(_base_draws=(T(c["tprime"]), T(c["g"])))
+    assert rel_err(z.detach().cpu(), c["z"]) < 1e-5
+    dloc, dkap = torch.autograd.grad((z * T(c["grad_z"])).sum(), [loc, kap])
+    assert rel_err(dkap.cpu(), c["dkappa"]) < 3e-4
+    assert q.concentration.shape == loc.shape
+
+
+@pytest.mark.parametrize("name", ["uni_s7_d16", "uni_s3_d512", "uni_s4_d5"])
+def test_uniform_prior_injected(golden_clifford, name):
+    from dists.clifford import CliffordTorusUniform
+    c = golden_clifford[name]
+    S, d = c["u"].shape
+    p = CliffordTorusUniform(d, device=DEV)
+    z = p.rsample(torch.Size([S]), _base_draws=T(c["u"]))
+    assert rel_err(z.cpu(), c["z"]) < 1e-5
+    assert abs(p.entropy() - float(c["entropy"])) < 1e-9
+
+
+@pytest.mark.parametrize("B,d", [(64, 512), (7, 2048), (33, 64), (5, 8192), (9, 24), (16, 1024)])
+def test_rng_mode_invariants_and_backward_vs_oracle(B, d):
+    """Device-RNG samples: |rfft z| = 1, ||z|| = 1, sum z = 1; and the backward kernel agrees with
+    the oracle's autograd when the oracle is fed the draws the kernel saved."""
+    from dists.clifford import CliffordPowerSphericalDistribution
+    from oracle import latent_oracle as O
+    torch.manual_seed(d + B)
+    loc = (torch.randn(B, d, device=DEV) * 2).requires_grad_()
+    kap = (torch.rand(B, 1, device=DEV) * 9.9 + 0.03).requires_grad_()
+    q = CliffordPowerSphericalDistribution(loc, kap)
+    z = q.rsample()
+    F = torch.fft.rfft(z.detach().double(), dim=-1)
+    assert float((F.abs() - 1).abs().max()) < 2e-5
+    assert float((z.detach().double().norm(dim=-1) - 1).abs().max()) < 1e-5
+    assert float((z.detach().double().sum(-1) - 1).abs().max()) < 1e-4
+    gz = torch.randn_like(z)
+    dloc, dkap = torch.autograd.grad((z * gz).sum(), [loc, kap])
+    # recover the draws from the phases the kernel produced: theta_k - loc_k = phi_k -> t' = (1+cos phi)/2
+    th = torch.angle(F[:, :d]).float()
+    phi = th - loc.detach()
+    tprime = ((1 + torch.cos(phi.double())) / 2).float().clamp(1e-30, 1 - 6e-8).cpu()
+    g = torch.sign(torch.sin(phi)).cpu()
+    lo = loc.detach().cpu().requires_grad_()
+    ka = kap.detach().cpu().requires_grad_()
+    zo = O.clifford_ps_rsample(lo, ka, tprime, g)
+    k1 = slice(1, None)
+    assert rel_err(zo.detach(), z.detach().cpu()) < 5e-5
+    dlo, dka = torch.autograd.grad((zo * gz.cpu()).sum(), [lo, ka])
+    assert rel_err(dloc.cpu()[:, k1], dlo[:, k1]) < 1e-4
+    assert rel_err(dkap.cpu(), dka) < 2e-3
+
+
+def test_ks_phase_distribution_vs_reference(golden_ks):
+    """Two-sample KS of the on-device Beta/sign sampler against samples from the reference class."""
+    from scipy.stats import ks_2samp
+    from dists.clifford import CliffordPowerSphericalDistribution
+    torch.manual_seed(7)
+    n = 8192
+    for kap in (0.1, 1.0, 10.0):
+        loc = torch.zeros(n, 16, device=DEV)
+        q = CliffordPowerSphericalDistribution(loc, torch.full((n, 1), kap, device=DEV))
+        z = q.rsample()
+        th = torch.angle(torch.fft.fft(z, dim=-1)[:, 1:16]).cpu().numpy()
+        ref = golden_ks[f"clifford_phi_k{kap}"]
+        for col in (0, 7, 14):
+            stat, pval = ks_2samp(th[:, col], ref)
+            assert pval > 1e-3, (kap, col, stat, pval)
+        # circles are independent: correlation between two columns is small
+        assert abs(np.corrcoef(th[:, 0], th[:, 1])[0, 1]) < 0.05
+
+
+def test_full_size_properties_c3():
+    """BASELINE config 3 latent shape (B=4096, d=2048): size-independent identities."""
+    from dists.clifford import CliffordPowerSphericalDistribution
+    torch.manual_seed(0)
+    B, d = 4096, 2048
+    loc = torch.randn(B, d, device=DEV)
+    kap = torch.rand(B, 1, device=DEV) * 9 + 0.13
+    q = CliffordPowerSphericalDistribution(loc, kap)
+    z = q.rsample()
+    assert z.shape == (B, 2 * d)
+    assert float((z.norm(dim=-1) - 1).abs().max()) < 2e-5
+    assert float((torch.fft.rfft(z, dim=-1).abs() - 1).abs().max()) < 1e-4
+    ent = q.entropy()
+    assert ent.shape == (B,)
+    # log_prob of its own samples equals the sum of per-circle log densities at the sampled phases
+    lp = q.log_prob(z)
+    assert torch.isfinite(lp).all()
+
+
+def test_cpu_tensors_are_refused():
+    from dists.clifford import CliffordPowerSphericalDistribution
+    from clifford_b200._lib import CliffordB200Error
+    q = CliffordPowerSphericalDistribution(torch.zeros(2, 16), torch.ones(2, 1))
+    with pytest.raises(CliffordB200Error):
+        q.rsample()

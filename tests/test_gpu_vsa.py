@@ -1,0 +1,161 @@
+"""GPU parity: utils.vsa ops (ctypes -> C ABI) vs golden vectors from the reference and the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+VSA = ["k5_d64", "k3_d1024", "k4_d37", "k2_d513", "k2_d4096", "k1_d16384", "k3_d144"]
+
+
+def T(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+@pytest.mark.parametrize("name", VSA)
+def test_vsa_ops_match_reference(golden_vsa, name):
+    from utils import vsa
+    c = golden_vsa[name]
+    a = T(c["a"]).requires_grad_()
+    cc = T(c["c"]).requires_grad_()
+    b = T(c["b_unitary"])
+    ab = vsa.bind(a, cc)
+    assert rel_err(ab.detach().cpu(), c["bind_ac"]) < 1e-5
+    da, dc = torch.autograd.grad((ab * T(c["grad_out"])).sum(), [a, cc])
+    assert rel_err(da.cpu(), c["da"]) < 2e-5
+    assert rel_err(dc.cpu(), c["dc"]) < 2e-5
+    a_, c_ = a.detach(), cc.detach()
+    assert rel_err(vsa.unbind(T(c["bind_ac"]), c_, "inv").cpu(), c["unbind_inv"]) < 1e-5
+    assert rel_err(vsa.unbind(T(c["bind_ac"]), c_, "*").cpu(), c["unbind_inv"]) < 1e-5
+    # deconvolution divides by |F_c|^2 which can be tiny for an HRR vector: conditioning-limited
+    assert rel_err(vsa.unbind(T(c["bind_ac"]), c_, "†").cpu(), c["unbind_deconv"]) < 2e-3
+    assert rel_err(vsa.unbind(T(c["bind_ac"]), c_, "deconv").cpu(), c["unbind_deconv"]) < 2e-3
+    assert rel_err(vsa.bind(a_, b).cpu(), c["bind_a_unitary"]) < 1e-5
+    rec = vsa.unbind(T(c["bind_a_unitary"]), b, "inv")
+    assert rel_err(rec.cpu(), c["unbind_unitary"]) < 1e-5
+    assert rel_err(rec.cpu(), c["a"]) < 1e-4                       # unitary unbind recovers a
+    assert rel_err(vsa.unbind(vsa.bind(a_, b), b, "†").cpu(), c["a"]) < 1e-4
+    assert rel_err(vsa.invert(a_).cpu(), c["invert_a"]) == 0
+    assert rel_err(vsa.bundle(a_, True).cpu(), c["bundle_norm"]) < 1e-5
+    assert rel_err(vsa.bundle(a_, False).cpu(), c["bundle_raw"]) < 1e-5
+    assert rel_err(vsa.normalize_vectors(a_).cpu(), c["normalize_a"]) < 1e-6
+    assert rel_err(vsa.similarity(a_, c_).cpu(), c["sim_ac"]) < 1e-4
+    assert np.max(np.abs(vsa.similarity(a_[0], c_).cpu().numpy() - c["sim_bcast"])) < 1e-6
+    perm = T(c["perm"])
+    assert rel_err(vsa.permute_vector(a_, perm).cpu(), c["permute_a"]) == 0
+    assert rel_err(vsa.unpermute_vector(a_, perm).cpu(), c["unpermute_a"]) == 0
+    with pytest.raises(ValueError):
+        vsa.unbind(a_, c_, "nope")
+
+
+@pytest.mark.parametrize("d", [32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 100, 513])
+def test_bind_all_sizes_vs_oracle_and_identities(d):
+    from utils import vsa
+    from oracle import latent_oracle as O
+    torch.manual_seed(d)
+    k = 37 if d <= 4096 else 5
+    a = torch.randn(k, d) / d ** 0.5
+    b = torch.randn(k, d) / d ** 0.5
+    ag, bg = a.to(DEV), b.to(DEV)
+    out = vsa.bind(ag, bg)
+    assert rel_err(out.cpu(), O.bind(a, b)) < 1e-5
+    # commutative, associative, invert(invert) = id, broadcasting (1,d) and (d,)
+    assert rel_err(vsa.bind(bg, ag).cpu(), out.cpu()) < 1e-6
+    c = torch.randn(k, d, device=DEV) / d ** 0.5
+    assert rel_err(vsa.bind(vsa.bind(ag, bg), c).cpu(), vsa.bind(ag, vsa.bind(bg, c)).cpu()) < 2e-5
+    assert torch.equal(vsa.invert(vsa.invert(ag)), ag)
+    assert rel_err(vsa.bind(ag, bg[:1]).cpu(), O.bind(a, b[:1])) < 1e-5
+    assert rel_err(vsa.bind(ag, bg[0]).cpu(), O.bind(a, b[0])) < 1e-5
+    assert rel_err(vsa.unbind(ag, bg, "inv").cpu(), O.unbind(a, b, "inv")) < 1e-5
+    # unbind == bind with the explicit invert
+    assert rel_err(vsa.unbind(ag, bg, "inv").cpu(), vsa.bind(ag, vsa.invert(bg)).cpu()) < 1e-5
+
+
+@pytest.mark.parametrize("d", [64, 1024, 37])
+def test_autograd_of_unbind_and_friends_vs_oracle(d):
+    from utils import vsa
+    from oracle import latent_oracle as O
+    torch.manual_seed(3 * d)
+    k = 6
+    a = torch.randn(k, d) / d ** 0.5
+    b = O.unitary_init_from_uniform(torch.rand(k, (d - 1) // 2), torch.rand(k, (d - 1) // 2), d) \
+        + 0.05 * torch.randn(k, d) / d ** 0.5
+    g = torch.randn(k, d)
+    for method in ("inv", "deconv"):
+        ac, bc = a.clone().requires_grad_(), b.clone().requires_grad_()
+        ag, bg = a.to(DEV).requires_grad_(), b.to(DEV).requires_grad_()
+        ro = O.unbind(ac, bc, method)
+        rg = vsa.unbind(ag, bg, method)
+        assert rel_err(rg.detach().cpu(), ro.detach()) < 2e-5
+        dao, dbo = torch.autograd.grad((ro * g).sum(), [ac, bc])
+        dag, dbg = torch.autograd.grad((rg * g.to(DEV)).sum(), [ag, bg])
+        assert rel_err(dag.cpu(), dao) < 5e-5, method
+        assert rel_err(dbg.cpu(), dbo) < 5e-5, method
+    # similarity / normalize / bundle / invert / permute backward
+    ac, bc = a.clone().requires_grad_(), b.clone().requires_grad_()
+    ag, bg = a.to(DEV).requires_grad_(), b.to(DEV).requires_grad_()
+    w = torch.randn(k)
+    perm = torch.randperm(d)
+    fo = (O.similarity(O.normalize_vectors(ac), O.invert(bc)) * w).sum() + \
+        (O.bundle(O.permute_vector(ac, perm)) * g[0]).sum() + (O.similarity(ac[0], bc) * w).sum()
+    fg = (vsa.similarity(vsa.normalize_vectors(ag), vsa.invert(bg)) * w.to(DEV)).sum() + \
+        (vsa.bundle(vsa.permute_vector(ag, perm.to(DEV))) * g[0].to(DEV)).sum() + \
+        (vsa.similarity(ag[0], bg) * w.to(DEV)).sum()
+    assert abs(float(fo) - float(fg)) < 1e-4 * max(1.0, abs(float(fo)))
+    dao, dbo = torch.autograd.grad(fo, [ac, bc])
+    dag, dbg = torch.autograd.grad(fg, [ag, bg])
+    assert rel_err(dag.cpu(), dao) < 5e-5
+    assert rel_err(dbg.cpu(), dbo) < 5e-5
+
+
+def test_init_generators():
+    from utils import vsa
+    torch.manual_seed(11)
+    for d in (1024, 513, 64, 144):
+        u = vsa.unitary_init(50, d, device=DEV)
+        F = torch.fft.fft(u.double(), dim=-1)
+        assert float((F.abs() - 1).abs().max()) < 5e-5, d           # unit Fourier magnitude
+        assert float(F[:, 0].real.min()) > 0.999                    # DC = 1
+        ph = torch.angle(F[:, 1:(d + 1) // 2]).abs() / np.pi
+        assert float(ph.min()) >= 1e-3 - 1e-4 and float(ph.max()) <= 1 - 1e-3 + 1e-4
+        h = vsa.hrr_init(4096, d, device=DEV)
+        assert abs(float(h.mean())) < 3e-3 / d ** 0.5 * 10
+        assert abs(float(h.var()) * d - 1) < 0.02
+    from scipy.stats import kstest
+    h = vsa.hrr_init(64, 1024, device=DEV).flatten().cpu().numpy() * 32.0
+    assert kstest(h, "norm").pvalue > 1e-3
+    # unitary vectors give exact unbinding
+    a = vsa.hrr_init(8, 1024, device=DEV)
+    b = vsa.unitary_init(8, 1024, device=DEV)
+    assert rel_err(vsa.unbind(vsa.bind(a, b), b).cpu(), a.cpu()) < 1e-4
+
+
+def test_bundle_large_and_full_size_bind_properties():
+    """C4-sized pieces: 2^16 x 1024 bind round trip with unitary keys and a 2^16-vector bundle."""
+    from utils import vsa
+    torch.manual_seed(5)
+    N, d = 1 << 16, 1024
+    a = vsa.hrr_init(N, d, device=DEV)
+    b = vsa.unitary_init(N, d, device=DEV)
+    rec = vsa.unbind(vsa.bind(a, b), b)
+    assert float((rec - a).abs().max()) < 1e-4 * float(a.abs().max()) * 10
+    s = vsa.bundle(a, normalize=True)
+    ref = a.double().sum(0) / N ** 0.5
+    assert rel_err(s.cpu(), ref.cpu()) < 1e-5
+    cs = vsa.similarity(rec, a)
+    assert float((cs - 1).abs().max()) < 1e-5
+
+
+def test_philox_known_answer():
+    """Philox4x32-10 known-answer test (Random123 kat_vectors: counter 0, key 0)."""
+    import ctypes
+    from clifford_b200 import _lib
+    _lib.ensure_device(torch.device("cuda:0"))
+    lib = _lib.load()
+    out = torch.empty(8, dtype=torch.int32, device=DEV)
+    rc = lib.cvb_philox_fill(out.data_ptr(), 2, 0, 0, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    w = [int(x) & 0xFFFFFFFF for x in out.cpu().tolist()]
+    assert w[:4] == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
