@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""bench.py -- latent hot-path throughput on B200 (contract: one JSON line on stdout).
+
+Workload (BASELINE.json configs[2] latent shape, the one the north_star's 70 %-of-HBM target is
+quoted on): per step and per GPU, B = 4096 rows of the Clifford-torus latent at d = 2048
+  1. fused Clifford power-spherical rsample + entropy/KL (device Philox RNG, one kappa per row)
+     -> z (B, 4096)                                   [reference dists/clifford.py:295-327]
+  2. vsa.bind(z, roles) with per-row roles (B, 4096)  [reference utils/vsa.py:43-46]
+`value` = samples/s with inputs resident in HBM (two rotating buffer sets, 2 x 224 MB > 126 MB L2);
+`e2e` = the same step through the reference-named Python API with HOST (pinned) inputs/outputs.
+`--impl reference` times the CPU restatement of the reference's torch path (oracle/) instead.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "clifford-vae_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+B_ROWS, D_LAT = 4096, 2048          # per GPU
+N_VEC = 2 * D_LAT
+METRIC = "latent rsample+KL+bind samples/s"
+UNIT = "samples/s"
+WORKLOAD = ("C3 latent: Clifford-PS fused rsample+KL (device RNG, row-scalar kappa) d=2048 -> z (4096 x 4096), "
+            "then vsa.bind(z, roles) n=4096; B=4096 rows per GPU per step")
+# algorithmic bytes per sample: rsample+KL 12d+8, bind 12n
+BYTES_RSAMPLE = 12 * D_LAT + 8
+BYTES_BIND = 12 * N_VEC
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i] == "Active"})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle's restatement of the reference's torch CPU path
+# --------------------------------------------------------------------------------------------------
+def cpu_step(torch, O, rows, loc, kap, roles):
+    """One pass of the same step on the host: draws + rsample + KL + bind (reference call sequence:
+    Beta.rsample then randn, dists/clifford.py:295-308; kl :325-327; bind utils/vsa.py:43-46)."""
+    d = loc.shape[1]
+    alpha = 0.5 + kap + 1e-7
+    tprime = torch.distributions.Beta(alpha.expand(rows, d), torch.full((rows, d), 0.5)).sample()
+    g = torch.randn(rows, d)
+    z = O.clifford_ps_rsample(loc, kap, tprime, g)
+    kl = O.clifford_ps_kl(kap.expand(rows, d))
+    out = O.bind(z, roles)
+    return out, kl
+
+
+def cpu_timing(rows, reps):
+    import torch
+    from oracle import latent_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    loc = torch.randn(rows, D_LAT)
+    kap = torch.rand(rows, 1) * 9.87 + 0.13
+    roles = torch.randn(rows, N_VEC) / math.sqrt(N_VEC)
+    with torch.no_grad():
+        cpu_step(torch, O, rows, loc, kap, roles)          # warm-up
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            cpu_step(torch, O, rows, loc, kap, roles)
+            ts.append(time.perf_counter() - t0)
+    return rows / statistics.median(ts), torch.get_num_threads(), ts
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import torch
+    from oracle import latent_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    rows = 128       # bounded sample of the 4096-row step
+    torch.manual_seed(0)
+    loc = torch.randn(rows, D_LAT)
+    kap = torch.rand(rows, 1) * 9.87 + 0.13
+    roles = torch.randn(rows, N_VEC) / math.sqrt(N_VEC)
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            cpu_step(torch, O, rows, loc, kap, roles)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            cpu_step(torch, O, rows, loc, kap, roles)
+        dt = time.perf_counter() - t0
+    val = rows * args.steps / dt
+    sample = f"{rows} of the {B_ROWS} rows per step (same d={D_LAT}), torch {torch.__version__} CPU"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from clifford_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.ensure_device(dev)
+    lib = _lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    B, d, n = B_ROWS, D_LAT, N_VEC
+    torch.manual_seed(1234 + rank)
+    NSETS = 2
+    sets = []
+    for _ in range(NSETS):
+        sets.append(dict(
+            loc=torch.randn(B, d, device=dev), kap=(torch.rand(B, device=dev) * 9.87 + 0.13),
+            roles=torch.randn(B, n, device=dev) / math.sqrt(n), z=torch.empty(B, n, device=dev),
+            out=torch.empty(B, n, device=dev), kl=torch.empty(B, device=dev), ent=torch.empty(B, device=dev)))
+    seed = 1234 + rank
+
+    def step(i, ev=None):
+        s = sets[i % NSETS]
+        if ev:
+            ev[0].record()
+        rc = lib.cvb_clifford_ps_rsample(s["loc"].data_ptr(), s["kap"].data_ptr(), 1, 0, B, None, None, seed, i,
+                                         s["z"].data_ptr(), None, s["ent"].data_ptr(), s["kl"].data_ptr(), None, B, d, st)
+        if ev:
+            ev[1].record()
+        rc |= lib.cvb_vsa_bind(s["z"].data_ptr(), s["roles"].data_ptr(), s["out"].data_ptr(), B, B, B, n, 0, st)
+        if ev:
+            ev[2].record()
+        if rc:
+            raise RuntimeError(lib.cvb_last_error_string().decode())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    l0 = _lib.launch_count()
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_start.record()
+    for i in range(args.steps):
+        step(args.warmup + i, evs[i])
+    t_end.record()
+    barrier()
+    launches = _lib.launch_count() - l0
+    ms_total = t_start.elapsed_time(t_end)
+    ms_rs = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
+    ms_bind = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
+
+    # ---- e2e: reference-named Python API, host (pinned) buffers in and out ------------------------
+    from dists.clifford import CliffordPowerSphericalDistribution, CliffordTorusUniform
+    from utils import vsa
+    h_loc = torch.randn(B, d).pin_memory()
+    h_kap = (torch.rand(B, 1) * 9.87 + 0.13).pin_memory()
+    h_roles = (torch.randn(B, n) / math.sqrt(n)).pin_memory()
+    h_out = torch.empty(B, n).pin_memory()
+    h_kl = torch.empty(B).pin_memory()
+    prior = CliffordTorusUniform(d, device=dev)
+
+    def e2e_step():
+        with torch.no_grad():
+            loc_d = h_loc.to(dev, non_blocking=True)
+            kap_d = h_kap.to(dev, non_blocking=True)
+            roles_d = h_roles.to(dev, non_blocking=True)
+            q = CliffordPowerSphericalDistribution(loc_d, kap_d, validate_args=False)
+            z = q.rsample()
+            kl = torch.distributions.kl.kl_divergence(q, prior)
+            out = vsa.bind(z, roles_d)
+            h_out.copy_(out, non_blocking=True)
+            h_kl.copy_(kl, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    e2e_steps = max(3, min(args.steps, 20))
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    clk = clocks.stop() if rank == 0 else None
+
+    # max over ranks
+    if world > 1:
+        t = torch.tensor([ms_total, ms_e2e, ms_rs, ms_bind], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, ms_e2e, ms_rs, ms_bind = (float(x) for x in t.tolist())
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        value = world * B * args.steps / (ms_total * 1e-3)
+        e2e_val = world * B * e2e_steps / (ms_e2e * 1e-3)
+        k_rs = {"name": "clifford_fwd_kernel<11,PsRng,rowk>", "ms": ms_rs, "bytes": B * BYTES_RSAMPLE}
+        k_bd = {"name": "bind_kernel<11,Mul>", "ms": ms_bind, "bytes": B * BYTES_BIND}
+        dom = k_rs if ms_rs >= ms_bind else k_bd
+        achieved = dom["bytes"] / (dom["ms"] * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "rows_per_gpu": B, "d": d, "rng": "philox4x32-10 on device",
+                       "l2": f"inputs rotate over {NSETS} buffer sets of 224 MB (> 126 MB L2)"},
+            "roofline": {"bound": "hbm", "kernel": dom["name"], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": dom["bytes"], "ms_per_launch": dom["ms"]},
+            "kernels": {
+                "rsample_kl": {"ms": ms_rs, "GBps": k_rs["bytes"] / (ms_rs * 1e-3) / 1e9,
+                               "frac": k_rs["bytes"] / (ms_rs * 1e-3) / 1e9 / peak},
+                "bind": {"ms": ms_bind, "GBps": k_bd["bytes"] / (ms_bind * 1e-3) / 1e9,
+                         "frac": k_bd["bytes"] / (ms_bind * 1e-3) / 1e9 / peak}},
+            "e2e": {"value": e2e_val, "unit": UNIT, "steps": e2e_steps,
+                    "h2d_bytes_per_step": world * (h_loc.numel() + h_kap.numel() + h_roles.numel()) * 4,
+                    "d2h_bytes_per_step": world * (h_out.numel() + h_kl.numel()) * 4,
+                    "api": "dists.clifford.CliffordPowerSphericalDistribution.rsample + kl_divergence + utils.vsa.bind"},
+            "gpu_launches": int(launches), "clocks": clk,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            v, cores, ts = cpu_timing(256, 3)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"256 of the {B} rows (same d={d}), median of 3 passes "
+                                              f"({sum(ts):.1f} s CPU), oracle port of the reference's torch CPU path"}
+        if args.extras:
+            line["extras"] = extras(torch, lib, dev, st, peak)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def extras(torch, lib, dev, st, peak):
+    """Per-op throughput at the other BASELINE shapes (not bench lines; context for the headline)."""
+    out = {}
+
+    def timeit(fn, reps=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    for dd in (1024, 4096, 16384):
+        N = (1 << 30) // (12 * dd) // 2 * 2          # ~1 GiB of traffic per launch
+        a = torch.randn(N, dd, device=dev)
+        b = torch.randn(N, dd, device=dev)
+        o = torch.empty(N, dd, device=dev)
+        ms = timeit(lambda: lib.cvb_vsa_bind(a.data_ptr(), b.data_ptr(), o.data_ptr(), N, N, N, dd, 0, st))
+        gb = N * 12 * dd / (ms * 1e-3) / 1e9
+        out[f"bind_d{dd}"] = {"vectors": N, "ms": ms, "vec_per_s": N / (ms * 1e-3), "GBps": gb, "frac": gb / peak}
+        del a, b, o
+    for name, B, d in (("clifford_fwd_c1", 128, 512), ("clifford_fwd_big", 65536, 2048), ("clifford_fwd_d512", 262144, 512)):
+        loc = torch.randn(B, d, device=dev)
+        kap = torch.rand(B, device=dev) * 9.87 + 0.13
+        z = torch.empty(B, 2 * d, device=dev)
+        kl = torch.empty(B, device=dev)
+        ms = timeit(lambda: lib.cvb_clifford_ps_rsample(loc.data_ptr(), kap.data_ptr(), 1, 0, B, None, None, 7, 0,
+                                                        z.data_ptr(), None, None, kl.data_ptr(), None, B, d, st))
+        gb = B * (12 * d + 8) / (ms * 1e-3) / 1e9
+        out[name] = {"rows": B, "d": d, "ms": ms, "samples_per_s": B / (ms * 1e-3), "GBps": gb, "frac": gb / peak}
+        del loc, z
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--extras", action="store_true", help="also time the other BASELINE shapes (bind sweep, C1)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

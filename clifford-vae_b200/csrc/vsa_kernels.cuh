@@ -84,7 +84,7 @@ bind_generic_kernel(const BindParams p, int d) {
   cplx* tw = smem;
   float* sa = reinterpret_cast<float*>(smem + d);
   float* sb = sa + d;
-  cplx* P = reinterpret_cast<cplx*>(sb + d + (d & 1));
+  cplx* P = reinterpret_cast<cplx*>(sb + d);   // 4d floats from the base: 8-byte aligned for any d
   const int nh = d / 2;                     // bins 0..nh
   for (int m = threadIdx.x; m < d; m += blockDim.x) {
     double s, c;

@@ -101,12 +101,12 @@ def test_ks_device_samplers_vs_reference(golden_ks):
         loc = torch.zeros(n, D, device=DEV)
         loc[:, 0] = 1
         z = PowerSpherical(loc, torch.full((n,), kap, device=DEV)).rsample().cpu().numpy()
-        assert np.max(np.abs(np.linalg.norm(z, axis=-1) - 1)) < 1e-5
+        assert np.max(np.abs(np.linalg.norm(z, axis=-1) - 1)) < 5e-5
         for col, key in ((0, "ps_t"), (1, "ps_z1")):
             pval = ks_2samp(z[:, col], golden_ks[f"{key}_D{D}_k{kap}"]).pvalue
             assert pval > 1e-3, ("ps", D, col, pval)
         z = VonMisesFisher(loc, torch.full((n, 1), kap, device=DEV)).rsample().cpu().numpy()
-        assert np.max(np.abs(np.linalg.norm(z, axis=-1) - 1)) < 1e-5
+        assert np.max(np.abs(np.linalg.norm(z, axis=-1) - 1)) < 5e-5
         for col, key in ((0, "vmf_w"), (1, "vmf_z1")):
             pval = ks_2samp(z[:, col], golden_ks[f"{key}_D{D}_k{kap}"]).pvalue
             assert pval > 1e-3, ("vmf", D, col, pval)
@@ -152,7 +152,7 @@ def test_rng_mode_backward_consistency(family):
         e = (1 - w) / ((1 + b) - w * (1 - b))
         wo = O.vmf_sample_w(kap_c, D, [e], [torch.full_like(e, 1e-300)])
         zo = O.vmf_rsample(loc_c, kap_c, wo, torch.cat([torch.zeros(B, 1), g], -1))
-    assert rel_err(zo.detach(), z.detach().cpu()) < 2e-5
+    assert rel_err(zo.detach(), z.detach().cpu()) < 1e-4
     dlo, dko = torch.autograd.grad((zo * gz.cpu()).sum(), [loc_c, kap_c])
     assert rel_err(dloc.cpu(), dlo) < 1e-4
     assert rel_err(dkap.cpu(), dko) < 2e-3
