@@ -295,9 +295,9 @@ def run_gpu(args):
             "gpu_launches": int(launches), "clocks": clk,
         }
         if world == 1 and not args.no_cpu_baseline:
-            v, cores, ts = cpu_timing(256, 3)
+            v, cores, ts = cpu_timing(2048, 5)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"256 of the {B} rows (same d={d}), median of 3 passes "
+                                    "sample": f"2048 of the {B} rows (same d={d}), median of 5 passes "
                                               f"({sum(ts):.1f} s CPU), oracle port of the reference's torch CPU path"}
         if args.extras:
             line["extras"] = extras(torch, lib, dev, st, peak)

@@ -14,7 +14,7 @@ int launch_fwd_fast(const CliffordFwdParams& p, cudaStream_t st) {
   using Pl = FftPlan<LOG2N>;
   const cplx* tw = device_twiddles();
   if (!tw) return kCudaError;
-  const size_t smem = sizeof(cplx) * Pl::XCH * Pl::GROUPS;
+  const size_t smem = clifford_fwd_smem_bytes<LOG2N>();
   auto kern = clifford_fwd_kernel<LOG2N, MODE, ROWK>;
   int grid = 0;
   const long long work = (p.rows + Pl::GROUPS - 1) / Pl::GROUPS;

@@ -1,4 +1,5 @@
 // C ABI entry points for the VSA / HRR kernels (include/clifford_b200.h).
+#include <cstdlib>
 #include "launch.cuh"
 #include "vsa_kernels.cuh"
 #include "../../include/clifford_b200.h"
@@ -15,10 +16,20 @@ int launch_bind_fast(const BindParams& p, cudaStream_t st) {
   using Pl = FftPlan<LOG2N>;
   const cplx* tw = device_twiddles();
   if (!tw) return kCudaError;
+  static const bool force_direct = getenv("CVB_BIND_DIRECT") != nullptr;
+  const bool tma_ok = !force_direct && aligned(p.a, 16) && aligned(p.b, 16);
+  const long long work = (p.rows + Pl::GROUPS - 1) / Pl::GROUPS;
+  int grid = 0;
+  if (tma_ok) {
+    // production path: cp.async.bulk-staged rows, parked spectrum, <= 128 registers
+    const size_t smem = bind_tma_smem_bytes<LOG2N>();
+    auto kern = bind_tma_kernel<LOG2N, MODE>;
+    if (int rc = persistent_grid(kern, Pl::THREADS, smem, work, &grid)) return rc;
+    kern<<<grid, Pl::THREADS, smem, st>>>(p, tw);
+    return check_launch("bind_tma_kernel");
+  }
   const size_t smem = sizeof(cplx) * Pl::XCH * Pl::GROUPS;
   auto kern = bind_kernel<LOG2N, MODE>;
-  int grid = 0;
-  const long long work = (p.rows + Pl::GROUPS - 1) / Pl::GROUPS;
   if (int rc = persistent_grid(kern, Pl::THREADS, smem, work, &grid)) return rc;
   kern<<<grid, Pl::THREADS, smem, st>>>(p, tw);
   return check_launch("bind_kernel");

@@ -67,42 +67,77 @@ __device__ __forceinline__ CirclePhase circle_phase(float tp, float sgn) {
   return o;
 }
 
-// e^{i theta_k} for bin k (1 <= k <= d-1) of `row`
+// sin/cos of an arbitrary-range angle.  FAST: two-constant Cody-Waite reduction to [-pi, pi] + the
+// MUFU approximations (abs error ~4e-7; used with device RNG where the draw itself is random);
+// otherwise the accurate library routine (parity mode).
+template <bool FAST>
+__device__ __forceinline__ void sincos_any(float x, float& s, float& c) {
+  if (FAST) {
+    const float n = rintf(x * 0.15915494309189535f);
+    float r = fmaf(-n, 6.28318548202514648f, x);        // 2 pi rounded to fp32 ...
+    r = fmaf(-n, -1.74845553146951715e-7f, r);          // ... and its remainder
+    __sincosf(r, &s, &c);
+  } else {
+    sincosf(x, &s, &c);
+  }
+}
+
+// e^{i (loc + phi)} from a Beta draw t' and a sign
+template <bool FAST>
+__device__ __forceinline__ cplx ps_phasor(float tp, float sgn, float loc) {
+  const CirclePhase ph = circle_phase(tp, sgn);
+  float sl, cl;
+  sincos_any<FAST>(loc, sl, cl);
+  return make_float2(fmaf(cl, ph.c, -sl * ph.s), fmaf(sl, ph.c, cl * ph.s));
+}
+
+// e^{i theta_k} for bin k (1 <= k <= d-1) of `row`.  For kPsRng a rejected first Marsaglia-Tsang
+// proposal returns false (the caller queues k and finishes it with clifford_phasor_retry).
 template <int MODE, bool ROWK>
-__device__ __forceinline__ cplx clifford_phasor(const CliffordFwdParams& p, long long row, long long prow, int k,
-                                                GammaMT& gm) {
+__device__ __forceinline__ bool clifford_phasor(const CliffordFwdParams& p, long long row, long long prow, int k,
+                                                GammaMT& gm, cplx& out) {
   const long long idx = row * p.d + k;
-  if (MODE == kPsInjected || MODE == kPsRng) {
+  if (MODE == kPsInjected) {
+    const float tp = ldg_stream1(p.tprime + idx);
+    const float s = sign_from_normal(ldg_stream1(p.gnoise + idx));
+    out = ps_phasor<false>(tp, s, ldg_stream1(p.loc + prow * p.d + k));
+    return true;
+  }
+  if (MODE == kPsRng) {
+    if (!ROWK) gm = GammaMT(0.5f + (__ldg(p.kappa + prow * p.kappa_row_stride + (long long)k * p.kappa_el_stride) + kEps));
     float tp, s;
-    if (MODE == kPsInjected) {
-      tp = ldg_stream1(p.tprime + idx);
-      s = sign_from_normal(ldg_stream1(p.gnoise + idx));
-    } else {
-      if (!ROWK) gm = GammaMT(0.5f + (__ldg(p.kappa + prow * p.kappa_row_stride + (long long)k * p.kappa_el_stride) + kEps));
-      tp = beta_half_draw(gm, p.key, (uint64_t)idx, s);
-      if (p.tp_signed) stg_stream1(p.tp_signed + idx, copysignf(tp, s));
-    }
-    const CirclePhase ph = circle_phase(tp, s);
-    float sl, cl;
-    sincosf(ldg_stream1(p.loc + prow * p.d + k), &sl, &cl);
-    return make_float2(fmaf(cl, ph.c, -sl * ph.s), fmaf(sl, ph.c, cl * ph.s));
+    if (!beta_half_first(gm, p.key, (uint64_t)idx, tp, s)) return false;
+    if (p.tp_signed) stg_stream1(p.tp_signed + idx, copysignf(tp, s));
+    out = ps_phasor<true>(tp, s, ldg_stream1(p.loc + prow * p.d + k));
+    return true;
   }
   float th;
   if (MODE == kPhases) {
     th = p.phase_scale * ldg_stream1(p.phases + idx);
-  } else {
-    const uint4 r = philox_draw(p.key, (uint64_t)idx, 0);
-    if (MODE == kUniformRng) {
-      th = 6.283185307179586f * u01_open1(r.x);
-    } else {
-      const float a = u01_open1(r.x);
-      const float sg = (r.y & 0x80000000u) ? -1.0f : 1.0f;
-      th = sg * 3.14159265358979f * (p.phase_scale + a * (1.0f - 2.0f * p.phase_scale));
-    }
+    sincosf(th, &out.y, &out.x);
+    return true;
   }
-  cplx x;
-  sincosf(th, &x.y, &x.x);
-  return x;
+  const uint4 r = philox_draw(p.key, (uint64_t)idx, 0);
+  if (MODE == kUniformRng) {
+    th = 6.283185307179586f * u01_open1(r.x) - 3.14159265358979f;      // same law as 2 pi U, kept in [-pi, pi)
+  } else {
+    const float a = u01_open1(r.x);
+    const float sg = (r.y & 0x80000000u) ? -1.0f : 1.0f;
+    th = sg * 3.14159265358979f * (p.phase_scale + a * (1.0f - 2.0f * p.phase_scale));
+  }
+  __sincosf(th, &out.y, &out.x);
+  return true;
+}
+
+template <bool ROWK>
+__device__ __forceinline__ cplx clifford_phasor_retry(const CliffordFwdParams& p, long long row, long long prow, int k,
+                                                      GammaMT& gm) {
+  const long long idx = row * p.d + k;
+  if (!ROWK) gm = GammaMT(0.5f + (__ldg(p.kappa + prow * p.kappa_row_stride + (long long)k * p.kappa_el_stride) + kEps));
+  float s;
+  const float tp = beta_half_retry(gm, p.key, (uint64_t)idx, s);
+  if (p.tp_signed) stg_stream1(p.tp_signed + idx, copysignf(tp, s));
+  return ps_phasor<true>(tp, s, ldg_stream1(p.loc + prow * p.d + k));
 }
 
 __device__ __forceinline__ void clifford_row_entropy(const CliffordFwdParams& p, long long row, float kap_row) {
@@ -113,36 +148,76 @@ __device__ __forceinline__ void clifford_row_entropy(const CliffordFwdParams& p,
   if (p.dentropy) p.dentropy[row] = (float)((double)(p.d - 1) * c.dentropy);
 }
 
+// Shared memory per group: exchange buffer (XCH cplx) + retry queue (N ints) ; one int counter per group
+// at the end of the block's dynamic smem.
+template <int LOG2N>
+constexpr size_t clifford_fwd_smem_bytes() {
+  using Pl = FftPlan<LOG2N>;
+  return (sizeof(cplx) * Pl::XCH + sizeof(int) * Pl::N) * Pl::GROUPS + sizeof(int) * Pl::GROUPS;
+}
+
 template <int LOG2N, int MODE, bool ROWK>
-__global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS)
+__global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS, (FftPlan<LOG2N>::THREADS <= 128 ? 4 : 1))
 clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw) {
   using Pl = FftPlan<LOG2N>;
   constexpr int d = Pl::N, T = Pl::T, E = Pl::E, G = Pl::GROUPS;
   extern __shared__ cplx smem[];
   const int group = threadIdx.x / T, t = threadIdx.x % T;
   cplx* xch = smem + group * Pl::XCH;
+  int* queue = reinterpret_cast<int*>(smem + G * Pl::XCH) + group * d;
+  int* qcount = reinterpret_cast<int*>(smem + G * Pl::XCH) + G * d + group;
   constexpr bool PS = (MODE == kPsInjected || MODE == kPsRng);
+  const long long stride = (long long)gridDim.x * G;
 
-  for (long long base = (long long)blockIdx.x * G; base < p.rows; base += (long long)gridDim.x * G) {
+  // Prologue: the closed-form row entropy / KL / dH/dkappa (fp64 special functions) of every row this
+  // group will process, one row per thread, so the per-row loop carries no serial fp64 chain.
+  if (PS && ROWK && (p.entropy || p.kl || p.dentropy)) {
+    for (long long row = (long long)blockIdx.x * G + group + (long long)t * stride; row < p.rows; row += (long long)T * stride)
+      clifford_row_entropy(p, row, __ldg(p.kappa + (row % p.loc_rows) * p.kappa_row_stride));
+  }
+  if (t == 0) *qcount = 0;
+
+  for (long long base = (long long)blockIdx.x * G; base < p.rows; base += stride) {
     const long long row = base + group;
     const bool valid = row < p.rows;
     const long long prow = valid ? (row % p.loc_rows) : 0;
-    cplx v[E];
     float kap_row = 1.0f;
     if (PS && valid) kap_row = __ldg(p.kappa + prow * p.kappa_row_stride);
     GammaMT gm(0.5f + (kap_row + kEps));
-#pragma unroll
+    __syncthreads();                       // the previous row's exchange-buffer readers are done
+    // phase 1: phasors of the half spectrum into the exchange buffer (rolled loop: small code)
+#pragma unroll 1
     for (int e = 0; e < E; ++e) {
       const int k = t + e * T;
-      v[e] = (valid && k != 0) ? clifford_phasor<MODE, ROWK>(p, row, prow, k, gm) : make_float2(1.0f, 0.0f);
+      cplx x = make_float2(1.0f, 0.0f);
+      if (valid && k != 0) {
+        if (!clifford_phasor<MODE, ROWK>(p, row, prow, k, gm, x)) queue[atomicAdd(qcount, 1)] = k;
+      }
+      xch[pad16(k)] = x;
     }
-    c2r_pretangle<LOG2N>(v, 1.0f, xch, t, tw);
+    if (t == 0) xch[pad16(d)] = make_float2(1.0f, 0.0f);
+    if (MODE == kPsRng) {
+      // phase 1b: rejected proposals, spread evenly over the group's threads
+      __syncthreads();
+      const int nq = *qcount;
+#pragma unroll 1
+      for (int i = t; i < nq; i += T) {
+        const int k = queue[i];
+        xch[pad16(k)] = clifford_phasor_retry<ROWK>(p, row, prow, k, gm);
+      }
+      __syncthreads();
+      if (t == 0) *qcount = 0;
+    } else {
+      __syncthreads();
+    }
+    // phase 2: Hermitian half spectrum -> packed complex spectrum -> inverse FFT -> real row
+    cplx v[E];
+    c2r_pretangle_load<LOG2N>(v, xch, t, tw);
     fft_run<LOG2N, true>(v, xch, t, tw);
     if (valid) {
       float2* zr = reinterpret_cast<float2*>(p.z + row * (2LL * d));
 #pragma unroll
       for (int e = 0; e < E; ++e) stg_stream2(zr + t + e * T, v[e]);
-      if (PS && ROWK && t == 0 && (p.entropy || p.kl || p.dentropy)) clifford_row_entropy(p, row, kap_row);
     }
   }
 }
@@ -180,7 +255,8 @@ __device__ __forceinline__ float clifford_bwd_element(const CliffordBwdParams& p
   }
   const CirclePhase ph = circle_phase(tp, s);       // identical arithmetic to the forward
   float sl, cl;
-  sincosf(ldg_stream1(p.loc + prow * p.d + k), &sl, &cl);
+  if (p.tp_signed) sincos_any<true>(ldg_stream1(p.loc + prow * p.d + k), sl, cl);
+  else sincos_any<false>(ldg_stream1(p.loc + prow * p.d + k), sl, cl);
   const cplx x = make_float2(fmaf(cl, ph.c, -sl * ph.s), fmaf(sl, ph.c, cl * ph.s));
   // dL/dtheta_k = -(2/n) Im(X_k conj(G_k)), 2/n = 1/d
   const float dth = -inv_d * (x.y * Gk.x - x.x * Gk.y);
@@ -372,7 +448,11 @@ clifford_fwd_generic_kernel(const CliffordFwdParams p) {
     if (PS) kap_row = __ldg(p.kappa + prow * p.kappa_row_stride);
     GammaMT gm(0.5f + (kap_row + kEps));
     __syncthreads();
-    for (int k = 1 + threadIdx.x; k <= nph; k += blockDim.x) X[k] = clifford_phasor<MODE, ROWK>(p, row, prow, k, gm);
+    for (int k = 1 + threadIdx.x; k <= nph; k += blockDim.x) {
+      cplx x;
+      if (!clifford_phasor<MODE, ROWK>(p, row, prow, k, gm, x)) x = clifford_phasor_retry<ROWK>(p, row, prow, k, gm);
+      X[k] = x;
+    }
     __syncthreads();
     const float inv_n = 1.0f / (float)n;
     for (int j = threadIdx.x; j < n; j += blockDim.x) {

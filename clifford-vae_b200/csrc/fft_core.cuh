@@ -227,6 +227,26 @@ __device__ __forceinline__ void c2r_pretangle(cplx (&v)[FftPlan<LOG2N>::E], floa
   }
 }
 
+// C2R pre-processing when the half spectrum X[0..N] already sits in the exchange buffer (written by
+// the caller, followed by a __syncthreads()).  Out: v = Z as in c2r_pretangle.
+template <int LOG2N>
+__device__ __forceinline__ void c2r_pretangle_load(cplx (&v)[FftPlan<LOG2N>::E], const cplx* xch, int t,
+                                                   const cplx* __restrict__ tw) {
+  using Pl = FftPlan<LOG2N>;
+  constexpr int N = Pl::N;
+  constexpr float scale = 1.0f / (2.0f * N);
+#pragma unroll
+  for (int e = 0; e < Pl::E; ++e) {
+    const int k = t + e * Pl::T;
+    const cplx x = xch[pad16(k)];
+    const cplx xp = cconj(xch[pad16(N - k)]);
+    const cplx w = cconj(__ldg(&tw[k << (kTwiddleCircleLog2 - LOG2N - 1)]));   // exp(+2 pi i k / n)
+    const cplx s = cadd(x, xp), d = csub(x, xp);
+    const cplx wd = cmul_i(cmul(w, d));
+    v[e] = make_float2(scale * (s.x + wd.x), scale * (s.y + wd.y));
+  }
+}
+
 // sum over the T threads of a group; scratch: >= 32 floats per group; uses __syncthreads when T > 32
 template <int T>
 __device__ __forceinline__ float group_sum(float val, float* scratch, int t) {

@@ -83,28 +83,49 @@ __device__ __forceinline__ bool gamma_mt_attempt(const GammaMT& g, float x, floa
   return ok;
 }
 
-// t' ~ Beta(alpha, 1/2) as X/(X+Y), X ~ Gamma(alpha), Y ~ Gamma(1/2) = N^2/2.  Returns t' and the
-// sign of the normal that produced Y (an independent fair sign, used as the circle's sign draw).
-__device__ __forceinline__ float beta_half_draw(const GammaMT& g, const PhiloxKey& key, uint64_t elem, float& sign) {
+// t' ~ Beta(alpha, 1/2) as X/(X+Y), X ~ Gamma(alpha) (Marsaglia-Tsang), Y ~ Gamma(1/2) = N^2/2.
+// The sign of the normal that produced Y is an independent fair sign, used as the circle's sign draw.
+// First attempt (Philox attempt 0): returns false if the Marsaglia-Tsang proposal was rejected -- the
+// caller queues the element and finishes it with beta_half_retry so that a warp never loops on one
+// lane's rejection.
+__device__ __forceinline__ float beta_ratio(float x, float y) {
+  // keep t' inside [FLT_MIN, 1 - 2^-24] like torch's _sample_dirichlet clamp
+  return fminf(fmaxf(__fdividef(x, x + y), 1.17549435e-38f), 1.0f - 5.9604645e-8f);
+}
+__device__ __forceinline__ bool beta_half_first(const GammaMT& g, const PhiloxKey& key, uint64_t elem, float& tp,
+                                                float& sign) {
+  const uint4 r = philox_draw(key, elem, 0);
+  const float2 nn = box_muller(r.x, r.y);
+  const float y = 0.5f * nn.y * nn.y;
+  sign = (nn.y < 0.f) ? -1.0f : 1.0f;
+  float x;
+  const bool ok = gamma_mt_attempt(g, nn.x, u01_open0(r.z), x);
+  if (g.inv_alpha > 0.f) x *= __powf(u01_open0(r.w), g.inv_alpha);
+  tp = beta_ratio(x, y);
+  return ok;
+}
+// Same element after a rejected first attempt: recomputes Y / sign / boost from attempt 0 and draws
+// fresh proposals (attempts 1, 2, ...) until one is accepted.
+__device__ __forceinline__ float beta_half_retry(const GammaMT& g, const PhiloxKey& key, uint64_t elem, float& sign) {
   uint4 r = philox_draw(key, elem, 0);
   float2 nn = box_muller(r.x, r.y);
   const float y = 0.5f * nn.y * nn.y;
   sign = (nn.y < 0.f) ? -1.0f : 1.0f;
-  float boost = 1.0f;
-  if (g.inv_alpha > 0.f) boost = __powf(u01_open0(r.w), g.inv_alpha);
-  float x;
-  bool ok = gamma_mt_attempt(g, nn.x, u01_open0(r.z), x);
-  uint32_t attempt = 1;
-  while (!ok) {
-    r = philox_draw(key, elem, attempt++);
+  const float boost = (g.inv_alpha > 0.f) ? __powf(u01_open0(r.w), g.inv_alpha) : 1.0f;
+  float x = 1.0f;
+  bool ok = false;
+  for (uint32_t attempt = 1; !ok && attempt < 64; ++attempt) {
+    r = philox_draw(key, elem, attempt);
     nn = box_muller(r.x, r.y);
     ok = gamma_mt_attempt(g, nn.x, u01_open0(r.z), x);
     if (!ok) ok = gamma_mt_attempt(g, nn.y, u01_open0(r.w), x);
   }
-  x *= boost;
-  const float tp = x / (x + y);
-  // keep t' inside [FLT_MIN, 1 - 2^-24] like torch's _sample_dirichlet clamp
-  return fminf(fmaxf(tp, 1.17549435e-38f), 1.0f - 5.9604645e-8f);
+  return beta_ratio(x * boost, y);
+}
+__device__ __forceinline__ float beta_half_draw(const GammaMT& g, const PhiloxKey& key, uint64_t elem, float& sign) {
+  float tp;
+  if (beta_half_first(g, key, elem, tp, sign)) return tp;
+  return beta_half_retry(g, key, elem, sign);
 }
 
 // Gamma(alpha) in double for alpha >= 1 (Marsaglia-Tsang), used by the per-row Beta draws of the

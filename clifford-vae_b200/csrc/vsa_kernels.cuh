@@ -3,6 +3,7 @@
 // Reference semantics: utils/vsa.py:43-72.
 #pragma once
 #include "fft_core.cuh"
+#include "tma.cuh"
 
 namespace cvb {
 
@@ -74,6 +75,91 @@ bind_kernel(const BindParams p, const cplx* __restrict__ tw) {
   }
 }
 
+
+// ---- TMA-staged bind: the production kernel -------------------------------------------------------
+// Per group: stage_a / stage_b (one real row each = N complex slots) filled by cp.async.bulk, and the
+// padded exchange buffer.  The spectrum of a is parked in stage_a while b is transformed, so only one
+// 16-point register array is live at a time (<= 128 registers, 4 CTAs per SM for d <= 4096).
+template <int LOG2N>
+constexpr size_t bind_tma_smem_bytes() {
+  using Pl = FftPlan<LOG2N>;
+  return (sizeof(cplx) * (Pl::XCH + 2 * Pl::N) + 2 * sizeof(uint64_t)) * Pl::GROUPS;
+}
+
+template <int LOG2N, int MODE>
+__global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS, (FftPlan<LOG2N>::THREADS <= 128 ? 4 : (FftPlan<LOG2N>::THREADS <= 256 ? 2 : 1)))
+bind_tma_kernel(const BindParams p, const cplx* __restrict__ tw) {
+  using Pl = FftPlan<LOG2N>;
+  constexpr int N = Pl::N, T = Pl::T, E = Pl::E, G = Pl::GROUPS;
+  constexpr uint32_t kRowBytes = 2u * N * sizeof(float);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int group = threadIdx.x / T, t = threadIdx.x % T;
+  // layout: [G x stage_a][G x stage_b][G x xch][G x 2 mbarriers]
+  cplx* stage_a = reinterpret_cast<cplx*>(smem_raw) + (size_t)group * N;
+  cplx* stage_b = reinterpret_cast<cplx*>(smem_raw) + (size_t)(G + group) * N;
+  cplx* xch = reinterpret_cast<cplx*>(smem_raw) + (size_t)2 * G * N + (size_t)group * Pl::XCH;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<cplx*>(smem_raw) + (size_t)2 * G * N + (size_t)G * Pl::XCH) + 2 * group;
+  const long long stride = (long long)gridDim.x * G;
+  const long long row0 = (long long)blockIdx.x * G + group;
+
+  if (t == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_init_fence();
+  }
+  __syncthreads();
+  if (t == 0 && row0 < p.rows) {
+    mbar_expect_tx(&bars[0], kRowBytes);
+    tma_load_1d(stage_a, p.a + (row0 % p.a_rows) * (2LL * N), kRowBytes, &bars[0]);
+    mbar_expect_tx(&bars[1], kRowBytes);
+    tma_load_1d(stage_b, p.b + (row0 % p.b_rows) * (2LL * N), kRowBytes, &bars[1]);
+  }
+
+  uint32_t parity = 0;
+  for (long long base = (long long)blockIdx.x * G; base < p.rows; base += stride, parity ^= 1u) {
+    const long long row = base + group;
+    const bool valid = row < p.rows;
+    const bool next_valid = row + stride < p.rows;
+    cplx v[E];
+    // ---- a: staged row -> registers -> FFT -> real-FFT untangle -> park the spectrum in stage_a
+    if (valid) mbar_wait(&bars[0], parity);
+#pragma unroll
+    for (int e = 0; e < E; ++e) v[e] = valid ? stage_a[t + e * T] : make_float2(0.f, 0.f);
+    fft_run<LOG2N, false>(v, xch, t, tw);
+    const float a_nyq = r2c_untangle<LOG2N>(v, xch, t, tw);
+#pragma unroll
+    for (int e = 0; e < E; ++e) stage_a[t + e * T] = v[e];      // own slots only: no barrier needed
+    // ---- b
+    if (valid) mbar_wait(&bars[1], parity);
+#pragma unroll
+    for (int e = 0; e < E; ++e) v[e] = valid ? stage_b[t + e * T] : make_float2(1.f, 0.f);
+    fft_run<LOG2N, false>(v, xch, t, tw);                        // its barriers: every thread has read stage_b
+    if (t == 0 && next_valid) {
+      mbar_expect_tx(&bars[1], kRowBytes);
+      tma_load_1d(stage_b, p.b + ((row + stride) % p.b_rows) * (2LL * N), kRowBytes, &bars[1]);
+    }
+    const float b_nyq = r2c_untangle<LOG2N>(v, xch, t, tw);
+    // ---- pointwise op in the frequency domain
+#pragma unroll
+    for (int e = 0; e < E; ++e) v[e] = bind_op(MODE, stage_a[t + e * T], v[e]);
+    float p_nyq;
+    if (MODE == kBindDiv || MODE == kBindDivConj) p_nyq = a_nyq / (b_nyq + 1e-12f);
+    else if (MODE == kBindNegMulConj) p_nyq = -a_nyq * b_nyq;
+    else p_nyq = a_nyq * b_nyq;
+    fence_proxy_async();                                         // parked-spectrum writes before the next TMA write
+    c2r_pretangle<LOG2N>(v, p_nyq, xch, t, tw);                  // its barriers: every thread is done with stage_a
+    if (t == 0 && next_valid) {
+      mbar_expect_tx(&bars[0], kRowBytes);
+      tma_load_1d(stage_a, p.a + ((row + stride) % p.a_rows) * (2LL * N), kRowBytes, &bars[0]);
+    }
+    fft_run<LOG2N, true>(v, xch, t, tw);
+    if (valid) {
+      float2* o = reinterpret_cast<float2*>(p.out + row * (2LL * N));
+#pragma unroll
+      for (int e = 0; e < E; ++e) stg_stream2(o + t + e * T, v[e]);
+    }
+  }
+}
 
 // ---- any-length bind (direct DFT, O(d^2) per pair): covers odd / non power-of-two d -----------
 // smem: tw[d] cplx, a[d], b[d] float, P[d/2+1] cplx
