@@ -1,4 +1,5 @@
 // C ABI entry points for the Clifford-torus kernels (include/clifford_b200.h).
+#include <cstdlib>
 #include "launch.cuh"
 #include "clifford_kernels.cuh"
 #include "../../include/clifford_b200.h"
@@ -14,7 +15,7 @@ int launch_fwd_fast(const CliffordFwdParams& p, cudaStream_t st) {
   using Pl = FftPlan<LOG2N>;
   const cplx* tw = device_twiddles();
   if (!tw) return kCudaError;
-  const size_t smem = clifford_fwd_smem_bytes<LOG2N>();
+  const size_t smem = clifford_fwd_smem_bytes<LOG2N, MODE>();
   auto kern = clifford_fwd_kernel<LOG2N, MODE, ROWK>;
   int grid = 0;
   const long long work = (p.rows + Pl::GROUPS - 1) / Pl::GROUPS;
@@ -24,7 +25,10 @@ int launch_fwd_fast(const CliffordFwdParams& p, cudaStream_t st) {
 }
 
 template <int MODE, bool ROWK>
-int dispatch_fwd(const CliffordFwdParams& p, cudaStream_t st) {
+int dispatch_fwd(const CliffordFwdParams& p_in, cudaStream_t st) {
+  CliffordFwdParams p = p_in;
+  p.staged = (!p.loc || aligned(p.loc, 16)) && (!p.tprime || aligned(p.tprime, 16)) && (!p.gnoise || aligned(p.gnoise, 16)) &&
+             (!p.phases || aligned(p.phases, 16)) && getenv("CVB_NO_TMA") == nullptr;
   const bool fast = is_pow2(p.d) && p.d >= 16 && p.d <= 8192 && p.n == 2 * p.d && aligned(p.z, 8);
   if (fast) {
     switch (ilog2(p.d)) {

@@ -9,6 +9,7 @@
 // SURVEY.md section 8(a).
 #pragma once
 #include "fft_core.cuh"
+#include "tma.cuh"
 #include "rng.cuh"
 #include "special.cuh"
 
@@ -39,7 +40,8 @@ struct CliffordFwdParams {
   float* dentropy;         // (rows) out, optional: d entropy / d kappa (row-scalar kappa only)
   long long rows;
   int d;                   // phases per row (row pitch of loc / draws / phases)
-  int n;                   // output length: 2d for the torus; any n >= 2 with d = n/2 rounded down... see generic kernel
+  int n;                   // output length: 2d for the torus (fast path); any n >= 2 on the direct-DFT path
+  int staged;              // 1: input rows are 16-byte aligned -> stage them with cp.async.bulk
   PhiloxKey key;
 };
 
@@ -91,16 +93,33 @@ __device__ __forceinline__ cplx ps_phasor(float tp, float sgn, float loc) {
   return make_float2(fmaf(cl, ph.c, -sl * ph.s), fmaf(sl, ph.c, cl * ph.s));
 }
 
+// Per-row input pointers, indexed by the bin k: either the global rows or their staged copies in
+// shared memory (generic loads serve both).
+struct RowSrc {
+  const float* loc;
+  const float* tprime;
+  const float* gnoise;
+  const float* phases;
+};
+__device__ __forceinline__ RowSrc global_row_src(const CliffordFwdParams& p, long long row, long long prow) {
+  RowSrc s;
+  s.loc = p.loc ? p.loc + prow * p.d : nullptr;
+  s.tprime = p.tprime ? p.tprime + row * p.d : nullptr;
+  s.gnoise = p.gnoise ? p.gnoise + row * p.d : nullptr;
+  s.phases = p.phases ? p.phases + row * p.d : nullptr;
+  return s;
+}
+
 // e^{i theta_k} for bin k (1 <= k <= d-1) of `row`.  For kPsRng a rejected first Marsaglia-Tsang
 // proposal returns false (the caller queues k and finishes it with clifford_phasor_retry).
 template <int MODE, bool ROWK>
-__device__ __forceinline__ bool clifford_phasor(const CliffordFwdParams& p, long long row, long long prow, int k,
-                                                GammaMT& gm, cplx& out) {
+__device__ __forceinline__ bool clifford_phasor(const CliffordFwdParams& p, const RowSrc& src, long long row,
+                                                long long prow, int k, GammaMT& gm, cplx& out) {
   const long long idx = row * p.d + k;
   if (MODE == kPsInjected) {
-    const float tp = ldg_stream1(p.tprime + idx);
-    const float s = sign_from_normal(ldg_stream1(p.gnoise + idx));
-    out = ps_phasor<false>(tp, s, ldg_stream1(p.loc + prow * p.d + k));
+    const float tp = src.tprime[k];
+    const float s = sign_from_normal(src.gnoise[k]);
+    out = ps_phasor<false>(tp, s, src.loc[k]);
     return true;
   }
   if (MODE == kPsRng) {
@@ -108,12 +127,12 @@ __device__ __forceinline__ bool clifford_phasor(const CliffordFwdParams& p, long
     float tp, s;
     if (!beta_half_first(gm, p.key, (uint64_t)idx, tp, s)) return false;
     if (p.tp_signed) stg_stream1(p.tp_signed + idx, copysignf(tp, s));
-    out = ps_phasor<true>(tp, s, ldg_stream1(p.loc + prow * p.d + k));
+    out = ps_phasor<true>(tp, s, src.loc[k]);
     return true;
   }
   float th;
   if (MODE == kPhases) {
-    th = p.phase_scale * ldg_stream1(p.phases + idx);
+    th = p.phase_scale * src.phases[k];
     sincosf(th, &out.y, &out.x);
     return true;
   }
@@ -130,14 +149,14 @@ __device__ __forceinline__ bool clifford_phasor(const CliffordFwdParams& p, long
 }
 
 template <bool ROWK>
-__device__ __forceinline__ cplx clifford_phasor_retry(const CliffordFwdParams& p, long long row, long long prow, int k,
-                                                      GammaMT& gm) {
+__device__ __forceinline__ cplx clifford_phasor_retry(const CliffordFwdParams& p, const RowSrc& src, long long row,
+                                                      long long prow, int k, GammaMT& gm) {
   const long long idx = row * p.d + k;
   if (!ROWK) gm = GammaMT(0.5f + (__ldg(p.kappa + prow * p.kappa_row_stride + (long long)k * p.kappa_el_stride) + kEps));
   float s;
   const float tp = beta_half_retry(gm, p.key, (uint64_t)idx, s);
   if (p.tp_signed) stg_stream1(p.tp_signed + idx, copysignf(tp, s));
-  return ps_phasor<true>(tp, s, ldg_stream1(p.loc + prow * p.d + k));
+  return ps_phasor<true>(tp, s, src.loc[k]);
 }
 
 __device__ __forceinline__ void clifford_row_entropy(const CliffordFwdParams& p, long long row, float kap_row) {
@@ -148,12 +167,14 @@ __device__ __forceinline__ void clifford_row_entropy(const CliffordFwdParams& p,
   if (p.dentropy) p.dentropy[row] = (float)((double)(p.d - 1) * c.dentropy);
 }
 
-// Shared memory per group: exchange buffer (XCH cplx) + retry queue (N ints) ; one int counter per group
-// at the end of the block's dynamic smem.
-template <int LOG2N>
+// Shared memory per group: exchange buffer (XCH cplx) | retry queue (N ints) | up to 3 staged input
+// rows (N floats each) ; then per group one mbarrier and one queue counter.
+constexpr int clifford_fwd_stages(int mode) { return mode == kPsInjected ? 3 : ((mode == kPsRng || mode == kPhases) ? 1 : 0); }
+template <int LOG2N, int MODE>
 constexpr size_t clifford_fwd_smem_bytes() {
   using Pl = FftPlan<LOG2N>;
-  return (sizeof(cplx) * Pl::XCH + sizeof(int) * Pl::N) * Pl::GROUPS + sizeof(int) * Pl::GROUPS;
+  return (sizeof(cplx) * Pl::XCH + sizeof(int) * Pl::N + sizeof(float) * Pl::N * clifford_fwd_stages(MODE)) * Pl::GROUPS +
+         (sizeof(uint64_t) + sizeof(int) * 2) * Pl::GROUPS;
 }
 
 template <int LOG2N, int MODE, bool ROWK>
@@ -161,55 +182,92 @@ __global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS, (FftPlan<LOG2N>::THRE
 clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw) {
   using Pl = FftPlan<LOG2N>;
   constexpr int d = Pl::N, T = Pl::T, E = Pl::E, G = Pl::GROUPS;
-  extern __shared__ cplx smem[];
+  constexpr int NST = clifford_fwd_stages(MODE);
+  constexpr uint32_t kRowBytes = d * sizeof(float);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int group = threadIdx.x / T, t = threadIdx.x % T;
-  cplx* xch = smem + group * Pl::XCH;
-  int* queue = reinterpret_cast<int*>(smem + G * Pl::XCH) + group * d;
-  int* qcount = reinterpret_cast<int*>(smem + G * Pl::XCH) + G * d + group;
+  // layout: [G x NST x stage rows][G x xch][G x queue][G x mbarrier][G x (qcount, pad)]
+  float* stage = reinterpret_cast<float*>(smem_raw) + (size_t)group * NST * d;
+  unsigned char* after_stage = smem_raw + sizeof(float) * (size_t)G * NST * d;
+  cplx* xch = reinterpret_cast<cplx*>(after_stage) + (size_t)group * Pl::XCH;
+  int* queue = reinterpret_cast<int*>(after_stage + sizeof(cplx) * (size_t)G * Pl::XCH) + (size_t)group * d;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(after_stage + (sizeof(cplx) * Pl::XCH + sizeof(int) * d) * (size_t)G) + group;
+  int* qcount = reinterpret_cast<int*>(after_stage + (sizeof(cplx) * Pl::XCH + sizeof(int) * d + sizeof(uint64_t)) * (size_t)G) + 2 * group;
   constexpr bool PS = (MODE == kPsInjected || MODE == kPsRng);
   const long long stride = (long long)gridDim.x * G;
+  const bool staged = NST > 0 && p.staged;
+
+  // issue the bulk copies of one row's inputs (thread 0 of the group)
+  auto issue = [&](long long row) {
+    const long long prow = row % p.loc_rows;
+    mbar_expect_tx(bar, NST * kRowBytes);
+    if (MODE == kPsInjected) {
+      tma_load_1d(stage, p.loc + prow * d, kRowBytes, bar);
+      tma_load_1d(stage + d, p.tprime + row * d, kRowBytes, bar);
+      tma_load_1d(stage + 2 * d, p.gnoise + row * d, kRowBytes, bar);
+    } else if (MODE == kPsRng) {
+      tma_load_1d(stage, p.loc + prow * d, kRowBytes, bar);
+    } else if (MODE == kPhases) {
+      tma_load_1d(stage, p.phases + row * d, kRowBytes, bar);
+    }
+  };
+
+  if (t == 0) {
+    *qcount = 0;
+    if (staged) { mbar_init(bar, 1); mbar_init_fence(); }
+  }
+  __syncthreads();
+  const long long first_row = (long long)blockIdx.x * G + group;
+  if (staged && t == 0 && first_row < p.rows) issue(first_row);
 
   // Prologue: the closed-form row entropy / KL / dH/dkappa (fp64 special functions) of every row this
   // group will process, one row per thread, so the per-row loop carries no serial fp64 chain.
   if (PS && ROWK && (p.entropy || p.kl || p.dentropy)) {
-    for (long long row = (long long)blockIdx.x * G + group + (long long)t * stride; row < p.rows; row += (long long)T * stride)
+    for (long long row = first_row + (long long)t * stride; row < p.rows; row += (long long)T * stride)
       clifford_row_entropy(p, row, __ldg(p.kappa + (row % p.loc_rows) * p.kappa_row_stride));
   }
-  if (t == 0) *qcount = 0;
 
-  for (long long base = (long long)blockIdx.x * G; base < p.rows; base += stride) {
+  uint32_t parity = 0;
+  for (long long base = (long long)blockIdx.x * G; base < p.rows; base += stride, parity ^= 1u) {
     const long long row = base + group;
     const bool valid = row < p.rows;
     const long long prow = valid ? (row % p.loc_rows) : 0;
     float kap_row = 1.0f;
     if (PS && valid) kap_row = __ldg(p.kappa + prow * p.kappa_row_stride);
     GammaMT gm(0.5f + (kap_row + kEps));
+    RowSrc src;
+    if (staged) {
+      src.loc = stage; src.tprime = stage + d; src.gnoise = stage + 2 * d; src.phases = stage;
+      if (valid) mbar_wait(bar, parity);
+    } else {
+      src = global_row_src(p, valid ? row : 0, prow);
+    }
     __syncthreads();                       // the previous row's exchange-buffer readers are done
-    // phase 1: phasors of the half spectrum into the exchange buffer (rolled loop: small code)
-#pragma unroll 1
+    // phase 1: phasors of the half spectrum into the exchange buffer (lightly unrolled: small code, ILP 2)
+#pragma unroll 2
     for (int e = 0; e < E; ++e) {
       const int k = t + e * T;
       cplx x = make_float2(1.0f, 0.0f);
       if (valid && k != 0) {
-        if (!clifford_phasor<MODE, ROWK>(p, row, prow, k, gm, x)) queue[atomicAdd(qcount, 1)] = k;
+        if (!clifford_phasor<MODE, ROWK>(p, src, row, prow, k, gm, x)) queue[atomicAdd(qcount, 1)] = k;
       }
       xch[pad16(k)] = x;
     }
     if (t == 0) xch[pad16(d)] = make_float2(1.0f, 0.0f);
+    __syncthreads();
     if (MODE == kPsRng) {
       // phase 1b: rejected proposals, spread evenly over the group's threads
-      __syncthreads();
       const int nq = *qcount;
 #pragma unroll 1
       for (int i = t; i < nq; i += T) {
         const int k = queue[i];
-        xch[pad16(k)] = clifford_phasor_retry<ROWK>(p, row, prow, k, gm);
+        xch[pad16(k)] = clifford_phasor_retry<ROWK>(p, src, row, prow, k, gm);
       }
       __syncthreads();
       if (t == 0) *qcount = 0;
-    } else {
-      __syncthreads();
     }
+    // every thread is done with the staged inputs: fetch the next row's while this one is transformed
+    if (staged && t == 0 && row + stride < p.rows) issue(row + stride);
     // phase 2: Hermitian half spectrum -> packed complex spectrum -> inverse FFT -> real row
     cplx v[E];
     c2r_pretangle_load<LOG2N>(v, xch, t, tw);
@@ -448,9 +506,10 @@ clifford_fwd_generic_kernel(const CliffordFwdParams p) {
     if (PS) kap_row = __ldg(p.kappa + prow * p.kappa_row_stride);
     GammaMT gm(0.5f + (kap_row + kEps));
     __syncthreads();
+    const RowSrc src = global_row_src(p, row, prow);
     for (int k = 1 + threadIdx.x; k <= nph; k += blockDim.x) {
       cplx x;
-      if (!clifford_phasor<MODE, ROWK>(p, row, prow, k, gm, x)) x = clifford_phasor_retry<ROWK>(p, row, prow, k, gm);
+      if (!clifford_phasor<MODE, ROWK>(p, src, row, prow, k, gm, x)) x = clifford_phasor_retry<ROWK>(p, src, row, prow, k, gm);
       X[k] = x;
     }
     __syncthreads();
