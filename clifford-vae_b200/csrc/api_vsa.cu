@@ -16,23 +16,32 @@ int launch_bind_fast(const BindParams& p, cudaStream_t st) {
   using Pl = FftPlan<LOG2N>;
   const cplx* tw = device_twiddles();
   if (!tw) return kCudaError;
-  static const bool force_direct = getenv("CVB_BIND_DIRECT") != nullptr;
-  const bool tma_ok = !force_direct && aligned(p.a, 16) && aligned(p.b, 16);
+  // CVB_BIND_VARIANT: "staged" (TMA-staged rows), "direct" (plain loads), "v1" (first kernel); default by size
+  static const char* variant = getenv("CVB_BIND_VARIANT");
   const long long work = (p.rows + Pl::GROUPS - 1) / Pl::GROUPS;
   int grid = 0;
-  if (tma_ok) {
-    // production path: cp.async.bulk-staged rows, parked spectrum, <= 128 registers
-    const size_t smem = bind_tma_smem_bytes<LOG2N>();
-    auto kern = bind_tma_kernel<LOG2N, MODE>;
+  if (variant && variant[0] == 'v') {
+    const size_t smem = sizeof(cplx) * Pl::XCH * Pl::GROUPS;
+    auto kern = bind_kernel<LOG2N, MODE>;
     if (int rc = persistent_grid(kern, Pl::THREADS, smem, work, &grid)) return rc;
     kern<<<grid, Pl::THREADS, smem, st>>>(p, tw);
-    return check_launch("bind_tma_kernel");
+    return check_launch("bind_kernel");
   }
-  const size_t smem = sizeof(cplx) * Pl::XCH * Pl::GROUPS;
-  auto kern = bind_kernel<LOG2N, MODE>;
+  // measured on B200 (tools/bench_ops.py): TMA staging wins once a row pair no longer fits many CTAs per SM
+  bool staged = aligned(p.a, 16) && aligned(p.b, 16) && (LOG2N >= 12 || (variant && variant[0] == 's'));
+  if (variant && variant[0] == 'd') staged = false;
+  if (staged) {
+    const size_t smem = bind_v3_smem_bytes<LOG2N, true>();
+    auto kern = bind_v3_kernel<LOG2N, MODE, true>;
+    if (int rc = persistent_grid(kern, Pl::THREADS, smem, work, &grid)) return rc;
+    kern<<<grid, Pl::THREADS, smem, st>>>(p, tw);
+    return check_launch("bind_v3_kernel<staged>");
+  }
+  const size_t smem = bind_v3_smem_bytes<LOG2N, false>();
+  auto kern = bind_v3_kernel<LOG2N, MODE, false>;
   if (int rc = persistent_grid(kern, Pl::THREADS, smem, work, &grid)) return rc;
   kern<<<grid, Pl::THREADS, smem, st>>>(p, tw);
-  return check_launch("bind_kernel");
+  return check_launch("bind_v3_kernel<direct>");
 }
 
 template <int MODE>

@@ -327,7 +327,7 @@ __device__ __forceinline__ float clifford_bwd_element(const CliffordBwdParams& p
 }
 
 template <int LOG2N, bool ROWK>
-__global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS)
+__global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS, (FftPlan<LOG2N>::THREADS <= 128 ? 4 : 1))
 clifford_bwd_kernel(const CliffordBwdParams p, const cplx* __restrict__ tw) {
   using Pl = FftPlan<LOG2N>;
   constexpr int d = Pl::N, T = Pl::T, E = Pl::E, G = Pl::GROUPS;
@@ -347,15 +347,20 @@ clifford_bwd_kernel(const CliffordBwdParams p, const cplx* __restrict__ tw) {
     fft_run<LOG2N, false>(v, xch, t, tw);
     r2c_untangle<LOG2N>(v, xch, t, tw);        // v[e] = G[k]
 
+    // G[k] goes back to this thread's own exchange slots so that the (large, divergent) element
+    // routine runs in a rolled loop: keeps the kernel inside the instruction cache
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < E; ++e) xch[pad16(t + e * T)] = v[e];
     const float kap_row = valid ? __ldg(p.kappa + prow * p.kappa_row_stride) : 1.0f;
     BetaGradConsts bc(0.5f + (kap_row + kEps), 0.5f);
     float dk_sum = 0.f;
-#pragma unroll
+#pragma unroll 1
     for (int e = 0; e < E; ++e) {
       const int k = t + e * T;
       float dk = 0.f;
       if (valid && k != 0) {
-        clifford_bwd_element<ROWK>(p, row, prow, k, v[e], bc, 1.0f / (float)d, dk);
+        clifford_bwd_element<ROWK>(p, row, prow, k, xch[pad16(k)], bc, 1.0f / (float)d, dk);
       } else if (valid) {
         stg_stream1(p.dloc + row * d, 0.0f);
         if (!ROWK) stg_stream1(p.dkappa + row * d, 0.0f);
@@ -386,7 +391,7 @@ struct CliffordLogProbParams {
 
 template <bool ROWK>
 __device__ __forceinline__ void clifford_lp_element(const CliffordLogProbParams& p, long long row, long long prow, int k,
-                                                    cplx Fk, float kap, float logc, float dlogc, float& acc,
+                                                    cplx Fk, float loc_k, float kap, float logc, float dlogc, float& acc,
                                                     float& dk_acc) {
   if (!ROWK) {
     kap = __ldg(p.kappa + prow * p.kappa_row_stride + (long long)k * p.kappa_el_stride);
@@ -403,7 +408,7 @@ __device__ __forceinline__ void clifford_lp_element(const CliffordLogProbParams&
     sa = Fk.y * ri;
   }
   float sl, cl;
-  sincosf(ldg_stream1(p.loc + prow * p.d + k), &sl, &cl);
+  sincosf(loc_k, &sl, &cl);
   const float dot_raw = fmaf(cl, ca, sl * sa);
   const float dot = fminf(fmaxf(dot_raw, -1.0f + kEps), 1.0f - kEps);
   const float l1p = log1pf(dot);
@@ -418,8 +423,10 @@ __device__ __forceinline__ void clifford_lp_element(const CliffordLogProbParams&
   }
 }
 
+constexpr int kLpConstCache = 256;   // rows per group whose log-normaliser constants are precomputed
+
 template <int LOG2N, bool ROWK>
-__global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS)
+__global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS, (FftPlan<LOG2N>::THREADS <= 128 ? 4 : 1))
 clifford_log_prob_kernel(const CliffordLogProbParams p, const cplx* __restrict__ tw) {
   using Pl = FftPlan<LOG2N>;
   constexpr int d = Pl::N, T = Pl::T, E = Pl::E, G = Pl::GROUPS;
@@ -427,8 +434,24 @@ clifford_log_prob_kernel(const CliffordLogProbParams p, const cplx* __restrict__
   const int group = threadIdx.x / T, t = threadIdx.x % T;
   cplx* xch = smem + group * Pl::XCH;
   float* scratch = reinterpret_cast<float*>(smem + G * Pl::XCH) + group * 32;
+  float2* ccache = reinterpret_cast<float2*>(reinterpret_cast<float*>(smem + G * Pl::XCH) + G * 32) + group * kLpConstCache;
+  const long long stride = (long long)gridDim.x * G;
+  const long long first_row = (long long)blockIdx.x * G + group;
 
-  for (long long base = (long long)blockIdx.x * G; base < p.rows; base += (long long)gridDim.x * G) {
+  // Prologue: (log C, dlog C/dkappa) of the first kLpConstCache rows of this group, one row per thread (fp64)
+  if (ROWK) {
+    for (int i = t; i < kLpConstCache; i += T) {
+      const long long row = first_row + (long long)i * stride;
+      if (row < p.rows) {
+        const PsConsts c = ps_consts((double)__ldg(p.kappa + (row % p.loc_rows) * p.kappa_row_stride), 0.5);
+        ccache[i] = make_float2((float)c.log_norm, (float)c.dlog_norm);
+      }
+    }
+  }
+  __syncthreads();
+
+  int iter = 0;
+  for (long long base = (long long)blockIdx.x * G; base < p.rows; base += stride, ++iter) {
     const long long row = base + group;
     const bool valid = row < p.rows;
     const long long prow = valid ? (row % p.loc_rows) : 0;
@@ -436,20 +459,28 @@ clifford_log_prob_kernel(const CliffordLogProbParams p, const cplx* __restrict__
     const float2* vz = reinterpret_cast<const float2*>(p.value + (valid ? row : 0) * (2LL * d));
 #pragma unroll
     for (int e = 0; e < E; ++e) v[e] = valid ? ldg_stream2(vz + t + e * T) : make_float2(1.f, 0.f);
+    float locv[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) locv[e] = valid ? ldg_stream1(p.loc + prow * d + t + e * T) : 0.f;   // in flight during the FFT
     fft_run<LOG2N, false>(v, xch, t, tw);
     r2c_untangle<LOG2N>(v, xch, t, tw);        // v[e] = F[k], k = 0..d-1
 
     const float kap_row = valid ? __ldg(p.kappa + prow * p.kappa_row_stride) : 1.0f;
     float logc = 0.f, dlogc = 0.f;
     if (ROWK) {
-      const PsConsts c = ps_consts((double)kap_row, 0.5);
-      logc = (float)c.log_norm;
-      dlogc = (float)c.dlog_norm;
+      if (iter < kLpConstCache) {
+        const float2 c = ccache[iter];
+        logc = c.x; dlogc = c.y;
+      } else {
+        const PsConsts c = ps_consts((double)kap_row, 0.5);
+        logc = (float)c.log_norm;
+        dlogc = (float)c.dlog_norm;
+      }
     }
     float acc = 0.f, dk_acc = 0.f;
 #pragma unroll
     for (int e = 0; e < E; ++e) {
-      if (valid) clifford_lp_element<ROWK>(p, row, prow, t + e * T, v[e], kap_row, logc, dlogc, acc, dk_acc);
+      if (valid) clifford_lp_element<ROWK>(p, row, prow, t + e * T, v[e], locv[e], kap_row, logc, dlogc, acc, dk_acc);
     }
     const float tot = group_sum<T>(acc, scratch, t);
     float dk_tot = 0.f;
@@ -608,7 +639,8 @@ clifford_log_prob_generic_kernel(const CliffordLogProbParams p) {
         if (m >= n) m -= n;
       }
       if (k == 0) fi = 0.0;
-      clifford_lp_element<ROWK>(p, row, prow, k, make_float2((float)fr, (float)fi), kap_row, logc, dlogc, acc, dk_acc);
+      clifford_lp_element<ROWK>(p, row, prow, k, make_float2((float)fr, (float)fi), p.loc[prow * d + k], kap_row, logc, dlogc,
+                                acc, dk_acc);
     }
     const float tot = block_sum_256(acc, scratch);
     float dk_tot = 0.f;

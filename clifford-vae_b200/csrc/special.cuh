@@ -34,6 +34,16 @@ __device__ __forceinline__ double trigamma_d(double x) {
   return r + s;
 }
 
+// fp32 digamma for x > 0 with the same structure (recurrence to x >= 10, asymptotic series) -- the
+// per-row constants of the Beta gradient need only float accuracy (ATen evaluates them in float too)
+__device__ __forceinline__ float digamma_f(float x) {
+  float r = 0.f;
+  while (x < 10.f) { r -= __frcp_rn(x); x += 1.f; }
+  const float ix = __frcp_rn(x), z = ix * ix;
+  const float y = z * (8.33333333e-2f + z * (-8.33333333e-3f + z * (3.96825397e-3f + z * (-4.16666667e-3f + z * 7.57575758e-3f))));
+  return r + logf(x) - 0.5f * ix - y;
+}
+
 // ---- power-spherical normaliser / entropy for sphere dimension `dim` (reference clifford.py:187-212)
 // alpha = (dim-1)/2 + kappa + 1e-7, beta = (dim-1)/2.  fp64: evaluated once per row.
 struct PsConsts {
@@ -81,8 +91,8 @@ struct BetaGradConsts {
   float log_alpha, log_total;
   __device__ __forceinline__ BetaGradConsts(float a, float b) {
     alpha = a; beta = b; total = a + b;
-    psi_alpha = (float)digamma_d((double)a);
-    psi_total = (float)digamma_d((double)total);
+    psi_alpha = digamma_f(a);
+    psi_total = digamma_f(total);
     log_alpha = logf(a);
     log_total = logf(total);
   }

@@ -76,43 +76,50 @@ bind_kernel(const BindParams p, const cplx* __restrict__ tw) {
 }
 
 
-// ---- TMA-staged bind: the production kernel -------------------------------------------------------
-// Per group: stage_a / stage_b (one real row each = N complex slots) filled by cp.async.bulk, and the
-// padded exchange buffer.  The spectrum of a is parked in stage_a while b is transformed, so only one
-// 16-point register array is live at a time (<= 128 registers, 4 CTAs per SM for d <= 4096).
-template <int LOG2N>
-constexpr size_t bind_tma_smem_bytes() {
+// ---- production bind kernel ------------------------------------------------------------------------
+// Z_a = FFT(a packed as N complex) is parked in shared memory, Z_b = FFT(b) stays in registers; one
+// partner exchange then gives every thread Z_a[k], Z_a[N-k], Z_b[k], Z_b[N-k], from which it forms the
+// real-FFT bins A, B at k and N-k, applies the pointwise op, and re-packs the Hermitian product for
+// the inverse half-length FFT -- the two R2C untangles and the C2R pre-processing of the textbook
+// pipeline collapse into one exchange.  Only one 16-point register array is live (<= 128 registers,
+// 4 CTAs per SM for d <= 4096).  STAGED: rows arrive through cp.async.bulk (TMA) + mbarrier so the
+// next row's HBM read overlaps this row's passes; otherwise plain coalesced 64-bit loads.
+template <int LOG2N, bool STAGED>
+constexpr size_t bind_v3_smem_bytes() {
   using Pl = FftPlan<LOG2N>;
-  return (sizeof(cplx) * (Pl::XCH + 2 * Pl::N) + 2 * sizeof(uint64_t)) * Pl::GROUPS;
+  return (sizeof(cplx) * (Pl::XCH + Pl::N + (STAGED ? Pl::N : 0)) + 2 * sizeof(uint64_t)) * Pl::GROUPS;
 }
 
-template <int LOG2N, int MODE>
+template <int LOG2N, int MODE, bool STAGED>
 __global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS, (FftPlan<LOG2N>::THREADS <= 128 ? 4 : (FftPlan<LOG2N>::THREADS <= 256 ? 2 : 1)))
-bind_tma_kernel(const BindParams p, const cplx* __restrict__ tw) {
+bind_v3_kernel(const BindParams p, const cplx* __restrict__ tw) {
   using Pl = FftPlan<LOG2N>;
   constexpr int N = Pl::N, T = Pl::T, E = Pl::E, G = Pl::GROUPS;
   constexpr uint32_t kRowBytes = 2u * N * sizeof(float);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int group = threadIdx.x / T, t = threadIdx.x % T;
-  // layout: [G x stage_a][G x stage_b][G x xch][G x 2 mbarriers]
-  cplx* stage_a = reinterpret_cast<cplx*>(smem_raw) + (size_t)group * N;
+  // layout: [G x park/stage_a][G x stage_b (STAGED)][G x xch][G x 2 mbarriers]
+  cplx* park = reinterpret_cast<cplx*>(smem_raw) + (size_t)group * N;
   cplx* stage_b = reinterpret_cast<cplx*>(smem_raw) + (size_t)(G + group) * N;
-  cplx* xch = reinterpret_cast<cplx*>(smem_raw) + (size_t)2 * G * N + (size_t)group * Pl::XCH;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<cplx*>(smem_raw) + (size_t)2 * G * N + (size_t)G * Pl::XCH) + 2 * group;
+  cplx* xch = reinterpret_cast<cplx*>(smem_raw) + (size_t)(STAGED ? 2 : 1) * G * N + (size_t)group * Pl::XCH;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<cplx*>(smem_raw) + (size_t)(STAGED ? 2 : 1) * G * N + (size_t)G * Pl::XCH) + 2 * group;
   const long long stride = (long long)gridDim.x * G;
   const long long row0 = (long long)blockIdx.x * G + group;
+  constexpr float scale = 1.0f / (2.0f * N);
 
-  if (t == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
-    mbar_init_fence();
-  }
-  __syncthreads();
-  if (t == 0 && row0 < p.rows) {
-    mbar_expect_tx(&bars[0], kRowBytes);
-    tma_load_1d(stage_a, p.a + (row0 % p.a_rows) * (2LL * N), kRowBytes, &bars[0]);
-    mbar_expect_tx(&bars[1], kRowBytes);
-    tma_load_1d(stage_b, p.b + (row0 % p.b_rows) * (2LL * N), kRowBytes, &bars[1]);
+  if (STAGED) {
+    if (t == 0) {
+      mbar_init(&bars[0], 1);
+      mbar_init(&bars[1], 1);
+      mbar_init_fence();
+    }
+    __syncthreads();
+    if (t == 0 && row0 < p.rows) {
+      mbar_expect_tx(&bars[0], kRowBytes);
+      tma_load_1d(park, p.a + (row0 % p.a_rows) * (2LL * N), kRowBytes, &bars[0]);
+      mbar_expect_tx(&bars[1], kRowBytes);
+      tma_load_1d(stage_b, p.b + (row0 % p.b_rows) * (2LL * N), kRowBytes, &bars[1]);
+    }
   }
 
   uint32_t parity = 0;
@@ -121,38 +128,63 @@ bind_tma_kernel(const BindParams p, const cplx* __restrict__ tw) {
     const bool valid = row < p.rows;
     const bool next_valid = row + stride < p.rows;
     cplx v[E];
-    // ---- a: staged row -> registers -> FFT -> real-FFT untangle -> park the spectrum in stage_a
-    if (valid) mbar_wait(&bars[0], parity);
+    // ---- a -> Z_a, parked
+    if (STAGED) {
+      if (valid) mbar_wait(&bars[0], parity);
 #pragma unroll
-    for (int e = 0; e < E; ++e) v[e] = valid ? stage_a[t + e * T] : make_float2(0.f, 0.f);
+      for (int e = 0; e < E; ++e) v[e] = valid ? park[t + e * T] : make_float2(0.f, 0.f);
+    } else {
+      const float2* ar = reinterpret_cast<const float2*>(p.a + (valid ? row % p.a_rows : 0) * (2LL * N));
+#pragma unroll
+      for (int e = 0; e < E; ++e) v[e] = valid ? ldg_stream2(ar + t + e * T) : make_float2(0.f, 0.f);
+    }
+    fft_run<LOG2N, false>(v, xch, t, tw);      // (STAGED: its barriers order every thread's stage read before the park write)
+#pragma unroll
+    for (int e = 0; e < E; ++e) park[t + e * T] = v[e];
+    // ---- b -> Z_b in registers
+    if (STAGED) {
+      if (valid) mbar_wait(&bars[1], parity);
+#pragma unroll
+      for (int e = 0; e < E; ++e) v[e] = valid ? stage_b[t + e * T] : make_float2(1.f, 0.f);
+    } else {
+      const float2* br = reinterpret_cast<const float2*>(p.b + (valid ? row % p.b_rows : 0) * (2LL * N));
+#pragma unroll
+      for (int e = 0; e < E; ++e) v[e] = valid ? ldg_stream2(br + t + e * T) : make_float2(1.f, 0.f);
+    }
     fft_run<LOG2N, false>(v, xch, t, tw);
-    const float a_nyq = r2c_untangle<LOG2N>(v, xch, t, tw);
-#pragma unroll
-    for (int e = 0; e < E; ++e) stage_a[t + e * T] = v[e];      // own slots only: no barrier needed
-    // ---- b
-    if (valid) mbar_wait(&bars[1], parity);
-#pragma unroll
-    for (int e = 0; e < E; ++e) v[e] = valid ? stage_b[t + e * T] : make_float2(1.f, 0.f);
-    fft_run<LOG2N, false>(v, xch, t, tw);                        // its barriers: every thread has read stage_b
-    if (t == 0 && next_valid) {
+    if (STAGED && t == 0 && next_valid) {        // every thread has read stage_b (barriers inside fft_run)
       mbar_expect_tx(&bars[1], kRowBytes);
       tma_load_1d(stage_b, p.b + ((row + stride) % p.b_rows) * (2LL * N), kRowBytes, &bars[1]);
     }
-    const float b_nyq = r2c_untangle<LOG2N>(v, xch, t, tw);
-    // ---- pointwise op in the frequency domain
+    // ---- one partner exchange: untangle a and b, pointwise op, re-pack for the inverse transform
+    __syncthreads();
 #pragma unroll
-    for (int e = 0; e < E; ++e) v[e] = bind_op(MODE, stage_a[t + e * T], v[e]);
-    float p_nyq;
-    if (MODE == kBindDiv || MODE == kBindDivConj) p_nyq = a_nyq / (b_nyq + 1e-12f);
-    else if (MODE == kBindNegMulConj) p_nyq = -a_nyq * b_nyq;
-    else p_nyq = a_nyq * b_nyq;
-    fence_proxy_async();                                         // parked-spectrum writes before the next TMA write
-    c2r_pretangle<LOG2N>(v, p_nyq, xch, t, tw);                  // its barriers: every thread is done with stage_a
-    if (t == 0 && next_valid) {
-      mbar_expect_tx(&bars[0], kRowBytes);
-      tma_load_1d(stage_a, p.a + ((row + stride) % p.a_rows) * (2LL * N), kRowBytes, &bars[0]);
+    for (int e = 0; e < E; ++e) xch[pad16(t + e * T)] = v[e];
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int k = t + e * T, kp = (N - k) & (N - 1);
+      const cplx za = park[k], zap = cconj(park[kp]);
+      const cplx zb = v[e], zbp = cconj(xch[pad16(kp)]);
+      const cplx w = __ldg(&tw[k << (kTwiddleCircleLog2 - LOG2N - 1)]);    // exp(-2 pi i k / n)
+      // bins k and N-k of the real FFTs (X[N-k] uses W^(N-k) = -conj(W^k)); factor 1/2 each
+      const cplx sa = cadd(za, zap), da = cmul_mi(cmul(w, csub(za, zap)));
+      const cplx sb = cadd(zb, zbp), db = cmul_mi(cmul(w, csub(zb, zbp)));
+      const cplx Ak = cscale(cadd(sa, da), 0.5f), Akp = cscale(cconj(csub(sa, da)), 0.5f);
+      const cplx Bk = cscale(cadd(sb, db), 0.5f), Bkp = cscale(cconj(csub(sb, db)), 0.5f);
+      const cplx Pk = bind_op(MODE, Ak, Bk), Pkpc = cconj(bind_op(MODE, Akp, Bkp));
+      const cplx s = cadd(Pk, Pkpc), d = cmul_i(cmul(cconj(w), csub(Pk, Pkpc)));
+      v[e] = make_float2(scale * (s.x + d.x), scale * (s.y + d.y));
     }
-    fft_run<LOG2N, true>(v, xch, t, tw);
+    if (STAGED) {
+      fence_proxy_async();                       // parked-spectrum accesses before the next TMA write
+      __syncthreads();
+      if (t == 0 && next_valid) {
+        mbar_expect_tx(&bars[0], kRowBytes);
+        tma_load_1d(park, p.a + ((row + stride) % p.a_rows) * (2LL * N), kRowBytes, &bars[0]);
+      }
+    }
+    fft_run<LOG2N, true>(v, xch, t, tw);        // begins with a barrier: partner reads are complete
     if (valid) {
       float2* o = reinterpret_cast<float2*>(p.out + row * (2LL * N));
 #pragma unroll
