@@ -159,3 +159,17 @@ def test_philox_known_answer():
     assert rc == 0
     w = [int(x) & 0xFFFFFFFF for x in out.cpu().tolist()]
     assert w[:4] == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+
+
+def test_sharded_ops_single_rank_use_kernels():
+    """clifford_b200.distributed with the real kernels (world size 1 path)."""
+    from clifford_b200 import distributed as D
+    from utils import vsa
+    torch.manual_seed(2)
+    items = vsa.normalize_vectors(vsa.hrr_init(300, 256, device=DEV))
+    stack = vsa.hrr_init(40, 256, device=DEV)
+    got = D.sharded_bundle(stack, 40)
+    assert rel_err(got.cpu(), (stack.double().sum(0) / 40 ** 0.5).cpu()) < 1e-5
+    q = items[[5, 77, 299]] + 0.01 * torch.randn(3, 256, device=DEV)
+    best, idx = D.sharded_cleanup(q, items, 0)
+    assert idx.tolist() == [5, 77, 299] and float(best.min()) > 0.9
