@@ -57,7 +57,7 @@ struct CirclePhase {
 __device__ __forceinline__ CirclePhase circle_phase(float tp, float sgn) {
   const float t = 2.0f * tp - 1.0f;
   const float om = fmaf(-t, t, 1.0f);
-  const float sq = sqrtf(fmaxf(om, kEps));
+  const float sq = fast_sqrt(fmaxf(om, kEps));
   const float y1 = sgn * sq;
   const float r2 = fmaf(t, t, y1 * y1);
   const float rinv = rsqrtf(r2);
@@ -244,7 +244,7 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw) {
     }
     __syncthreads();                       // the previous row's exchange-buffer readers are done
     // phase 1: phasors of the half spectrum into the exchange buffer (lightly unrolled: small code, ILP 2)
-#pragma unroll 2
+#pragma unroll 4
     for (int e = 0; e < E; ++e) {
       const int k = t + e * T;
       cplx x = make_float2(1.0f, 0.0f);

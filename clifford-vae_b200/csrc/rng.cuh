@@ -48,7 +48,7 @@ __device__ __forceinline__ double u01_double(uint32_t hi, uint32_t lo) {
 // Box-Muller: two independent N(0,1) from two 32-bit words
 __device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
   const float u = u01_open0(a);
-  const float r = sqrtf(-2.0f * __logf(u));
+  const float r = fast_sqrt(-2.0f * __logf(u));
   float s, c;
   __sincosf(6.283185307179586f * u01_open1(b), &s, &c);
   return make_float2(r * c, r * s);
@@ -74,13 +74,13 @@ struct GammaMT {
 
 // One Marsaglia-Tsang attempt from proposal normal x and uniform u (0,1]; returns accepted flag.
 __device__ __forceinline__ bool gamma_mt_attempt(const GammaMT& g, float x, float u, float& out) {
+  // branch-free: in a warp some lane nearly always needs the log test, so every lane evaluates it
   const float y = fmaf(g.c, x, 1.0f);
-  if (y <= 0.f) return false;
   const float v = y * y * y;
   const float xx = x * x;
-  const bool ok = (u < 1.0f - 0.0331f * xx * xx) || (__logf(u) < 0.5f * xx + g.d * (1.0f - v + __logf(v)));
+  const float rhs = fmaf(0.5f, xx, g.d * (1.0f - v + __logf(fmaxf(v, 1e-30f))));
   out = g.d * v;
-  return ok;
+  return (y > 0.f) & ((u < fmaf(-0.0331f * xx, xx, 1.0f)) | (__logf(u) < rhs));
 }
 
 // t' ~ Beta(alpha, 1/2) as X/(X+Y), X ~ Gamma(alpha) (Marsaglia-Tsang), Y ~ Gamma(1/2) = N^2/2.
