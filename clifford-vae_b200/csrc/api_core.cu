@@ -79,10 +79,13 @@ int cvb_init(void) {
   CVB_CUDA(cudaGetDeviceProperties(&prop, dev));
   CVB_REQUIRE(prop.major == 10, kUnsupported,
               "clifford_b200 is built for sm_100a only; device %d is sm_%d%d", dev, prop.major, prop.minor);
-  std::vector<float2> host(kTwiddleEntries);
-  for (int m = 0; m < kTwiddleEntries; ++m) {
-    const double ang = -2.0 * 3.14159265358979323846264338327950288 * (double)m / (double)kTwiddleCircle;
-    host[m] = make_float2((float)cos(ang), (float)sin(ang));
+  std::vector<float2> host(kTwiddleEntries, make_float2(1.f, 0.f));
+  for (int L = 4; L <= kTwiddleMaxLog2N; ++L) {
+    const int N = 1 << L;
+    for (int m = 0; m < N; ++m) {
+      const double ang = -2.0 * 3.14159265358979323846264338327950288 * (double)m / (double)(2 * N);
+      host[twiddle_offset(L) + m] = make_float2((float)cos(ang), (float)sin(ang));
+    }
   }
   cplx* dptr = nullptr;
   CVB_CUDA(cudaMalloc(&dptr, sizeof(cplx) * kTwiddleEntries));

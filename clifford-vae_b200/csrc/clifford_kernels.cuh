@@ -242,7 +242,7 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw) {
     } else {
       src = global_row_src(p, valid ? row : 0, prow);
     }
-    __syncthreads();                       // the previous row's exchange-buffer readers are done
+    group_sync<LOG2N>();                       // the previous row's exchange-buffer readers are done
     // phase 1: phasors of the half spectrum into the exchange buffer (lightly unrolled: small code, ILP 2)
 #pragma unroll 4
     for (int e = 0; e < E; ++e) {
@@ -254,7 +254,7 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw) {
       xch[pad16(k)] = x;
     }
     if (t == 0) xch[pad16(d)] = make_float2(1.0f, 0.0f);
-    __syncthreads();
+    group_sync<LOG2N>();
     if (MODE == kPsRng) {
       // phase 1b: rejected proposals, spread evenly over the group's threads
       const int nq = *qcount;
@@ -263,7 +263,7 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw) {
         const int k = queue[i];
         xch[pad16(k)] = clifford_phasor_retry<ROWK>(p, src, row, prow, k, gm);
       }
-      __syncthreads();
+      group_sync<LOG2N>();
       if (t == 0) *qcount = 0;
     }
     // every thread is done with the staged inputs: fetch the next row's while this one is transformed
@@ -349,7 +349,7 @@ clifford_bwd_kernel(const CliffordBwdParams p, const cplx* __restrict__ tw) {
 
     // G[k] goes back to this thread's own exchange slots so that the (large, divergent) element
     // routine runs in a rolled loop: keeps the kernel inside the instruction cache
-    __syncthreads();
+    group_sync<LOG2N>();
 #pragma unroll
     for (int e = 0; e < E; ++e) xch[pad16(t + e * T)] = v[e];
     const float kap_row = valid ? __ldg(p.kappa + prow * p.kappa_row_stride) : 1.0f;
@@ -368,7 +368,7 @@ clifford_bwd_kernel(const CliffordBwdParams p, const cplx* __restrict__ tw) {
       dk_sum += dk;
     }
     if (ROWK) {
-      const float tot = group_sum<T>(dk_sum, scratch, t);
+      const float tot = group_sum<LOG2N>(dk_sum, scratch, t);
       if (valid && t == 0) p.dkappa[row] = tot;
     }
   }
@@ -448,7 +448,7 @@ clifford_log_prob_kernel(const CliffordLogProbParams p, const cplx* __restrict__
       }
     }
   }
-  __syncthreads();
+  group_sync<LOG2N>();
 
   int iter = 0;
   for (long long base = (long long)blockIdx.x * G; base < p.rows; base += stride, ++iter) {
@@ -482,9 +482,9 @@ clifford_log_prob_kernel(const CliffordLogProbParams p, const cplx* __restrict__
     for (int e = 0; e < E; ++e) {
       if (valid) clifford_lp_element<ROWK>(p, row, prow, t + e * T, v[e], locv[e], kap_row, logc, dlogc, acc, dk_acc);
     }
-    const float tot = group_sum<T>(acc, scratch, t);
+    const float tot = group_sum<LOG2N>(acc, scratch, t);
     float dk_tot = 0.f;
-    if (ROWK && p.dlp_dloc) dk_tot = group_sum<T>(dk_acc, scratch, t);
+    if (ROWK && p.dlp_dloc) dk_tot = group_sum<LOG2N>(dk_acc, scratch, t);
     if (valid && t == 0) {
       p.log_prob[row] = tot;
       if (ROWK && p.dlp_dkappa) p.dlp_dkappa[row] = dk_tot;

@@ -40,11 +40,13 @@ __device__ __forceinline__ cplx cmul_mi(cplx a) { return make_float2(a.y, -a.x);
 // the next pass are then both conflict-free for 64-bit accesses (DESIGN.md "smem layout").
 __host__ __device__ __forceinline__ constexpr int pad16(int i) { return i + (i >> 4); }
 
-// Twiddle table: g_twiddle[m] = exp(-2*pi*i*m / kTwiddleCircle), m in [0, kTwiddleCircle/2).
-// Filled once per device in double precision on the host (api.cu: ensure_device_tables()).
-constexpr int kTwiddleCircleLog2 = 14;
-constexpr int kTwiddleCircle = 1 << kTwiddleCircleLog2;     // supports real lengths up to 16384
-constexpr int kTwiddleEntries = kTwiddleCircle / 2;
+// Twiddle tables, one compact table per transform size so that consecutive lanes read consecutive
+// entries: for a complex length N = 2^L (real length n = 2N) the table exp(-2*pi*i*m / n), m in [0, N),
+// starts at entry 2^L of one concatenated per-device array (L = 4 .. 13, 16384 entries, 128 KB).
+// Filled once per device in double precision on the host (api_core.cu: cvb_init()).
+constexpr int kTwiddleMaxLog2N = 13;
+constexpr int kTwiddleEntries = 1 << (kTwiddleMaxLog2N + 1);
+__host__ __device__ __forceinline__ constexpr int twiddle_offset(int log2n) { return 1 << log2n; }
 
 // streaming (read-once / write-once) global accesses: keep them out of L1
 __device__ __forceinline__ float2 ldg_stream2(const float2* p) {

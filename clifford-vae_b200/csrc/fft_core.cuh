@@ -8,8 +8,8 @@
 // {t + e*T} is the same at the input of every pass and at the final output, so callers load
 // and store global memory with consecutive threads touching consecutive float2 (coalesced).
 //
-// All functions that touch the exchange buffer call __syncthreads(): every thread of the CTA
-// must call them the same number of times (callers keep loop trip counts CTA-uniform).
+// All functions that touch the exchange buffer call group_sync(): every thread of a group must call
+// them the same number of times (callers keep loop trip counts uniform).
 #pragma once
 #include "common.cuh"
 
@@ -27,6 +27,21 @@ struct FftPlan {
   static constexpr int THREADS = (T >= 128) ? T : 128;   // CTA size
   static constexpr int GROUPS = THREADS / T;       // FFTs processed side by side in one CTA
 };
+
+// Barrier among the T threads that own one FFT.  A group of <= 32 threads is (part of) one warp:
+// __syncwarp; a group that is a proper part of the CTA uses its own named barrier, so the groups of a
+// CTA run independently; a group that is the whole CTA uses __syncthreads.
+template <int LOG2N>
+__device__ __forceinline__ void group_sync() {
+  using Pl = FftPlan<LOG2N>;
+  if constexpr (Pl::T <= 32) {
+    __syncwarp();
+  } else if constexpr (Pl::T < Pl::THREADS) {
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)(threadIdx.x / Pl::T)), "n"(Pl::T) : "memory");
+  } else {
+    __syncthreads();
+  }
+}
 
 // ---- small in-register DFTs (natural order in, natural order out) ---------------------------
 template <bool INV>
@@ -137,7 +152,7 @@ __device__ __forceinline__ void fft_pass(cplx (&v)[FftPlan<LOG2N>::E], cplx* xch
   constexpr int LOGR = (LOG2N - LOGNS) < Pl::LOGE ? (LOG2N - LOGNS) : Pl::LOGE;
   constexpr int R = 1 << LOGR, Q = Pl::E / R, NS = 1 << LOGNS;
   constexpr bool LAST = (LOGNS + LOGR == LOG2N);
-  if (!LAST) __syncthreads();               // earlier readers of xch are done
+  if (!LAST) group_sync<LOG2N>();               // earlier readers of xch are done
 #pragma unroll
   for (int q = 0; q < Q; ++q) {
     cplx u[R];
@@ -146,7 +161,7 @@ __device__ __forceinline__ void fft_pass(cplx (&v)[FftPlan<LOG2N>::E], cplx* xch
     const int j = t + q * Pl::T;
     const int k = j & (NS - 1);
     if (P > 0) {
-      cplx w1 = __ldg(&tw[k << (kTwiddleCircleLog2 - LOGNS - LOGR)]);   // exp(-2 pi i k / (NS R))
+      cplx w1 = __ldg(&tw[twiddle_offset(LOG2N) + (k << (LOG2N + 1 - LOGNS - LOGR))]);   // exp(-2 pi i k / (NS R))
       if (INV) w1.y = -w1.y;
       apply_twiddle_powers<R>(u, w1);
     }
@@ -161,7 +176,7 @@ __device__ __forceinline__ void fft_pass(cplx (&v)[FftPlan<LOG2N>::E], cplx* xch
     }
   }
   if constexpr (!LAST) {
-    __syncthreads();
+    group_sync<LOG2N>();
 #pragma unroll
     for (int e = 0; e < Pl::E; ++e) v[e] = xch[pad16(t + e * Pl::T)];
     fft_pass<LOG2N, P + 1, INV>(v, xch, t, tw);
@@ -183,17 +198,17 @@ __device__ __forceinline__ float r2c_untangle(cplx (&v)[FftPlan<LOG2N>::E], cplx
                                               const cplx* __restrict__ tw) {
   using Pl = FftPlan<LOG2N>;
   constexpr int N = Pl::N;
-  __syncthreads();
+  group_sync<LOG2N>();
 #pragma unroll
   for (int e = 0; e < Pl::E; ++e) xch[pad16(t + e * Pl::T)] = v[e];
-  __syncthreads();
+  group_sync<LOG2N>();
   const float nyq = v[0].x - v[0].y;      // for t == 0: Re Z0 - Im Z0
 #pragma unroll
   for (int e = 0; e < Pl::E; ++e) {
     const int k = t + e * Pl::T;
     const cplx z = v[e];
     const cplx zp = cconj(xch[pad16((N - k) & (N - 1))]);
-    const cplx w = __ldg(&tw[k << (kTwiddleCircleLog2 - LOG2N - 1)]);   // exp(-2 pi i k / n)
+    const cplx w = __ldg(&tw[twiddle_offset(LOG2N) + k]);   // exp(-2 pi i k / n)
     const cplx s = cadd(z, zp), d = csub(z, zp);
     const cplx wd = cmul_mi(cmul(w, d));                                 // -i w (z - zp)
     v[e] = make_float2(0.5f * (s.x + wd.x), 0.5f * (s.y + wd.y));
@@ -210,17 +225,17 @@ __device__ __forceinline__ void c2r_pretangle(cplx (&v)[FftPlan<LOG2N>::E], floa
   using Pl = FftPlan<LOG2N>;
   constexpr int N = Pl::N;
   constexpr float scale = 1.0f / (2.0f * N);
-  __syncthreads();
+  group_sync<LOG2N>();
 #pragma unroll
   for (int e = 0; e < Pl::E; ++e) xch[pad16(t + e * Pl::T)] = v[e];
   if (t == 0) xch[pad16(N)] = make_float2(x_nyq, 0.0f);
-  __syncthreads();
+  group_sync<LOG2N>();
 #pragma unroll
   for (int e = 0; e < Pl::E; ++e) {
     const int k = t + e * Pl::T;
     const cplx x = v[e];
     const cplx xp = cconj(xch[pad16(N - k)]);
-    const cplx w = cconj(__ldg(&tw[k << (kTwiddleCircleLog2 - LOG2N - 1)]));   // exp(+2 pi i k / n)
+    const cplx w = cconj(__ldg(&tw[twiddle_offset(LOG2N) + k]));   // exp(+2 pi i k / n)
     const cplx s = cadd(x, xp), d = csub(x, xp);
     const cplx wd = cmul_i(cmul(w, d));                                       // +i w (x - xp)
     v[e] = make_float2(scale * (s.x + wd.x), scale * (s.y + wd.y));
@@ -240,7 +255,7 @@ __device__ __forceinline__ void c2r_pretangle_load(cplx (&v)[FftPlan<LOG2N>::E],
     const int k = t + e * Pl::T;
     const cplx x = xch[pad16(k)];
     const cplx xp = cconj(xch[pad16(N - k)]);
-    const cplx w = cconj(__ldg(&tw[k << (kTwiddleCircleLog2 - LOG2N - 1)]));   // exp(+2 pi i k / n)
+    const cplx w = cconj(__ldg(&tw[twiddle_offset(LOG2N) + k]));   // exp(+2 pi i k / n)
     const cplx s = cadd(x, xp), d = csub(x, xp);
     const cplx wd = cmul_i(cmul(w, d));
     v[e] = make_float2(scale * (s.x + wd.x), scale * (s.y + wd.y));
@@ -248,15 +263,16 @@ __device__ __forceinline__ void c2r_pretangle_load(cplx (&v)[FftPlan<LOG2N>::E],
 }
 
 // sum over the T threads of a group; scratch: >= 32 floats per group; uses __syncthreads when T > 32
-template <int T>
+template <int LOG2N>
 __device__ __forceinline__ float group_sum(float val, float* scratch, int t) {
+  constexpr int T = FftPlan<LOG2N>::T;
   constexpr int W = T < 32 ? T : 32;
 #pragma unroll
   for (int o = W / 2; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
   if constexpr (T > 32) {
-    __syncthreads();
+    group_sync<LOG2N>();
     if ((t & 31) == 0) scratch[t >> 5] = val;
-    __syncthreads();
+    group_sync<LOG2N>();
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < T / 32; ++i) s += scratch[i];

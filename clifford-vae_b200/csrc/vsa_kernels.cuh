@@ -157,16 +157,16 @@ bind_v3_kernel(const BindParams p, const cplx* __restrict__ tw) {
       tma_load_1d(stage_b, p.b + ((row + stride) % p.b_rows) * (2LL * N), kRowBytes, &bars[1]);
     }
     // ---- one partner exchange: untangle a and b, pointwise op, re-pack for the inverse transform
-    __syncthreads();
+    group_sync<LOG2N>();
 #pragma unroll
     for (int e = 0; e < E; ++e) xch[pad16(t + e * T)] = v[e];
-    __syncthreads();
+    group_sync<LOG2N>();
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       const int k = t + e * T, kp = (N - k) & (N - 1);
       const cplx za = park[k], zap = cconj(park[kp]);
       const cplx zb = v[e], zbp = cconj(xch[pad16(kp)]);
-      const cplx w = __ldg(&tw[k << (kTwiddleCircleLog2 - LOG2N - 1)]);    // exp(-2 pi i k / n)
+      const cplx w = __ldg(&tw[twiddle_offset(LOG2N) + k]);    // exp(-2 pi i k / n)
       // bins k and N-k of the real FFTs (X[N-k] uses W^(N-k) = -conj(W^k)); factor 1/2 each
       const cplx sa = cadd(za, zap), da = cmul_mi(cmul(w, csub(za, zap)));
       const cplx sb = cadd(zb, zbp), db = cmul_mi(cmul(w, csub(zb, zbp)));
@@ -178,7 +178,7 @@ bind_v3_kernel(const BindParams p, const cplx* __restrict__ tw) {
     }
     if (STAGED) {
       fence_proxy_async();                       // parked-spectrum accesses before the next TMA write
-      __syncthreads();
+      group_sync<LOG2N>();
       if (t == 0 && next_valid) {
         mbar_expect_tx(&bars[0], kRowBytes);
         tma_load_1d(park, p.a + ((row + stride) % p.a_rows) * (2LL * N), kRowBytes, &bars[0]);
