@@ -271,7 +271,7 @@ def run_gpu(args):
         value = world * B * args.steps / (ms_total * 1e-3)
         e2e_val = world * B * e2e_steps / (ms_e2e * 1e-3)
         k_rs = {"name": "clifford_fwd_kernel<11,PsRng,rowk>", "ms": ms_rs, "bytes": B * BYTES_RSAMPLE}
-        k_bd = {"name": "bind_kernel<11,Mul>", "ms": ms_bind, "bytes": B * BYTES_BIND}
+        k_bd = {"name": "bind_v3_kernel<11,Mul,direct>", "ms": ms_bind, "bytes": B * BYTES_BIND}
         dom = k_rs if ms_rs >= ms_bind else k_bd
         achieved = dom["bytes"] / (dom["ms"] * 1e-3) / 1e9
         line = {

@@ -16,8 +16,11 @@ BIND_MUL, BIND_MUL_CONJ, BIND_DIV, BIND_DIV_CONJ, BIND_NEG_MUL_CONJ = range(5)
 
 
 def _launch(name, *args):
-    """Call a C-ABI launcher on the device of its first tensor pointer's owner (set by _prep/_dev)."""
+    """Call a C-ABI launcher on the device of its first tensor pointer's owner (set by _prep/_dev).
+    Launches over zero rows are skipped (the outputs are already-empty tensors, like the reference)."""
     lib = _lib.load()
+    if _EMPTY[0]:
+        return
     dev = _CUR_DEV[0]
     if dev is not None and dev.index is not None and dev.index != torch.cuda.current_device():
         with torch.cuda.device(dev):
@@ -28,6 +31,7 @@ def _launch(name, *args):
 
 
 _CUR_DEV = [None]
+_EMPTY = [False]
 
 
 def _f32c(t: torch.Tensor) -> torch.Tensor:
@@ -41,6 +45,7 @@ def _prep(*tensors):
     dev = tensors[0].device
     _lib.ensure_device(dev)
     _CUR_DEV[0] = dev
+    _EMPTY[0] = any(t is not None and t.numel() == 0 for t in tensors)
     for t in tensors[1:]:
         if t is not None and t.device != dev:
             raise _lib.CliffordB200Error(f"tensors on different devices: {dev} vs {t.device}")

@@ -4,6 +4,9 @@
 #pragma once
 #include "fft_core.cuh"
 #include "tma.cuh"
+#ifndef CVB_BIND_MINB
+#define CVB_BIND_MINB 4
+#endif
 
 namespace cvb {
 
@@ -91,7 +94,7 @@ constexpr size_t bind_v3_smem_bytes() {
 }
 
 template <int LOG2N, int MODE, bool STAGED>
-__global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS, (FftPlan<LOG2N>::THREADS <= 128 ? 4 : (FftPlan<LOG2N>::THREADS <= 256 ? 2 : 1)))
+__global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS, (FftPlan<LOG2N>::THREADS <= 128 ? CVB_BIND_MINB : (FftPlan<LOG2N>::THREADS <= 256 ? 2 : 1)))
 bind_v3_kernel(const BindParams p, const cplx* __restrict__ tw) {
   using Pl = FftPlan<LOG2N>;
   constexpr int N = Pl::N, T = Pl::T, E = Pl::E, G = Pl::GROUPS;

@@ -173,3 +173,22 @@ def test_sharded_ops_single_rank_use_kernels():
     q = items[[5, 77, 299]] + 0.01 * torch.randn(3, 256, device=DEV)
     best, idx = D.sharded_cleanup(q, items, 0)
     assert idx.tolist() == [5, 77, 299] and float(best.min()) > 0.9
+
+
+def test_empty_and_ragged_batches():
+    """Edge cases: zero rows, one row, row counts that are not multiples of the CTA group size."""
+    from utils import vsa
+    from dists.clifford import CliffordPowerSphericalDistribution
+    from oracle import latent_oracle as O
+    e = torch.empty(0, 64, device=DEV)
+    assert vsa.bind(e, e).shape == (0, 64)
+    assert vsa.similarity(e, e).shape == (0,)
+    assert vsa.normalize_vectors(e).shape == (0, 64)
+    q = CliffordPowerSphericalDistribution(torch.empty(0, 32, device=DEV), torch.empty(0, 1, device=DEV))
+    assert q.rsample().shape == (0, 64)
+    assert q.entropy().shape == (0,)
+    torch.manual_seed(1)
+    for rows in (1, 3, 5, 129, 1031):
+        for d in (64, 256, 1024):
+            a, b = torch.randn(rows, d), torch.randn(rows, d)
+            assert rel_err(vsa.bind(a.to(DEV), b.to(DEV)).cpu(), O.bind(a, b)) < 1e-5, (rows, d)
