@@ -300,7 +300,7 @@ struct CliffordBwdParams {
 // Element k of the backward: returns dL/dtheta_k, accumulates / stores dL/dkappa_k.
 template <bool ROWK>
 __device__ __forceinline__ float clifford_bwd_element(const CliffordBwdParams& p, long long row, long long prow, int k,
-                                                      cplx Gk, BetaGradConsts& bc, float inv_d, float& dk) {
+                                                      cplx Gk, BetaGradRow& bc, float inv_d, float& dk) {
   const long long idx = row * p.d + k;
   float tp, s;
   if (p.tp_signed) {
@@ -318,8 +318,13 @@ __device__ __forceinline__ float clifford_bwd_element(const CliffordBwdParams& p
   const cplx x = make_float2(fmaf(cl, ph.c, -sl * ph.s), fmaf(sl, ph.c, cl * ph.s));
   // dL/dtheta_k = -(2/n) Im(X_k conj(G_k)), 2/n = 1/d
   const float dth = -inv_d * (x.y * Gk.x - x.x * Gk.y);
-  if (!ROWK) bc = BetaGradConsts(0.5f + (__ldg(p.kappa + prow * p.kappa_row_stride + (long long)k * p.kappa_el_stride) + kEps), 0.5f);
-  const float dtp = dirichlet_grad_one(tp, bc) * (1.0f - tp);
+  float dtp;
+  if (ROWK) {
+    dtp = bc.grad(tp) * (1.0f - tp);
+  } else {
+    const BetaGradConsts be(0.5f + (__ldg(p.kappa + prow * p.kappa_row_stride + (long long)k * p.kappa_el_stride) + kEps), 0.5f);
+    dtp = dirichlet_grad_one(tp, be) * (1.0f - tp);
+  }
   dk = dth * ph.dphi_dt * 2.0f * dtp;
   stg_stream1(p.dloc + idx, dth);
   if (!ROWK) stg_stream1(p.dkappa + idx, dk);
@@ -353,9 +358,9 @@ clifford_bwd_kernel(const CliffordBwdParams p, const cplx* __restrict__ tw) {
 #pragma unroll
     for (int e = 0; e < E; ++e) xch[pad16(t + e * T)] = v[e];
     const float kap_row = valid ? __ldg(p.kappa + prow * p.kappa_row_stride) : 1.0f;
-    BetaGradConsts bc(0.5f + (kap_row + kEps), 0.5f);
+    BetaGradRow bc(0.5f + (kap_row + kEps), 0.5f);
     float dk_sum = 0.f;
-#pragma unroll 1
+#pragma unroll 2
     for (int e = 0; e < E; ++e) {
       const int k = t + e * T;
       float dk = 0.f;
@@ -578,7 +583,7 @@ clifford_bwd_generic_kernel(const CliffordBwdParams p) {
     for (int j = threadIdx.x; j < n; j += blockDim.x) g[j] = p.grad_z[row * n + j];
     __syncthreads();
     const float kap_row = __ldg(p.kappa + prow * p.kappa_row_stride);
-    BetaGradConsts bc(0.5f + (kap_row + kEps), 0.5f);
+    BetaGradRow bc(0.5f + (kap_row + kEps), 0.5f);
     float dk_sum = 0.f;
     for (int k = threadIdx.x; k < d; k += blockDim.x) {
       if (k == 0) {
