@@ -39,6 +39,20 @@ BYTES_RSAMPLE = 12 * D_LAT + 8
 BYTES_BIND = 12 * N_VEC
 
 
+def load_traffic(kernel_name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    ncu --set full capture of this bench (profiles/r01_traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            t = json.load(f)
+        for k, v in t.items():
+            if kernel_name.startswith(k):
+                return v["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
+
+
 def load_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -234,27 +248,52 @@ def run_gpu(args):
     h_kl = torch.empty(B).pin_memory()
     prior = CliffordTorusUniform(d, device=dev)
 
-    def e2e_step():
+    # Double-buffered pipeline: copy-in (H2D), compute, copy-out (D2H) on three streams, two device buffer
+    # sets; every step still moves its own inputs from pinned host memory and its own results back.
+    s_in, s_cmp, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+    dbuf = [dict(loc=torch.empty(B, d, device=dev), kap=torch.empty(B, 1, device=dev), roles=torch.empty(B, n, device=dev),
+                 ev_in=torch.cuda.Event(), ev_cmp=torch.cuda.Event(), ev_out=torch.cuda.Event(), out=None, kl=None)
+            for _ in range(2)]
+
+    def e2e_step(i):
+        b = dbuf[i % 2]
         with torch.no_grad():
-            loc_d = h_loc.to(dev, non_blocking=True)
-            kap_d = h_kap.to(dev, non_blocking=True)
-            roles_d = h_roles.to(dev, non_blocking=True)
-            q = CliffordPowerSphericalDistribution(loc_d, kap_d, validate_args=False)
-            z = q.rsample()
-            kl = torch.distributions.kl.kl_divergence(q, prior)
-            out = vsa.bind(z, roles_d)
-            h_out.copy_(out, non_blocking=True)
-            h_kl.copy_(kl, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+            with torch.cuda.stream(s_in):
+                s_in.wait_event(b["ev_cmp"])                  # the compute that last read this set is done
+                b["loc"].copy_(h_loc, non_blocking=True)
+                b["kap"].copy_(h_kap, non_blocking=True)
+                b["roles"].copy_(h_roles, non_blocking=True)
+                b["ev_in"].record(s_in)
+            with torch.cuda.stream(s_cmp):
+                s_cmp.wait_event(b["ev_in"])
+                s_cmp.wait_event(b["ev_out"])                 # the previous outputs of this set were copied out
+                q = CliffordPowerSphericalDistribution(b["loc"], b["kap"], validate_args=False)
+                z = q.rsample()
+                b["kl"] = torch.distributions.kl.kl_divergence(q, prior)
+                b["out"] = vsa.bind(z, b["roles"])
+                b["ev_cmp"].record(s_cmp)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(b["ev_cmp"])
+                h_out.copy_(b["out"], non_blocking=True)
+                h_kl.copy_(b["kl"], non_blocking=True)
+                b["out"].record_stream(s_out)
+                b["kl"].record_stream(s_out)
+                b["ev_out"].record(s_out)
+
+    def e2e_drain():
+        s_in.synchronize(); s_cmp.synchronize(); s_out.synchronize()
 
     e2e_steps = max(3, min(args.steps, 20))
-    for _ in range(3):
-        e2e_step()
+    for i in range(4):
+        e2e_step(i)
+    e2e_drain()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(e2e_steps):
-        e2e_step()
+    s_in.wait_event(e0); s_cmp.wait_event(e0); s_out.wait_event(e0)
+    for i in range(e2e_steps):
+        e2e_step(i)
+    e2e_drain()
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
@@ -281,7 +320,7 @@ def run_gpu(args):
             "config": {"workload": WORKLOAD, "rows_per_gpu": B, "d": d, "rng": "philox4x32-10 on device",
                        "l2": f"inputs rotate over {NSETS} buffer sets of 224 MB (> 126 MB L2)"},
             "roofline": {"bound": "hbm", "kernel": dom["name"], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": load_traffic(dom["name"]), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": dom["bytes"], "ms_per_launch": dom["ms"]},
             "kernels": {
                 "rsample_kl": {"ms": ms_rs, "GBps": k_rs["bytes"] / (ms_rs * 1e-3) / 1e9,
@@ -291,7 +330,8 @@ def run_gpu(args):
             "e2e": {"value": e2e_val, "unit": UNIT, "steps": e2e_steps,
                     "h2d_bytes_per_step": world * (h_loc.numel() + h_kap.numel() + h_roles.numel()) * 4,
                     "d2h_bytes_per_step": world * (h_out.numel() + h_kl.numel()) * 4,
-                    "api": "dists.clifford.CliffordPowerSphericalDistribution.rsample + kl_divergence + utils.vsa.bind"},
+                    "api": "dists.clifford.CliffordPowerSphericalDistribution.rsample + kl_divergence + utils.vsa.bind",
+                    "pipeline": "double-buffered: H2D / compute / D2H on three streams"},
             "gpu_launches": int(launches), "clocks": clk,
         }
         if world == 1 and not args.no_cpu_baseline:
