@@ -114,7 +114,7 @@ __device__ __forceinline__ RowSrc global_row_src(const CliffordFwdParams& p, lon
 // proposal returns false (the caller queues k and finishes it with clifford_phasor_retry).
 template <int MODE, bool ROWK>
 __device__ __forceinline__ bool clifford_phasor(const CliffordFwdParams& p, const RowSrc& src, long long row,
-                                                long long prow, int k, GammaMT& gm, cplx& out) {
+                                                long long prow, int k, HalfAngle& gm, cplx& out) {
   const long long idx = row * p.d + k;
   if (MODE == kPsInjected) {
     const float tp = src.tprime[k];
@@ -123,9 +123,9 @@ __device__ __forceinline__ bool clifford_phasor(const CliffordFwdParams& p, cons
     return true;
   }
   if (MODE == kPsRng) {
-    if (!ROWK) gm = GammaMT(0.5f + (__ldg(p.kappa + prow * p.kappa_row_stride + (long long)k * p.kappa_el_stride) + kEps));
+    if (!ROWK) gm = HalfAngle(__ldg(p.kappa + prow * p.kappa_row_stride + (long long)k * p.kappa_el_stride) + kEps);
     float tp, s;
-    if (!beta_half_first(gm, p.key, (uint64_t)idx, tp, s)) return false;
+    if (!circle_beta_first(gm, p.key, (uint64_t)idx, tp, s)) return false;
     if (p.tp_signed) stg_stream1(p.tp_signed + idx, copysignf(tp, s));
     out = ps_phasor<true>(tp, s, src.loc[k]);
     return true;
@@ -150,11 +150,11 @@ __device__ __forceinline__ bool clifford_phasor(const CliffordFwdParams& p, cons
 
 template <bool ROWK>
 __device__ __forceinline__ cplx clifford_phasor_retry(const CliffordFwdParams& p, const RowSrc& src, long long row,
-                                                      long long prow, int k, GammaMT& gm) {
+                                                      long long prow, int k, HalfAngle& gm) {
   const long long idx = row * p.d + k;
-  if (!ROWK) gm = GammaMT(0.5f + (__ldg(p.kappa + prow * p.kappa_row_stride + (long long)k * p.kappa_el_stride) + kEps));
+  if (!ROWK) gm = HalfAngle(__ldg(p.kappa + prow * p.kappa_row_stride + (long long)k * p.kappa_el_stride) + kEps);
   float s;
-  const float tp = beta_half_retry(gm, p.key, (uint64_t)idx, s);
+  const float tp = circle_beta_retry(gm, p.key, (uint64_t)idx, s);
   if (p.tp_signed) stg_stream1(p.tp_signed + idx, copysignf(tp, s));
   return ps_phasor<true>(tp, s, src.loc[k]);
 }
@@ -234,7 +234,7 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw) {
     const long long prow = valid ? (row % p.loc_rows) : 0;
     float kap_row = 1.0f;
     if (PS && valid) kap_row = __ldg(p.kappa + prow * p.kappa_row_stride);
-    GammaMT gm(0.5f + (kap_row + kEps));
+    HalfAngle gm(kap_row + kEps);
     RowSrc src;
     if (staged) {
       src.loc = stage; src.tprime = stage + d; src.gnoise = stage + 2 * d; src.phases = stage;
@@ -243,15 +243,46 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw) {
       src = global_row_src(p, valid ? row : 0, prow);
     }
     group_sync<LOG2N>();                       // the previous row's exchange-buffer readers are done
-    // phase 1: phasors of the half spectrum into the exchange buffer (lightly unrolled: small code, ILP 2)
-#pragma unroll 4
-    for (int e = 0; e < E; ++e) {
-      const int k = t + e * T;
-      cplx x = make_float2(1.0f, 0.0f);
-      if (valid && k != 0) {
-        if (!clifford_phasor<MODE, ROWK>(p, src, row, prow, k, gm, x)) queue[atomicAdd(qcount, 1)] = k;
+    // phase 1: phasors of the half spectrum into the exchange buffer (lightly unrolled: small code, some ILP)
+    if (MODE == kPsRng) {
+      // device RNG: one Philox call + one Box-Muller per PAIR of bins (one envelope proposal each);
+      // rejected proposals are queued and finished in phase 1b
+      const uint64_t pair_base = (uint64_t)row * (uint64_t)(d / 2) + (uint64_t)t * (E / 2);
+      PhiloxKey pkey = p.key;
+      pkey.stream = 8;
+#pragma unroll 2
+      for (int e = 0; e < E; e += 2) {
+        const int k0 = t + e * T, k1 = k0 + T;
+        HalfAngle h0 = gm, h1 = gm;
+        if (!ROWK && valid) {
+          h0 = HalfAngle(__ldg(p.kappa + prow * p.kappa_row_stride + (long long)k0 * p.kappa_el_stride) + kEps);
+          h1 = HalfAngle(__ldg(p.kappa + prow * p.kappa_row_stride + (long long)k1 * p.kappa_el_stride) + kEps);
+        }
+        float tp[2], sg[2];
+        const uint32_t acc = half_angle_pair(h0, h1, philox_draw(pkey, pair_base + (e >> 1), 0), tp, sg);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int k = j ? k1 : k0;
+          cplx x = make_float2(1.0f, 0.0f);
+          if (valid && k != 0) {
+            if (acc & (1u << j)) {
+              if (p.tp_signed) stg_stream1(p.tp_signed + row * d + k, copysignf(tp[j], sg[j]));
+              x = ps_phasor<true>(tp[j], sg[j], src.loc[k]);
+            } else {
+              queue[atomicAdd(qcount, 1)] = k;
+            }
+          }
+          xch[pad16(k)] = x;
+        }
       }
-      xch[pad16(k)] = x;
+    } else {
+#pragma unroll 4
+      for (int e = 0; e < E; ++e) {
+        const int k = t + e * T;
+        cplx x = make_float2(1.0f, 0.0f);
+        if (valid && k != 0) clifford_phasor<MODE, ROWK>(p, src, row, prow, k, gm, x);
+        xch[pad16(k)] = x;
+      }
     }
     if (t == 0) xch[pad16(d)] = make_float2(1.0f, 0.0f);
     group_sync<LOG2N>();
@@ -540,7 +571,7 @@ clifford_fwd_generic_kernel(const CliffordFwdParams p) {
     const long long prow = row % p.loc_rows;
     float kap_row = 1.0f;
     if (PS) kap_row = __ldg(p.kappa + prow * p.kappa_row_stride);
-    GammaMT gm(0.5f + (kap_row + kEps));
+    HalfAngle gm(kap_row + kEps);
     __syncthreads();
     const RowSrc src = global_row_src(p, row, prow);
     for (int k = 1 + threadIdx.x; k <= nph; k += blockDim.x) {
