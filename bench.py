@@ -339,16 +339,17 @@ def run_gpu(args):
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"2048 of the {B} rows (same d={d}), median of 5 passes "
                                               f"({sum(ts):.1f} s CPU), oracle port of the reference's torch CPU path"}
-        if args.extras:
-            line["extras"] = extras(torch, lib, dev, st, peak)
+        if world == 1:
+            line["other_configs"] = extras(torch, lib, dev, st, peak, full=args.extras)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
-def extras(torch, lib, dev, st, peak):
-    """Per-op throughput at the other BASELINE shapes (not bench lines; context for the headline)."""
+def extras(torch, lib, dev, st, peak, full=False):
+    """Per-op throughput at the other BASELINE shapes (context for the headline, not bench lines):
+    C1 Clifford B=128 d=512, C2 PowerSpherical / vMF B=1024 D=513, C4 bind sweep (~1 GiB per launch)."""
     out = {}
 
     def timeit(fn, reps=10):
@@ -363,16 +364,16 @@ def extras(torch, lib, dev, st, peak):
         torch.cuda.synchronize()
         return a.elapsed_time(b) / reps
 
-    for dd in (1024, 4096, 16384):
-        N = (1 << 30) // (12 * dd) // 2 * 2          # ~1 GiB of traffic per launch
+    for dd in ((1024, 4096, 16384) if not full else (1024, 2048, 4096, 8192, 16384)):
+        N = (1 << 30) // (12 * dd)
         a = torch.randn(N, dd, device=dev)
         b = torch.randn(N, dd, device=dev)
         o = torch.empty(N, dd, device=dev)
         ms = timeit(lambda: lib.cvb_vsa_bind(a.data_ptr(), b.data_ptr(), o.data_ptr(), N, N, N, dd, 0, st))
         gb = N * 12 * dd / (ms * 1e-3) / 1e9
-        out[f"bind_d{dd}"] = {"vectors": N, "ms": ms, "vec_per_s": N / (ms * 1e-3), "GBps": gb, "frac": gb / peak}
+        out[f"C4_bind_d{dd}"] = {"vectors": N, "ms": ms, "vec_per_s": N / (ms * 1e-3), "GBps": gb, "frac": gb / peak}
         del a, b, o
-    for name, B, d in (("clifford_fwd_c1", 128, 512), ("clifford_fwd_big", 65536, 2048), ("clifford_fwd_d512", 262144, 512)):
+    for name, B, d in (("C1_clifford_rsample_kl_B128_d512", 128, 512), ("clifford_rsample_kl_B65536_d2048", 65536, 2048)):
         loc = torch.randn(B, d, device=dev)
         kap = torch.rand(B, device=dev) * 9.87 + 0.13
         z = torch.empty(B, 2 * d, device=dev)
@@ -382,6 +383,27 @@ def extras(torch, lib, dev, st, peak):
         gb = B * (12 * d + 8) / (ms * 1e-3) / 1e9
         out[name] = {"rows": B, "d": d, "ms": ms, "samples_per_s": B / (ms * 1e-3), "GBps": gb, "frac": gb / peak}
         del loc, z
+    B, D = 1024, 513
+    loc = torch.nn.functional.normalize(torch.randn(B, D, device=dev), dim=-1)
+    kap = torch.rand(B, device=dev) * 9.2 + 0.8
+    z = torch.empty(B, D, device=dev)
+    save = torch.empty(B, 2, device=dev)
+    ent = torch.empty(B, device=dev)
+    kl = torch.empty(B, device=dev)
+
+    def ps_step():
+        lib.cvb_powerspherical_rsample(loc.data_ptr(), kap.data_ptr(), B, None, None, 3, 0, z.data_ptr(), save.data_ptr(), B, D, st)
+        lib.cvb_ps_entropy_kl(kap.data_ptr(), 1, 0, B, D, (D - 1) / 2, 0, 0.0, ent.data_ptr(), kl.data_ptr(), None, st)
+
+    def vmf_step():
+        lib.cvb_vmf_rsample(loc.data_ptr(), kap.data_ptr(), B, None, None, 0, None, 3, 0, z.data_ptr(), save.data_ptr(), B, D, st)
+        lib.cvb_vmf_entropy_lognorm(kap.data_ptr(), B, D, ent.data_ptr(), None, None, None, st)
+
+    for name, fn in (("C2_powerspherical_rsample_kl_B1024_D513", ps_step), ("C2_vmf_rsample_kl_B1024_D513", vmf_step)):
+        ms = timeit(fn, reps=50)
+        gb = B * (8 * D + 8) / (ms * 1e-3) / 1e9
+        out[name] = {"rows": B, "D": D, "ms": ms, "samples_per_s": B / (ms * 1e-3), "GBps": gb, "frac": gb / peak,
+                     "note": "4 MB per launch: launch-latency bound at this batch"}
     return out
 
 
@@ -391,7 +413,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--extras", action="store_true", help="also time the other BASELINE shapes (bind sweep, C1)")
+    ap.add_argument("--extras", action="store_true", help="time the full bind sweep in other_configs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

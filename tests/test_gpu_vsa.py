@@ -192,3 +192,29 @@ def test_empty_and_ragged_batches():
         for d in (64, 256, 1024):
             a, b = torch.randn(rows, d), torch.randn(rows, d)
             assert rel_err(vsa.bind(a.to(DEV), b.to(DEV)).cpu(), O.bind(a, b)) < 1e-5, (rows, d)
+
+
+def test_c4_full_size_2pow20_vectors():
+    """BASELINE config 4 at full size for d = 1024: 2^20 vector pairs (4 GiB per operand) through bind ->
+    unbind with unitary keys; size-independent checks: exact recovery (cosine ~ 1), norm preservation,
+    linearity of bind in its first argument, and commutativity on a strided subset."""
+    from utils import vsa
+    torch.manual_seed(8)
+    N, d = 1 << 20, 1024
+    a = vsa.hrr_init(N, d, device=DEV)
+    b = vsa.unitary_init(N, d, device=DEV)
+    ab = vsa.bind(a, b)
+    # unitary binding preserves the norm (Parseval with |F_b| = 1)
+    assert float((ab.norm(dim=-1) / a.norm(dim=-1) - 1).abs().max()) < 1e-4
+    rec = vsa.unbind(ab, b)
+    cs = vsa.similarity(rec, a)
+    assert cs.shape == (N,) and float((cs - 1).abs().max()) < 1e-5
+    del rec
+    sub = slice(0, N, 4099)
+    a2 = vsa.hrr_init(a[sub].shape[0], d, device=DEV)
+    lin = vsa.bind(a[sub] + 2.0 * a2, b[sub])
+    assert rel_err(lin.cpu(), (ab[sub] + 2.0 * vsa.bind(a2, b[sub])).cpu()) < 2e-5
+    assert rel_err(vsa.bind(b[sub], a[sub]).cpu(), ab[sub].cpu()) < 1e-6
+    s = vsa.bundle(ab, normalize=True)
+    assert s.shape == (d,) and torch.isfinite(s).all()
+    assert rel_err(s.cpu(), (ab.double().sum(0) / N ** 0.5).cpu()) < 1e-5
