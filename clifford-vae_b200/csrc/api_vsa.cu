@@ -16,17 +16,10 @@ int launch_bind_fast(const BindParams& p, cudaStream_t st) {
   using Pl = FftPlan<LOG2N>;
   const cplx* tw = device_twiddles();
   if (!tw) return kCudaError;
-  // CVB_BIND_VARIANT: "staged" (TMA-staged rows), "direct" (plain loads), "v1" (first kernel); default by size
+  // CVB_BIND_VARIANT (experiments): "staged" (TMA-staged rows) or "direct" (plain loads); default by size
   static const char* variant = getenv("CVB_BIND_VARIANT");
   const long long work = (p.rows + Pl::GROUPS - 1) / Pl::GROUPS;
   int grid = 0;
-  if (variant && variant[0] == 'v') {
-    const size_t smem = sizeof(cplx) * Pl::XCH * Pl::GROUPS;
-    auto kern = bind_kernel<LOG2N, MODE>;
-    if (int rc = persistent_grid(kern, Pl::THREADS, smem, work, &grid)) return rc;
-    kern<<<grid, Pl::THREADS, smem, st>>>(p, tw);
-    return check_launch("bind_kernel");
-  }
   // measured on B200 (tools/bench_ops.py): TMA staging wins once a row pair no longer fits many CTAs per SM
   bool staged = aligned(p.a, 16) && aligned(p.b, 16) && (LOG2N >= 12 || (variant && variant[0] == 's'));
   if (variant && variant[0] == 'd') staged = false;

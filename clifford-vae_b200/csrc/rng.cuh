@@ -83,51 +83,6 @@ __device__ __forceinline__ bool gamma_mt_attempt(const GammaMT& g, float x, floa
   return (y > 0.f) & ((u < fmaf(-0.0331f * xx, xx, 1.0f)) | (__logf(u) < rhs));
 }
 
-// t' ~ Beta(alpha, 1/2) as X/(X+Y), X ~ Gamma(alpha) (Marsaglia-Tsang), Y ~ Gamma(1/2) = N^2/2.
-// The sign of the normal that produced Y is an independent fair sign, used as the circle's sign draw.
-// First attempt (Philox attempt 0): returns false if the Marsaglia-Tsang proposal was rejected -- the
-// caller queues the element and finishes it with beta_half_retry so that a warp never loops on one
-// lane's rejection.
-__device__ __forceinline__ float beta_ratio(float x, float y) {
-  // keep t' inside [FLT_MIN, 1 - 2^-24] like torch's _sample_dirichlet clamp
-  return fminf(fmaxf(__fdividef(x, x + y), 1.17549435e-38f), 1.0f - 5.9604645e-8f);
-}
-__device__ __forceinline__ bool beta_half_first(const GammaMT& g, const PhiloxKey& key, uint64_t elem, float& tp,
-                                                float& sign) {
-  const uint4 r = philox_draw(key, elem, 0);
-  const float2 nn = box_muller(r.x, r.y);
-  const float y = 0.5f * nn.y * nn.y;
-  sign = (nn.y < 0.f) ? -1.0f : 1.0f;
-  float x;
-  const bool ok = gamma_mt_attempt(g, nn.x, u01_open0(r.z), x);
-  if (g.inv_alpha > 0.f) x *= __powf(u01_open0(r.w), g.inv_alpha);
-  tp = beta_ratio(x, y);
-  return ok;
-}
-// Same element after a rejected first attempt: recomputes Y / sign / boost from attempt 0 and draws
-// fresh proposals (attempts 1, 2, ...) until one is accepted.
-__device__ __forceinline__ float beta_half_retry(const GammaMT& g, const PhiloxKey& key, uint64_t elem, float& sign) {
-  uint4 r = philox_draw(key, elem, 0);
-  float2 nn = box_muller(r.x, r.y);
-  const float y = 0.5f * nn.y * nn.y;
-  sign = (nn.y < 0.f) ? -1.0f : 1.0f;
-  const float boost = (g.inv_alpha > 0.f) ? __powf(u01_open0(r.w), g.inv_alpha) : 1.0f;
-  float x = 1.0f;
-  bool ok = false;
-  for (uint32_t attempt = 1; !ok && attempt < 64; ++attempt) {
-    r = philox_draw(key, elem, attempt);
-    nn = box_muller(r.x, r.y);
-    ok = gamma_mt_attempt(g, nn.x, u01_open0(r.z), x);
-    if (!ok) ok = gamma_mt_attempt(g, nn.y, u01_open0(r.w), x);
-  }
-  return beta_ratio(x * boost, y);
-}
-__device__ __forceinline__ float beta_half_draw(const GammaMT& g, const PhiloxKey& key, uint64_t elem, float& sign) {
-  float tp;
-  if (beta_half_first(g, key, elem, tp, sign)) return tp;
-  return beta_half_retry(g, key, elem, sign);
-}
-
 // ---- exact sampler for the circle's power-spherical phase ------------------------------------------
 // t' ~ Beta(1/2 + k, 1/2) is cos^2(psi) for a half-angle psi in (-pi/2, pi/2) with density ~ cos^{2k}(psi)
 // (phi = 2 psi is the phase whose density is ~ (1 + cos phi)^k, reference dists/clifford.py:124-134 with

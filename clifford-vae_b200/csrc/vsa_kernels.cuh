@@ -1,5 +1,5 @@
-// FFT-domain VSA kernels (power-of-two d): bind / unbind fused as R2C(a), R2C(b) ->
-// pointwise op -> C2R, one HBM round trip per vector pair (12 d bytes).
+// FFT-domain VSA kernels: bind / unbind fused as FFT(a), FFT(b) -> pointwise op -> inverse FFT in one
+// kernel, one HBM round trip per vector pair (12 d bytes); plus the streaming helpers.
 // Reference semantics: utils/vsa.py:43-72.
 #pragma once
 #include "fft_core.cuh"
@@ -37,47 +37,7 @@ __device__ __forceinline__ cplx bind_op(int mode, cplx a, cplx b) {
   return make_float2(q.x * inv, q.y * inv);
 }
 
-// LOG2N is log2 of the COMPLEX half length: d = 2 * 2^LOG2N.
-template <int LOG2N, int MODE>
-__global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS)
-bind_kernel(const BindParams p, const cplx* __restrict__ tw) {
-  using Pl = FftPlan<LOG2N>;
-  constexpr int N = Pl::N, T = Pl::T, E = Pl::E, G = Pl::GROUPS;
-  extern __shared__ cplx smem[];
-  const int group = threadIdx.x / T, t = threadIdx.x % T;
-  cplx* xch = smem + group * Pl::XCH;
-
-  for (long long base = (long long)blockIdx.x * G; base < p.rows; base += (long long)gridDim.x * G) {
-    const long long row = base + group;
-    const bool valid = row < p.rows;
-    const float2* ar = reinterpret_cast<const float2*>(p.a + (valid ? row % p.a_rows : 0) * (2LL * N));
-    const float2* br = reinterpret_cast<const float2*>(p.b + (valid ? row % p.b_rows : 0) * (2LL * N));
-    cplx va[E], vb[E];
-#pragma unroll
-    for (int e = 0; e < E; ++e) {
-      va[e] = valid ? ldg_stream2(ar + t + e * T) : make_float2(0.f, 0.f);
-      vb[e] = valid ? ldg_stream2(br + t + e * T) : make_float2(1.f, 0.f);
-    }
-    fft_run<LOG2N, false>(va, xch, t, tw);
-    const float a_nyq = r2c_untangle<LOG2N>(va, xch, t, tw);
-    fft_run<LOG2N, false>(vb, xch, t, tw);
-    const float b_nyq = r2c_untangle<LOG2N>(vb, xch, t, tw);
-#pragma unroll
-    for (int e = 0; e < E; ++e) va[e] = bind_op(MODE, va[e], vb[e]);
-    float p_nyq;
-    if (MODE == kBindDiv || MODE == kBindDivConj) p_nyq = a_nyq / (b_nyq + 1e-12f);
-    else if (MODE == kBindNegMulConj) p_nyq = -a_nyq * b_nyq;
-    else p_nyq = a_nyq * b_nyq;
-    c2r_pretangle<LOG2N>(va, p_nyq, xch, t, tw);
-    fft_run<LOG2N, true>(va, xch, t, tw);
-    if (valid) {
-      float2* o = reinterpret_cast<float2*>(p.out + row * (2LL * N));
-#pragma unroll
-      for (int e = 0; e < E; ++e) stg_stream2(o + t + e * T, va[e]);
-    }
-  }
-}
-
+// LOG2N below is log2 of the COMPLEX half length: d = 2 * 2^LOG2N.
 
 // ---- production bind kernel ------------------------------------------------------------------------
 // Z_a = FFT(a packed as N complex) is parked in shared memory, Z_b = FFT(b) stays in registers; one
