@@ -20,18 +20,19 @@ int launch_bind_fast(const BindParams& p, cudaStream_t st) {
   static const char* variant = getenv("CVB_BIND_VARIANT");
   const long long work = (p.rows + Pl::GROUPS - 1) / Pl::GROUPS;
   int grid = 0;
-  // measured on B200 (tools/bench_ops.py): TMA staging wins once a row pair no longer fits many CTAs per SM
-  bool staged = aligned(p.a, 16) && aligned(p.b, 16) && (LOG2N >= 12 || (variant && variant[0] == 's'));
-  if (variant && variant[0] == 'd') staged = false;
-  if (staged) {
-    const size_t smem = bind_v3_smem_bytes<LOG2N, true>();
-    auto kern = bind_v3_kernel<LOG2N, MODE, true>;
+  // staging mode measured on B200 (tools/bench_ops.py): 0 = plain loads, 2 = a and b through TMA (1 = a only was measured too: no gain)
+  int mode = (LOG2N >= 12) ? 2 : 0;
+  if (variant) mode = (variant[0] == 's') ? 2 : 0;
+  if (!(aligned(p.a, 16) && aligned(p.b, 16))) mode = 0;
+  if (mode == 2) {
+    const size_t smem = bind_v3_smem_bytes<LOG2N, 2>();
+    auto kern = bind_v3_kernel<LOG2N, MODE, 2>;
     if (int rc = persistent_grid(kern, Pl::THREADS, smem, work, &grid)) return rc;
     kern<<<grid, Pl::THREADS, smem, st>>>(p, tw);
-    return check_launch("bind_v3_kernel<staged>");
+    return check_launch("bind_v3_kernel<staged ab>");
   }
-  const size_t smem = bind_v3_smem_bytes<LOG2N, false>();
-  auto kern = bind_v3_kernel<LOG2N, MODE, false>;
+  const size_t smem = bind_v3_smem_bytes<LOG2N, 0>();
+  auto kern = bind_v3_kernel<LOG2N, MODE, 0>;
   if (int rc = persistent_grid(kern, Pl::THREADS, smem, work, &grid)) return rc;
   kern<<<grid, Pl::THREADS, smem, st>>>(p, tw);
   return check_launch("bind_v3_kernel<direct>");

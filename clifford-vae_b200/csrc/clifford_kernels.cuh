@@ -12,6 +12,9 @@
 #include "tma.cuh"
 #include "rng.cuh"
 #include "special.cuh"
+#ifndef CVB_FWD_MINB
+#define CVB_FWD_MINB 4
+#endif
 
 namespace cvb {
 
@@ -178,7 +181,7 @@ constexpr size_t clifford_fwd_smem_bytes() {
 }
 
 template <int LOG2N, int MODE, bool ROWK>
-__global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS, (FftPlan<LOG2N>::THREADS <= 128 ? 4 : 1))
+__global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS, (FftPlan<LOG2N>::THREADS <= 128 ? CVB_FWD_MINB : 1))
 clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw) {
   using Pl = FftPlan<LOG2N>;
   constexpr int d = Pl::N, T = Pl::T, E = Pl::E, G = Pl::GROUPS;

@@ -45,15 +45,15 @@ __device__ __forceinline__ cplx bind_op(int mode, cplx a, cplx b) {
 // real-FFT bins A, B at k and N-k, applies the pointwise op, and re-packs the Hermitian product for
 // the inverse half-length FFT -- the two R2C untangles and the C2R pre-processing of the textbook
 // pipeline collapse into one exchange.  Only one 16-point register array is live (<= 128 registers,
-// 4 CTAs per SM for d <= 4096).  STAGED: rows arrive through cp.async.bulk (TMA) + mbarrier so the
+// 4 CTAs per SM for d <= 4096).  STAGED (1: a only, 2: a and b): rows arrive through cp.async.bulk (TMA) + mbarrier so the
 // next row's HBM read overlaps this row's passes; otherwise plain coalesced 64-bit loads.
-template <int LOG2N, bool STAGED>
+template <int LOG2N, int STAGED>
 constexpr size_t bind_v3_smem_bytes() {
   using Pl = FftPlan<LOG2N>;
-  return (sizeof(cplx) * (Pl::XCH + Pl::N + (STAGED ? Pl::N : 0)) + 2 * sizeof(uint64_t)) * Pl::GROUPS;
+  return (sizeof(cplx) * (Pl::XCH + Pl::N + (STAGED == 2 ? Pl::N : 0)) + 2 * sizeof(uint64_t)) * Pl::GROUPS;
 }
 
-template <int LOG2N, int MODE, bool STAGED>
+template <int LOG2N, int MODE, int STAGED>
 __global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS, (FftPlan<LOG2N>::THREADS <= 128 ? CVB_BIND_MINB : (FftPlan<LOG2N>::THREADS <= 256 ? 2 : 1)))
 bind_v3_kernel(const BindParams p, const cplx* __restrict__ tw) {
   using Pl = FftPlan<LOG2N>;
@@ -64,8 +64,8 @@ bind_v3_kernel(const BindParams p, const cplx* __restrict__ tw) {
   // layout: [G x park/stage_a][G x stage_b (STAGED)][G x xch][G x 2 mbarriers]
   cplx* park = reinterpret_cast<cplx*>(smem_raw) + (size_t)group * N;
   cplx* stage_b = reinterpret_cast<cplx*>(smem_raw) + (size_t)(G + group) * N;
-  cplx* xch = reinterpret_cast<cplx*>(smem_raw) + (size_t)(STAGED ? 2 : 1) * G * N + (size_t)group * Pl::XCH;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<cplx*>(smem_raw) + (size_t)(STAGED ? 2 : 1) * G * N + (size_t)G * Pl::XCH) + 2 * group;
+  cplx* xch = reinterpret_cast<cplx*>(smem_raw) + (size_t)(STAGED == 2 ? 2 : 1) * G * N + (size_t)group * Pl::XCH;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<cplx*>(smem_raw) + (size_t)(STAGED == 2 ? 2 : 1) * G * N + (size_t)G * Pl::XCH) + 2 * group;
   const long long stride = (long long)gridDim.x * G;
   const long long row0 = (long long)blockIdx.x * G + group;
   constexpr float scale = 1.0f / (2.0f * N);
@@ -80,8 +80,10 @@ bind_v3_kernel(const BindParams p, const cplx* __restrict__ tw) {
     if (t == 0 && row0 < p.rows) {
       mbar_expect_tx(&bars[0], kRowBytes);
       tma_load_1d(park, p.a + (row0 % p.a_rows) * (2LL * N), kRowBytes, &bars[0]);
-      mbar_expect_tx(&bars[1], kRowBytes);
-      tma_load_1d(stage_b, p.b + (row0 % p.b_rows) * (2LL * N), kRowBytes, &bars[1]);
+      if (STAGED == 2) {
+        mbar_expect_tx(&bars[1], kRowBytes);
+        tma_load_1d(stage_b, p.b + (row0 % p.b_rows) * (2LL * N), kRowBytes, &bars[1]);
+      }
     }
   }
 
@@ -105,7 +107,7 @@ bind_v3_kernel(const BindParams p, const cplx* __restrict__ tw) {
 #pragma unroll
     for (int e = 0; e < E; ++e) park[t + e * T] = v[e];
     // ---- b -> Z_b in registers
-    if (STAGED) {
+    if (STAGED == 2) {
       if (valid) mbar_wait(&bars[1], parity);
 #pragma unroll
       for (int e = 0; e < E; ++e) v[e] = valid ? stage_b[t + e * T] : make_float2(1.f, 0.f);
@@ -115,7 +117,7 @@ bind_v3_kernel(const BindParams p, const cplx* __restrict__ tw) {
       for (int e = 0; e < E; ++e) v[e] = valid ? ldg_stream2(br + t + e * T) : make_float2(1.f, 0.f);
     }
     fft_run<LOG2N, false>(v, xch, t, tw);
-    if (STAGED && t == 0 && next_valid) {        // every thread has read stage_b (barriers inside fft_run)
+    if (STAGED == 2 && t == 0 && next_valid) {   // every thread has read stage_b (barriers inside fft_run)
       mbar_expect_tx(&bars[1], kRowBytes);
       tma_load_1d(stage_b, p.b + ((row + stride) % p.b_rows) * (2LL * N), kRowBytes, &bars[1]);
     }
