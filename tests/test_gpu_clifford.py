@@ -201,3 +201,44 @@ def test_cpu_tensors_are_refused():
     q = CliffordPowerSphericalDistribution(torch.zeros(2, 16), torch.ones(2, 1))
     with pytest.raises(CliffordB200Error):
         q.rsample()
+
+
+def test_api_shapes_dtypes_and_noncontiguous_inputs():
+    """Multi-dim batch shapes, tuple sample_shape, fp64 inputs (computed in fp32, returned in the input dtype),
+    non-contiguous loc, per-element concentration with sample_shape."""
+    from dists.clifford import CliffordPowerSphericalDistribution, CliffordTorusUniform
+    from oracle import latent_oracle as O
+    torch.manual_seed(3)
+    d = 16
+    loc = torch.randn(2, 3, d, device=DEV)
+    kap = torch.rand(2, 3, 1, device=DEV) * 3 + 0.2
+    q = CliffordPowerSphericalDistribution(loc, kap)
+    assert q.batch_shape == (2, 3) and q.event_shape == (2 * d,)
+    z = q.rsample((4,))
+    assert z.shape == (4, 2, 3, 2 * d)
+    lp = q.log_prob(z)
+    assert lp.shape == (4, 2, 3)
+    ref = O.clifford_ps_log_prob(z.cpu(), loc.cpu(), kap.cpu().expand(2, 3, d))
+    assert rel_err(lp.cpu(), ref) < 5e-5
+    assert q.entropy().shape == (2, 3)
+    kl = torch.distributions.kl.kl_divergence(q, CliffordTorusUniform(d, device=DEV))
+    assert kl.shape == (2, 3) and bool((kl > -1e-4).all())
+    # KL -> 0 as kappa -> 0+
+    q0 = CliffordPowerSphericalDistribution(loc, torch.full((2, 3, 1), 1e-4, device=DEV))
+    assert float(torch.distributions.kl.kl_divergence(q0, CliffordTorusUniform(d, device=DEV)).abs().max()) < 1e-3
+    # fp64 in -> fp64 out
+    q64 = CliffordPowerSphericalDistribution(loc.double(), kap.double())
+    assert q64.rsample().dtype == torch.float64 and q64.entropy().dtype == torch.float64
+    # non-contiguous loc (transposed storage) and per-element kappa with a sample_shape
+    loc_t = torch.randn(d, 5, device=DEV).t()
+    kap_full = torch.rand(5, d, device=DEV) * 3 + 0.2
+    assert not loc_t.is_contiguous()
+    tp = torch.rand(3, 5, d, device=DEV).clamp(1e-3, 1 - 1e-3)
+    g = torch.randn(3, 5, d, device=DEV)
+    qf = CliffordPowerSphericalDistribution(loc_t, kap_full)
+    zf = qf.rsample((3,), _base_draws=(tp, g))
+    zo = O.clifford_ps_rsample(loc_t.cpu(), kap_full.cpu(), tp.cpu(), g.cpu())
+    assert rel_err(zf.cpu(), zo) < 1e-5
+    assert rel_err(qf.entropy().cpu(), O.clifford_ps_entropy(kap_full.cpu())) < 1e-5
+    # prior sampling with a 2-d sample shape (cnn/fashion_train.py:550)
+    assert CliffordTorusUniform(d, device=DEV).rsample((3, 7)).shape == (3, 7, 2 * d)
