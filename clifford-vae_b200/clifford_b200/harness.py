@@ -36,7 +36,23 @@ def binding_depth_cell(vecs: torch.Tensor) -> torch.Tensor:
     return vsa.similarity(bound, target)
 
 
-def run_depth_sweep(init_fn: Callable, dims: Sequence[int], max_depth: int = 40, n_trials: int = 10, device="cuda"):
+def binding_depth_cell_fused(vecs: torch.Tensor) -> torch.Tensor:
+    """Same result as binding_depth_cell, in ONE kernel: the whole bind/unbind chain of a trial is evaluated in the
+    frequency domain (X0 * prod_j |Y_j|^2) and the cosine by Parseval -- every vector is read once and nothing but
+    the (T,) similarities is written.  Power-of-two d in [32, 16384]; no autograd (an evaluation workload)."""
+    from . import _lib, ops
+    T, mp1, d = vecs.shape
+    v = vecs.detach().float().contiguous()
+    _lib.ensure_device(v.device)
+    ops._CUR_DEV[0] = v.device
+    ops._EMPTY[0] = T == 0
+    out = torch.empty(T, device=v.device, dtype=torch.float32)
+    ops._launch("cvb_vsa_depth_chain_cosine", v.data_ptr(), out.data_ptr(), T, mp1, d)
+    return out
+
+
+def run_depth_sweep(init_fn: Callable, dims: Sequence[int], max_depth: int = 40, n_trials: int = 10, device="cuda",
+                    fused_chain: bool = True):
     """Same signature/return as the reference's run_depth_sweep minus the label: (sim_matrix, depths)."""
     depths = list(range(1, max_depth + 1))
     sim = np.full((len(dims), len(depths)), np.nan)
@@ -45,7 +61,9 @@ def run_depth_sweep(init_fn: Callable, dims: Sequence[int], max_depth: int = 40,
         for m in depths:
             vecs = vsa.normalize_vectors(init_fn(n_trials * (m + 1), d, device=device))
             vecs = vecs.view(n_trials, m + 1, vecs.shape[-1])
-            cells.append(binding_depth_cell(vecs).mean())
+            dd = vecs.shape[-1]
+            fused = fused_chain and dd >= 32 and dd <= 16384 and (dd & (dd - 1)) == 0
+            cells.append((binding_depth_cell_fused(vecs) if fused else binding_depth_cell(vecs)).mean())
         sim[i] = torch.stack(cells).cpu().numpy()            # one host sync per dimension
     return sim, depths
 

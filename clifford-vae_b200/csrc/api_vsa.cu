@@ -58,6 +58,19 @@ int dispatch_bind(const BindParams& p, int d, cudaStream_t st) {
   return check_launch("bind_generic_kernel");
 }
 
+template <int LOG2N>
+int launch_depth_chain(const float* vecs, float* out, long long trials, int mp1, cudaStream_t st) {
+  using Pl = FftPlan<LOG2N>;
+  const cplx* tw = device_twiddles();
+  if (!tw) return kCudaError;
+  const size_t smem = sizeof(cplx) * Pl::XCH * Pl::GROUPS + sizeof(float) * 32 * Pl::GROUPS;
+  auto kern = depth_chain_kernel<LOG2N>;
+  int grid = 0;
+  if (int rc = persistent_grid(kern, Pl::THREADS, smem, (trials + Pl::GROUPS - 1) / Pl::GROUPS, &grid)) return rc;
+  kern<<<grid, Pl::THREADS, smem, st>>>(vecs, out, trials, mp1, tw);
+  return check_launch("depth_chain_kernel");
+}
+
 __global__ void normal_fill_kernel(float* out, long long total, float scale, PhiloxKey key) {
   // each Philox call yields 4 normals
   const long long nvec = (total + 3) / 4;
@@ -96,6 +109,20 @@ int cvb_vsa_bind(const float* a, const float* b, float* out, long long rows, lon
   }
   set_last_error("cvb_vsa_bind: unknown mode %d", mode);
   return kBadArgument;
+}
+
+int cvb_vsa_depth_chain_cosine(const float* vecs, float* out, long long trials, int m_plus_1, int d, void* stream) {
+  CVB_REQUIRE(vecs && out && trials > 0 && m_plus_1 >= 1, kBadArgument, "cvb_vsa_depth_chain_cosine: bad arguments");
+  CVB_REQUIRE(is_pow2(d) && d >= 32 && d <= 16384 && aligned(vecs, 8), kUnsupported,
+              "cvb_vsa_depth_chain_cosine: d=%d must be a power of two in [32, 16384] (use bind/unbind otherwise)", d);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (ilog2(d) - 1) {
+#define CVB_CASE(L) case L: return launch_depth_chain<L>(vecs, out, trials, m_plus_1, st);
+    CVB_CASE(4) CVB_CASE(5) CVB_CASE(6) CVB_CASE(7) CVB_CASE(8) CVB_CASE(9) CVB_CASE(10) CVB_CASE(11) CVB_CASE(12)
+    CVB_CASE(13)
+#undef CVB_CASE
+  }
+  return kUnsupported;
 }
 
 int cvb_vsa_invert(const float* a, float* out, long long rows, int d, void* stream) {

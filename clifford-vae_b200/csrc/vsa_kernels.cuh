@@ -158,6 +158,67 @@ bind_v3_kernel(const BindParams p, const cplx* __restrict__ tw) {
   }
 }
 
+// ---- fused binding-depth chain (BASELINE config 5) --------------------------------------------------
+// reference scripts/binding_depth_heatmap.py:25-35: bound = x0 (*) y1 (*) ... (*) ym, then unbind ym ... y1
+// with the "inv" method, then cos(recovered, x0).  In the frequency domain the chain is X0 * prod_j |Y_j|^2,
+// and by Parseval the cosine needs no inverse transform:
+//     cos = sum_k w_k |X0_k|^2 P_k / sqrt(sum_k w_k |X0_k|^2 P_k^2 * sum_k w_k |X0_k|^2),   P_k = prod_j |Y_jk|^2,
+// with Hermitian weights w_k = 1 for k in {0, N}, 2 otherwise.  One trial = (m+1) forward half-length FFTs,
+// 4 d (m+1) bytes read and 4 bytes written, instead of 2m fused bind launches (24 m d bytes).
+template <int LOG2N>
+__global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS, (FftPlan<LOG2N>::THREADS <= 128 ? 4 : (FftPlan<LOG2N>::THREADS <= 256 ? 2 : 1)))
+depth_chain_kernel(const float* __restrict__ vecs, float* __restrict__ out, long long trials, int mp1,
+                   const cplx* __restrict__ tw) {
+  using Pl = FftPlan<LOG2N>;
+  constexpr int N = Pl::N, T = Pl::T, E = Pl::E, G = Pl::GROUPS;
+  extern __shared__ cplx smem[];
+  const int group = threadIdx.x / T, t = threadIdx.x % T;
+  cplx* xch = smem + group * Pl::XCH;
+  float* scratch = reinterpret_cast<float*>(smem + G * Pl::XCH) + group * 32;
+  for (long long base = (long long)blockIdx.x * G; base < trials; base += (long long)gridDim.x * G) {
+    const long long trial = base + group;
+    const bool valid = trial < trials;
+    float x2[E], P[E];            // |X0_k|^2 and the running product for this thread's bins
+    float x2_nyq = 0.f, P_nyq = 1.f;
+#pragma unroll
+    for (int e = 0; e < E; ++e) { x2[e] = 0.f; P[e] = 1.f; }
+    for (int j = 0; j < mp1; ++j) {
+      const float2* r = reinterpret_cast<const float2*>(vecs + ((valid ? trial : 0) * mp1 + j) * (2LL * N));
+      cplx v[E];
+#pragma unroll
+      for (int e = 0; e < E; ++e) v[e] = valid ? ldg_stream2(r + t + e * T) : make_float2(0.f, 0.f);
+      fft_run<LOG2N, false>(v, xch, t, tw);
+      const float nyq = r2c_untangle<LOG2N>(v, xch, t, tw);
+      if (j == 0) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) x2[e] = fmaf(v[e].x, v[e].x, v[e].y * v[e].y);
+        x2_nyq = nyq * nyq;
+      } else {
+#pragma unroll
+        for (int e = 0; e < E; ++e) P[e] *= fmaf(v[e].x, v[e].x, v[e].y * v[e].y);
+        P_nyq *= nyq * nyq;
+      }
+    }
+    float num = 0.f, rr = 0.f, xx = 0.f;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const float w = (t + e * T == 0) ? 1.0f : 2.0f;
+      const float a = w * x2[e] * P[e];
+      num += a; rr += a * P[e]; xx += w * x2[e];
+    }
+    if (t == 0) { const float a = x2_nyq * P_nyq; num += a; rr += a * P_nyq; xx += x2_nyq; }
+    num = group_sum<LOG2N>(num, scratch, t);
+    rr = group_sum<LOG2N>(rr, scratch, t);
+    xx = group_sum<LOG2N>(xx, scratch, t);
+    if (valid && t == 0) {
+      // time-domain norms are sqrt(sum / n); the 1/n cancels; clamp like F.cosine_similarity (eps 1e-8 on each norm)
+      const float inv_n = 1.0f / (2.0f * N);
+      const float nr = fmaxf(sqrtf(rr * inv_n), 1e-8f), nx = fmaxf(sqrtf(xx * inv_n), 1e-8f);
+      out[trial] = (num * inv_n) / (nr * nx);
+    }
+  }
+}
+
 // ---- any-length bind (direct DFT, O(d^2) per pair): covers odd / non power-of-two d -----------
 // smem: tw[d] cplx, a[d], b[d] float, P[d/2+1] cplx
 template <int MODE>

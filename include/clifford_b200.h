@@ -95,6 +95,11 @@ CVB_API int cvb_clifford_phases_to_vector(const float* phases, float phase_scale
 /* bind / unbind family: out[r] = irfft(op(rfft a[r % a_rows], rfft b[r % b_rows])), rows of length d. */
 CVB_API int cvb_vsa_bind(const float* a, const float* b, float* out, long long rows, long long a_rows, long long b_rows, int d,
                  int mode, void* stream);
+/* Fused binding-depth chain (scripts/binding_depth_heatmap.py:25-35): vecs (trials, m_plus_1, d); per trial bind
+ * vecs[:,0] with vecs[:,1..m] in order, unbind ("inv") in reverse order, out[trial] = cos(recovered, vecs[:,0]).
+ * Evaluated in the frequency domain (X0 * prod |Y_j|^2, Parseval): 4 d (m+1) bytes read per trial.  d: power of
+ * two in [32, 16384]. */
+CVB_API int cvb_vsa_depth_chain_cosine(const float* vecs, float* out, long long trials, int m_plus_1, int d, void* stream);
 /* invert (utils/vsa.py:49-53) */
 CVB_API int cvb_vsa_invert(const float* a, float* out, long long rows, int d, void* stream);
 /* permute_vector / unpermute_vector (utils/vsa.py:82-90); perm is int64 (d). */

@@ -34,6 +34,9 @@ def test_depth_cell_matches_oracle_loops(d, m):
     got = harness.binding_depth_cell(vecs.to(DEV)).cpu()
     ref = _depth_cell_oracle(vecs)
     assert float((got - ref).abs().max()) < 5e-5
+    if d & (d - 1) == 0:
+        fused = harness.binding_depth_cell_fused(vecs.to(DEV)).cpu()     # frequency-domain chain, one kernel
+        assert float((fused - ref).abs().max()) < 5e-5
 
 
 def test_rolefiller_cell_matches_oracle_loops():
