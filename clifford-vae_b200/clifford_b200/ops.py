@@ -103,7 +103,6 @@ class CliffordPSRsample(torch.autograd.Function):
     def backward(ctx, grad_z, grad_ent):
         loc_c, kap_c, tp, g, tp_signed, dent = ctx.saved_tensors
         B, d, rows, n_samples, krs, kes, kshape = ctx.meta
-        lib = _lib.load()
         dloc = dkap = None
         if grad_z is not None:
             gz = _f32c(grad_z)
@@ -192,7 +191,6 @@ class CliffordPSLogProb(torch.autograd.Function):
 def clifford_phases_to_vector(phases, scale, rows, d, device):
     """phases (rows, d) * scale -> (rows, 2d); phases None draws U[0,1) on the device."""
     _lib.ensure_device(torch.device(device))
-    lib = _lib.load()
     z = torch.empty(rows, 2 * d, device=device, dtype=torch.float32)
     _CUR_DEV[0] = z.device
     if phases is None:
@@ -209,7 +207,6 @@ def clifford_phases_to_vector(phases, scale, rows, d, device):
 # VSA
 # =================================================================================================
 def _bind_raw(a2, b2, rows, d, mode):
-    lib = _lib.load()
     out = torch.empty(rows, d, device=a2.device, dtype=torch.float32)
     _launch("cvb_vsa_bind", ptr(a2), ptr(b2), ptr(out), rows, a2.shape[0], b2.shape[0], d, mode)
     return out
@@ -364,7 +361,6 @@ class Cosine(torch.autograd.Function):
         a2, b2 = ctx.saved_tensors
         rows, out_shape, ashape, bshape = ctx.meta
         d = out_shape[-1]
-        lib = _lib.load()
         g = _f32c(grad).reshape(rows)
         da = torch.empty(rows, d, device=g.device, dtype=torch.float32) if ctx.needs_input_grad[0] else None
         db = torch.empty(rows, d, device=g.device, dtype=torch.float32) if ctx.needs_input_grad[1] else None
@@ -391,7 +387,6 @@ class Normalize(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad):
         (x2,) = ctx.saved_tensors
-        lib = _lib.load()
         g = _f32c(grad).reshape(x2.shape)
         dx = torch.empty_like(x2)
         _launch("cvb_vsa_normalize_backward", ptr(x2), ptr(g), ptr(dx), x2.shape[0], x2.shape[1])
@@ -401,7 +396,6 @@ class Normalize(torch.autograd.Function):
 def hrr_init(n, d, device):
     dev = torch.device(device)
     _lib.ensure_device(dev)
-    lib = _lib.load()
     out = torch.empty(n, d, device=dev, dtype=torch.float32)
     _CUR_DEV[0] = out.device
     seed, off = _lib.next_rng()
@@ -413,7 +407,6 @@ def hrr_init(n, d, device):
 def unitary_init(n, d, device, eps):
     dev = torch.device(device)
     _lib.ensure_device(dev)
-    lib = _lib.load()
     out = torch.empty(n, d, device=dev, dtype=torch.float32)
     _CUR_DEV[0] = out.device
     seed, off = _lib.next_rng()

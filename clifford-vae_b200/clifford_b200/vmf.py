@@ -79,7 +79,6 @@ class VonMisesFisher(torch.distributions.Distribution):
 
     @property
     def mean(self):
-        from math import sqrt  # noqa: F401
         ratio = _ive_fraction_approx2(torch.tensor(self._m / 2, dtype=torch.float64, device=self.device),
                                       self.scale.to(torch.float64))
         return (self.loc.to(torch.float64) * ratio).type(self.dtype)

@@ -1,5 +1,5 @@
 """Per-op timing helper (CUDA events, ~1 GiB of traffic per launch): python tools/bench_ops.py [bind|clifford|all]"""
-import json, math, os, sys
+import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "clifford-vae_b200")]
 import torch
