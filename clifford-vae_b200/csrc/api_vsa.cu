@@ -6,57 +6,12 @@
 
 using namespace cvb;
 
+extern "C" int cvb_internal_bind_a(const cvb::BindParams* p, int d, int mode, void* stream);
+extern "C" int cvb_internal_bind_b(const cvb::BindParams* p, int d, int mode, void* stream);
 extern "C" int cvb_internal_unitary(float* out, long long n, int d, float eps, unsigned long long seed,
                                     unsigned long long offset, void* stream);
 
 namespace {
-
-template <int LOG2N, int MODE>
-int launch_bind_fast(const BindParams& p, cudaStream_t st) {
-  using Pl = FftPlan<LOG2N>;
-  const cplx* tw = device_twiddles();
-  if (!tw) return kCudaError;
-  // CVB_BIND_VARIANT (experiments): "staged" (TMA-staged rows) or "direct" (plain loads); default by size
-  static const char* variant = getenv("CVB_BIND_VARIANT");
-  const long long work = (p.rows + Pl::GROUPS - 1) / Pl::GROUPS;
-  int grid = 0;
-  // staging mode measured on B200 (tools/bench_ops.py): 0 = plain loads, 2 = a and b through TMA (1 = a only was measured too: no gain)
-  int mode = (LOG2N >= 12) ? 2 : 0;
-  if (variant) mode = (variant[0] == 's') ? 2 : 0;
-  if (!(aligned(p.a, 16) && aligned(p.b, 16))) mode = 0;
-  if (mode == 2) {
-    const size_t smem = bind_v3_smem_bytes<LOG2N, 2>();
-    auto kern = bind_v3_kernel<LOG2N, MODE, 2>;
-    if (int rc = persistent_grid(kern, Pl::THREADS, smem, work, &grid)) return rc;
-    kern<<<grid, Pl::THREADS, smem, st>>>(p, tw);
-    return check_launch("bind_v3_kernel<staged ab>");
-  }
-  const size_t smem = bind_v3_smem_bytes<LOG2N, 0>();
-  auto kern = bind_v3_kernel<LOG2N, MODE, 0>;
-  if (int rc = persistent_grid(kern, Pl::THREADS, smem, work, &grid)) return rc;
-  kern<<<grid, Pl::THREADS, smem, st>>>(p, tw);
-  return check_launch("bind_v3_kernel<direct>");
-}
-
-template <int MODE>
-int dispatch_bind(const BindParams& p, int d, cudaStream_t st) {
-  const bool fast = is_pow2(d) && d >= 32 && d <= 16384 && aligned(p.a, 8) && aligned(p.b, 8) && aligned(p.out, 8);
-  if (fast) {
-    switch (ilog2(d) - 1) {
-#define CVB_CASE(L) case L: return launch_bind_fast<L, MODE>(p, st);
-      CVB_CASE(4) CVB_CASE(5) CVB_CASE(6) CVB_CASE(7) CVB_CASE(8) CVB_CASE(9) CVB_CASE(10) CVB_CASE(11) CVB_CASE(12)
-      CVB_CASE(13)
-#undef CVB_CASE
-    }
-  }
-  const size_t smem = sizeof(cplx) * d + sizeof(float) * (2 * d + 2) + sizeof(cplx) * (d / 2 + 1);
-  CVB_REQUIRE(smem <= 200 * 1024, kUnsupported, "vsa bind: d=%d too large for the direct-DFT path", d);
-  auto kern = bind_generic_kernel<MODE>;
-  int grid = 0;
-  if (int rc = persistent_grid(kern, 256, smem, p.rows, &grid)) return rc;
-  kern<<<grid, 256, smem, st>>>(p, d);
-  return check_launch("bind_generic_kernel");
-}
 
 template <int LOG2N>
 int launch_depth_chain(const float* vecs, float* out, long long trials, int mp1, cudaStream_t st) {
@@ -99,14 +54,8 @@ int cvb_vsa_bind(const float* a, const float* b, float* out, long long rows, lon
   CVB_REQUIRE(a && b && out, kBadArgument, "cvb_vsa_bind: null pointer");
   CVB_REQUIRE(rows > 0 && a_rows > 0 && b_rows > 0 && d >= 1, kBadArgument, "cvb_vsa_bind: bad sizes");
   BindParams p{a, b, out, rows, a_rows, b_rows};
-  cudaStream_t st = (cudaStream_t)stream;
-  switch (mode) {
-    case CVB_BIND_MUL: return dispatch_bind<kBindMul>(p, d, st);
-    case CVB_BIND_MUL_CONJ: return dispatch_bind<kBindMulConj>(p, d, st);
-    case CVB_BIND_DIV: return dispatch_bind<kBindDiv>(p, d, st);
-    case CVB_BIND_DIV_CONJ: return dispatch_bind<kBindDivConj>(p, d, st);
-    case CVB_BIND_NEG_MUL_CONJ: return dispatch_bind<kBindNegMulConj>(p, d, st);
-  }
+  if (mode == CVB_BIND_MUL || mode == CVB_BIND_MUL_CONJ) return cvb_internal_bind_a(&p, d, mode, stream);
+  if (mode == CVB_BIND_DIV || mode == CVB_BIND_DIV_CONJ || mode == CVB_BIND_NEG_MUL_CONJ) return cvb_internal_bind_b(&p, d, mode, stream);
   set_last_error("cvb_vsa_bind: unknown mode %d", mode);
   return kBadArgument;
 }

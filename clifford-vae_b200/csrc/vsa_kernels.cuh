@@ -275,7 +275,7 @@ bind_generic_kernel(const BindParams p, int d) {
 
 // ---- elementwise / reduction VSA helpers --------------------------------------------------------
 // invert (vsa.py:49-53): out[r, j] = a[r, (d - j) mod d]
-__global__ void invert_kernel(const float* __restrict__ a, float* __restrict__ out, long long rows, int d) {
+static __global__ void invert_kernel(const float* __restrict__ a, float* __restrict__ out, long long rows, int d) {
   const long long total = rows * d;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / d;
@@ -285,7 +285,7 @@ __global__ void invert_kernel(const float* __restrict__ a, float* __restrict__ o
 }
 
 // permute (vsa.py:82-84): out[r, j] = v[r, perm[j]];  unpermute (:87-90): out[r, perm[j]] = v[r, j]
-__global__ void permute_kernel(const float* __restrict__ v, const long long* __restrict__ perm, float* __restrict__ out,
+static __global__ void permute_kernel(const float* __restrict__ v, const long long* __restrict__ perm, float* __restrict__ out,
                                long long rows, int d, int inverse) {
   const long long total = rows * d;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -299,7 +299,7 @@ __global__ void permute_kernel(const float* __restrict__ v, const long long* __r
 
 // bundle (vsa.py:75-79), stage 1: partial column sums of a (k, d) stack over row chunks.
 // grid = (ceil(d / 128), chunks); partial[(chunk, j)].
-__global__ void __launch_bounds__(128)
+static __global__ void __launch_bounds__(128)
 bundle_partial_kernel(const float* __restrict__ v, float* __restrict__ partial, long long k, int d,
                       long long rows_per_chunk) {
   const int j = blockIdx.x * 128 + threadIdx.x;
@@ -319,7 +319,7 @@ bundle_partial_kernel(const float* __restrict__ v, float* __restrict__ partial, 
   partial[(long long)blockIdx.y * d + j] = (acc0 + acc1) + (acc2 + acc3);
 }
 // stage 2: out[j] = scale * sum_chunks partial
-__global__ void bundle_final_kernel(const float* __restrict__ partial, float* __restrict__ out, int chunks, int d,
+static __global__ void bundle_final_kernel(const float* __restrict__ partial, float* __restrict__ out, int chunks, int d,
                                     float scale) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= d) return;
@@ -330,7 +330,7 @@ __global__ void bundle_final_kernel(const float* __restrict__ partial, float* __
 
 // similarity (vsa.py:93-96): cosine with each norm clamped at 1e-8.  One warp per output row;
 // operand row = r % operand_rows (broadcast).  Optional backward outputs handled by cosine_bwd_kernel.
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 cosine_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, long long rows,
               long long a_rows, long long b_rows, int d) {
   const int lane = threadIdx.x & 31;
@@ -362,7 +362,7 @@ cosine_kernel(const float* __restrict__ a, const float* __restrict__ b, float* _
 }
 
 // d cos / d a = g (b / (|a||b|) - cos a / |a|^2), same for b; per expanded row (caller reduces broadcasts)
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 cosine_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ gout,
                   float* __restrict__ da, float* __restrict__ db, long long rows, long long a_rows, long long b_rows,
                   int d) {
@@ -395,7 +395,7 @@ cosine_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, cons
 }
 
 // normalize_vectors (vsa.py:39-40): x / max(||x||, 1e-12); backward dx = (g - y (y.g)) / max(||x||, eps)
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 normalize_kernel(const float* __restrict__ x, float* __restrict__ out, long long rows, int d) {
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -409,7 +409,7 @@ normalize_kernel(const float* __restrict__ x, float* __restrict__ out, long long
     for (int i = lane; i < d; i += 32) out[row * (long long)d + i] = xr[i] * inv;
   }
 }
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 normalize_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gout, float* __restrict__ dx,
                      long long rows, int d) {
   const int lane = threadIdx.x & 31;
