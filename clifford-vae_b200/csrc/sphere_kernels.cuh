@@ -52,15 +52,24 @@ __device__ __forceinline__ float gamma_draw_float(float alpha, const PhiloxKey& 
   return x * boost;
 }
 
-// tangent normal for component i (1 <= i <= D-1) of `row`
-__device__ __forceinline__ float tangent_normal(const SphereParams& p, long long row, int i) {
-  if (p.gnoise) return p.gnoise[row * p.g_pitch + p.g_off + i - 1];
+// Four N(0,1) draws for element group q of `row` (elements 4q .. 4q+3): ONE Philox call + two Box-Muller
+// transforms per four elements.  `first` is the tangent index of element 0 of the row (1 for the samplers,
+// whose element 0 is the scalar coordinate; 1 for the uniform sphere too, which has no such slot but uses
+// the same injected layout gnoise[row * g_pitch + g_off + tangent_index - 1]).
+__device__ __forceinline__ void normals4(const SphereParams& p, long long row, int q, int elem_to_tangent, float (&g)[4]) {
+  if (p.gnoise) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int ti = 4 * q + j + elem_to_tangent;          // tangent index (>= 1 is a real draw)
+      g[j] = (ti >= 1 && ti - 1 < p.g_pitch - p.g_off) ? p.gnoise[row * p.g_pitch + p.g_off + ti - 1] : 0.0f;
+    }
+    return;
+  }
   PhiloxKey k = p.key;
   k.stream = 7;
-  const uint4 r = philox_draw(k, (uint64_t)(row * (long long)((p.D + 3) / 4) + (i >> 2)), 0);
-  const int j = i & 3;
-  const float2 nn = (j < 2) ? box_muller(r.x, r.y) : box_muller(r.z, r.w);
-  return (j & 1) ? nn.y : nn.x;
+  const uint4 r = philox_draw(k, (uint64_t)(row * (long long)((p.D + 3) / 4) + q), 0);
+  const float2 a = box_muller(r.x, r.y), b = box_muller(r.z, r.w);
+  g[0] = a.x; g[1] = a.y; g[2] = b.x; g[3] = b.y;
 }
 
 struct WoodDraw { float w, dw_dkappa; };
@@ -137,14 +146,24 @@ sphere_rsample_kernel(const SphereParams p) {
     float* zr = p.z + row * D;
     if (FAMILY == kFamilyUniform) {
       float ss = 0.f;
-      for (int i = lane; i < D; i += 32) {
-        const float g = tangent_normal(p, row, i + 1);
-        zr[i] = g;
-        ss += g * g;
+      for (int q = lane; 4 * q < D; q += 32) {
+        float g[4];
+        normals4(p, row, q, 1, g);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int i = 4 * q + j;
+          if (i < D) { zr[i] = g[j]; ss += g[j] * g[j]; }
+        }
       }
       ss = warp_sum(ss);
       const float inv = 1.0f / (sqrtf(ss) + p.norm_eps);
-      for (int i = lane; i < D; i += 32) zr[i] *= inv;
+      for (int q = lane; 4 * q < D; q += 32) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int i = 4 * q + j;
+          if (i < D) zr[i] *= inv;        // same lane that stashed it
+        }
+      }
       continue;
     }
     const long long prow = row % p.loc_rows;
@@ -176,14 +195,21 @@ sphere_rsample_kernel(const SphereParams p) {
     }
     // pass 1: stash g in the output row; ||g||^2, ||u||^2, sum g u
     float sgg = 0.f, suu = 0.f, sgu = 0.f;
-    for (int i = lane; i < D; i += 32) {
-      const float u = (i == 0 ? 1.0f : 0.0f) - lr[i];
-      suu += u * u;
-      if (i > 0) {
-        const float g = tangent_normal(p, row, i);
-        zr[i] = g;
-        sgg += g * g;
-        sgu += g * u;
+    for (int q = lane; 4 * q < D; q += 32) {
+      float g[4];
+      normals4(p, row, q, 0, g);           // element i has tangent index i (element 0 = scalar coordinate)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = 4 * q + j;
+        if (i < D) {
+          const float u = (i == 0 ? 1.0f : 0.0f) - lr[i];
+          suu += u * u;
+          if (i > 0) {
+            zr[i] = g[j];
+            sgg += g[j] * g[j];
+            sgu += g[j] * u;
+          }
+        }
       }
     }
     sgg = warp_sum(sgg); suu = warp_sum(suu); sgu = warp_sum(sgu);
@@ -194,10 +220,16 @@ sphere_rsample_kernel(const SphereParams p) {
     const float u0 = 1.0f - lr[0];
     const float ydotu = (t * u0 + cg * sgu) * iu;               // y . u_hat
     // pass 2: z = y - 2 (y.u_hat) u_hat
-    for (int i = lane; i < D; i += 32) {
-      const float u = ((i == 0 ? 1.0f : 0.0f) - lr[i]) * iu;
-      const float y = (i == 0) ? t : cg * zr[i];
-      zr[i] = y - 2.0f * ydotu * u;
+    for (int q = lane; 4 * q < D; q += 32) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = 4 * q + j;
+        if (i < D) {
+          const float u = ((i == 0 ? 1.0f : 0.0f) - lr[i]) * iu;
+          const float y = (i == 0) ? t : cg * zr[i];      // stashed by this same lane in pass 1
+          zr[i] = y - 2.0f * ydotu * u;
+        }
+      }
     }
     if (p.save && lane == 0) { p.save[2 * row] = save0; p.save[2 * row + 1] = save1; }
   }
@@ -227,17 +259,24 @@ sphere_rsample_bwd_kernel(const SphereParams p) {
     }
     // pass 1: five reductions; stash g in the dloc row
     float sgg = 0.f, suu = 0.f, sgu = 0.f, sug = 0.f, szg = 0.f;
-    for (int i = lane; i < D; i += 32) {
-      const float u = (i == 0 ? 1.0f : 0.0f) - lr[i];
-      const float gzi = gz[i];
-      suu += u * u;
-      sug += u * gzi;
-      if (i > 0) {
-        const float g = tangent_normal(p, row, i);
-        dl[i] = g;
-        sgg += g * g;
-        sgu += g * u;
-        szg += gzi * g;
+    for (int q = lane; 4 * q < D; q += 32) {
+      float g[4];
+      normals4(p, row, q, 0, g);           // replays the forward's draws from the counter-based generator
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = 4 * q + j;
+        if (i < D) {
+          const float u = (i == 0 ? 1.0f : 0.0f) - lr[i];
+          const float gzi = gz[i];
+          suu += u * u;
+          sug += u * gzi;
+          if (i > 0) {
+            dl[i] = g[j];
+            sgg += g[j] * g[j];
+            sgu += g[j] * u;
+            szg += gzi * g[j];
+          }
+        }
       }
     }
     sgg = warp_sum(sgg); suu = warp_sum(suu); sgu = warp_sum(sgu); sug = warp_sum(sug); szg = warp_sum(szg);
@@ -257,10 +296,16 @@ sphere_rsample_bwd_kernel(const SphereParams p) {
     const float gt = gy0 + dsq * s_gv;
     // dloc_i = -gu_i,  gu_i = -2 (a y_i + b gz_i)/ne + u_i 4ab / (un ne)
     const float k2 = (un > 0.f) ? 4.0f * a * b / (un * ne) : 0.0f;
-    for (int i = lane; i < D; i += 32) {
-      const float u = (i == 0 ? 1.0f : 0.0f) - lr[i];
-      const float y = (i == 0) ? t : cg * dl[i];
-      dl[i] = 2.0f * (a * y + b * gz[i]) / ne - u * k2;
+    for (int q = lane; 4 * q < D; q += 32) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = 4 * q + j;
+        if (i < D) {
+          const float u = (i == 0 ? 1.0f : 0.0f) - lr[i];
+          const float y = (i == 0) ? t : cg * dl[i];
+          dl[i] = 2.0f * (a * y + b * gz[i]) / ne - u * k2;
+        }
+      }
     }
     if (lane == 0) {
       float dk;
