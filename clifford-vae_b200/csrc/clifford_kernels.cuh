@@ -278,6 +278,32 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw) {
           xch[pad16(k)] = x;
         }
       }
+    } else if (MODE == kUniformRng || MODE == kUnitaryRng) {
+      // one uniform phase per circle: one Philox call serves four circles (one 32-bit word each; for the
+      // unitary initialiser the top bit is the sign draw and the next 24 bits the magnitude draw)
+      PhiloxKey pkey = p.key;
+      pkey.stream = 9;
+      const uint64_t quad_base = (uint64_t)row * (uint64_t)(d / 4) + (uint64_t)t * (E / 4);
+#pragma unroll 2
+      for (int e = 0; e < E; e += 4) {
+        const uint4 r = philox_draw(pkey, quad_base + (e >> 2), 0);
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = t + (e + j) * T;
+          float th;
+          if (MODE == kUniformRng) {
+            th = 6.283185307179586f * u01_open1(w[j]) - 3.14159265358979f;        // same law as 2 pi U, kept in [-pi, pi)
+          } else {
+            const float a = (float)((w[j] >> 7) & 0xFFFFFFu) * 0x1p-24f;
+            const float sg = (w[j] & 0x80000000u) ? -1.0f : 1.0f;
+            th = sg * 3.14159265358979f * (p.phase_scale + a * (1.0f - 2.0f * p.phase_scale));
+          }
+          cplx x = make_float2(1.0f, 0.0f);
+          if (valid && k != 0) __sincosf(th, &x.y, &x.x);
+          xch[pad16(k)] = x;
+        }
+      }
     } else {
 #pragma unroll 4
       for (int e = 0; e < E; ++e) {
