@@ -321,7 +321,50 @@ def main():
     gen_vsa(rv)
     gen_special()
     gen_ks(rc, VMF)
+    gen_vae_step()
+
+
+def gen_vae_step():
+    """One training-loss evaluation of the reference's MLP VAE (mnist/mlp_vae.py:19-143) per latent family, with
+    seeded weights (torch.manual_seed -> deterministic nn.Linear / xavier init under the same torch version),
+    seeded synthetic binarised inputs and RECORDED latent draws: loss terms and parameter gradients."""
+    sys.path.insert(0, REF)
+    sys.path.insert(0, os.path.join(REF, "vmf"))
+    from mnist.mlp_vae import MLPVAE, vae_loss
+    out = {}
+    for dist_name, z_dim in (("clifford", 16), ("powerspherical", 9), ("vmf", 9)):
+        torch.manual_seed(20240 + z_dim)
+        model = MLPVAE(h_dim=128, z_dim=z_dim, distribution=dist_name)
+        x = (torch.rand(8, 1, 28, 28) > torch.rand(8, 1, 28, 28)).float()
+        with Recorder() as r:
+            res = vae_loss(model, x, beta=1.0, return_dict=True)
+        res["total"].backward()
+        c = {"x": np_(x), "recon": np_(res["recon"]), "kl": np_(res["kl"]), "total": np_(res["total"]),
+             "entropy": np_(res["entropy"])}
+        if dist_name == "vmf":
+            c["e_rounds"] = np.stack([np_(e) for e in r.get("beta_sample")])
+            c["u_rounds"] = np.stack([np_(u) for u in r.get("uniform_sample")])
+            c["g"] = np_(r.get("normal_sample")[0])
+        else:
+            c["tprime"] = np_(r.get("beta_rsample")[0])
+            g = r.get("randn")[0]
+            c["g"] = np_(g.squeeze(-1) if dist_name == "clifford" else g)
+        for name, prm in model.named_parameters():
+            c["grad_norm/" + name] = np.float64(prm.grad.norm().item())
+        c["grad/fc_scale.weight"] = np_(model.fc_scale.weight.grad)
+        c["grad/fc_mean.bias"] = np_(model.fc_mean.bias.grad)
+        c["grad/decoder.0.bias"] = np_(model.decoder[0].bias.grad)
+        c["param_checksum"] = np.float64(sum(p.double().sum().item() for p in model.parameters()))
+        for k, v in c.items():
+            out[f"{dist_name}/{k}"] = v
+    np.savez_compressed(os.path.join(OUT, "vae_step.npz"), **out)
+    print("vae_step.npz", len(out), "arrays")
 
 
 if __name__ == "__main__":
-    main()
+    if os.environ.get("GEN_ONLY") == "vae_step":      # regenerate just this fixture
+        os.makedirs(OUT, exist_ok=True)
+        _import_reference()
+        gen_vae_step()
+    else:
+        main()
