@@ -31,7 +31,8 @@ _SIGNATURES = {
     "cvb_launch_count": ([], _ll),
     "cvb_clifford_ps_rsample": ([_f, _f, _ll, _i, _ll, _f, _f, _ull, _ull, _f, _f, _f, _f, _f, _ll, _i, _f], _i),
     "cvb_clifford_ps_rsample_backward": ([_f, _f, _f, _ll, _i, _ll, _f, _f, _f, _f, _f, _ll, _i, _f], _i),
-    "cvb_clifford_ps_log_prob": ([_f, _f, _f, _ll, _i, _ll, _f, _f, _f, _ll, _i, _f], _i),
+    "cvb_clifford_ps_log_prob": ([_f, _f, _f, _ll, _i, _ll, _f, _f, _f, _f, _ll, _i, _f], _i),
+    "cvb_clifford_spectrum_adjoint": ([_f, _f, _ll, _i, _f], _i),
     "cvb_ps_entropy_kl": ([_f, _ll, _i, _ll, _i, _db, _i, _db, _f, _f, _f, _f], _i),
     "cvb_clifford_phases_to_vector": ([_f, _fl, _ull, _ull, _f, _ll, _i, _f], _i),
     "cvb_vsa_bind": ([_f, _f, _f, _ll, _ll, _ll, _i, _i, _f], _i),

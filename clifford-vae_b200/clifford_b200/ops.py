@@ -154,7 +154,8 @@ class PSEntropy(torch.autograd.Function):
 
 
 class CliffordPSLogProb(torch.autograd.Function):
-    """log_prob (rows,) of value (rows, 2d) under (loc (B,d), kappa (B,1)|(B,d)); rows = S*B."""
+    """log_prob (rows,) of value (rows, 2d) under (loc (B,d), kappa (B,1)|(B,d)); rows = S*B.
+    Differentiable in loc, kappa and value (the value gradient goes through the adjoint of the truncated real FFT)."""
 
     @staticmethod
     def forward(ctx, value, loc, kappa):
@@ -165,27 +166,32 @@ class CliffordPSLogProb(torch.autograd.Function):
         kap_c, krs, kes = _kappa_layout(kappa, d)
         lp = torch.empty(rows, device=dev, dtype=torch.float32)
         need = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
-        if ctx.needs_input_grad[0]:
-            raise NotImplementedError(
-                "clifford log_prob: gradient with respect to `value` is not implemented (the reference only "
-                "evaluates log_prob under no_grad, mnist/mlp_vae.py:181); detach the value")
         dl = torch.empty(rows, d, device=dev, dtype=torch.float32) if need else None
         dk = torch.empty((rows,) if kes == 0 else (rows, d), device=dev, dtype=torch.float32) if need else None
+        dF = torch.empty(rows, d, 2, device=dev, dtype=torch.float32) if ctx.needs_input_grad[0] else None
         _launch("cvb_clifford_ps_log_prob", ptr(val_c), ptr(loc_c), ptr(kap_c), krs, kes, B, ptr(lp), ptr(dl), ptr(dk),
-                                           rows, d)
-        ctx.save_for_backward(dl, dk)
+                ptr(dF), rows, d)
+        ctx.save_for_backward(dl, dk, dF)
         ctx.meta = (B, d, rows, kes, tuple(kappa.shape))
         return lp
 
     @staticmethod
     def backward(ctx, grad):
-        dl, dk = ctx.saved_tensors
+        dl, dk, dF = ctx.saved_tensors
         B, d, rows, kes, kshape = ctx.meta
         S = rows // B
         g = grad.reshape(rows)
-        dloc = (g[:, None] * dl).view(S, B, d).sum(0)
-        dkap = (g * dk).view(S, B).sum(0) if kes == 0 else (g[:, None] * dk).view(S, B, d).sum(0)
-        return None, dloc, dkap.reshape(kshape)
+        dval = dloc = dkap = None
+        if dF is not None:
+            _CUR_DEV[0] = g.device
+            _EMPTY[0] = rows == 0
+            h = (g[:, None, None] * dF).contiguous()
+            dval = torch.empty(rows, 2 * d, device=g.device, dtype=torch.float32)
+            _launch("cvb_clifford_spectrum_adjoint", ptr(h), ptr(dval), rows, d)
+        if dl is not None:
+            dloc = (g[:, None] * dl).view(S, B, d).sum(0)
+            dkap = ((g * dk).view(S, B).sum(0) if kes == 0 else (g[:, None] * dk).view(S, B, d).sum(0)).reshape(kshape)
+        return dval, dloc, dkap
 
 
 def clifford_phases_to_vector(phases, scale, rows, d, device):

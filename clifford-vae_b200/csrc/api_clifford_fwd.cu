@@ -82,6 +82,16 @@ int cvb_clifford_phases_to_vector(const float* phases, float phase_scale, unsign
   return phases ? dispatch_fwd<kPhases, true>(p, st) : dispatch_fwd<kUniformRng, true>(p, st);
 }
 
+// adjoint of "first d bins of the real FFT of a length-2d row": grad_value (rows, 2d) from H (rows, d) complex
+int cvb_clifford_spectrum_adjoint(const float* h_complex, float* grad_value, long long rows, int d, void* stream) {
+  CVB_REQUIRE(h_complex && grad_value && rows > 0 && d >= 1, kBadArgument, "cvb_clifford_spectrum_adjoint: bad arguments");
+  CliffordFwdParams p{};
+  // X_k = (n/2) H_k so that irfft's 1/n leaves H_k / 2 (and Re H_0 after the DC doubling)
+  p.loc_rows = 1; p.phases = h_complex; p.phase_scale = (float)d; p.z = grad_value; p.rows = rows; p.d = d; p.n = 2 * d;
+  p.spectrum_input = 1;
+  return dispatch_fwd<kSpectrum, true>(p, (cudaStream_t)stream);
+}
+
 // used by api_vsa.cu
 int cvb_internal_unitary(float* out, long long n, int d, float eps, unsigned long long seed, unsigned long long offset,
                          void* stream) {

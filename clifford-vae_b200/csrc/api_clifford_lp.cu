@@ -50,14 +50,14 @@ extern "C" {
 
 int cvb_clifford_ps_log_prob(const float* value, const float* loc, const float* kappa, long long kappa_row_stride,
                              int kappa_el_stride, long long loc_rows, float* log_prob, float* dlp_dloc,
-                             float* dlp_dkappa, long long rows, int d, void* stream) {
+                             float* dlp_dkappa, float* dlp_dF, long long rows, int d, void* stream) {
   CVB_REQUIRE(value && loc && kappa && log_prob, kBadArgument, "cvb_clifford_ps_log_prob: null pointer");
   CVB_REQUIRE(rows > 0 && d >= 1 && loc_rows > 0, kBadArgument, "cvb_clifford_ps_log_prob: bad sizes");
   CVB_REQUIRE((dlp_dloc == nullptr) == (dlp_dkappa == nullptr), kBadArgument, "cvb_clifford_ps_log_prob: give both derivative outputs or neither");
   CliffordLogProbParams p{};
   p.value = value; p.loc = loc; p.kappa = kappa; p.kappa_row_stride = kappa_row_stride;
   p.kappa_el_stride = kappa_el_stride; p.loc_rows = (int)loc_rows; p.log_prob = log_prob; p.dlp_dloc = dlp_dloc;
-  p.dlp_dkappa = dlp_dkappa; p.rows = rows; p.d = d;
+  p.dlp_dkappa = dlp_dkappa; p.dlp_dF = dlp_dF; p.rows = rows; p.d = d;
   cudaStream_t st = (cudaStream_t)stream;
   return kappa_el_stride == 0 ? dispatch_lp<true>(p, st) : dispatch_lp<false>(p, st);
 }

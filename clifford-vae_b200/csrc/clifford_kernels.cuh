@@ -24,6 +24,7 @@ enum CliffordMode : int {
   kPhases = 2,       // theta = phase_scale * phases[row, k]   (uniform prior with injected u; unitary init)
   kUniformRng = 3,   // theta = 2 pi U
   kUnitaryRng = 4,   // theta = sign * pi * (eps + a (1 - 2 eps))   (utils/vsa.py:15-36)
+  kSpectrum = 5,     // X_k = phase_scale * H[row, k] given as complex (rows, d): adjoint of the truncated real FFT
 };
 
 struct CliffordFwdParams {
@@ -45,6 +46,7 @@ struct CliffordFwdParams {
   int d;                   // phases per row (row pitch of loc / draws / phases)
   int n;                   // output length: 2d for the torus (fast path); any n >= 2 on the direct-DFT path
   int staged;              // 1: input rows are 16-byte aligned -> stage them with cp.async.bulk
+  int spectrum_input;      // kSpectrum: `phases` holds (rows, d) complex values
   PhiloxKey key;
 };
 
@@ -109,7 +111,7 @@ __device__ __forceinline__ RowSrc global_row_src(const CliffordFwdParams& p, lon
   s.loc = p.loc ? p.loc + prow * p.d : nullptr;
   s.tprime = p.tprime ? p.tprime + row * p.d : nullptr;
   s.gnoise = p.gnoise ? p.gnoise + row * p.d : nullptr;
-  s.phases = p.phases ? p.phases + row * p.d : nullptr;
+  s.phases = p.phases ? p.phases + row * p.d * (p.spectrum_input ? 2 : 1) : nullptr;
   return s;
 }
 
@@ -134,6 +136,11 @@ __device__ __forceinline__ bool clifford_phasor(const CliffordFwdParams& p, cons
     return true;
   }
   float th;
+  if (MODE == kSpectrum) {
+    const float2 hv = reinterpret_cast<const float2*>(src.phases)[k];
+    out = make_float2(p.phase_scale * hv.x, p.phase_scale * hv.y);
+    return true;
+  }
   if (MODE == kPhases) {
     th = p.phase_scale * src.phases[k];
     sincosf(th, &out.y, &out.x);
@@ -309,11 +316,20 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw) {
       for (int e = 0; e < E; ++e) {
         const int k = t + e * T;
         cplx x = make_float2(1.0f, 0.0f);
-        if (valid && k != 0) clifford_phasor<MODE, ROWK>(p, src, row, prow, k, gm, x);
+        if (MODE == kSpectrum) {
+          // adjoint of F_k = sum_j v_j e^{-2 pi i jk/n}, k < d: grad_v = n irfft(X), X_0 = Re H_0, X_k = H_k / 2, X_d = 0
+          x = make_float2(0.f, 0.f);
+          if (valid) {
+            clifford_phasor<MODE, ROWK>(p, src, row, prow, k, gm, x);
+            if (k == 0) x = make_float2(2.0f * x.x, 0.0f);
+          }
+        } else if (valid && k != 0) {
+          clifford_phasor<MODE, ROWK>(p, src, row, prow, k, gm, x);
+        }
         xch[pad16(k)] = x;
       }
     }
-    if (t == 0) xch[pad16(d)] = make_float2(1.0f, 0.0f);
+    if (t == 0) xch[pad16(d)] = make_float2(MODE == kSpectrum ? 0.0f : 1.0f, 0.0f);
     group_sync<LOG2N>();
     if (MODE == kPsRng) {
       // phase 1b: rejected proposals, spread evenly over the group's threads
@@ -450,6 +466,7 @@ struct CliffordLogProbParams {
   float* log_prob;         // (rows) out
   float* dlp_dloc;         // optional (rows, d): d log_prob / d loc_k
   float* dlp_dkappa;       // optional; ROWK: (rows), else (rows, d)
+  float* dlp_dF;           // optional (rows, d) complex: d log_prob / d (Re F_k, Im F_k), for the gradient w.r.t. value
   long long rows;
   int d;
 };
@@ -478,6 +495,15 @@ __device__ __forceinline__ void clifford_lp_element(const CliffordLogProbParams&
   const float dot = fminf(fmaxf(dot_raw, -1.0f + kEps), 1.0f - kEps);
   const float l1p = log1pf(dot);
   acc += logc + kap * l1p;
+  if (p.dlp_dF) {
+    // d/dF of kappa log1p(u_hat(F) . m), m = (cos loc, sin loc): kappa / (1 + dot) * (m - dot u_hat) / |F|
+    float2 gF = make_float2(0.f, 0.f);
+    if (mag2 > 0.f && dot_raw >= -1.0f + kEps && dot_raw <= 1.0f - kEps) {
+      const float c = kap / (1.0f + dot) * rsqrtf(mag2);
+      gF = make_float2(c * (cl - dot * ca), c * (sl - dot * sa));
+    }
+    reinterpret_cast<float2*>(p.dlp_dF)[row * p.d + k] = gF;
+  }
   if (p.dlp_dloc) {
     // d dot / d loc = -sin(loc) cos(a) + cos(loc) sin(a); zero where the clamp is active
     const bool inside = (dot_raw >= -1.0f + kEps) && (dot_raw <= 1.0f - kEps);
@@ -608,6 +634,11 @@ clifford_fwd_generic_kernel(const CliffordFwdParams p) {
       if (!clifford_phasor<MODE, ROWK>(p, src, row, prow, k, gm, x)) x = clifford_phasor_retry<ROWK>(p, src, row, prow, k, gm);
       X[k] = x;
     }
+    float dc = 1.0f, nyq = 1.0f;
+    if (MODE == kSpectrum) {             // X_0 = 2 scale Re H_0 (so that the common factor 2 below halves it), X_d = 0
+      dc = p.phase_scale * reinterpret_cast<const float2*>(src.phases)[0].x;
+      nyq = 0.0f;
+    }
     __syncthreads();
     const float inv_n = 1.0f / (float)n;
     for (int j = threadIdx.x; j < n; j += blockDim.x) {
@@ -619,8 +650,8 @@ clifford_fwd_generic_kernel(const CliffordFwdParams p) {
         const cplx w = tw[m], x = X[k];
         acc += (double)(x.x * w.x - x.y * w.y);      // Re(X_k e^{+2 pi i jk/n})
       }
-      float base = 1.0f;
-      if ((n & 1) == 0) base += (j & 1) ? -1.0f : 1.0f;
+      float base = (MODE == kSpectrum) ? 2.0f * dc : dc;
+      if ((n & 1) == 0) base += (j & 1) ? -nyq : nyq;
       p.z[row * n + j] = inv_n * (base + 2.0f * (float)acc);
     }
     if (PS && ROWK && threadIdx.x == 0 && (p.entropy || p.kl || p.dentropy)) clifford_row_entropy(p, row, kap_row);

@@ -70,10 +70,14 @@ CVB_API int cvb_clifford_ps_rsample_backward(const float* grad_z, const float* l
                                      float* dkappa, long long rows, int d, void* stream);
 
 /* CliffordPowerSphericalDistribution.log_prob (dists/clifford.py:310-316, :198-202).  value (rows, 2d)
- * -> log_prob (rows).  Optional derivative outputs: dlp_dloc (rows, d), dlp_dkappa ((rows) or (rows, d)). */
+ * -> log_prob (rows).  Optional derivative outputs: dlp_dloc (rows, d) and dlp_dkappa ((rows) or (rows, d)) (give both
+ * or neither), and dlp_dF (rows, d) complex = d log_prob / d (Re, Im) of the value's Fourier bin k. */
 CVB_API int cvb_clifford_ps_log_prob(const float* value, const float* loc, const float* kappa, long long kappa_row_stride,
                              int kappa_el_stride, long long loc_rows, float* log_prob, float* dlp_dloc,
-                             float* dlp_dkappa, long long rows, int d, void* stream);
+                             float* dlp_dkappa, float* dlp_dF, long long rows, int d, void* stream);
+/* Adjoint of value (rows, 2d) -> first d bins of its real FFT: grad_value = Re sum_k H_k e^{+2 pi i jk/(2d)} for
+ * H (rows, d) complex (the autograd of fft(value)[..., :d] in dists/clifford.py:311). */
+CVB_API int cvb_clifford_spectrum_adjoint(const float* h_complex, float* grad_value, long long rows, int d, void* stream);
 
 /* Power-spherical entropy / KL-to-uniform and dH/dkappa without sampling.
  * torus != 0: dists/clifford.py:318-327 -- sum over circles k >= 1 of the dim-2 entropy, kl = -H + (d-1) ln 2pi.

@@ -242,3 +242,27 @@ def test_api_shapes_dtypes_and_noncontiguous_inputs():
     assert rel_err(qf.entropy().cpu(), O.clifford_ps_entropy(kap_full.cpu())) < 1e-5
     # prior sampling with a 2-d sample shape (cnn/fashion_train.py:550)
     assert CliffordTorusUniform(d, device=DEV).rsample((3, 7)).shape == (3, 7, 2 * d)
+
+
+@pytest.mark.parametrize("B,d", [(5, 64), (3, 1024), (4, 20), (2, 16)])
+def test_log_prob_gradient_wrt_value_vs_oracle_autograd(B, d):
+    """d log_prob / d value (through the adjoint of the truncated real FFT) vs autograd of the oracle."""
+    from dists.clifford import CliffordPowerSphericalDistribution
+    from oracle import latent_oracle as O
+    torch.manual_seed(B * d)
+    loc = torch.randn(B, d)
+    kap = torch.rand(B, 1) * 4 + 0.2
+    # a value near the torus (a sample plus noise) keeps 1 + dot away from the ill-conditioned corner
+    tp = torch.distributions.Beta(0.5 + kap.expand(B, d), torch.tensor(0.5)).sample().clamp(1e-3, 1 - 1e-3)
+    z = O.clifford_ps_rsample(loc, kap, tp, torch.randn(B, d))
+    value = (z + 0.02 * torch.randn(B, 2 * d) / (2 * d) ** 0.5)
+    w = torch.randn(B)
+    vc = value.clone().requires_grad_()
+    lpo = O.clifford_ps_log_prob(vc, loc, kap.expand(B, d))
+    (go,) = torch.autograd.grad((lpo * w).sum(), [vc])
+    vg = value.to(DEV).requires_grad_()
+    q = CliffordPowerSphericalDistribution(loc.to(DEV), kap.to(DEV))
+    lpg = q.log_prob(vg)
+    (gg,) = torch.autograd.grad((lpg * w.to(DEV)).sum(), [vg])
+    assert rel_err(lpg.detach().cpu(), lpo.detach()) < 2e-5
+    assert rel_err(gg.cpu(), go) < 2e-4
