@@ -16,6 +16,7 @@ from . import ops
 class HypersphericalUniform(torch.distributions.Distribution):
     """Uniform on S^dim (dim = m - 1), reference hyperspherical_uniform.py:5-54."""
 
+    arg_constraints = {}
     support = torch.distributions.constraints.real
     has_rsample = False
     _mean_carrier_measure = 0
