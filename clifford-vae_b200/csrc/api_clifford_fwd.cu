@@ -20,7 +20,10 @@ int launch_fwd_fast(const CliffordFwdParams& p, cudaStream_t st) {
   int grid = 0;
   const long long work = (p.rows + Pl::GROUPS - 1) / Pl::GROUPS;
   if (int rc = persistent_grid(kern, Pl::THREADS, smem, work, &grid)) return rc;
-  kern<<<grid, Pl::THREADS, smem, st>>>(p, tw);
+  CliffordFwdParams q = p;
+  static const bool static_sched = getenv("CVB_STATIC_SCHEDULE") != nullptr;
+  q.sched = (!static_sched && work > grid) ? next_sched_slot() : nullptr;   // dynamic rows only when CTAs loop
+  kern<<<grid, Pl::THREADS, smem, st>>>(q, tw);
   return check_launch("clifford_fwd_kernel");
 }
 

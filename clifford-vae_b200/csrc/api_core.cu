@@ -15,6 +15,9 @@ std::atomic<long long> g_launch_count{0};
 static std::mutex g_mu;
 static const cplx* g_tw[64] = {nullptr};
 static int g_sms[64] = {0};
+static int* g_sched[64] = {nullptr};
+static std::atomic<unsigned> g_sched_seq{0};
+constexpr int kSchedSlots = 64;
 static std::unordered_map<const void*, int> g_occ;
 
 void set_last_error(const char* fmt, ...) {
@@ -31,6 +34,12 @@ const cplx* device_twiddles() {
     return nullptr;
   }
   return g_tw[dev];
+}
+
+int* next_sched_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || !g_sched[dev]) return nullptr;
+  return g_sched[dev] + 2 * (g_sched_seq.fetch_add(1, std::memory_order_relaxed) % kSchedSlots);
 }
 
 int sm_count() {
@@ -90,6 +99,10 @@ int cvb_init(void) {
   cplx* dptr = nullptr;
   CVB_CUDA(cudaMalloc(&dptr, sizeof(cplx) * kTwiddleEntries));
   CVB_CUDA(cudaMemcpy(dptr, host.data(), sizeof(cplx) * kTwiddleEntries, cudaMemcpyHostToDevice));
+  int* sched = nullptr;
+  CVB_CUDA(cudaMalloc(&sched, sizeof(int) * 2 * kSchedSlots));
+  CVB_CUDA(cudaMemset(sched, 0, sizeof(int) * 2 * kSchedSlots));
+  g_sched[dev] = sched;
   g_tw[dev] = dptr;
   g_sms[dev] = prop.multiProcessorCount;
   return kOk;

@@ -47,6 +47,7 @@ struct CliffordFwdParams {
   int n;                   // output length: 2d for the torus (fast path); any n >= 2 on the direct-DFT path
   int staged;              // 1: input rows are 16-byte aligned -> stage them with cp.async.bulk
   int spectrum_input;      // kSpectrum: `phases` holds (rows, d) complex values
+  int* sched;              // [0] next-row counter, [1] finished-group counter (both zero between launches); null = static
   PhiloxKey key;
 };
 
@@ -237,14 +238,20 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw) {
       clifford_row_entropy(p, row, __ldg(p.kappa + (row % p.loc_rows) * p.kappa_row_stride));
   }
 
+  // Row schedule.  Static: group g of CTA b takes rows b*G + g + i*stride.  Dynamic (sched != null, groups of
+  // >= 32 threads): after its first row a group fetches the next unprocessed row from a global counter, which
+  // removes the tail imbalance when rows / (CTAs * G) is small (4096 rows over 740 CTAs: 5 vs 6 rows each).
+  const bool dynamic = (T >= 32) && p.sched != nullptr;
   uint32_t parity = 0;
-  for (long long base = (long long)blockIdx.x * G; base < p.rows; base += stride, parity ^= 1u) {
-    const long long row = base + group;
+  long long row = first_row;
+  const long long loop_end = dynamic ? p.rows : p.rows + (long long)group;   // static: keep trip counts CTA-uniform
+  for (; row < loop_end; parity ^= 1u) {
     const bool valid = row < p.rows;
     const long long prow = valid ? (row % p.loc_rows) : 0;
     float kap_row = 1.0f;
     if (PS && valid) kap_row = __ldg(p.kappa + prow * p.kappa_row_stride);
     HalfAngle gm(kap_row + kEps);
+    if (dynamic && t == 0) qcount[1] = atomicAdd(p.sched, 1);              // broadcast through smem after the barrier
     RowSrc src;
     if (staged) {
       src.loc = stage; src.tprime = stage + d; src.gnoise = stage + 2 * d; src.phases = stage;
@@ -253,6 +260,7 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw) {
       src = global_row_src(p, valid ? row : 0, prow);
     }
     group_sync<LOG2N>();                       // the previous row's exchange-buffer readers are done
+    const long long next_row = dynamic ? (long long)qcount[1] + stride : row + stride;
     // phase 1: phasors of the half spectrum into the exchange buffer (lightly unrolled: small code, some ILP)
     if (MODE == kPsRng) {
       // device RNG: one Philox call + one Box-Muller per PAIR of bins (one envelope proposal each);
@@ -343,7 +351,7 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw) {
       if (t == 0) *qcount = 0;
     }
     // every thread is done with the staged inputs: fetch the next row's while this one is transformed
-    if (staged && t == 0 && row + stride < p.rows) issue(row + stride);
+    if (staged && t == 0 && next_row < p.rows) issue(next_row);
     // phase 2: Hermitian half spectrum -> packed complex spectrum -> inverse FFT -> real row
     cplx v[E];
     c2r_pretangle_load<LOG2N>(v, xch, t, tw);
@@ -353,6 +361,11 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw) {
 #pragma unroll
       for (int e = 0; e < E; ++e) stg_stream2(zr + t + e * T, v[e]);
     }
+    row = next_row;
+  }
+  if (dynamic && t == 0) {
+    // the last group to finish re-arms the counters for the next launch that uses this slot
+    if (atomicAdd(p.sched + 1, 1) == (int)stride - 1) { p.sched[0] = 0; p.sched[1] = 0; }
   }
 }
 

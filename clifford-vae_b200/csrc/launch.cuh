@@ -11,6 +11,9 @@ void set_last_error(const char* fmt, ...);
 // Device twiddle table for the current device (nullptr + error set if cvb_init() was not called).
 const cplx* device_twiddles();
 int sm_count();
+// A zero-initialised (next-row, finished-groups) counter pair for one dynamically scheduled launch; a ring of 64
+// pairs lets launches on different streams overlap (each kernel re-arms its pair when its last group finishes).
+int* next_sched_slot();
 extern std::atomic<long long> g_launch_count;
 
 #define CVB_REQUIRE(cond, code, ...)          \

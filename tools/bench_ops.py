@@ -55,7 +55,7 @@ if what in ("clifford", "all"):
         gb = B * (20 * d + 8) / (ms * 1e-3) / 1e9
         print(f"clifford bwd rng   B={B:7d} d={d:5d} {ms:8.3f} ms {B/(ms*1e-3):.3e} rows/s {gb:7.1f} GB/s {100*gb/PEAK:5.1f}% (20d+8 B/row)")
         lp = torch.empty(B, device=dev)
-        ms = timeit(lambda: lib.cvb_clifford_ps_log_prob(z.data_ptr(), loc.data_ptr(), kap.data_ptr(), 1, 0, B, lp.data_ptr(), None, None, B, d, st))
+        ms = timeit(lambda: lib.cvb_clifford_ps_log_prob(z.data_ptr(), loc.data_ptr(), kap.data_ptr(), 1, 0, B, lp.data_ptr(), None, None, None, B, d, st))
         gb = B * (12 * d + 8) / (ms * 1e-3) / 1e9
         print(f"clifford log_prob  B={B:7d} d={d:5d} {ms:8.3f} ms {B/(ms*1e-3):.3e} rows/s {gb:7.1f} GB/s {100*gb/PEAK:5.1f}%")
         del loc, z, tp, g, gz, dloc, tps
