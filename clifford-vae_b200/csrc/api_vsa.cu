@@ -53,7 +53,7 @@ int cvb_vsa_bind(const float* a, const float* b, float* out, long long rows, lon
                  int mode, void* stream) {
   CVB_REQUIRE(a && b && out, kBadArgument, "cvb_vsa_bind: null pointer");
   CVB_REQUIRE(rows > 0 && a_rows > 0 && b_rows > 0 && d >= 1, kBadArgument, "cvb_vsa_bind: bad sizes");
-  BindParams p{a, b, out, rows, a_rows, b_rows};
+  BindParams p{a, b, out, rows, a_rows, b_rows, nullptr};
   if (mode == CVB_BIND_MUL || mode == CVB_BIND_MUL_CONJ) return cvb_internal_bind_a(&p, d, mode, stream);
   if (mode == CVB_BIND_DIV || mode == CVB_BIND_DIV_CONJ || mode == CVB_BIND_NEG_MUL_CONJ) return cvb_internal_bind_b(&p, d, mode, stream);
   set_last_error("cvb_vsa_bind: unknown mode %d", mode);

@@ -8,7 +8,8 @@
 namespace cvb {
 
 template <int LOG2N, int MODE>
-int launch_bind_fast(const BindParams& p, cudaStream_t st) {
+int launch_bind_fast(const BindParams& p_in, cudaStream_t st) {
+  BindParams p = p_in;
   using Pl = FftPlan<LOG2N>;
   const cplx* tw = device_twiddles();
   if (!tw) return kCudaError;
@@ -16,6 +17,7 @@ int launch_bind_fast(const BindParams& p, cudaStream_t st) {
   static const char* variant = getenv("CVB_BIND_VARIANT");
   const long long work = (p.rows + Pl::GROUPS - 1) / Pl::GROUPS;
   int grid = 0;
+  static const bool static_sched = getenv("CVB_STATIC_SCHEDULE") != nullptr;
   // staging mode measured on B200 (tools/bench_ops.py): 0 = plain loads, 2 = a and b through TMA (1 = a only was measured too: no gain)
   int mode = (LOG2N >= 12) ? 2 : 0;
   if (variant) mode = (variant[0] == 's') ? 2 : 0;
@@ -26,13 +28,15 @@ int launch_bind_fast(const BindParams& p, cudaStream_t st) {
     if constexpr (LOG2N >= 11) {
       auto kern = bind_v3_kernel<LOG2N, MODE, 2>;
       if (int rc = persistent_grid(kern, Pl::THREADS, smem, work, &grid)) return rc;
-      kern<<<grid, Pl::THREADS, smem, st>>>(p, tw);
+      p.sched = (!static_sched && work > grid) ? next_sched_slot() : nullptr;
+    kern<<<grid, Pl::THREADS, smem, st>>>(p, tw);
       return check_launch("bind_v3_kernel<staged ab>");
     }
   }
   const size_t smem = bind_v3_smem_bytes<LOG2N, 0>();
   auto kern = bind_v3_kernel<LOG2N, MODE, 0>;
   if (int rc = persistent_grid(kern, Pl::THREADS, smem, work, &grid)) return rc;
+  p.sched = (!static_sched && work > grid) ? next_sched_slot() : nullptr;
   kern<<<grid, Pl::THREADS, smem, st>>>(p, tw);
   return check_launch("bind_v3_kernel<direct>");
 }

@@ -24,6 +24,7 @@ struct BindParams {
   float* out;          // (rows, d)
   long long rows;
   long long a_rows, b_rows;   // broadcasting: operand row = r % operand_rows
+  int* sched;                 // dynamic row schedule counters (see clifford_kernels.cuh); null = static
 };
 
 __device__ __forceinline__ cplx bind_op(int mode, cplx a, cplx b) {
@@ -50,7 +51,7 @@ __device__ __forceinline__ cplx bind_op(int mode, cplx a, cplx b) {
 template <int LOG2N, int STAGED>
 constexpr size_t bind_v3_smem_bytes() {
   using Pl = FftPlan<LOG2N>;
-  return (sizeof(cplx) * (Pl::XCH + Pl::N + (STAGED == 2 ? Pl::N : 0)) + 2 * sizeof(uint64_t)) * Pl::GROUPS;
+  return (sizeof(cplx) * (Pl::XCH + Pl::N + (STAGED == 2 ? Pl::N : 0)) + 3 * sizeof(uint64_t)) * Pl::GROUPS;
 }
 
 template <int LOG2N, int MODE, int STAGED>
@@ -65,10 +66,12 @@ bind_v3_kernel(const BindParams p, const cplx* __restrict__ tw) {
   cplx* park = reinterpret_cast<cplx*>(smem_raw) + (size_t)group * N;
   cplx* stage_b = reinterpret_cast<cplx*>(smem_raw) + (size_t)(G + group) * N;
   cplx* xch = reinterpret_cast<cplx*>(smem_raw) + (size_t)(STAGED == 2 ? 2 : 1) * G * N + (size_t)group * Pl::XCH;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<cplx*>(smem_raw) + (size_t)(STAGED == 2 ? 2 : 1) * G * N + (size_t)G * Pl::XCH) + 2 * group;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<cplx*>(smem_raw) + (size_t)(STAGED == 2 ? 2 : 1) * G * N + (size_t)G * Pl::XCH) + 3 * group;
+  int* next_slot = reinterpret_cast<int*>(&bars[2]);
   const long long stride = (long long)gridDim.x * G;
   const long long row0 = (long long)blockIdx.x * G + group;
   constexpr float scale = 1.0f / (2.0f * N);
+  const bool dynamic = (T >= 32) && p.sched != nullptr;
 
   if (STAGED) {
     if (t == 0) {
@@ -88,10 +91,11 @@ bind_v3_kernel(const BindParams p, const cplx* __restrict__ tw) {
   }
 
   uint32_t parity = 0;
-  for (long long base = (long long)blockIdx.x * G; base < p.rows; base += stride, parity ^= 1u) {
-    const long long row = base + group;
+  long long row = row0;
+  const long long loop_end = dynamic ? p.rows : p.rows + (long long)group;    // static: trip counts uniform over the CTA
+  for (; row < loop_end; parity ^= 1u) {
     const bool valid = row < p.rows;
-    const bool next_valid = row + stride < p.rows;
+    if (dynamic && t == 0) *next_slot = atomicAdd(p.sched, 1);
     cplx v[E];
     // ---- a -> Z_a, parked
     if (STAGED) {
@@ -104,6 +108,8 @@ bind_v3_kernel(const BindParams p, const cplx* __restrict__ tw) {
       for (int e = 0; e < E; ++e) v[e] = valid ? ldg_stream2(ar + t + e * T) : make_float2(0.f, 0.f);
     }
     fft_run<LOG2N, false>(v, xch, t, tw);      // (STAGED: its barriers order every thread's stage read before the park write)
+    const long long next_row = dynamic ? (long long)*next_slot + stride : row + stride;   // visible after the barriers above
+    const bool next_valid = next_row < p.rows;
 #pragma unroll
     for (int e = 0; e < E; ++e) park[t + e * T] = v[e];
     // ---- b -> Z_b in registers
@@ -119,7 +125,7 @@ bind_v3_kernel(const BindParams p, const cplx* __restrict__ tw) {
     fft_run<LOG2N, false>(v, xch, t, tw);
     if (STAGED == 2 && t == 0 && next_valid) {   // every thread has read stage_b (barriers inside fft_run)
       mbar_expect_tx(&bars[1], kRowBytes);
-      tma_load_1d(stage_b, p.b + ((row + stride) % p.b_rows) * (2LL * N), kRowBytes, &bars[1]);
+      tma_load_1d(stage_b, p.b + (next_row % p.b_rows) * (2LL * N), kRowBytes, &bars[1]);
     }
     // ---- one partner exchange: untangle a and b, pointwise op, re-pack for the inverse transform
     group_sync<LOG2N>();
@@ -146,7 +152,7 @@ bind_v3_kernel(const BindParams p, const cplx* __restrict__ tw) {
       group_sync<LOG2N>();
       if (t == 0 && next_valid) {
         mbar_expect_tx(&bars[0], kRowBytes);
-        tma_load_1d(park, p.a + ((row + stride) % p.a_rows) * (2LL * N), kRowBytes, &bars[0]);
+        tma_load_1d(park, p.a + (next_row % p.a_rows) * (2LL * N), kRowBytes, &bars[0]);
       }
     }
     fft_run<LOG2N, true>(v, xch, t, tw);        // begins with a barrier: partner reads are complete
@@ -155,6 +161,10 @@ bind_v3_kernel(const BindParams p, const cplx* __restrict__ tw) {
 #pragma unroll
       for (int e = 0; e < E; ++e) stg_stream2(o + t + e * T, v[e]);
     }
+    row = next_row;
+  }
+  if (dynamic && t == 0) {
+    if (atomicAdd(p.sched + 1, 1) == (int)stride - 1) { p.sched[0] = 0; p.sched[1] = 0; }
   }
 }
 
