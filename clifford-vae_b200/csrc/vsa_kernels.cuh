@@ -38,6 +38,17 @@ __device__ __forceinline__ cplx bind_op(int mode, cplx a, cplx b) {
   return make_float2(q.x * inv, q.y * inv);
 }
 
+// bind_op on operands that both carry a factor 2 (A' = 2A, B' = 2B): A'B' = 4AB, A'/(B' + 2 eps) = A/(B + eps)
+__device__ __forceinline__ cplx bind_op_unscaled(int mode, cplx a, cplx b) {
+  if (mode == kBindMul) return cmul(a, b);
+  if (mode == kBindMulConj) return cmulc(a, b);
+  if (mode == kBindNegMulConj) { const cplx q = cmulc(a, b); return make_float2(-q.x, -q.y); }
+  const cplx be = make_float2(b.x + 2e-12f, mode == kBindDivConj ? -b.y : b.y);
+  const float inv = 1.0f / fmaf(be.x, be.x, be.y * be.y);
+  const cplx q = cmulc(a, be);
+  return make_float2(q.x * inv, q.y * inv);
+}
+
 // LOG2N below is log2 of the COMPLEX half length: d = 2 * 2^LOG2N.
 
 // ---- production bind kernel ------------------------------------------------------------------------
@@ -141,11 +152,14 @@ bind_v3_kernel(const BindParams p, const cplx* __restrict__ tw) {
       // bins k and N-k of the real FFTs (X[N-k] uses W^(N-k) = -conj(W^k)); factor 1/2 each
       const cplx sa = cadd(za, zap), da = cmul_mi(cmul(w, csub(za, zap)));
       const cplx sb = cadd(zb, zbp), db = cmul_mi(cmul(w, csub(zb, zbp)));
-      const cplx Ak = cscale(cadd(sa, da), 0.5f), Akp = cscale(cconj(csub(sa, da)), 0.5f);
-      const cplx Bk = cscale(cadd(sb, db), 0.5f), Bkp = cscale(cconj(csub(sb, db)), 0.5f);
-      const cplx Pk = bind_op(MODE, Ak, Bk), Pkpc = cconj(bind_op(MODE, Akp, Bkp));
+      // A = (sa +- da)/2, B = (sb +- db)/2: the halves are folded into one final constant -- the bilinear modes
+      // pick up 1/4; for the quotient modes they cancel (only the 1e-12 regulariser has to be doubled to match)
+      const cplx Ak = cadd(sa, da), Akp = cconj(csub(sa, da));
+      const cplx Bk = cadd(sb, db), Bkp = cconj(csub(sb, db));
+      const cplx Pk = bind_op_unscaled(MODE, Ak, Bk), Pkpc = cconj(bind_op_unscaled(MODE, Akp, Bkp));
       const cplx s = cadd(Pk, Pkpc), d = cmul_i(cmul(cconj(w), csub(Pk, Pkpc)));
-      v[e] = make_float2(scale * (s.x + d.x), scale * (s.y + d.y));
+      constexpr float fold = (MODE == kBindDiv || MODE == kBindDivConj) ? scale : 0.25f * scale;
+      v[e] = make_float2(fold * (s.x + d.x), fold * (s.y + d.y));
     }
     if (STAGED) {
       fence_proxy_async();                       // parked-spectrum accesses before the next TMA write
