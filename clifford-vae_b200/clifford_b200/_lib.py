@@ -11,7 +11,7 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libclifford_b200.so")
+LIB_PATH = os.environ.get("CLIFFORD_B200_LIB", os.path.join(_HERE, "libclifford_b200.so"))
 
 _lib = None
 _lock = threading.Lock()
