@@ -1,4 +1,5 @@
 // C ABI entry points for the Clifford-torus kernels (include/clifford_b200.h).
+#include <cstdlib>
 #include "launch.cuh"
 #include "clifford_kernels.cuh"
 #include "../../include/clifford_b200.h"
@@ -14,7 +15,7 @@ int launch_bwd_fast(const CliffordBwdParams& p, cudaStream_t st) {
   using Pl = FftPlan<LOG2N>;
   const cplx* tw = device_twiddles();
   if (!tw) return kCudaError;
-  const size_t smem = sizeof(cplx) * Pl::XCH * Pl::GROUPS + sizeof(float) * 32 * Pl::GROUPS;
+  const size_t smem = clifford_bwd_smem_bytes<LOG2N>();
   auto kern = clifford_bwd_kernel<LOG2N, ROWK>;
   int grid = 0;
   const long long work = (p.rows + Pl::GROUPS - 1) / Pl::GROUPS;
@@ -24,7 +25,10 @@ int launch_bwd_fast(const CliffordBwdParams& p, cudaStream_t st) {
 }
 
 template <bool ROWK>
-int dispatch_bwd(const CliffordBwdParams& p, cudaStream_t st) {
+int dispatch_bwd(const CliffordBwdParams& p_in, cudaStream_t st) {
+  CliffordBwdParams p = p_in;
+  p.staged = aligned(p.loc, 16) && (!p.tp_signed || aligned(p.tp_signed, 16)) && (!p.tprime || aligned(p.tprime, 16)) &&
+             (!p.gnoise || aligned(p.gnoise, 16)) && getenv("CVB_NO_TMA") == nullptr;
   const bool fast = is_pow2(p.d) && p.d >= 16 && p.d <= 8192 && aligned(p.grad_z, 8);
   if (fast) {
     switch (ilog2(p.d)) {

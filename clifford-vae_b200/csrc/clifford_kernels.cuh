@@ -384,26 +384,36 @@ struct CliffordBwdParams {
   float* dkappa;           // ROWK: (rows) row sums; else (rows, d)
   long long rows;
   int d;
+  int staged;              // 1: element-input rows are 16-byte aligned -> stage them with cp.async.bulk
+};
+
+// Per-row inputs of the backward, indexed by the bin k (global rows or their TMA-staged copies in smem).
+struct BwdRowSrc {
+  const float* loc;
+  const float* tps;      // saved copysign(t', s)  (RNG forward), or null
+  const float* tprime;   // injected draws
+  const float* gnoise;
 };
 
 // Element k of the backward: returns dL/dtheta_k, accumulates / stores dL/dkappa_k.
 template <bool ROWK>
-__device__ __forceinline__ float clifford_bwd_element(const CliffordBwdParams& p, long long row, long long prow, int k,
-                                                      cplx Gk, BetaGradRow& bc, float inv_d, float& dk) {
+__device__ __forceinline__ float clifford_bwd_element(const CliffordBwdParams& p, const BwdRowSrc& src, long long row,
+                                                      long long prow, int k, cplx Gk, BetaGradRow& bc, float inv_d,
+                                                      float& dk) {
   const long long idx = row * p.d + k;
   float tp, s;
-  if (p.tp_signed) {
-    const float ts = ldg_stream1(p.tp_signed + idx);
+  if (src.tps) {
+    const float ts = src.tps[k];
     tp = fabsf(ts);
     s = (ts < 0.f) ? -1.0f : 1.0f;
   } else {
-    tp = ldg_stream1(p.tprime + idx);
-    s = sign_from_normal(ldg_stream1(p.gnoise + idx));
+    tp = src.tprime[k];
+    s = sign_from_normal(src.gnoise[k]);
   }
   const CirclePhase ph = circle_phase(tp, s);       // identical arithmetic to the forward
   float sl, cl;
-  if (p.tp_signed) sincos_any<true>(ldg_stream1(p.loc + prow * p.d + k), sl, cl);
-  else sincos_any<false>(ldg_stream1(p.loc + prow * p.d + k), sl, cl);
+  if (src.tps) sincos_any<true>(src.loc[k], sl, cl);
+  else sincos_any<false>(src.loc[k], sl, cl);
   const cplx x = make_float2(fmaf(cl, ph.c, -sl * ph.s), fmaf(sl, ph.c, cl * ph.s));
   // dL/dtheta_k = -(2/n) Im(X_k conj(G_k)), 2/n = 1/d
   const float dth = -inv_d * (x.y * Gk.x - x.x * Gk.y);
@@ -420,17 +430,52 @@ __device__ __forceinline__ float clifford_bwd_element(const CliffordBwdParams& p
   return dth;
 }
 
+// smem per group: exchange buffer | 32 floats reduction scratch | 3 staged rows (loc, tp_signed | tprime, gnoise) | mbarrier
+template <int LOG2N>
+constexpr size_t clifford_bwd_smem_bytes() {
+  using Pl = FftPlan<LOG2N>;
+  return (sizeof(cplx) * Pl::XCH + sizeof(float) * 32 + sizeof(float) * 3 * Pl::N + sizeof(uint64_t)) * Pl::GROUPS;
+}
+
 template <int LOG2N, bool ROWK>
 __global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS, (FftPlan<LOG2N>::THREADS <= 128 ? 4 : 1))
 clifford_bwd_kernel(const CliffordBwdParams p, const cplx* __restrict__ tw) {
   using Pl = FftPlan<LOG2N>;
   constexpr int d = Pl::N, T = Pl::T, E = Pl::E, G = Pl::GROUPS;
-  extern __shared__ cplx smem[];
+  constexpr uint32_t kRowBytes = d * sizeof(float);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int group = threadIdx.x / T, t = threadIdx.x % T;
-  cplx* xch = smem + group * Pl::XCH;
-  float* scratch = reinterpret_cast<float*>(smem + G * Pl::XCH) + group * 32;
+  // layout: [G x 3 staged rows][G x xch][G x scratch][G x mbarrier]
+  float* stage = reinterpret_cast<float*>(smem_raw) + (size_t)group * 3 * d;
+  unsigned char* after_stage = smem_raw + sizeof(float) * (size_t)G * 3 * d;
+  cplx* xch = reinterpret_cast<cplx*>(after_stage) + (size_t)group * Pl::XCH;
+  float* scratch = reinterpret_cast<float*>(after_stage + sizeof(cplx) * (size_t)G * Pl::XCH) + group * 32;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(after_stage + (sizeof(cplx) * Pl::XCH + sizeof(float) * 32) * (size_t)G) + group;
+  const long long stride = (long long)gridDim.x * G;
+  const bool staged = p.staged != 0;
+  const bool saved = p.tp_signed != nullptr;
 
-  for (long long base = (long long)blockIdx.x * G; base < p.rows; base += (long long)gridDim.x * G) {
+  // bulk copies of one row's element inputs (thread 0 of the group); they land while grad_z is transformed
+  auto issue = [&](long long row) {
+    const long long prow = row % p.loc_rows;
+    mbar_expect_tx(bar, (saved ? 2u : 3u) * kRowBytes);
+    tma_load_1d(stage, p.loc + prow * d, kRowBytes, bar);
+    if (saved) {
+      tma_load_1d(stage + d, p.tp_signed + row * d, kRowBytes, bar);
+    } else {
+      tma_load_1d(stage + d, p.tprime + row * d, kRowBytes, bar);
+      tma_load_1d(stage + 2 * d, p.gnoise + row * d, kRowBytes, bar);
+    }
+  };
+  if (staged) {
+    if (t == 0) { mbar_init(bar, 1); mbar_init_fence(); }
+    __syncthreads();
+    const long long first_row = (long long)blockIdx.x * G + group;
+    if (t == 0 && first_row < p.rows) issue(first_row);
+  }
+
+  uint32_t parity = 0;
+  for (long long base = (long long)blockIdx.x * G; base < p.rows; base += stride, parity ^= 1u) {
     const long long row = base + group;
     const bool valid = row < p.rows;
     const long long prow = valid ? (row % p.loc_rows) : 0;
@@ -448,18 +493,36 @@ clifford_bwd_kernel(const CliffordBwdParams p, const cplx* __restrict__ tw) {
     for (int e = 0; e < E; ++e) xch[pad16(t + e * T)] = v[e];
     const float kap_row = valid ? __ldg(p.kappa + prow * p.kappa_row_stride) : 1.0f;
     BetaGradRow bc(0.5f + (kap_row + kEps), 0.5f);
+    BwdRowSrc src;
+    if (staged) {
+      src.loc = stage;
+      src.tps = saved ? stage + d : nullptr;
+      src.tprime = stage + d;
+      src.gnoise = stage + 2 * d;
+      if (valid) mbar_wait(bar, parity);
+    } else {
+      const long long r0 = valid ? row : 0;
+      src.loc = p.loc + prow * d;
+      src.tps = saved ? p.tp_signed + r0 * d : nullptr;
+      src.tprime = p.tprime ? p.tprime + r0 * d : nullptr;
+      src.gnoise = p.gnoise ? p.gnoise + r0 * d : nullptr;
+    }
     float dk_sum = 0.f;
 #pragma unroll 2
     for (int e = 0; e < E; ++e) {
       const int k = t + e * T;
       float dk = 0.f;
       if (valid && k != 0) {
-        clifford_bwd_element<ROWK>(p, row, prow, k, xch[pad16(k)], bc, 1.0f / (float)d, dk);
+        clifford_bwd_element<ROWK>(p, src, row, prow, k, xch[pad16(k)], bc, 1.0f / (float)d, dk);
       } else if (valid) {
         stg_stream1(p.dloc + row * d, 0.0f);
         if (!ROWK) stg_stream1(p.dkappa + row * d, 0.0f);
       }
       dk_sum += dk;
+    }
+    if (staged) {
+      group_sync<LOG2N>();                       // every thread is done with the staged rows
+      if (t == 0 && row + stride < p.rows) issue(row + stride);
     }
     if (ROWK) {
       const float tot = group_sum<LOG2N>(dk_sum, scratch, t);
@@ -688,6 +751,11 @@ clifford_bwd_generic_kernel(const CliffordBwdParams p) {
     __syncthreads();
     const float kap_row = __ldg(p.kappa + prow * p.kappa_row_stride);
     BetaGradRow bc(0.5f + (kap_row + kEps), 0.5f);
+    BwdRowSrc gsrc;
+    gsrc.loc = p.loc + prow * d;
+    gsrc.tps = p.tp_signed ? p.tp_signed + row * d : nullptr;
+    gsrc.tprime = p.tprime ? p.tprime + row * d : nullptr;
+    gsrc.gnoise = p.gnoise ? p.gnoise + row * d : nullptr;
     float dk_sum = 0.f;
     for (int k = threadIdx.x; k < d; k += blockDim.x) {
       if (k == 0) {
@@ -705,7 +773,7 @@ clifford_bwd_generic_kernel(const CliffordBwdParams p) {
         if (m >= n) m -= n;
       }
       float dk = 0.f;
-      clifford_bwd_element<ROWK>(p, row, prow, k, make_float2((float)gr, (float)gi), bc, 1.0f / (float)d, dk);
+      clifford_bwd_element<ROWK>(p, gsrc, row, prow, k, make_float2((float)gr, (float)gi), bc, 1.0f / (float)d, dk);
       dk_sum += dk;
     }
     if (ROWK) {
