@@ -15,7 +15,6 @@ import argparse
 import json
 import os
 import sys
-import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "clifford-vae_b200")]
@@ -35,7 +34,6 @@ def main():
     ap.add_argument("--trials", type=int, default=4096, help="trials per depth over all ranks")
     ap.add_argument("--init", default="unitary", choices=["unitary", "hrr", "clifford"])
     ap.add_argument("--unfused", action="store_true", help="2m bind/unbind launches per cell instead of the fused chain kernel")
-    ap.add_argument("--cpu-trials", type=int, default=2, help="trials of the CPU oracle loop timed for comparison (rank 0)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -85,21 +83,6 @@ def main():
                 "init": args.init, "chain": "unfused" if args.unfused else "fused", "n_gpus": world, "ms": ms, "bind_unbind_ops_per_s": bind_ops / (ms * 1e-3),
                 "trial_depth_cells_per_s": args.trials * len(depths) / (ms * 1e-3),
                 "similarity_depth_1_8_32": [sims[0], sims[min(7, len(sims) - 1)], sims[-1]]}
-        if args.cpu_trials > 0:
-            from oracle import latent_oracle as O          # comparison leg only
-            torch.set_num_threads(os.cpu_count() or 1)
-            m = args.max_depth
-            v = O.normalize_vectors(torch.randn(args.cpu_trials, m + 1, args.d) / args.d ** 0.5)
-            t = time.perf_counter()
-            for tr in range(args.cpu_trials):
-                bound = v[tr, 0:1].clone()
-                for k in range(1, m + 1):
-                    bound = O.bind(bound, v[tr, k:k + 1])
-                for k in range(m, 0, -1):
-                    bound = O.unbind(bound, v[tr, k:k + 1])
-            dt = time.perf_counter() - t
-            line["cpu_port_bind_unbind_ops_per_s"] = args.cpu_trials * 2 * m / dt
-            line["cpu_port_sample"] = f"{args.cpu_trials} depth-{m} trials, {os.cpu_count()} host threads"
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

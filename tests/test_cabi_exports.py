@@ -87,3 +87,17 @@ def test_distribution_metadata_matches_reference_contract():
     v = VonMisesFisher(torch.nn.functional.normalize(torch.randn(4, 5), dim=-1), torch.ones(4, 1))
     assert v.batch_shape == (4, 5)
     assert torch.distributions.kl._dispatch_kl(type(v), VU).__name__ == "_kl_vmf_uniform"
+
+
+def test_only_test_infrastructure_imports_the_oracle():
+    """oracle/ may be imported by tests/, __graft_entry__.smoke() and bench.py's CPU legs only."""
+    allowed = {os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")}
+    for top in ("clifford-vae_b200", "examples", "tools"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
+            for f in files:
+                if f.endswith(".py"):
+                    path = os.path.join(dirpath, f)
+                    txt = open(path).read()
+                    assert "from oracle" not in txt and "import oracle" not in txt, path
+    for path in allowed:
+        assert "oracle" in open(path).read()
