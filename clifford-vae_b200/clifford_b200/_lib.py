@@ -130,18 +130,32 @@ _rng_seed = None
 _rng_offset = 0
 
 
-def next_rng(n_calls: int = 1):
+def _rank_mix(seed: int) -> int:
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        seed ^= (torch.distributed.get_rank() * 0x9E3779B97F4A7C15)
+    return seed & 0xFFFFFFFFFFFFFFFF
+
+
+def next_rng(device=None):
     """(seed, offset) for the next kernel that draws on the device.
 
-    The seed follows torch's global generator (torch.manual_seed) xor the distributed rank, so DDP
-    ranks draw disjoint streams; the offset counts launches since the seed last changed.
+    On a CUDA device the pair comes from torch's own CUDA generator for that device: the seed is
+    `torch.manual_seed`'s, the offset is reserved from (and advances) the generator's Philox offset, so
+    re-seeding restarts the stream and our draws interleave consistently with torch's.  The seed is
+    xor-ed with the distributed rank so DDP ranks draw disjoint streams.  Without a device (CPU unit
+    tests of the host logic) a process-local call counter stands in for the offset.
     """
     global _rng_seed, _rng_offset
-    seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
-    if torch.distributed.is_available() and torch.distributed.is_initialized():
-        seed ^= (torch.distributed.get_rank() * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+    if device is not None and torch.device(device).type == "cuda":
+        dev = torch.device(device)
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        gen = torch.cuda.default_generators[idx]
+        off = gen.get_offset()
+        gen.set_offset(off + 4)
+        return _rank_mix(gen.initial_seed()), off // 4
+    seed = _rank_mix(torch.initial_seed())
     if seed != _rng_seed:
         _rng_seed, _rng_offset = seed, 0
     off = _rng_offset
-    _rng_offset += n_calls
+    _rng_offset += 1
     return seed, off

@@ -86,7 +86,7 @@ class CliffordPSRsample(torch.autograd.Function):
         if draws is None:
             tp = g = None
             tp_signed = torch.empty(rows, d, device=dev, dtype=torch.float32) if need_grad else None
-            seed, off = _lib.next_rng()
+            seed, off = _lib.next_rng(_CUR_DEV[0])
         else:
             tp, g = (_f32c(t.reshape(rows, d)) for t in draws)
             tp_signed = None
@@ -200,7 +200,7 @@ def clifford_phases_to_vector(phases, scale, rows, d, device):
     z = torch.empty(rows, 2 * d, device=device, dtype=torch.float32)
     _CUR_DEV[0] = z.device
     if phases is None:
-        seed, off = _lib.next_rng()
+        seed, off = _lib.next_rng(_CUR_DEV[0])
         ph = None
     else:
         ph, seed, off = _f32c(phases.reshape(rows, d)), 0, 0
@@ -404,7 +404,7 @@ def hrr_init(n, d, device):
     _lib.ensure_device(dev)
     out = torch.empty(n, d, device=dev, dtype=torch.float32)
     _CUR_DEV[0] = out.device
-    seed, off = _lib.next_rng()
+    seed, off = _lib.next_rng(_CUR_DEV[0])
     with torch.cuda.device(out.device):
         _launch("cvb_vsa_hrr_init", ptr(out), n, d, seed, off)
     return out
@@ -415,7 +415,7 @@ def unitary_init(n, d, device, eps):
     _lib.ensure_device(dev)
     out = torch.empty(n, d, device=dev, dtype=torch.float32)
     _CUR_DEV[0] = out.device
-    seed, off = _lib.next_rng()
+    seed, off = _lib.next_rng(_CUR_DEV[0])
     with torch.cuda.device(out.device):
         _launch("cvb_vsa_unitary_init", ptr(out), n, d, float(eps), seed, off)
     return out
@@ -430,7 +430,7 @@ def sphere_uniform_rsample(rows, D, device, norm_eps, gnoise=None):
     z = torch.empty(rows, D, device=dev, dtype=torch.float32)
     _CUR_DEV[0] = z.device
     if gnoise is None:
-        seed, off = _lib.next_rng()
+        seed, off = _lib.next_rng(_CUR_DEV[0])
         g = None
     else:
         g, seed, off = _f32c(gnoise.reshape(rows, D)), 0, 0
@@ -451,7 +451,7 @@ class PowerSphericalRsample(torch.autograd.Function):
         if draws is None:
             tp = g = None
             save = torch.empty(rows, 2, device=dev, dtype=torch.float32)
-            seed, off = _lib.next_rng()
+            seed, off = _lib.next_rng(_CUR_DEV[0])
         else:
             tp = _f32c(draws[0].reshape(rows))
             g = _f32c(draws[1].reshape(rows, D - 1))
@@ -540,7 +540,7 @@ class VMFRsample(torch.autograd.Function):
         if draws is None:
             e = u = g = None
             R = 0
-            seed, off = _lib.next_rng()
+            seed, off = _lib.next_rng(_CUR_DEV[0])
         else:
             e, u, g = draws
             u = u.to(torch.float64).reshape(-1, rows).contiguous()
