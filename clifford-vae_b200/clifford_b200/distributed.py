@@ -65,7 +65,8 @@ def sharded_cleanup(query: torch.Tensor, local_items: torch.Tensor, global_offse
     (M_local, d) with global row index global_offset + local index.  Returns (best_sim (Q,), best_idx (Q,))."""
     if local_similarity is None:
         from . import vsa
-        local_similarity = lambda q, m: vsa.similarity(q.unsqueeze(1), m.unsqueeze(0))   # noqa: E731
+        # many-query cleanup is a (Q x d) x (d x M) GEMM on unit vectors (cuBLAS), as SURVEY 8(d) allows
+        local_similarity = lambda q, m: vsa.normalize_vectors(q) @ vsa.normalize_vectors(m).T   # noqa: E731
     sims = local_similarity(query, local_items)              # (Q, M_local)
     best, arg = sims.max(dim=1)
     arg = arg + global_offset
