@@ -204,6 +204,30 @@ class CliffordPowerSphericalDistribution(CliffordTorusDistribution):
             self._fused_entropy = ent.reshape(self.batch_shape)
         return z.reshape(tuple(sample_shape) + tuple(self.batch_shape) + (2 * self.orig_dim,)).to(self.dtype)
 
+    def rsample_bind(self, other, sample_shape=torch.Size(), return_sample=True, _base_draws=None):
+        """Extension (not in the reference): draw z and return bind(z, other) from ONE kernel.  The sample's
+        spectrum is the unit phasors themselves, so binding it costs one forward FFT of `other` and one inverse
+        FFT, and z is never re-read.  `other`: (2d,), (1, 2d) or sample_shape + batch_shape + (2d,).  Forward only
+        (under autograd use rsample() and utils.vsa.bind).  Returns (z, bound), or bound if return_sample=False."""
+        from . import vsa
+        sample_shape = torch.Size(sample_shape)
+        loc2, kap2 = self._flat()
+        d = self.orig_dim
+        n = _numel(sample_shape)
+        out_shape = tuple(sample_shape) + tuple(self.batch_shape) + (2 * d,)
+        fast = kap2.shape[-1] == 1 and d >= 16 and d <= 8192 and (d & (d - 1)) == 0
+        if not fast:
+            z = self.rsample(sample_shape, _base_draws=_base_draws)
+            bound = vsa.bind(z, other)
+            return (z, bound) if return_sample else bound
+        oth = other if other.numel() == 2 * d else other.expand(out_shape)
+        with torch.no_grad():
+            z, bound, ent = ops.clifford_rsample_bind(loc2, kap2, oth, n, _base_draws, return_sample)
+        if ent is not None and not (kap2.requires_grad and torch.is_grad_enabled()):
+            self._fused_entropy = ent.reshape(self.batch_shape)     # forward-only value: never cached under autograd
+        bound = bound.reshape(out_shape).to(self.dtype)
+        return (z.reshape(out_shape).to(self.dtype), bound) if return_sample else bound
+
     def log_prob(self, value):
         loc2, kap2 = self._flat()
         n = 2 * self.orig_dim

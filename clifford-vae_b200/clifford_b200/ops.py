@@ -123,6 +123,32 @@ class CliffordPSRsample(torch.autograd.Function):
         return dloc, dkap, None, None, None
 
 
+def clifford_rsample_bind(loc, kappa, other, n_samples=1, draws=None, want_sample=True):
+    """Fused forward-only op: z ~ CliffordPS(loc (B,d), kappa (B,1)) for n_samples * B rows, bound = bind(z, other)
+    with other (1 | rows, 2d).  Returns (z | None, bound, entropy (B,) | None).  No autograd (evaluation / VSA
+    workloads on fresh latents); raises NotImplementedError for shapes the fused kernel does not cover."""
+    lib, dev = _prep(loc, kappa, other)
+    B, d = loc.shape
+    rows = B * n_samples
+    if kappa.shape[-1] != 1:
+        raise NotImplementedError("rsample_bind needs one concentration per row")
+    loc_c, kap_c, oth_c = _f32c(loc), _f32c(kappa.reshape(-1)), _f32c(other.reshape(-1, 2 * d))
+    if oth_c.shape[0] not in (1, rows):
+        raise ValueError(f"`other` must have 1 or {rows} rows, got {oth_c.shape[0]}")
+    z = torch.empty(rows, 2 * d, device=dev, dtype=torch.float32) if want_sample else None
+    bound = torch.empty(rows, 2 * d, device=dev, dtype=torch.float32)
+    ent = torch.empty(B, device=dev, dtype=torch.float32) if n_samples == 1 else None
+    if draws is None:
+        tp = g = None
+        seed, off = _lib.next_rng(_CUR_DEV[0])
+    else:
+        tp, g = (_f32c(t.reshape(rows, d)) for t in draws)
+        seed, off = 0, 0
+    _launch("cvb_clifford_ps_rsample_bind", ptr(loc_c), ptr(kap_c), B, ptr(tp), ptr(g), seed, off, ptr(oth_c),
+            oth_c.shape[0], ptr(z), ptr(bound), ptr(ent), None, None, rows, d)
+    return z, bound, ent
+
+
 class PSEntropy(torch.autograd.Function):
     """Power-spherical entropy per row.  torus=True: sum over circles k>=1 of kappa (B,1)|(B,d)
     (dists/clifford.py:318-322).  torus=False: one D-dim PowerSpherical per row, kappa (B,)."""

@@ -27,6 +27,37 @@ int launch_fwd_fast(const CliffordFwdParams& p, cudaStream_t st) {
   return check_launch("clifford_fwd_kernel");
 }
 
+template <int LOG2N, int MODE>
+int launch_fwd_bind(const CliffordFwdParams& p, cudaStream_t st) {
+  using Pl = FftPlan<LOG2N>;
+  const cplx* tw = device_twiddles();
+  if (!tw) return kCudaError;
+  const size_t smem = clifford_fwd_smem_bytes<LOG2N, MODE, true>();
+  auto kern = clifford_fwd_kernel<LOG2N, MODE, true, true>;
+  int grid = 0;
+  const long long work = (p.rows + Pl::GROUPS - 1) / Pl::GROUPS;
+  if (int rc = persistent_grid(kern, Pl::THREADS, smem, work, &grid)) return rc;
+  CliffordFwdParams q = p;
+  static const bool static_sched = getenv("CVB_STATIC_SCHEDULE") != nullptr;
+  q.sched = (!static_sched && work > grid) ? next_sched_slot() : nullptr;
+  kern<<<grid, Pl::THREADS, smem, st>>>(q, tw);
+  return check_launch("clifford_fwd_kernel<bind>");
+}
+
+template <int MODE>
+int dispatch_fwd_bind(const CliffordFwdParams& p_in, cudaStream_t st) {
+  CliffordFwdParams p = p_in;
+  p.staged = aligned(p.loc, 16) && (!p.tprime || aligned(p.tprime, 16)) && (!p.gnoise || aligned(p.gnoise, 16)) &&
+             getenv("CVB_NO_TMA") == nullptr;
+  switch (ilog2(p.d)) {
+#define CVB_CASE(L) case L: return launch_fwd_bind<L, MODE>(p, st);
+    CVB_CASE(4) CVB_CASE(5) CVB_CASE(6) CVB_CASE(7) CVB_CASE(8) CVB_CASE(9) CVB_CASE(10) CVB_CASE(11) CVB_CASE(12)
+    CVB_CASE(13)
+#undef CVB_CASE
+  }
+  return kUnsupported;
+}
+
 template <int MODE, bool ROWK>
 int dispatch_fwd(const CliffordFwdParams& p_in, cudaStream_t st) {
   CliffordFwdParams p = p_in;
@@ -83,6 +114,24 @@ int cvb_clifford_phases_to_vector(const float* phases, float phase_scale, unsign
   p.key = make_key(seed, offset, 1);
   cudaStream_t st = (cudaStream_t)stream;
   return phases ? dispatch_fwd<kPhases, true>(p, st) : dispatch_fwd<kUniformRng, true>(p, st);
+}
+
+// fused sample + entropy/KL + bind with a second vector (one concentration per row; power-of-two d in [16, 8192])
+int cvb_clifford_ps_rsample_bind(const float* loc, const float* kappa, long long loc_rows, const float* tprime,
+                                 const float* gnoise, unsigned long long seed, unsigned long long offset, const float* b,
+                                 long long b_rows, float* z, float* bound, float* entropy, float* kl, float* dentropy,
+                                 long long rows, int d, void* stream) {
+  CVB_REQUIRE(loc && kappa && b && bound, kBadArgument, "cvb_clifford_ps_rsample_bind: null pointer");
+  CVB_REQUIRE(rows > 0 && loc_rows > 0 && b_rows > 0, kBadArgument, "cvb_clifford_ps_rsample_bind: bad sizes");
+  CVB_REQUIRE((tprime == nullptr) == (gnoise == nullptr), kBadArgument, "cvb_clifford_ps_rsample_bind: give both tprime and gnoise or neither");
+  CVB_REQUIRE(is_pow2(d) && d >= 16 && d <= 8192 && aligned(b, 8) && aligned(bound, 8) && (!z || aligned(z, 8)), kUnsupported,
+              "cvb_clifford_ps_rsample_bind: d=%d must be a power of two in [16, 8192] (use rsample + vsa_bind otherwise)", d);
+  CliffordFwdParams p{};
+  p.loc = loc; p.kappa = kappa; p.kappa_row_stride = 1; p.kappa_el_stride = 0; p.loc_rows = (int)loc_rows;
+  p.tprime = tprime; p.gnoise = gnoise; p.z = z; p.entropy = entropy; p.kl = kl; p.dentropy = dentropy; p.rows = rows;
+  p.d = d; p.n = 2 * d; p.key = make_key(seed, offset, 0); p.bind_b = b; p.bind_b_rows = b_rows; p.bind_out = bound;
+  cudaStream_t st = (cudaStream_t)stream;
+  return tprime ? dispatch_fwd_bind<kPsInjected>(p, st) : dispatch_fwd_bind<kPsRng>(p, st);
 }
 
 // adjoint of "first d bins of the real FFT of a length-2d row": grad_value (rows, 2d) from H (rows, d) complex

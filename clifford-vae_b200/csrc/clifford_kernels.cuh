@@ -48,6 +48,9 @@ struct CliffordFwdParams {
   int staged;              // 1: input rows are 16-byte aligned -> stage them with cp.async.bulk
   int spectrum_input;      // kSpectrum: `phases` holds (rows, d) complex values
   int* sched;              // [0] next-row counter, [1] finished-group counter (both zero between launches); null = static
+  const float* bind_b;     // fused bind tail: rows of length 2d to bind each sample with (row r uses r % bind_b_rows), or null
+  long long bind_b_rows;
+  float* bind_out;         // (rows, 2d): irfft(S * rfft(bind_b)) = bind(z, b) without re-transforming z (its spectrum S is known)
   PhiloxKey key;
 };
 
@@ -181,14 +184,18 @@ __device__ __forceinline__ void clifford_row_entropy(const CliffordFwdParams& p,
 // Shared memory per group: exchange buffer (XCH cplx) | retry queue (N ints) | up to 3 staged input
 // rows (N floats each) ; then per group one mbarrier and one queue counter.
 constexpr int clifford_fwd_stages(int mode) { return mode == kPsInjected ? 3 : ((mode == kPsRng || mode == kPhases) ? 1 : 0); }
-template <int LOG2N, int MODE>
+template <int LOG2N, int MODE, bool BIND = false>
 constexpr size_t clifford_fwd_smem_bytes() {
   using Pl = FftPlan<LOG2N>;
-  return (sizeof(cplx) * Pl::XCH + sizeof(int) * Pl::N + sizeof(float) * Pl::N * clifford_fwd_stages(MODE)) * Pl::GROUPS +
+  return (sizeof(cplx) * Pl::XCH + sizeof(int) * Pl::N + sizeof(float) * Pl::N * clifford_fwd_stages(MODE) +
+          (BIND ? sizeof(cplx) * Pl::N : 0)) * Pl::GROUPS +
          (sizeof(uint64_t) + sizeof(int) * 2) * Pl::GROUPS;
 }
 
-template <int LOG2N, int MODE, bool ROWK>
+// BIND: after the sample is written, the row is also bound with a second vector -- out = irfft(S * rfft(b)) -- reusing
+// the sample's known spectrum S (the phasors), i.e. bind(z, b) for two transforms instead of three and without
+// reading z back.  p.z may then be null (only the bound vector is wanted): the sample's own inverse FFT is skipped.
+template <int LOG2N, int MODE, bool ROWK, bool BIND = false>
 __global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS, (FftPlan<LOG2N>::THREADS <= 128 ? CVB_FWD_MINB : 1))
 clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw) {
   using Pl = FftPlan<LOG2N>;
@@ -204,6 +211,7 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw) {
   int* queue = reinterpret_cast<int*>(after_stage + sizeof(cplx) * (size_t)G * Pl::XCH) + (size_t)group * d;
   uint64_t* bar = reinterpret_cast<uint64_t*>(after_stage + (sizeof(cplx) * Pl::XCH + sizeof(int) * d) * (size_t)G) + group;
   int* qcount = reinterpret_cast<int*>(after_stage + (sizeof(cplx) * Pl::XCH + sizeof(int) * d + sizeof(uint64_t)) * (size_t)G) + 2 * group;
+  cplx* spec = reinterpret_cast<cplx*>(after_stage + (sizeof(cplx) * Pl::XCH + sizeof(int) * d + sizeof(uint64_t) + 2 * sizeof(int)) * (size_t)G) + (size_t)group * d;   // BIND only
   constexpr bool PS = (MODE == kPsInjected || MODE == kPsRng);
   const long long stride = (long long)gridDim.x * G;
   const bool staged = NST > 0 && p.staged;
@@ -354,12 +362,36 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw) {
     if (staged && t == 0 && next_row < p.rows) issue(next_row);
     // phase 2: Hermitian half spectrum -> packed complex spectrum -> inverse FFT -> real row
     cplx v[E];
-    c2r_pretangle_load<LOG2N>(v, xch, t, tw);
-    fft_run<LOG2N, true>(v, xch, t, tw);
-    if (valid) {
-      float2* zr = reinterpret_cast<float2*>(p.z + row * (2LL * d));
+    if (BIND) {
+      // keep this thread's phasors S[k] for the bind tail (own slots only: no barrier needed)
 #pragma unroll
-      for (int e = 0; e < E; ++e) stg_stream2(zr + t + e * T, v[e]);
+      for (int e = 0; e < E; ++e) spec[t + e * T] = xch[pad16(t + e * T)];
+    }
+    if (!BIND || p.z) {
+      c2r_pretangle_load<LOG2N>(v, xch, t, tw);
+      fft_run<LOG2N, true>(v, xch, t, tw);
+      if (valid) {
+        float2* zr = reinterpret_cast<float2*>(p.z + row * (2LL * d));
+#pragma unroll
+        for (int e = 0; e < E; ++e) stg_stream2(zr + t + e * T, v[e]);
+      }
+    }
+    if (BIND) {
+      // bind tail: R = rfft(b) (half-length FFT + untangle), P = S * R (S[0] = S[d] = 1), out = irfft(P)
+      const float2* br = reinterpret_cast<const float2*>(p.bind_b + (valid ? row % p.bind_b_rows : 0) * (2LL * d));
+#pragma unroll
+      for (int e = 0; e < E; ++e) v[e] = valid ? ldg_stream2(br + t + e * T) : make_float2(0.f, 0.f);
+      fft_run<LOG2N, false>(v, xch, t, tw);
+      const float r_nyq = r2c_untangle<LOG2N>(v, xch, t, tw);
+#pragma unroll
+      for (int e = 0; e < E; ++e) v[e] = cmul(spec[t + e * T], v[e]);
+      c2r_pretangle<LOG2N>(v, r_nyq, xch, t, tw);
+      fft_run<LOG2N, true>(v, xch, t, tw);
+      if (valid) {
+        float2* orow = reinterpret_cast<float2*>(p.bind_out + row * (2LL * d));
+#pragma unroll
+        for (int e = 0; e < E; ++e) stg_stream2(orow + t + e * T, v[e]);
+      }
     }
     row = next_row;
   }

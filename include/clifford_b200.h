@@ -69,6 +69,15 @@ CVB_API int cvb_clifford_ps_rsample_backward(const float* grad_z, const float* l
                                      const float* tprime, const float* gnoise, const float* tp_signed, float* dloc,
                                      float* dkappa, long long rows, int d, void* stream);
 
+/* cvb_clifford_ps_rsample fused with a bind of every sample: bound[r] = bind(z[r], b[r % b_rows]) (utils/vsa.py:43-46 applied
+ * to the fresh sample).  The sample's spectrum is known in closed form (the unit phasors), so the bind costs one forward
+ * FFT of b and one inverse FFT instead of three transforms, and z is never read back from HBM.  One concentration per
+ * row (kappa (loc_rows)); d a power of two in [16, 8192]; z may be NULL when only the bound vectors are wanted. */
+CVB_API int cvb_clifford_ps_rsample_bind(const float* loc, const float* kappa, long long loc_rows, const float* tprime,
+                                         const float* gnoise, unsigned long long seed, unsigned long long offset,
+                                         const float* b, long long b_rows, float* z, float* bound, float* entropy,
+                                         float* kl, float* dentropy, long long rows, int d, void* stream);
+
 /* CliffordPowerSphericalDistribution.log_prob (dists/clifford.py:310-316, :198-202).  value (rows, 2d)
  * -> log_prob (rows).  Optional derivative outputs: dlp_dloc (rows, d) and dlp_dkappa ((rows) or (rows, d)) (give both
  * or neither), and dlp_dF (rows, d) complex = d log_prob / d (Re, Im) of the value's Fourier bin k. */

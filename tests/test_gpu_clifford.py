@@ -285,3 +285,29 @@ def test_device_rng_is_reproducible_and_rank_keyed():
     c1, _ = draw(124)
     assert torch.equal(a1, b1) and torch.equal(a2, b2)
     assert not torch.equal(a1, a2) and not torch.equal(a1, c1)
+
+
+@pytest.mark.parametrize("name", ["b4_d16_rowk", "b2_d512_rowk", "b6_d2048_rowk", "b3_d64_rowk_s2", "b5_d5_rowk"])
+def test_fused_rsample_bind_matches_separate_ops(golden_clifford, name):
+    """rsample_bind (one kernel: sample, KL, bind with the known spectrum) == reference sample followed by the
+    oracle's bind, for per-row and broadcast second operands; d = 5 exercises the unfused fallback."""
+    from dists.clifford import CliffordPowerSphericalDistribution
+    from oracle import latent_oracle as O
+    c = golden_clifford[name]
+    torch.manual_seed(1)
+    zref = torch.from_numpy(c["z"])
+    sshape = zref.shape[:-2]
+    roles = torch.randn(*zref.shape) / zref.shape[-1] ** 0.5
+    q = CliffordPowerSphericalDistribution(T(c["loc"]), T(c["kappa"]))
+    z, bound = q.rsample_bind(roles.to(DEV), torch.Size(sshape), _base_draws=(T(c["tprime"]), T(c["g"])))
+    assert rel_err(z.cpu(), c["z"]) < 1e-5
+    assert rel_err(bound.cpu(), O.bind(zref, roles)) < 2e-5
+    if not sshape:
+        assert rel_err(q.entropy().cpu(), c["entropy"]) < 1e-5          # fused entropy was cached
+    one = roles.reshape(-1, roles.shape[-1])[0]
+    b2 = q.rsample_bind(one.to(DEV), torch.Size(sshape), return_sample=False, _base_draws=(T(c["tprime"]), T(c["g"])))
+    assert rel_err(b2.cpu(), O.bind(zref, one)) < 2e-5
+    # device-RNG path: bound really is bind(z, roles) of the z it returns
+    from utils import vsa
+    z3, b3 = q.rsample_bind(roles.to(DEV), torch.Size(sshape))
+    assert rel_err(b3.cpu(), vsa.bind(z3, roles.to(DEV)).cpu()) < 2e-5

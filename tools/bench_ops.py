@@ -59,6 +59,24 @@ if what in ("clifford", "all"):
         gb = B * (12 * d + 8) / (ms * 1e-3) / 1e9
         print(f"clifford log_prob  B={B:7d} d={d:5d} {ms:8.3f} ms {B/(ms*1e-3):.3e} rows/s {gb:7.1f} GB/s {100*gb/PEAK:5.1f}%")
         del loc, z, tp, g, gz, dloc, tps
+if what in ("fused", "all"):
+    for B, d in ((4096, 2048), (65536, 2048), (262144, 512)):
+        n = 2 * d
+        loc = torch.randn(B, d, device=dev); kap = torch.rand(B, device=dev) * 9.87 + 0.13
+        roles = torch.randn(B, n, device=dev) / n ** 0.5
+        z = torch.empty(B, n, device=dev); out = torch.empty(B, n, device=dev); kl = torch.empty(B, device=dev)
+        def sep():
+            lib.cvb_clifford_ps_rsample(loc.data_ptr(), kap.data_ptr(), 1, 0, B, None, None, 7, 0, z.data_ptr(), None, None, kl.data_ptr(), None, B, d, st)
+            lib.cvb_vsa_bind(z.data_ptr(), roles.data_ptr(), out.data_ptr(), B, B, B, n, 0, st)
+        def fused(zp):
+            return lambda: lib.cvb_clifford_ps_rsample_bind(loc.data_ptr(), kap.data_ptr(), B, None, None, 7, 0, roles.data_ptr(), B,
+                                                            zp, out.data_ptr(), None, kl.data_ptr(), None, B, d, st)
+        for name, fn, byts in (("separate rsample+KL, bind", sep, 36 * d + 8 + 8 * d), ("fused rsample+KL+bind (z written)", fused(z.data_ptr()), 28 * d + 12),
+                               ("fused rsample+KL+bind (z skipped)", fused(None), 20 * d + 12)):
+            ms = timeit(fn)
+            gb = B * byts / (ms * 1e-3) / 1e9
+            print(f"{name:36s} B={B:7d} d={d:5d} {ms:8.3f} ms {B/(ms*1e-3):.3e} samples/s {gb:7.1f} GB/s {100*gb/PEAK:5.1f}%")
+        del loc, roles, z, out
 if what in ("sphere", "all"):
     for fam in ("ps", "vmf"):
         B, D = 1 << 18, 513
