@@ -311,3 +311,28 @@ def test_fused_rsample_bind_matches_separate_ops(golden_clifford, name):
     from utils import vsa
     z3, b3 = q.rsample_bind(roles.to(DEV), torch.Size(sshape))
     assert rel_err(b3.cpu(), vsa.bind(z3, roles.to(DEV)).cpu()) < 2e-5
+
+
+def test_extreme_concentrations_are_stable():
+    """kappa from 1e-6 to 500: finite samples on the torus, finite gradients, KL >= 0 and increasing in kappa,
+    and the phase spread shrinks like 1/sqrt(kappa)."""
+    from dists.clifford import CliffordPowerSphericalDistribution, CliffordTorusUniform
+    torch.manual_seed(0)
+    d = 256
+    kappas = [1e-6, 1e-3, 0.05, 0.3, 0.32, 1.0, 10.0, 50.0, 500.0]
+    loc = torch.zeros(len(kappas) * 64, d, device=DEV, requires_grad=True)
+    kap = torch.tensor(kappas, device=DEV).repeat_interleave(64).unsqueeze(-1).requires_grad_()
+    q = CliffordPowerSphericalDistribution(loc, kap)
+    z = q.rsample()
+    F = torch.fft.rfft(z.detach().double(), dim=-1)
+    assert torch.isfinite(z).all() and float((F.abs() - 1).abs().max()) < 5e-5
+    kl = torch.distributions.kl.kl_divergence(q, CliffordTorusUniform(d, device=DEV))
+    g_loc, g_kap = torch.autograd.grad((z * torch.randn_like(z)).sum() + kl.sum(), [loc, kap])
+    assert torch.isfinite(g_loc).all() and torch.isfinite(g_kap).all()
+    klm = kl.detach().view(len(kappas), 64).mean(1).cpu()
+    assert float(klm.min()) > -1e-3 and bool((klm[1:] >= klm[:-1] - 1e-3).all())
+    phi = torch.angle(F[:, 1:d]).view(len(kappas), -1)
+    spread = phi.std(dim=1).cpu()
+    assert abs(float(spread[0]) - np.pi / 3 ** 0.5) < 0.05          # kappa -> 0: uniform on (-pi, pi)
+    assert float(spread[-1]) < 0.08 and float(spread[-2]) < 0.25     # ~ 1/sqrt(kappa)
+    assert bool((spread[1:] <= spread[:-1] + 0.02).all())
