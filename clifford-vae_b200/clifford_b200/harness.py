@@ -100,3 +100,143 @@ def run_rolefiller_sweep(init_fn: Callable, dims: Sequence[int], k_range: Sequen
         if cells:
             acc[i, cols] = torch.stack(cells).cpu().numpy()
     return acc
+
+
+def _cleanup_argmax(recovered: torch.Tensor, items: torch.Tensor) -> torch.Tensor:
+    """argmax_j cos(recovered_i, items_j): one (rows x d) x (d x M) GEMM (cuBLAS) + argmax.  The query norm does not
+    change the argmax, so only the item memory is normalised (items with ||.|| < 1e-8 would be clamped by
+    F.cosine_similarity; harness item memories are unit rows)."""
+    items_n = items / items.norm(dim=-1, keepdim=True).clamp_min(1e-8)
+    return (recovered @ items_n.T).argmax(dim=1)
+
+
+def bundle_capacity_cell(items: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """utils/vsa.py:99-167 (`test_bundle_capacity`), one k for all trials at once.  items (M, d); idx (T, 2k)
+    distinct indices per trial: X = idx[:, :k], X' = idx[:, k:].  Per-trial accuracy (T,) = fraction of x in X
+    with cos(x, bundle(X)) > cos(x, bundle(X'))."""
+    T, k2 = idx.shape
+    k = k2 // 2
+    X = items[idx[:, :k].T.contiguous()]                      # (k, T, d)
+    Xp = items[idx[:, k:2 * k].T.contiguous()]
+    C1 = vsa.bundle(X, normalize=True)                        # (T, d)
+    C2 = vsa.bundle(Xp, normalize=True)
+    s1 = vsa.similarity(X, C1.unsqueeze(0))                   # (k, T): C rows broadcast over k inside the kernel
+    s2 = vsa.similarity(X, C2.unsqueeze(0))
+    return (s1 > s2).float().mean(dim=0)
+
+
+def run_bundle_capacity(d: int = 1024, n_items: int = 1000, k_range: Optional[Sequence[int]] = None, n_trials: int = 20,
+                        normalize: bool = True, device="cuda", item_memory: Optional[torch.Tensor] = None,
+                        generator: Optional[torch.Generator] = None):
+    """Same arguments / result dict ({"k", "accuracy", "std"}) as the reference's `test_bundle_capacity`
+    (plotting arguments dropped); one host sync per k."""
+    if k_range is None:
+        k_range = list(range(2, min(51, n_items // 2), 2))
+    items = vsa.hrr_init(n_items, d, device=device) if item_memory is None else item_memory[:n_items].to(device)
+    if normalize:
+        items = vsa.normalize_vectors(items)
+    results = {"k": [], "accuracy": [], "std": []}
+    for k in k_range:
+        n_needed = min(2 * k, n_items)
+        if n_needed < 2:
+            acc = torch.zeros(n_trials)
+        else:
+            idx = torch.stack([torch.randperm(n_items, generator=generator)[:n_needed] for _ in range(n_trials)])
+            acc = bundle_capacity_cell(items, idx.to(device)).cpu()
+        results["k"].append(k)
+        results["accuracy"].append(float(acc.mean()))
+        results["std"].append(float(acc.std(unbiased=False)))
+    return results
+
+
+def binding_pairs_cell(items: torch.Tensor, filler_idx: torch.Tensor, roles: torch.Tensor, unbind_method: str = "inv",
+                       perms: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """utils/vsa.py:224-332 (`test_binding_unbinding_pairs`), one k for all trials at once.  items (M, d);
+    filler_idx (T, k) item indices; roles (k, T, d) -- fresh unitary vectors (bind_with_random) or item rows
+    (role-filler mode); perms (k, T, d) int64 for the braided variant (each pair permuted before bundling and the
+    bundle un-permuted before unbinding).  Per-trial accuracy (T,) of recovering every filler index."""
+    T, k = filler_idx.shape
+    d = items.shape[-1]
+    fillers = items[filler_idx.T.contiguous()]                # (k, T, d)
+    pairs = vsa.bind(roles, fillers)
+    if perms is not None:
+        pairs = torch.gather(pairs, -1, perms)                # permute_vector per pair: v[perm]
+    bundled = vsa.bundle(pairs, normalize=True)               # (T, d)
+    if perms is not None:
+        # unpermute_vector(bundled, perm_i) = bundled[argsort(perm_i)]
+        noisy = torch.gather(bundled.unsqueeze(0).expand(k, T, d), -1, torch.argsort(perms, dim=-1))
+    else:
+        noisy = bundled.unsqueeze(0)
+    recovered = vsa.unbind(noisy, roles, method=unbind_method)            # (k, T, d)
+    best = _cleanup_argmax(recovered.reshape(k * T, d), items).view(k, T)
+    return (best == filler_idx.T).float().mean(dim=0)
+
+
+def run_binding_unbinding_pairs(d: int = 1024, n_items: int = 1000, k_range: Optional[Sequence[int]] = None,
+                                n_trials: int = 20, normalize: bool = True, device="cuda", unbind_method: str = "inv",
+                                item_memory: Optional[torch.Tensor] = None, use_braiding: bool = False,
+                                bind_with_random: bool = True, generator: Optional[torch.Generator] = None):
+    """Same arguments / result dict as the reference's `test_binding_unbinding_pairs` (plotting arguments dropped).
+    The item memory stays on the GPU (the reference pins it to the CPU, utils/vsa.py:266-267)."""
+    if unbind_method not in ("inv", "*", "†", "deconv"):
+        raise ValueError(f"unsupported unbind method: {unbind_method}")
+    if k_range is None:
+        k_range = list(range(2, min(31, n_items // 4), 2))
+    items = vsa.hrr_init(n_items, d, device=device) if item_memory is None else item_memory[:n_items].to(device)
+    if normalize:
+        items = vsa.normalize_vectors(items)
+    dd = items.shape[-1]
+    results = {"k": [], "accuracy": [], "std": []}
+    for k in k_range:
+        if bind_with_random:
+            idx = torch.stack([torch.randperm(n_items, generator=generator)[:k] for _ in range(n_trials)]).to(device)
+            roles = vsa.unitary_init(k * n_trials, dd, device=device)
+            if normalize:
+                roles = vsa.normalize_vectors(roles)
+            roles, filler_idx = roles.view(k, n_trials, dd), idx
+        else:
+            idx = torch.stack([torch.randperm(n_items, generator=generator)[:2 * k] for _ in range(n_trials)]).to(device)
+            roles, filler_idx = items[idx[:, :k].T.contiguous()], idx[:, k:]
+        perms = None
+        if use_braiding:
+            perms = torch.rand(k, n_trials, dd, device=device).argsort(dim=-1)          # one random permutation per pair
+        acc = binding_pairs_cell(items, filler_idx, roles, unbind_method, perms).cpu()
+        results["k"].append(k)
+        results["accuracy"].append(float(acc.mean()))
+        results["std"].append(float(acc.std(unbiased=False)))
+    return results
+
+
+def self_binding_curves(all_z: torch.Tensor, target_idx: torch.Tensor, partner_idx: torch.Tensor, max_depth: int,
+                        unbind_method: str = "inv"):
+    """utils/wandb_utils.py:93-126 (`test_self_binding`), all trials of every depth batched.  all_z (N, d) latent
+    vectors (normalised by the caller as the reference does); target_idx (T,) the trial targets; partner_idx
+    (T, max_depth) the random partners of curve 2 (distinct from the target).  Returns (self_sims, rand_sims),
+    each (max_depth, T): cos(recovered, target) after binding m times (with itself | with partners 1..m) and
+    unbinding in reverse order, m = 1..max_depth."""
+    target = all_z[target_idx]                                             # (T, d)
+    partners = all_z[partner_idx]                                          # (T, max_depth, d)
+    T, d = target.shape
+    fused = unbind_method in ("inv", "*") and 32 <= d <= 16384 and (d & (d - 1)) == 0
+    self_sims, rand_sims = [], []
+    for m in range(1, max_depth + 1):
+        v_self = target.unsqueeze(1).expand(T, m + 1, d).contiguous()
+        v_rand = torch.cat([target.unsqueeze(1), partners[:, :m]], dim=1).contiguous()
+        if fused:
+            self_sims.append(binding_depth_cell_fused(v_self))
+            rand_sims.append(binding_depth_cell_fused(v_rand))
+        else:
+            self_sims.append(_depth_cell_method(v_self, unbind_method))
+            rand_sims.append(_depth_cell_method(v_rand, unbind_method))
+    return torch.stack(self_sims), torch.stack(rand_sims)
+
+
+def _depth_cell_method(vecs: torch.Tensor, method: str) -> torch.Tensor:
+    target = vecs[:, 0].contiguous()
+    bound = target
+    m = vecs.shape[1] - 1
+    for k in range(1, m + 1):
+        bound = vsa.bind(bound, vecs[:, k].contiguous())
+    for k in range(m, 0, -1):
+        bound = vsa.unbind(bound, vecs[:, k].contiguous(), method=method)
+    return vsa.similarity(bound, target)

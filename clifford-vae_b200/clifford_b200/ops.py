@@ -246,8 +246,8 @@ def _bind_raw(a2, b2, rows, d, mode):
 
 def _flatten_pair(a, b):
     """Broadcast leading dims of a, b (..., d). Returns (a2 (Ra,d), b2 (Rb,d), rows, out_shape) where
-    each operand is either fully expanded or a single broadcast row (Rx == 1) -- the kernel indexes
-    operand rows modulo Rx."""
+    each operand is fully expanded, a single broadcast row (Rx == 1), or broadcast over leading dims only
+    (Rx = product of its trailing batch dims) -- the kernel indexes operand rows modulo Rx."""
     d = a.shape[-1]
     if b.shape[-1] != d:
         raise ValueError(f"last dims differ: {a.shape} vs {b.shape}")
@@ -259,6 +259,11 @@ def _flatten_pair(a, b):
             return _f32c(x).reshape(rows, d)
         if x.numel() == d:
             return _f32c(x).reshape(1, d)
+        xl = tuple(x.shape[:-1])
+        while xl and xl[0] == 1:
+            xl = xl[1:]
+        if xl and xl == tuple(lead[len(lead) - len(xl):]):
+            return _f32c(x).reshape(-1, d)        # broadcast over leading dims only: row r of the result uses r % Rx
         return _f32c(x.expand(*lead, d)).reshape(rows, d)
 
     return flat(a), flat(b), rows, tuple(lead) + (d,)

@@ -74,3 +74,112 @@ def test_c5_curve_shapes_d8192():
     assert sim_h[0, 0] > sim_h[0, 3] > sim_h[0, 7] and sim_h[0, 0] < 0.95
     acc = harness.run_rolefiller_sweep(vsa.hrr_init, [1024], [2, 8, 600], n_items=1000, n_trials=8, device=DEV)
     assert acc[0, 0] > 0.95 and np.isnan(acc[0, 2]) and acc[0, 1] <= acc[0, 0] + 1e-6
+
+
+def test_bundle_capacity_cell_matches_oracle_loops():
+    from clifford_b200 import harness
+    from oracle import latent_oracle as O
+    torch.manual_seed(1)
+    M, d, k, T = 120, 256, 6, 5
+    items = O.normalize_vectors(torch.randn(M, d) / d ** 0.5)
+    idx = torch.stack([torch.randperm(M)[:2 * k] for _ in range(T)])
+    got = harness.bundle_capacity_cell(items.to(DEV), idx.to(DEV)).cpu()
+    ref = []
+    for t in range(T):                  # utils/vsa.py:138-160
+        X, Xp = items[idx[t, :k]], items[idx[t, k:]]
+        C1, C2 = O.bundle(X, normalize=True), O.bundle(Xp, normalize=True)
+        ref.append(float((O.similarity(X, C1.unsqueeze(0).expand(k, -1)) >
+                          O.similarity(X, C2.unsqueeze(0).expand(k, -1))).float().mean()))
+    assert torch.allclose(got, torch.tensor(ref))
+    res = harness.run_bundle_capacity(d=512, n_items=200, k_range=[2, 40], n_trials=8, device=DEV)
+    assert res["k"] == [2, 40] and res["accuracy"][0] == 1.0 and 0.5 < res["accuracy"][1] <= 1.0
+
+
+@pytest.mark.parametrize("method,braid,random_roles", [("inv", False, True), ("†", False, True), ("inv", True, True),
+                                                         ("inv", False, False)])
+def test_binding_pairs_cell_matches_oracle_loops(method, braid, random_roles):
+    from clifford_b200 import harness
+    from oracle import latent_oracle as O
+    torch.manual_seed(2)
+    M, d, k, T = 150, 512, 4, 3
+    items = O.normalize_vectors(torch.randn(M, d) / d ** 0.5)
+    if random_roles:
+        fidx = torch.stack([torch.randperm(M)[:k] for _ in range(T)])
+        a, r = torch.rand(k * T, d // 2 - 1), torch.rand(k * T, d // 2 - 1)
+        roles = O.normalize_vectors(O.unitary_init_from_uniform(a, r, d)).view(k, T, d)
+    else:
+        idx = torch.stack([torch.randperm(M)[:2 * k] for _ in range(T)])
+        fidx, roles = idx[:, k:], items[idx[:, :k].T]
+    perms = torch.stack([torch.randperm(d) for _ in range(k * T)]).view(k, T, d) if braid else None
+    got = harness.binding_pairs_cell(items.to(DEV), fidx.to(DEV), roles.to(DEV), method,
+                                     None if perms is None else perms.to(DEV)).cpu()
+    ref = []
+    for t in range(T):                  # utils/vsa.py:273-322
+        pairs = O.bind(roles[:, t], items[fidx[t]])
+        if braid:
+            pairs = torch.stack([O.permute_vector(pairs[i], perms[i, t]) for i in range(k)])
+        bundled = O.bundle(pairs, normalize=True)
+        correct = 0
+        for i in range(k):
+            src = O.unpermute_vector(bundled, perms[i, t]) if braid else bundled
+            rec = O.unbind(src.unsqueeze(0), roles[i, t].unsqueeze(0), method=method).squeeze()
+            correct += int(torch.argmax(O.similarity(rec, items)) == fidx[t, i])
+        ref.append(correct / k)
+    assert torch.allclose(got, torch.tensor(ref))
+
+
+def test_run_binding_unbinding_pairs_contract():
+    from clifford_b200 import harness
+    torch.manual_seed(3)
+    res = harness.run_binding_unbinding_pairs(d=1024, n_items=300, k_range=[2, 6], n_trials=6, device=DEV)
+    assert res["k"] == [2, 6] and res["accuracy"][0] > 0.9 and len(res["std"]) == 2
+    res_b = harness.run_binding_unbinding_pairs(d=1024, n_items=300, k_range=[2], n_trials=6, device=DEV,
+                                                use_braiding=True, bind_with_random=False)
+    assert res_b["accuracy"][0] > 0.9
+    with pytest.raises(ValueError):
+        harness.run_binding_unbinding_pairs(d=64, n_items=20, k_range=[2], n_trials=1, device=DEV, unbind_method="x")
+
+
+@pytest.mark.parametrize("d,method", [(256, "inv"), (200, "inv"), (256, "†")])
+def test_self_binding_curves_match_oracle_loops(d, method):
+    from clifford_b200 import harness
+    from oracle import latent_oracle as O
+    torch.manual_seed(5)
+    N, T, D = 40, 4, 3
+    all_z = O.normalize_vectors(torch.randn(N, d) / d ** 0.5)
+    tidx = torch.randint(0, N, (T,))
+    pidx = torch.stack([torch.tensor([j for j in torch.randperm(N).tolist() if j != int(tidx[t])][:D]) for t in range(T)])
+    s_self, s_rand = harness.self_binding_curves(all_z.to(DEV), tidx.to(DEV), pidx.to(DEV), D, method)
+    for t in range(T):                  # utils/wandb_utils.py:96-124
+        target, partners = all_z[tidx[t]:tidx[t] + 1], all_z[pidx[t]]
+        for m in range(1, D + 1):
+            b1 = target.clone()
+            b2 = target.clone()
+            for i in range(m):
+                b1 = O.bind(b1, target)
+                b2 = O.bind(b2, partners[i:i + 1])
+            for i in range(m - 1, -1, -1):
+                b1 = O.unbind(b1, target, method=method)
+                b2 = O.unbind(b2, partners[i:i + 1], method=method)
+            tol = 5e-5 if method == "inv" else 2e-3      # deconvolution amplifies round-off at small |F_b|
+            assert abs(float(s_self[m - 1, t]) - float(O.similarity(b1, target).mean())) < tol
+            assert abs(float(s_rand[m - 1, t]) - float(O.similarity(b2, target).mean())) < tol
+
+
+def test_leading_dim_broadcast_is_not_materialised():
+    """(k, T, d) op (1, T, d): the (T, d) operand is indexed modulo T inside the kernel, forward and backward."""
+    from utils import vsa
+    torch.manual_seed(6)
+    k, T, d = 3, 5, 128
+    a = torch.randn(k, T, d, device=DEV, requires_grad=True)
+    b = torch.randn(1, T, d, device=DEV, requires_grad=True)
+    out = vsa.bind(a, b)
+    ref = torch.fft.irfft(torch.fft.rfft(a.detach().double()) * torch.fft.rfft(b.detach().double()), n=d)
+    assert rel_err(out.detach().cpu(), ref.cpu()) < 1e-5
+    w = torch.randn_like(out)
+    ga, gb = torch.autograd.grad((out * w).sum(), [a, b])
+    a64, b64 = a.detach().double().requires_grad_(), b.detach().double().requires_grad_()
+    (torch.fft.irfft(torch.fft.rfft(a64) * torch.fft.rfft(b64), n=d) * w.double()).sum().backward()
+    assert gb.shape == b.shape and rel_err(ga.cpu(), a64.grad.cpu()) < 1e-5 and rel_err(gb.cpu(), b64.grad.cpu()) < 1e-5
+    s = vsa.similarity(a, b[0])
+    assert rel_err(s.detach().cpu(), torch.nn.functional.cosine_similarity(a.detach().double(), b.detach().double(), dim=-1).cpu()) < 1e-5
