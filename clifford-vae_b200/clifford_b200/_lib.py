@@ -31,6 +31,7 @@ _SIGNATURES = {
     "cvb_launch_count": ([], _ll),
     "cvb_clifford_ps_rsample": ([_f, _f, _ll, _i, _ll, _f, _f, _ull, _ull, _f, _f, _f, _f, _f, _ll, _i, _f], _i),
     "cvb_clifford_ps_rsample_bind": ([_f, _f, _ll, _f, _f, _ull, _ull, _f, _ll, _f, _f, _f, _f, _f, _ll, _i, _f], _i),
+    "cvb_clifford_ps_rsample_log_prob": ([_f, _f, _ll, _f, _f, _ull, _ull, _f, _f, _f, _f, _ll, _i, _f], _i),
     "cvb_clifford_ps_rsample_backward": ([_f, _f, _f, _ll, _i, _ll, _f, _f, _f, _f, _f, _ll, _i, _f], _i),
     "cvb_clifford_ps_log_prob": ([_f, _f, _f, _ll, _i, _ll, _f, _f, _f, _f, _ll, _i, _f], _i),
     "cvb_clifford_spectrum_adjoint": ([_f, _f, _ll, _i, _f], _i),

@@ -7,6 +7,7 @@ These are re-exported as ``dists.clifford`` so the reference's model files
 from __future__ import annotations
 
 import math
+import weakref
 from typing import Dict
 
 import torch
@@ -180,6 +181,7 @@ class CliffordPowerSphericalDistribution(CliffordTorusDistribution):
         self.normalize_ifft = normalize_ifft
         self.dtype = loc.dtype
         self._fused_entropy = None
+        self._sample_log_prob = None      # (weakref to the last no-grad sample, its version, its log_prob)
         d = self.orig_dim
         conc = self.concentration
         # one concentration per row (every reference driver) vs a full (.., d) tensor
@@ -199,10 +201,22 @@ class CliffordPowerSphericalDistribution(CliffordTorusDistribution):
         sample_shape = torch.Size(sample_shape)
         loc2, kap2 = self._flat()
         n = _numel(sample_shape)
+        d = self.orig_dim
+        out_shape = tuple(sample_shape) + tuple(self.batch_shape) + (2 * d,)
+        no_grad = not (torch.is_grad_enabled() and (loc2.requires_grad or kap2.requires_grad))
+        if no_grad and kap2.shape[-1] == 1 and 16 <= d <= 8192 and (d & (d - 1)) == 0 and loc2.shape[0] > 0 and n > 0:
+            # evaluation path (IWAE, mnist/mlp_vae.py:161,181): the same launch also yields log q(z) of the sample,
+            # which log_prob() returns when it is handed this very tensor back
+            z, lp, ent = ops.clifford_rsample_log_prob(loc2.detach(), kap2.detach(), n, _base_draws)
+            if ent is not None:
+                self._fused_entropy = ent.reshape(self.batch_shape)
+            z = z.reshape(out_shape).to(self.dtype)
+            self._sample_log_prob = (weakref.ref(z), z._version, lp.reshape(out_shape[:-1]))
+            return z
         z, ent = ops.CliffordPSRsample.apply(loc2, kap2, n, _base_draws, True)
         if ent.numel():
             self._fused_entropy = ent.reshape(self.batch_shape)
-        return z.reshape(tuple(sample_shape) + tuple(self.batch_shape) + (2 * self.orig_dim,)).to(self.dtype)
+        return z.reshape(out_shape).to(self.dtype)
 
     def rsample_bind(self, other, sample_shape=torch.Size(), return_sample=True, _base_draws=None):
         """Extension (not in the reference): draw z and return bind(z, other) from ONE kernel.  The sample's
@@ -229,6 +243,10 @@ class CliffordPowerSphericalDistribution(CliffordTorusDistribution):
         return (z.reshape(out_shape).to(self.dtype), bound) if return_sample else bound
 
     def log_prob(self, value):
+        cached = self._sample_log_prob
+        if cached is not None and cached[0]() is value and value._version == cached[1] and not (
+                torch.is_grad_enabled() and (value.requires_grad or self.loc.requires_grad or self._kappa.requires_grad)):
+            return cached[2].to(self.dtype)
         loc2, kap2 = self._flat()
         n = 2 * self.orig_dim
         lead = torch.broadcast_shapes(value.shape[:-1], tuple(self.batch_shape))

@@ -149,6 +149,30 @@ def clifford_rsample_bind(loc, kappa, other, n_samples=1, draws=None, want_sampl
     return z, bound, ent
 
 
+def clifford_rsample_log_prob(loc, kappa, n_samples=1, draws=None):
+    """Fused forward-only op for the IWAE / evaluation path: z ~ CliffordPS(loc (B,d), kappa (B,1)) for n_samples * B
+    rows together with log q(z) of every row (the sampler knows its own phases: no FFT -> angle pass over z).
+    Returns (z (rows, 2d), log_prob (rows,), entropy (B,) | None).  Power-of-two d in [16, 8192]."""
+    lib, dev = _prep(loc, kappa)
+    B, d = loc.shape
+    rows = B * n_samples
+    if kappa.shape[-1] != 1:
+        raise NotImplementedError("rsample_log_prob needs one concentration per row")
+    loc_c, kap_c = _f32c(loc), _f32c(kappa.reshape(-1))
+    z = torch.empty(rows, 2 * d, device=dev, dtype=torch.float32)
+    lp = torch.empty(rows, device=dev, dtype=torch.float32)
+    ent = torch.empty(B, device=dev, dtype=torch.float32) if n_samples == 1 else None
+    if draws is None:
+        tp = g = None
+        seed, off = _lib.next_rng(_CUR_DEV[0])
+    else:
+        tp, g = (_f32c(t.reshape(rows, d)) for t in draws)
+        seed, off = 0, 0
+    _launch("cvb_clifford_ps_rsample_log_prob", ptr(loc_c), ptr(kap_c), B, ptr(tp), ptr(g), seed, off, ptr(z), ptr(lp),
+            ptr(ent), None, rows, d)
+    return z, lp, ent
+
+
 class PSEntropy(torch.autograd.Function):
     """Power-spherical entropy per row.  torus=True: sum over circles k>=1 of kappa (B,1)|(B,d)
     (dists/clifford.py:318-322).  torus=False: one D-dim PowerSpherical per row, kappa (B,)."""

@@ -106,6 +106,24 @@ int cvb_clifford_ps_rsample(const float* loc, const float* kappa, long long kapp
   return rowk ? dispatch_fwd<kPsRng, true>(p, st) : dispatch_fwd<kPsRng, false>(p, st);
 }
 
+// rsample + log q(z) of the drawn sample in one pass (IWAE / evaluation path, mnist/mlp_vae.py:146-190)
+int cvb_clifford_ps_rsample_log_prob(const float* loc, const float* kappa, long long loc_rows, const float* tprime,
+                                     const float* gnoise, unsigned long long seed, unsigned long long offset, float* z,
+                                     float* log_prob, float* entropy, float* kl, long long rows, int d, void* stream) {
+  CVB_REQUIRE(loc && kappa && z && log_prob, kBadArgument, "cvb_clifford_ps_rsample_log_prob: null pointer");
+  CVB_REQUIRE(rows > 0 && loc_rows > 0, kBadArgument, "cvb_clifford_ps_rsample_log_prob: rows=%lld loc_rows=%lld", rows, loc_rows);
+  CVB_REQUIRE((tprime == nullptr) == (gnoise == nullptr), kBadArgument, "cvb_clifford_ps_rsample_log_prob: give both tprime and gnoise or neither");
+  CVB_REQUIRE(is_pow2(d) && d >= 16 && d <= 8192 && aligned(z, 8), kUnsupported,
+              "cvb_clifford_ps_rsample_log_prob: d=%d must be a power of two in [16, 8192] (use rsample + log_prob otherwise)", d);
+  cudaStream_t st = (cudaStream_t)stream;
+  CVB_CUDA(cudaMemsetAsync(log_prob, 0, sizeof(float) * (size_t)rows, st));     // the kernel accumulates two addends per row
+  CliffordFwdParams p{};
+  p.loc = loc; p.kappa = kappa; p.kappa_row_stride = 1; p.kappa_el_stride = 0; p.loc_rows = (int)loc_rows;
+  p.tprime = tprime; p.gnoise = gnoise; p.z = z; p.entropy = entropy; p.kl = kl; p.log_prob = log_prob; p.rows = rows;
+  p.d = d; p.n = 2 * d; p.key = make_key(seed, offset, 0);
+  return tprime ? dispatch_fwd<kPsInjected, true>(p, st) : dispatch_fwd<kPsRng, true>(p, st);
+}
+
 int cvb_clifford_phases_to_vector(const float* phases, float phase_scale, unsigned long long seed,
                                   unsigned long long offset, float* z, long long rows, int d, void* stream) {
   CVB_REQUIRE(z && rows > 0 && d >= 1, kBadArgument, "cvb_clifford_phases_to_vector: bad arguments");

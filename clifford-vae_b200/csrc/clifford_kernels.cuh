@@ -42,6 +42,8 @@ struct CliffordFwdParams {
   float* entropy;          // (rows) out, optional (row-scalar kappa only)
   float* kl;               // (rows) out, optional (row-scalar kappa only)
   float* dentropy;         // (rows) out, optional: d entropy / d kappa (row-scalar kappa only)
+  float* log_prob;         // (rows) in/out, optional, ZERO on entry: log q(z) of the drawn sample itself (row-scalar kappa,
+                           // FFT path only) -- the phases are known, so no FFT -> angle round trip (clifford.py:310-316)
   long long rows;
   int d;                   // phases per row (row pitch of loc / draws / phases)
   int n;                   // output length: 2d for the torus (fast path); any n >= 2 on the direct-DFT path
@@ -164,13 +166,22 @@ __device__ __forceinline__ bool clifford_phasor(const CliffordFwdParams& p, cons
 
 template <bool ROWK>
 __device__ __forceinline__ cplx clifford_phasor_retry(const CliffordFwdParams& p, const RowSrc& src, long long row,
-                                                      long long prow, int k, HalfAngle& gm) {
+                                                      long long prow, int k, HalfAngle& gm, float& tp_out) {
   const long long idx = row * p.d + k;
   if (!ROWK) gm = HalfAngle(__ldg(p.kappa + prow * p.kappa_row_stride + (long long)k * p.kappa_el_stride) + kEps);
   float s;
   const float tp = circle_beta_retry(gm, p.key, (uint64_t)idx, s);
   if (p.tp_signed) stg_stream1(p.tp_signed + idx, copysignf(tp, s));
+  tp_out = tp;
   return ps_phasor<true>(tp, s, src.loc[k]);
+}
+
+// log1p(clamp(t, -1 + eps, 1 - eps)) - ln 2 for t = 2 t' - 1, i.e. ln of t' clamped to the fp32 images of the
+// reference's bounds (clifford.py:200-201: float32(-1 + 1e-7) = -1 + 2^-23, float32(1 - 1e-7) = 1 - 2^-23)
+template <bool FAST>
+__device__ __forceinline__ float circle_log_half_1pt(float tp) {
+  const float c = fminf(fmaxf(tp, 5.9604645e-8f), 0.99999994f);
+  return FAST ? __logf(c) : logf(c);
 }
 
 __device__ __forceinline__ void clifford_row_entropy(const CliffordFwdParams& p, long long row, float kap_row) {
@@ -179,17 +190,26 @@ __device__ __forceinline__ void clifford_row_entropy(const CliffordFwdParams& p,
   if (p.entropy) p.entropy[row] = (float)ent;
   if (p.kl) p.kl[row] = (float)((double)(p.d - 1) * 1.83787706640934548356 - ent);
   if (p.dentropy) p.dentropy[row] = (float)((double)(p.d - 1) * c.dentropy);
+  if (p.log_prob) {
+    // the sample-independent part of log q(z): d log C + kappa ((d-1) ln 2 + log1p(clamp(cos loc_0)))  (bin 0 has angle 0);
+    // the row loop adds kappa * sum_k ln t'_k.  Two commutative adds onto zero: order-independent.
+    const float c0 = cosf(__ldg(p.loc + (row % p.loc_rows) * p.d));
+    const double l0 = log1p((double)fminf(fmaxf(c0, -1.0f + kEps), 1.0f - kEps));
+    atomicAdd(p.log_prob + row, (float)((double)p.d * c.log_norm +
+                                        (double)kap_row * ((double)(p.d - 1) * 0.69314718055994530942 + l0)));
+  }
 }
 
 // Shared memory per group: exchange buffer (XCH cplx) | retry queue (N ints) | up to 3 staged input
 // rows (N floats each) ; then per group one mbarrier and one queue counter.
+constexpr int kLpSlots = 16;   // per-warp partial sums of the fused log_prob (groups of up to 512 threads)
 constexpr int clifford_fwd_stages(int mode) { return mode == kPsInjected ? 3 : ((mode == kPsRng || mode == kPhases) ? 1 : 0); }
 template <int LOG2N, int MODE, bool BIND = false>
 constexpr size_t clifford_fwd_smem_bytes() {
   using Pl = FftPlan<LOG2N>;
   return (sizeof(cplx) * Pl::XCH + sizeof(int) * Pl::N + sizeof(float) * Pl::N * clifford_fwd_stages(MODE) +
           (BIND ? sizeof(cplx) * Pl::N : 0)) * Pl::GROUPS +
-         (sizeof(uint64_t) + sizeof(int) * 2) * Pl::GROUPS;
+         (sizeof(uint64_t) + sizeof(int) * 2 + sizeof(float) * kLpSlots) * Pl::GROUPS;
 }
 
 // BIND: after the sample is written, the row is also bound with a second vector -- out = irfft(S * rfft(b)) -- reusing
@@ -211,7 +231,8 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw) {
   int* queue = reinterpret_cast<int*>(after_stage + sizeof(cplx) * (size_t)G * Pl::XCH) + (size_t)group * d;
   uint64_t* bar = reinterpret_cast<uint64_t*>(after_stage + (sizeof(cplx) * Pl::XCH + sizeof(int) * d) * (size_t)G) + group;
   int* qcount = reinterpret_cast<int*>(after_stage + (sizeof(cplx) * Pl::XCH + sizeof(int) * d + sizeof(uint64_t)) * (size_t)G) + 2 * group;
-  cplx* spec = reinterpret_cast<cplx*>(after_stage + (sizeof(cplx) * Pl::XCH + sizeof(int) * d + sizeof(uint64_t) + 2 * sizeof(int)) * (size_t)G) + (size_t)group * d;   // BIND only
+  float* lps = reinterpret_cast<float*>(after_stage + (sizeof(cplx) * Pl::XCH + sizeof(int) * d + sizeof(uint64_t) + 2 * sizeof(int)) * (size_t)G) + kLpSlots * group;
+  cplx* spec = reinterpret_cast<cplx*>(after_stage + (sizeof(cplx) * Pl::XCH + sizeof(int) * d + sizeof(uint64_t) + 2 * sizeof(int) + kLpSlots * sizeof(float)) * (size_t)G) + (size_t)group * d;   // BIND only
   constexpr bool PS = (MODE == kPsInjected || MODE == kPsRng);
   const long long stride = (long long)gridDim.x * G;
   const bool staged = NST > 0 && p.staged;
@@ -241,7 +262,8 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw) {
 
   // Prologue: the closed-form row entropy / KL / dH/dkappa (fp64 special functions) of every row this
   // group will process, one row per thread, so the per-row loop carries no serial fp64 chain.
-  if (PS && ROWK && (p.entropy || p.kl || p.dentropy)) {
+  const bool want_lp = PS && ROWK && p.log_prob != nullptr;
+  if (PS && ROWK && (p.entropy || p.kl || p.dentropy || p.log_prob)) {
     for (long long row = first_row + (long long)t * stride; row < p.rows; row += (long long)T * stride)
       clifford_row_entropy(p, row, __ldg(p.kappa + (row % p.loc_rows) * p.kappa_row_stride));
   }
@@ -269,6 +291,23 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw) {
     }
     group_sync<LOG2N>();                       // the previous row's exchange-buffer readers are done
     const long long next_row = dynamic ? (long long)qcount[1] + stride : row + stride;
+    float lp_acc = 0.0f;                       // fused log_prob: this thread's sum of ln t'_k
+    // per-warp partial sums into the group's slots (read by thread 0 after the next group barrier)
+    auto lp_reduce = [&]() {
+      constexpr int W = T < 32 ? T : 32;
+      float sum = lp_acc;
+#pragma unroll
+      for (int o = W / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      if ((t & 31) == 0) lps[t >> 5] = sum;
+    };
+    auto lp_emit = [&]() {
+      if (t == 0 && valid) {
+        float sum = 0.0f;
+#pragma unroll
+        for (int i = 0; i < (T + 31) / 32; ++i) sum += lps[i];
+        atomicAdd(p.log_prob + row, kap_row * sum);
+      }
+    };
     // phase 1: phasors of the half spectrum into the exchange buffer (lightly unrolled: small code, some ILP)
     if (MODE == kPsRng) {
       // device RNG: one Philox call + one Box-Muller per PAIR of bins (one envelope proposal each);
@@ -293,6 +332,7 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw) {
           if (valid && k != 0) {
             if (acc & (1u << j)) {
               if (p.tp_signed) stg_stream1(p.tp_signed + row * d + k, copysignf(tp[j], sg[j]));
+              if (want_lp) lp_acc += circle_log_half_1pt<true>(tp[j]);
               x = ps_phasor<true>(tp[j], sg[j], src.loc[k]);
             } else {
               queue[atomicAdd(qcount, 1)] = k;
@@ -341,21 +381,28 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw) {
           }
         } else if (valid && k != 0) {
           clifford_phasor<MODE, ROWK>(p, src, row, prow, k, gm, x);
+          if (MODE == kPsInjected && want_lp) lp_acc += circle_log_half_1pt<false>(src.tprime[k]);
         }
         xch[pad16(k)] = x;
       }
     }
     if (t == 0) xch[pad16(d)] = make_float2(MODE == kSpectrum ? 0.0f : 1.0f, 0.0f);
+    if (MODE == kPsInjected && want_lp) lp_reduce();
     group_sync<LOG2N>();
+    if (MODE == kPsInjected && want_lp) lp_emit();
     if (MODE == kPsRng) {
       // phase 1b: rejected proposals, spread evenly over the group's threads
       const int nq = *qcount;
 #pragma unroll 1
       for (int i = t; i < nq; i += T) {
         const int k = queue[i];
-        xch[pad16(k)] = clifford_phasor_retry<ROWK>(p, src, row, prow, k, gm);
+        float tp_r;
+        xch[pad16(k)] = clifford_phasor_retry<ROWK>(p, src, row, prow, k, gm, tp_r);
+        if (want_lp) lp_acc += circle_log_half_1pt<true>(tp_r);
       }
+      if (want_lp) lp_reduce();
       group_sync<LOG2N>();
+      if (want_lp) lp_emit();
       if (t == 0) *qcount = 0;
     }
     // every thread is done with the staged inputs: fetch the next row's while this one is transformed
@@ -739,7 +786,8 @@ clifford_fwd_generic_kernel(const CliffordFwdParams p) {
     const RowSrc src = global_row_src(p, row, prow);
     for (int k = 1 + threadIdx.x; k <= nph; k += blockDim.x) {
       cplx x;
-      if (!clifford_phasor<MODE, ROWK>(p, src, row, prow, k, gm, x)) x = clifford_phasor_retry<ROWK>(p, src, row, prow, k, gm);
+      float tp_unused;
+      if (!clifford_phasor<MODE, ROWK>(p, src, row, prow, k, gm, x)) x = clifford_phasor_retry<ROWK>(p, src, row, prow, k, gm, tp_unused);
       X[k] = x;
     }
     float dc = 1.0f, nyq = 1.0f;

@@ -78,6 +78,16 @@ CVB_API int cvb_clifford_ps_rsample_bind(const float* loc, const float* kappa, l
                                          const float* b, long long b_rows, float* z, float* bound, float* entropy,
                                          float* kl, float* dentropy, long long rows, int d, void* stream);
 
+/* cvb_clifford_ps_rsample that also returns log q(z) of every drawn sample -- the pair the IWAE estimator evaluates
+ * (mnist/mlp_vae.py:161,181: q_z.rsample([S]) then q_z.log_prob(z)).  The sampled phase offsets are known, so
+ * log_prob[r] = d log C(kappa) + kappa (log1p(clamp(cos loc_0)) + sum_{k>=1} log1p(clamp(t_k))) needs no FFT -> angle
+ * pass over z (dists/clifford.py:310-316 evaluated on the sampler's own t).  One concentration per row (kappa
+ * (loc_rows)); d a power of two in [16, 8192]; forward only.  log_prob (rows) is overwritten. */
+CVB_API int cvb_clifford_ps_rsample_log_prob(const float* loc, const float* kappa, long long loc_rows, const float* tprime,
+                                             const float* gnoise, unsigned long long seed, unsigned long long offset,
+                                             float* z, float* log_prob, float* entropy, float* kl, long long rows, int d,
+                                             void* stream);
+
 /* CliffordPowerSphericalDistribution.log_prob (dists/clifford.py:310-316, :198-202).  value (rows, 2d)
  * -> log_prob (rows).  Optional derivative outputs: dlp_dloc (rows, d) and dlp_dkappa ((rows) or (rows, d)) (give both
  * or neither), and dlp_dF (rows, d) complex = d log_prob / d (Re, Im) of the value's Fourier bin k. */

@@ -336,3 +336,62 @@ def test_extreme_concentrations_are_stable():
     assert abs(float(spread[0]) - np.pi / 3 ** 0.5) < 0.05          # kappa -> 0: uniform on (-pi, pi)
     assert float(spread[-1]) < 0.08 and float(spread[-2]) < 0.25     # ~ 1/sqrt(kappa)
     assert bool((spread[1:] <= spread[:-1] + 0.02).all())
+
+
+@pytest.mark.parametrize("B,d,S", [(5, 16, 1), (3, 256, 4), (4, 2048, 2), (2, 8192, 1)])
+def test_fused_sample_log_prob_vs_oracle(B, d, S):
+    """Evaluation path (mnist/mlp_vae.py:161,181): under no_grad rsample also yields log q(z) of its own sample (known
+    phases, no FFT -> angle pass); log_prob(z) on that very tensor returns it.  Checked against the oracle's log_prob of
+    the oracle's sample from the same injected draws, and against the stand-alone log_prob kernel."""
+    from dists.clifford import CliffordPowerSphericalDistribution, CliffordTorusUniform
+    from oracle import latent_oracle as O
+    torch.manual_seed(B * d + S)
+    loc = torch.randn(B, d)
+    kap = torch.rand(B, 1) * 6 + 0.15
+    tp = torch.distributions.Beta(0.5 + kap.expand(S, B, d), torch.tensor(0.5)).sample().clamp(1e-3, 1 - 1e-3)
+    g = torch.randn(S, B, d)
+    z_o = O.clifford_ps_rsample(loc, kap, tp, g)
+    lp_o = O.clifford_ps_log_prob(z_o, loc, kap.expand(B, d))
+    q = CliffordPowerSphericalDistribution(loc.to(DEV), kap.to(DEV))
+    with torch.no_grad():
+        z = q.rsample(torch.Size([S]) if S > 1 else torch.Size(), _base_draws=(tp.to(DEV), g.to(DEV)))
+        assert q._sample_log_prob is not None and q._sample_log_prob[0]() is z
+        lp = q.log_prob(z)                                   # cached: no kernel
+        lp_kernel = q.log_prob(z.clone())                    # different tensor object: FFT -> angle kernel
+    assert lp.shape == lp_o.reshape(lp.shape).shape
+    assert rel_err(z.cpu(), z_o.reshape(z.shape)) < 1e-5
+    assert rel_err(lp.cpu(), lp_o.reshape(lp.shape)) < 2e-5
+    assert rel_err(lp_kernel.cpu(), lp_o.reshape(lp.shape)) < 2e-5
+    if S == 1:   # the fused entropy still rides along
+        kl = torch.distributions.kl.kl_divergence(q, CliffordTorusUniform(d, device=DEV))
+        assert rel_err(kl.cpu(), O.clifford_ps_kl(kap.expand(B, d))) < 1e-5
+
+
+def test_fused_sample_log_prob_device_rng_and_cache_rules():
+    from dists.clifford import CliffordPowerSphericalDistribution
+    torch.manual_seed(11)
+    B, d, S = 300, 512, 3                                  # enough rows for the dynamic schedule
+    loc = torch.randn(B, d, device=DEV)
+    kap = torch.rand(B, 1, device=DEV) * 8 + 0.05
+    q = CliffordPowerSphericalDistribution(loc, kap, validate_args=False)
+    z = q.rsample(torch.Size([S]))                         # no input requires grad -> fused path
+    lp = q.log_prob(z)
+    lp_kernel = q.log_prob(z.clone())
+    assert lp.shape == (S, B)
+    assert float((lp - lp_kernel).abs().max() / lp_kernel.abs().max()) < 1e-4
+    # reproducible bit for bit (two commutative float adds per row)
+    torch.manual_seed(11)
+    torch.randn(B, d, device=DEV); torch.rand(B, 1, device=DEV)          # replay the generator state
+    q2 = CliffordPowerSphericalDistribution(loc, kap, validate_args=False)
+    z2 = q2.rsample(torch.Size([S]))
+    assert torch.equal(z, z2) and torch.equal(q2.log_prob(z2), lp)
+    # an in-place edit of the sample invalidates the cached value
+    z2.mul_(0.5)
+    assert not torch.equal(q2.log_prob(z2), lp)
+    # under autograd the differentiable ops run and log_prob carries gradients
+    loc_g = loc.clone().requires_grad_()
+    q3 = CliffordPowerSphericalDistribution(loc_g, kap, validate_args=False)
+    z3 = q3.rsample()
+    assert q3._sample_log_prob is None and z3.requires_grad
+    (gl,) = torch.autograd.grad(q3.log_prob(z3.detach()).sum(), [loc_g])
+    assert torch.isfinite(gl).all() and float(gl.abs().max()) > 0

@@ -89,3 +89,20 @@ if what in ("sphere", "all"):
         ms = timeit(f)
         gb = B * (8 * D + 8) / (ms * 1e-3) / 1e9
         print(f"{fam} rsample B={B} D={D} {ms:8.3f} ms {B/(ms*1e-3):.3e} rows/s {gb:7.1f} GB/s {100*gb/PEAK:5.1f}%")
+if what in ("iwae", "all"):
+    # IWAE latent terms (mnist/mlp_vae.py:161,181): S samples per posterior + log q(z|x) of each
+    for B, d, S in ((4096, 2048, 1), (1024, 512, 10), (4096, 512, 10), (8192, 2048, 10)):
+        rows = B * S
+        loc = torch.randn(B, d, device=dev); kap = torch.rand(B, device=dev) * 9.87 + 0.13
+        z = torch.empty(rows, 2 * d, device=dev); lp = torch.empty(rows, device=dev)
+        def sep():
+            lib.cvb_clifford_ps_rsample(loc.data_ptr(), kap.data_ptr(), 1, 0, B, None, None, 7, 0, z.data_ptr(), None, None, None, None, rows, d, st)
+            lib.cvb_clifford_ps_log_prob(z.data_ptr(), loc.data_ptr(), kap.data_ptr(), 1, 0, B, lp.data_ptr(), None, None, None, rows, d, st)
+        def fused():
+            lib.cvb_clifford_ps_rsample_log_prob(loc.data_ptr(), kap.data_ptr(), B, None, None, 7, 0, z.data_ptr(), lp.data_ptr(), None, None, rows, d, st)
+        def plain():
+            lib.cvb_clifford_ps_rsample(loc.data_ptr(), kap.data_ptr(), 1, 0, B, None, None, 7, 0, z.data_ptr(), None, None, None, None, rows, d, st)
+        for name, fn in (("rsample only", plain), ("separate rsample, log_prob", sep), ("fused rsample+log_prob", fused)):
+            ms = timeit(fn)
+            print(f"iwae {name:28s} B={B:6d} S={S:3d} d={d:5d} {ms:8.3f} ms {rows/(ms*1e-3):.3e} samples/s")
+        del loc, z, lp
