@@ -240,3 +240,26 @@ def _depth_cell_method(vecs: torch.Tensor, method: str) -> torch.Tensor:
     for k in range(m, 0, -1):
         bound = vsa.unbind(bound, vecs[:, k].contiguous(), method=method)
     return vsa.similarity(bound, target)
+
+
+def angles_to_clifford_vector(angles: torch.Tensor, normalize_ifft: bool = True, ortho: bool = False) -> torch.Tensor:
+    """Phase angles (..., d) -> torus vector (..., 2d) through the same Hermitian-spectrum inverse FFT kernel as the
+    samplers (utils/wandb_utils.py:506-521 `_angles_to_clifford_vector`; both of its branches equal the 1/n-normalised
+    inverse FFT).  ortho=True gives the sqrt(n)-scaled variant the interpolation utilities use
+    (mnist/mnist_clifpws.py:121-135: `ifft(..., norm="ortho")` of the unscaled spectrum).  angles[..., 0] is unused."""
+    from . import ops
+    d = angles.shape[-1]
+    lead = tuple(angles.shape[:-1])
+    rows = int(np.prod(lead)) if lead else 1
+    z = ops.clifford_phases_to_vector(angles.reshape(rows, d), 1.0, rows, d, angles.device).reshape(lead + (2 * d,))
+    return z * (2 * d) ** 0.5 if ortho else z
+
+
+def clifford_interpolate(z_mean1: torch.Tensor, z_mean2: torch.Tensor, steps: int, ortho: bool = True) -> torch.Tensor:
+    """Shortest-arc interpolation between two angle vectors (d,) mapped to the torus: (steps, 2d)
+    (mnist/mnist_clifpws.py:121-135)."""
+    import math
+    alphas = torch.linspace(0, 1, steps, device=z_mean1.device)
+    delta = z_mean2 - z_mean1
+    delta_wrapped = (delta + math.pi) % (2 * math.pi) - math.pi
+    return angles_to_clifford_vector(z_mean1 + alphas.view(-1, 1) * delta_wrapped, ortho=ortho)

@@ -98,10 +98,19 @@ __device__ __forceinline__ void sincos_any(float x, float& s, float& c) {
 // e^{i (loc + phi)} from a Beta draw t' and a sign
 template <bool FAST>
 __device__ __forceinline__ cplx ps_phasor(float tp, float sgn, float loc) {
-  const CirclePhase ph = circle_phase(tp, sgn);
+  float pc, psn;
+  if (FAST) {
+    // (t, s sqrt(max(1 - t^2, eps))) already has norm 1 to within 1e-7 (also when the clamp is active), so the
+    // atan2 -> exp round trip of the reference is the identity here: skip the renormalisation
+    pc = fmaf(2.0f, tp, -1.0f);
+    psn = sgn * fast_sqrt(fmaxf(fmaf(-pc, pc, 1.0f), kEps));
+  } else {
+    const CirclePhase ph = circle_phase(tp, sgn);
+    pc = ph.c; psn = ph.s;
+  }
   float sl, cl;
   sincos_any<FAST>(loc, sl, cl);
-  return make_float2(fmaf(cl, ph.c, -sl * ph.s), fmaf(sl, ph.c, cl * ph.s));
+  return make_float2(fmaf(cl, pc, -sl * psn), fmaf(sl, pc, cl * psn));
 }
 
 // Per-row input pointers, indexed by the bin k: either the global rows or their staged copies in

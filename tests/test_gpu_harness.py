@@ -183,3 +183,32 @@ def test_leading_dim_broadcast_is_not_materialised():
     assert gb.shape == b.shape and rel_err(ga.cpu(), a64.grad.cpu()) < 1e-5 and rel_err(gb.cpu(), b64.grad.cpu()) < 1e-5
     s = vsa.similarity(a, b[0])
     assert rel_err(s.detach().cpu(), torch.nn.functional.cosine_similarity(a.detach().double(), b.detach().double(), dim=-1).cpu()) < 1e-5
+
+
+@pytest.mark.parametrize("d", [16, 100, 512])
+def test_angles_to_clifford_vector_and_interpolation(d):
+    """utils/wandb_utils.py:506-521 and mnist/mnist_clifpws.py:121-135 restated with torch.fft in fp64."""
+    import math
+    from clifford_b200 import harness
+    torch.manual_seed(d)
+    n = 2 * d
+
+    def ref(angles, ortho):
+        th = torch.zeros(*angles.shape[:-1], n, dtype=torch.float64)
+        th[..., 1:d] = angles[..., 1:]
+        th[..., -d + 1:] = -torch.flip(angles[..., 1:], (-1,))
+        s = torch.exp(1j * th)
+        return torch.fft.ifft(s, dim=-1, norm="ortho" if ortho else None).real
+
+    ang = (torch.rand(3, 7, d, dtype=torch.float64) * 2 - 1) * math.pi
+    got = harness.angles_to_clifford_vector(ang.float().to(DEV))
+    assert got.shape == (3, 7, n) and rel_err(got.cpu(), ref(ang.float().double(), False)) < 1e-5
+    got_o = harness.angles_to_clifford_vector(ang.float().to(DEV), ortho=True)
+    assert rel_err(got_o.cpu(), ref(ang.float().double(), True)) < 1e-5
+    a1, a2 = ang[0, 0].float(), ang[0, 1].float()
+    steps = 9
+    zi = harness.clifford_interpolate(a1.to(DEV), a2.to(DEV), steps)
+    delta = (a2 - a1 + math.pi) % (2 * math.pi) - math.pi
+    ia = a1 + torch.linspace(0, 1, steps).view(-1, 1) * delta
+    assert rel_err(zi.cpu(), ref(ia.double(), True)) < 2e-5
+    assert float((zi.norm(dim=-1) - n ** 0.5).abs().max()) < 1e-3       # ortho scaling: ||z|| = sqrt(n)
