@@ -484,9 +484,9 @@ struct BwdRowSrc {
 };
 
 // Element k of the backward: returns dL/dtheta_k, accumulates / stores dL/dkappa_k.
-template <bool ROWK>
+template <bool ROWK, class RowGrad>
 __device__ __forceinline__ float clifford_bwd_element(const CliffordBwdParams& p, const BwdRowSrc& src, long long row,
-                                                      long long prow, int k, cplx Gk, BetaGradRow& bc, float inv_d,
+                                                      long long prow, int k, cplx Gk, RowGrad& bc, float inv_d,
                                                       float& dk) {
   const long long idx = row * p.d + k;
   float tp, s;
@@ -510,7 +510,7 @@ __device__ __forceinline__ float clifford_bwd_element(const CliffordBwdParams& p
     dtp = bc.grad(tp) * (1.0f - tp);
   } else {
     const BetaGradConsts be(0.5f + (__ldg(p.kappa + prow * p.kappa_row_stride + (long long)k * p.kappa_el_stride) + kEps), 0.5f);
-    dtp = dirichlet_grad_one(tp, be) * (1.0f - tp);
+    dtp = dirichlet_grad_one<false>(tp, be) * (1.0f - tp);
   }
   dk = dth * ph.dphi_dt * 2.0f * dtp;
   stg_stream1(p.dloc + idx, dth);
@@ -522,7 +522,8 @@ __device__ __forceinline__ float clifford_bwd_element(const CliffordBwdParams& p
 template <int LOG2N>
 constexpr size_t clifford_bwd_smem_bytes() {
   using Pl = FftPlan<LOG2N>;
-  return (sizeof(cplx) * Pl::XCH + sizeof(float) * 32 + sizeof(float) * 3 * Pl::N + sizeof(uint64_t)) * Pl::GROUPS;
+  return (sizeof(cplx) * Pl::XCH + sizeof(float) * (32 + 2 * kBetaRowFloats) + sizeof(float) * 3 * Pl::N + sizeof(uint64_t)) *
+         Pl::GROUPS;
 }
 
 template <int LOG2N, bool ROWK>
@@ -537,8 +538,10 @@ clifford_bwd_kernel(const CliffordBwdParams p, const cplx* __restrict__ tw) {
   float* stage = reinterpret_cast<float*>(smem_raw) + (size_t)group * 3 * d;
   unsigned char* after_stage = smem_raw + sizeof(float) * (size_t)G * 3 * d;
   cplx* xch = reinterpret_cast<cplx*>(after_stage) + (size_t)group * Pl::XCH;
-  float* scratch = reinterpret_cast<float*>(after_stage + sizeof(cplx) * (size_t)G * Pl::XCH) + group * 32;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(after_stage + (sizeof(cplx) * Pl::XCH + sizeof(float) * 32) * (size_t)G) + group;
+  constexpr int kScratch = 32 + 2 * kBetaRowFloats;   // reduction scratch | two (double-buffered) row-constant blocks
+  float* scratch = reinterpret_cast<float*>(after_stage + sizeof(cplx) * (size_t)G * Pl::XCH) + group * kScratch;
+  float* rowconst = scratch + 32;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(after_stage + (sizeof(cplx) * Pl::XCH + sizeof(float) * kScratch) * (size_t)G) + group;
   const long long stride = (long long)gridDim.x * G;
   const bool staged = p.staged != 0;
   const bool saved = p.tp_signed != nullptr;
@@ -571,6 +574,11 @@ clifford_bwd_kernel(const CliffordBwdParams p, const cplx* __restrict__ tw) {
     const float2* gz = reinterpret_cast<const float2*>(p.grad_z + (valid ? row : 0) * (2LL * d));
 #pragma unroll
     for (int e = 0; e < E; ++e) v[e] = valid ? ldg_stream2(gz + t + e * T) : make_float2(0.f, 0.f);
+    // the row's Beta-gradient constants, built once by the first lanes of the group while grad_z is in flight
+    // (published by the barriers of the FFT below; double-buffered against the previous row's readers)
+    const float kap_row = valid ? __ldg(p.kappa + prow * p.kappa_row_stride) : 1.0f;
+    float* rc = rowconst + (parity ? kBetaRowFloats : 0);
+    if (ROWK) beta_row_build<T>(rc, 0.5f + (kap_row + kEps), 0.5f, t);
     fft_run<LOG2N, false>(v, xch, t, tw);
     r2c_untangle<LOG2N>(v, xch, t, tw);        // v[e] = G[k]
 
@@ -579,8 +587,7 @@ clifford_bwd_kernel(const CliffordBwdParams p, const cplx* __restrict__ tw) {
     group_sync<LOG2N>();
 #pragma unroll
     for (int e = 0; e < E; ++e) xch[pad16(t + e * T)] = v[e];
-    const float kap_row = valid ? __ldg(p.kappa + prow * p.kappa_row_stride) : 1.0f;
-    BetaGradRow bc(0.5f + (kap_row + kEps), 0.5f);
+    BetaGradRowShared bc(rc);
     BwdRowSrc src;
     if (staged) {
       src.loc = stage;

@@ -96,6 +96,10 @@ struct BetaGradConsts {
     log_alpha = logf(a);
     log_total = logf(total);
   }
+  // from values stored by beta_row_build: {alpha, beta, total, psi_alpha, psi_total, log_alpha, log_total}
+  __device__ __forceinline__ BetaGradConsts(const float* v, int) {
+    alpha = v[0]; beta = v[1]; total = v[2]; psi_alpha = v[3]; psi_total = v[4]; log_alpha = v[5]; log_total = v[6];
+  }
 };
 
 __device__ __constant__ float kDirichletGradCoef[2][3][3][4] = {
@@ -181,11 +185,14 @@ __device__ __forceinline__ float beta_grad_alpha_mid(double x, double alpha, dou
 }
 
 // -(d/dalpha cdf(x; alpha, beta)) / pdf(x; alpha, beta) / (1 - x)
+// MID = false drops the (fp64) saddle-point branch for callers whose beta is known to be <= 6 (the torus: beta = 1/2);
+// otherwise the compiler hoists its row-invariant double-precision setup out of element loops and runs it per row.
+template <bool MID = true>
 __device__ __forceinline__ float dirichlet_grad_one(float x, const BetaGradConsts& c) {
   const float boundary = c.total * x * (1.f - x);
   if (x <= 0.5f && boundary < 2.5f) return beta_grad_alpha_small(x, c.alpha, c.beta, c.psi_alpha, c.psi_total);
   if (x >= 0.5f && boundary < 0.75f) return -beta_grad_beta_small(1.f - x, c.beta, c.alpha, c.psi_alpha, c.psi_total);
-  if (c.alpha > 6.f && c.beta > 6.f) return beta_grad_alpha_mid((double)x, (double)c.alpha, (double)c.beta);
+  if (MID && c.alpha > 6.f && c.beta > 6.f) return beta_grad_alpha_mid((double)x, (double)c.alpha, (double)c.beta);
   const float u = logf(x);
   const float a = c.log_alpha - u;
   const float b = c.log_total - a;
@@ -258,6 +265,138 @@ struct BetaGradRow {
       return isnan(r) ? 0.f : r;
     }
     return dirichlet_grad_one(x, c);     // saddle-point / rational branches unchanged
+  }
+};
+
+// Shared-memory form of BetaGradRow for the FFT-path backward: the row constants are computed ONCE per row by a
+// few lanes of the group (beta_row_build) instead of by every thread, and the general rational branch of
+// dirichlet_grad_one -- p(u, a, b) / q(u, a, b) with u = log x, a = log(alpha) - u, b = log(total) - a -- is expanded
+// into two degree-7 polynomials in u whose coefficients depend on the row only (a and b are affine in u), which
+// turns its ~100 FMAs + 72 constant loads per element into 14 FMAs.  Used for x >= 0.34 (|u| <= 1.08, where the
+// expansion agrees with the nested form to 4e-7); smaller x in that branch (total > 10 only) keeps the nested form.
+constexpr int kBetaRowFloats = 64;
+constexpr int kBetaRowP = 0, kBetaRowQ = 8, kBetaRowSa = 16, kBetaRowSb = 28, kBetaRowQs = 40, kBetaRowConst = 52;
+
+__device__ __forceinline__ void beta_row_poly(int which, float A, float B, float* out) {
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll
+  for (int i = 2; i >= 0; --i) {
+    float S[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) S[k] = 0.f;
+#pragma unroll
+    for (int j = 2; j >= 0; --j) {
+      // C(u) = c0 + b (c1 + b (c2 + b c3)), b = B + u   (degree 3)
+      const float* cf = kDirichletGradCoef[which][i][j];
+      float C[4] = {cf[3], 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int l = 2; l >= 0; --l) {
+#pragma unroll
+        for (int k = 3; k >= 1; --k) C[k] = fmaf(B, C[k], C[k - 1]);
+        C[0] = fmaf(B, C[0], cf[l]);
+      }
+      // S <- S (A - u) + C
+#pragma unroll
+      for (int k = 7; k >= 1; --k) S[k] = fmaf(A, S[k], -S[k - 1]) + (k < 4 ? C[k] : 0.f);
+      S[0] = fmaf(A, S[0], C[0]);
+    }
+    // acc <- acc u + S
+#pragma unroll
+    for (int k = 7; k >= 1; --k) acc[k] = acc[k - 1] + S[k];
+    acc[0] = S[0];
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) out[k] = acc[k];
+}
+
+// Cooperative construction of one row's constants into `out` (kBetaRowFloats floats of shared memory) by the T threads
+// of a group; the caller provides the barrier between this and the first BetaGradRowShared load.
+// The four job classes go to different warps of the group when it has them (P | Q | sa, sb | q, constants), so the
+// per-row setup adds about the same few hundred instructions to every warp instead of all of them to warp 0; within a
+// class the jobs run in parallel lanes.
+template <int T>
+__device__ __forceinline__ void beta_row_build(float* out, float a, float b, int t) {
+  const float total = a + b;
+  constexpr int kQOwner = T >= 64 ? 32 : 1;
+  if (t == 0 || t == kQOwner) {
+    const float log_alpha = logf(a), log_total = logf(total);
+    beta_row_poly(t != 0, log_alpha, log_total - log_alpha, out + (t != 0 ? kBetaRowQ : kBetaRowP));
+  }
+#pragma unroll 1
+  for (int i = (t + T - (64 % T)) % T; i < 11; i += T) {
+    float n = 1.f;
+    for (int j = 1; j <= i; ++j) n *= ((float)j - b) / (float)j;
+    const float inv = __frcp_rn(a + (float)i);
+    out[kBetaRowSa + i] = n * inv;
+    out[kBetaRowSb + i] = n * inv * inv;
+  }
+#pragma unroll 1
+  for (int i = (t + T - (96 % T)) % T; i < 10; i += T) {
+    const float psi_alpha = digamma_f(a), psi_total = digamma_f(total);
+    if (i < 9) {
+      const float fp = psi_total - psi_alpha;
+      float sgn_fact = 1.f, betas = 1.f, dbetas = 0.f;
+      for (int j = 1; j <= i; ++j) {
+        sgn_fact *= -1.f / (float)j;
+        dbetas = dbetas * (a - (float)j) + betas;
+        betas = betas * (a - (float)j);
+      }
+      out[kBetaRowQs + i] = (i == 0) ? fp / b : sgn_fact / (b + (float)i) * (dbetas + fp * betas);
+    } else {
+      float* c = out + kBetaRowConst;
+      c[0] = a; c[1] = b; c[2] = total; c[3] = psi_alpha; c[4] = psi_total; c[5] = logf(a); c[6] = logf(total);
+    }
+  }
+}
+
+struct BetaGradRowShared {
+  BetaGradConsts c;
+  float f0;
+  float sa[11], sb[11], q[9];
+  const float4* pq;     // P (2 x float4) then Q (2 x float4), in shared memory
+  __device__ __forceinline__ explicit BetaGradRowShared(const float* row) : c(row + kBetaRowConst, 0) {
+    f0 = c.psi_alpha - c.psi_total;
+#pragma unroll
+    for (int i = 0; i < 11; ++i) { sa[i] = row[kBetaRowSa + i]; sb[i] = row[kBetaRowSb + i]; }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) q[i] = row[kBetaRowQs + i];
+    pq = reinterpret_cast<const float4*>(row);
+  }
+  __device__ __forceinline__ float grad(float x) const {
+    const float boundary = c.total * x * (1.f - x);
+    if (x <= 0.5f && boundary < 2.5f) {
+      float pa = sa[10], pb = sb[10];
+#pragma unroll
+      for (int i = 9; i >= 0; --i) { pa = fmaf(pa, x, sa[i]); pb = fmaf(pb, x, sb[i]); }
+      const float series = fmaf(f0 - __logf(x), pa, pb);
+      const float pw = (c.beta == 0.5f) ? rsqrtf(1.f - x) : __powf(1.f - x, -c.beta);
+      const float r = x * pw * series;
+      return isnan(r) ? 0.f : r;
+    }
+    if (x >= 0.5f && boundary < 0.75f) {
+      const float xx = 1.f - x;
+      float ps = q[8];
+#pragma unroll
+      for (int i = 7; i >= 0; --i) ps = fmaf(ps, xx, q[i]);
+      const float r = __powf(x, 1.f - c.alpha) * ps;
+      return isnan(r) ? 0.f : r;
+    }
+    if (x >= 0.34f) {
+      const float u = __logf(x);
+      const float4 p0 = pq[0], p1 = pq[1], q0 = pq[2], q1 = pq[3];
+      float pv = p1.w, qv = q1.w;
+      pv = fmaf(pv, u, p1.z); qv = fmaf(qv, u, q1.z);
+      pv = fmaf(pv, u, p1.y); qv = fmaf(qv, u, q1.y);
+      pv = fmaf(pv, u, p1.x); qv = fmaf(qv, u, q1.x);
+      pv = fmaf(pv, u, p0.w); qv = fmaf(qv, u, q0.w);
+      pv = fmaf(pv, u, p0.z); qv = fmaf(qv, u, q0.z);
+      pv = fmaf(pv, u, p0.y); qv = fmaf(qv, u, q0.y);
+      pv = fmaf(pv, u, p0.x); qv = fmaf(qv, u, q0.x);
+      return __fdividef(pv, qv) * (x * (c.psi_total - c.psi_alpha) / c.beta);
+    }
+    return dirichlet_grad_one<false>(x, c);     // rational branch at small x (total > 10); beta = 1/2: no saddle branch
   }
 };
 
