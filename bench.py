@@ -299,6 +299,8 @@ def run_gpu(args):
     ms_e2e = e0.elapsed_time(e1)
     clk = clocks.stop() if rank == 0 else None
 
+    vae = None if args.no_vae_step else vae_train_leg(torch, dev, world, rank, local)
+
     # max over ranks
     if world > 1:
         t = torch.tensor([ms_total, ms_e2e, ms_rs, ms_bind], device=dev, dtype=torch.float64)
@@ -339,12 +341,33 @@ def run_gpu(args):
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"2048 of the {B} rows (same d={d}), median of 5 passes "
                                               f"({sum(ts):.1f} s CPU), oracle port of the reference's torch CPU path"}
+        if vae is not None:
+            line["vae_train_step"] = vae
         if world == 1:
             line["other_configs"] = extras(torch, lib, dev, st, peak, full=args.extras)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def vae_train_leg(torch, dev, world, rank, local, steps=8, warmup=3):
+    """Second half of BASELINE.json's metric: the C3 training step (conv VAE on 3x32x32 inputs, Clifford latent d=2048,
+    batch 4096 per GPU, L1 + KL, AdamW, clip 1.0; cnn/cifar10_train.py:62-121) with the latent drop-in classes, data
+    parallel over NCCL when world > 1.  Every rank runs it (DDP all-reduce); returns steps/s as max-over-ranks time."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("train_vae_ddp", os.path.join(ROOT, "examples", "train_vae_ddp.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    torch.manual_seed(1234 + rank)
+    batch = 4096
+    step = mod.make_training_step("conv", "clifford", D_LAT, batch, dev, world, local)
+    ms, loss = mod.time_training_steps(step, steps, warmup, dev, world)
+    del step
+    torch.cuda.empty_cache()
+    return {"model": "conv VAE 3x32x32, Clifford latent d=2048 (z 4096), AdamW, clip 1.0", "batch_per_gpu": batch,
+            "n_gpus": world, "parallelism": f"ddp{world}" if world > 1 else "single", "steps": steps, "warmup": warmup,
+            "ms_per_step": ms, "steps_per_s": 1e3 / ms, "samples_per_s": world * batch * 1e3 / ms, "loss": loss}
 
 
 def extras(torch, lib, dev, st, peak, full=False):
@@ -414,6 +437,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--extras", action="store_true", help="time the full bind sweep in other_configs")
+    ap.add_argument("--no-vae-step", action="store_true", help="skip the C3 VAE training-step leg (vae_train_step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -204,9 +204,11 @@ class CliffordPowerSphericalDistribution(CliffordTorusDistribution):
         d = self.orig_dim
         out_shape = tuple(sample_shape) + tuple(self.batch_shape) + (2 * d,)
         no_grad = not (torch.is_grad_enabled() and (loc2.requires_grad or kap2.requires_grad))
-        if no_grad and kap2.shape[-1] == 1 and 16 <= d <= 8192 and (d & (d - 1)) == 0 and loc2.shape[0] > 0 and n > 0:
-            # evaluation path (IWAE, mnist/mlp_vae.py:161,181): the same launch also yields log q(z) of the sample,
-            # which log_prob() returns when it is handed this very tensor back
+        if (no_grad and len(sample_shape) > 0 and kap2.shape[-1] == 1 and 16 <= d <= 8192 and (d & (d - 1)) == 0
+                and loc2.shape[0] > 0 and n > 0):
+            # evaluation path (IWAE, mnist/mlp_vae.py:161,181: q_z.rsample(torch.Size([n_samples])) then
+            # q_z.log_prob(z)): the same launch also yields log q(z) of the sample, which log_prob() returns when it
+            # is handed this very tensor back.  A plain rsample() (empty sample_shape) skips it.
             z, lp, ent = ops.clifford_rsample_log_prob(loc2.detach(), kap2.detach(), n, _base_draws)
             if ent is not None:
                 self._fused_entropy = ent.reshape(self.batch_shape)

@@ -79,6 +79,53 @@ class LatentVAE(nn.Module):
         return recon, kl
 
 
+def make_training_step(arch, latent, dim, batch, dev, world, local):
+    """Model + optimiser + synthetic batch for one rank; returns the closure that runs one full training step."""
+    model = LatentVAE(arch, latent, dim).to(dev)
+    net = nn.parallel.DistributedDataParallel(model, device_ids=[local]) if world > 1 else model
+    opt = torch.optim.AdamW(net.parameters(), lr=3e-4)
+    if arch == "mlp":
+        x = (torch.rand(batch, 1, 28, 28, device=dev) > torch.rand(batch, 1, 28, 28, device=dev)).float()
+    else:
+        x = torch.rand(batch, 3, 32, 32, device=dev) * 2 - 1
+
+    def step():
+        recon, kl = net(x)
+        if arch == "mlp":
+            rec = F.binary_cross_entropy_with_logits(recon, x.view(-1, 784), reduction="sum") / x.size(0)
+        else:
+            rec = F.l1_loss(recon, x, reduction="sum") / x.size(0)
+        loss = rec + kl
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(net.parameters(), 1.0)
+        opt.step()
+        return loss
+
+    return step
+
+
+def time_training_steps(step, steps, warmup, dev, world):
+    """ms per step over `steps` steps after `warmup`, CUDA events, max over ranks."""
+    for _ in range(warmup):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        loss = step()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms / steps, float(loss.detach())
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--arch", default="mlp", choices=["mlp", "conv"])
@@ -97,49 +144,15 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(1234 + rank)
-    model = LatentVAE(args.arch, args.latent, args.dim).to(dev)
-    net = nn.parallel.DistributedDataParallel(model, device_ids=[local]) if world > 1 else model
-    opt = torch.optim.AdamW(net.parameters(), lr=3e-4)
-    if args.arch == "mlp":
-        x = (torch.rand(args.batch, 1, 28, 28, device=dev) > torch.rand(args.batch, 1, 28, 28, device=dev)).float()
-    else:
-        x = torch.rand(args.batch, 3, 32, 32, device=dev) * 2 - 1
-
-    def step():
-        recon, kl = net(x)
-        if args.arch == "mlp":
-            rec = F.binary_cross_entropy_with_logits(recon, x.view(-1, 784), reduction="sum") / x.size(0)
-        else:
-            rec = F.l1_loss(recon, x, reduction="sum") / x.size(0)
-        loss = rec + kl
-        opt.zero_grad(set_to_none=True)
-        loss.backward()
-        torch.nn.utils.clip_grad_norm_(net.parameters(), 1.0)
-        opt.step()
-        return loss
-
-    for _ in range(args.warmup):
-        step()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(args.steps):
-        loss = step()
-    b.record()
-    torch.cuda.synchronize()
-    ms = a.elapsed_time(b)
-    if world > 1:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    step = make_training_step(args.arch, args.latent, args.dim, args.batch, dev, world, local)
+    ms_step, loss = time_training_steps(step, args.steps, args.warmup, dev, world)
+    ms = ms_step * args.steps
     if rank == 0:
         print(json.dumps({
             "harness": "train_vae_ddp", "arch": args.arch, "latent": args.latent, "dim": args.dim, "n_gpus": world,
             "batch_per_gpu": args.batch, "steps": args.steps, "ms_per_step": ms / args.steps,
             "steps_per_s": args.steps / (ms * 1e-3), "samples_per_s": world * args.batch * args.steps / (ms * 1e-3),
-            "final_loss": float(loss.item()), "params": sum(p.numel() for p in model.parameters())}))
+            "final_loss": loss}))
     if world > 1:
         dist.destroy_process_group()
 

@@ -354,11 +354,12 @@ def test_fused_sample_log_prob_vs_oracle(B, d, S):
     lp_o = O.clifford_ps_log_prob(z_o, loc, kap.expand(B, d))
     q = CliffordPowerSphericalDistribution(loc.to(DEV), kap.to(DEV))
     with torch.no_grad():
-        z = q.rsample(torch.Size([S]) if S > 1 else torch.Size(), _base_draws=(tp.to(DEV), g.to(DEV)))
+        z = q.rsample(torch.Size([S]), _base_draws=(tp.to(DEV), g.to(DEV)))
         assert q._sample_log_prob is not None and q._sample_log_prob[0]() is z
         lp = q.log_prob(z)                                   # cached: no kernel
         lp_kernel = q.log_prob(z.clone())                    # different tensor object: FFT -> angle kernel
-    assert lp.shape == lp_o.reshape(lp.shape).shape
+    assert lp.shape == (S, B) and z.shape == (S, B, 2 * d)
+    assert q.rsample()._version == 0 and q._sample_log_prob[0]() is z      # a plain rsample() does not touch the cache
     assert rel_err(z.cpu(), z_o.reshape(z.shape)) < 1e-5
     assert rel_err(lp.cpu(), lp_o.reshape(lp.shape)) < 2e-5
     assert rel_err(lp_kernel.cpu(), lp_o.reshape(lp.shape)) < 2e-5
