@@ -324,6 +324,7 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw) {
       const uint64_t pair_base = (uint64_t)row * (uint64_t)(d / 2) + (uint64_t)t * (E / 2);
       PhiloxKey pkey = p.key;
       pkey.stream = 8;
+      uint32_t rej_mask = 0;                    // bit e: this thread's element e was rejected
 #pragma unroll 2
       for (int e = 0; e < E; e += 2) {
         const int k0 = t + e * T, k1 = k0 + T;
@@ -344,10 +345,36 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw) {
               if (want_lp) lp_acc += circle_log_half_1pt<true>(tp[j]);
               x = ps_phasor<true>(tp[j], sg[j], src.loc[k]);
             } else {
-              queue[atomicAdd(qcount, 1)] = k;
+              rej_mask |= 1u << (e + j);
             }
           }
           xch[pad16(k)] = x;
+        }
+      }
+      // queue the rejected bins: one shared-memory atomic per warp (exclusive scan of the per-thread counts) instead
+      // of one contended atomic per rejected bin
+      if (T >= 32) {
+        const int lane = threadIdx.x & 31, cnt = __popc(rej_mask);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int up = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += up;
+        }
+        int base = 0;
+        if (lane == 31 && incl > 0) base = atomicAdd(qcount, incl);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        int pos = base + incl - cnt;
+        while (rej_mask) {
+          const int e = __ffs(rej_mask) - 1;
+          rej_mask &= rej_mask - 1;
+          queue[pos++] = t + e * T;
+        }
+      } else {
+        while (rej_mask) {
+          const int e = __ffs(rej_mask) - 1;
+          rej_mask &= rej_mask - 1;
+          queue[atomicAdd(qcount, 1)] = t + e * T;
         }
       }
     } else if (MODE == kUniformRng || MODE == kUnitaryRng) {

@@ -16,12 +16,10 @@ __host__ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, ui
   constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
-#ifdef __CUDA_ARCH__
-    const uint32_t hi0 = __umulhi(M0, c.x), hi1 = __umulhi(M1, c.z);
-#else
-    const uint32_t hi0 = (uint32_t)(((uint64_t)M0 * c.x) >> 32), hi1 = (uint32_t)(((uint64_t)M1 * c.z) >> 32);
-#endif
-    const uint32_t lo0 = M0 * c.x, lo1 = M1 * c.z;
+    // one 32x32->64 multiply per product (IMAD.WIDE.U32) instead of separate high / low halves
+    const uint64_t p0 = (uint64_t)M0 * c.x, p1 = (uint64_t)M1 * c.z;
+    const uint32_t hi0 = (uint32_t)(p0 >> 32), hi1 = (uint32_t)(p1 >> 32);
+    const uint32_t lo0 = (uint32_t)p0, lo1 = (uint32_t)p1;
     c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
     k0 += W0;
     k1 += W1;
