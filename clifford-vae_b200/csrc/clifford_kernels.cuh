@@ -12,9 +12,16 @@
 #include "tma.cuh"
 #include "rng.cuh"
 #include "special.cuh"
+// Minimum resident CTAs per SM requested for the forward kernel's 128-thread configurations (register cap 102 at 5).
+// Measured on B200 (device RNG, >= 1 GiB per launch): 5 beats 4 by 2-4 % at d = 512 / 2048 and loses 2 % at d = 1024.
 #ifndef CVB_FWD_MINB
-#define CVB_FWD_MINB 4
+#define CVB_FWD_MINB 5
 #endif
+// backward: 5 resident CTAs help at d = 2048 (+7 %), hurt at d = 1024 (-5 %); log_prob: 4 is best at every size
+template <int LOG2N>
+constexpr int clifford_bwd_min_blocks() { return LOG2N == 11 ? 5 : 4; }
+template <int LOG2N>
+constexpr int clifford_fwd_min_blocks() { return LOG2N == 10 ? 4 : CVB_FWD_MINB; }
 
 namespace cvb {
 
@@ -225,7 +232,7 @@ constexpr size_t clifford_fwd_smem_bytes() {
 // the sample's known spectrum S (the phasors), i.e. bind(z, b) for two transforms instead of three and without
 // reading z back.  p.z may then be null (only the bound vector is wanted): the sample's own inverse FFT is skipped.
 template <int LOG2N, int MODE, bool ROWK, bool BIND = false>
-__global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS, (FftPlan<LOG2N>::THREADS <= 128 ? CVB_FWD_MINB : 1))
+__global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS, (FftPlan<LOG2N>::THREADS <= 128 ? clifford_fwd_min_blocks<LOG2N>() : 1))
 clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw) {
   using Pl = FftPlan<LOG2N>;
   constexpr int d = Pl::N, T = Pl::T, E = Pl::E, G = Pl::GROUPS;
@@ -554,7 +561,7 @@ constexpr size_t clifford_bwd_smem_bytes() {
 }
 
 template <int LOG2N, bool ROWK>
-__global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS, (FftPlan<LOG2N>::THREADS <= 128 ? 4 : 1))
+__global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS, (FftPlan<LOG2N>::THREADS <= 128 ? clifford_bwd_min_blocks<LOG2N>() : 1))
 clifford_bwd_kernel(const CliffordBwdParams p, const cplx* __restrict__ tw) {
   using Pl = FftPlan<LOG2N>;
   constexpr int d = Pl::N, T = Pl::T, E = Pl::E, G = Pl::GROUPS;
@@ -724,6 +731,8 @@ clifford_log_prob_kernel(const CliffordLogProbParams p, const cplx* __restrict__
   cplx* xch = smem + group * Pl::XCH;
   float* scratch = reinterpret_cast<float*>(smem + G * Pl::XCH) + group * 32;
   float2* ccache = reinterpret_cast<float2*>(reinterpret_cast<float*>(smem + G * Pl::XCH) + G * 32) + group * kLpConstCache;
+  float* locs = reinterpret_cast<float*>(reinterpret_cast<float2*>(reinterpret_cast<float*>(smem + G * Pl::XCH) + G * 32) +
+                                         G * kLpConstCache) + (size_t)group * d;     // this row's loc, parked for the rolled loop
   const long long stride = (long long)gridDim.x * G;
   const long long first_row = (long long)blockIdx.x * G + group;
 
@@ -766,10 +775,16 @@ clifford_log_prob_kernel(const CliffordLogProbParams p, const cplx* __restrict__
         dlogc = (float)c.dlog_norm;
       }
     }
-    float acc = 0.f, dk_acc = 0.f;
+    // F[k] and loc[k] go to this thread's own shared-memory slots so that the (large: accurate sincos, log1p, optional
+    // gradient outputs) element routine runs in a rolled loop and the kernel stays inside the instruction cache
+    group_sync<LOG2N>();                         // the untangle's partner reads of the exchange buffer are done
 #pragma unroll
+    for (int e = 0; e < E; ++e) { xch[pad16(t + e * T)] = v[e]; locs[t + e * T] = locv[e]; }
+    float acc = 0.f, dk_acc = 0.f;
+#pragma unroll 2
     for (int e = 0; e < E; ++e) {
-      if (valid) clifford_lp_element<ROWK>(p, row, prow, t + e * T, v[e], locv[e], kap_row, logc, dlogc, acc, dk_acc);
+      const int k = t + e * T;
+      if (valid) clifford_lp_element<ROWK>(p, row, prow, k, xch[pad16(k)], locs[k], kap_row, logc, dlogc, acc, dk_acc);
     }
     const float tot = group_sum<LOG2N>(acc, scratch, t);
     float dk_tot = 0.f;
