@@ -10,19 +10,24 @@ namespace {
 
 constexpr size_t kGenericSmemLimit = 200 * 1024;
 
-template <int LOG2N, int MODE, bool ROWK>
+template <int LOG2N, int MODE, bool ROWK, bool LEAN = false>
 int launch_fwd_fast(const CliffordFwdParams& p, cudaStream_t st) {
   using Pl = FftPlan<LOG2N>;
   const cplx* tw = device_twiddles();
   if (!tw) return kCudaError;
   const size_t smem = clifford_fwd_smem_bytes<LOG2N, MODE>();
-  auto kern = clifford_fwd_kernel<LOG2N, MODE, ROWK>;
+  auto kern = clifford_fwd_kernel<LOG2N, MODE, ROWK, false, LEAN>;
   int grid = 0;
   const long long work = (p.rows + Pl::GROUPS - 1) / Pl::GROUPS;
   if (int rc = persistent_grid(kern, Pl::THREADS, smem, work, &grid)) return rc;
-  CliffordFwdParams q = p;
   static const bool static_sched = getenv("CVB_STATIC_SCHEDULE") != nullptr;
-  q.sched = (!static_sched && work > grid) ? next_sched_slot() : nullptr;   // dynamic rows only when CTAs loop
+  const bool dynamic = !static_sched && work > grid;                         // dynamic rows only when CTAs loop
+  if constexpr (MODE == kPsRng && ROWK && !LEAN) {
+    // plain forward sampling: the specialised variant (no optional outputs, staged inputs)
+    if (!p.tp_signed && !p.log_prob && p.staged) return launch_fwd_fast<LOG2N, MODE, ROWK, true>(p, st);
+  }
+  CliffordFwdParams q = p;
+  q.sched = dynamic ? next_sched_slot() : nullptr;
   kern<<<grid, Pl::THREADS, smem, st>>>(q, tw);
   return check_launch("clifford_fwd_kernel");
 }

@@ -125,7 +125,8 @@ def test_uniform_prior_injected(golden_clifford, name):
     assert abs(p.entropy() - float(c["entropy"])) < 1e-9
 
 
-@pytest.mark.parametrize("B,d", [(64, 512), (7, 2048), (33, 64), (5, 8192), (9, 24), (16, 1024)])
+@pytest.mark.parametrize("B,d", [(64, 512), (7, 2048), (33, 64), (5, 8192), (9, 24), (16, 1024), (3, 4096), (6, 256),
+                                 (4, 128), (5, 32), (4, 16)])
 def test_rng_mode_invariants_and_backward_vs_oracle(B, d):
     """Device-RNG samples: |rfft z| = 1, ||z|| = 1, sum z = 1; and the backward kernel agrees with
     the oracle's autograd when the oracle is fed the draws the kernel saved."""
