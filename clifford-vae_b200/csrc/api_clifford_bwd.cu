@@ -10,13 +10,16 @@ namespace {
 
 constexpr size_t kGenericSmemLimit = 200 * 1024;
 
-template <int LOG2N, bool ROWK>
+template <int LOG2N, bool ROWK, bool FAST = false>
 int launch_bwd_fast(const CliffordBwdParams& p, cudaStream_t st) {
+  if constexpr (ROWK && !FAST) {
+    if (p.tp_signed && p.staged) return launch_bwd_fast<LOG2N, ROWK, true>(p, st);   // the training path
+  }
   using Pl = FftPlan<LOG2N>;
   const cplx* tw = device_twiddles();
   if (!tw) return kCudaError;
   const size_t smem = clifford_bwd_smem_bytes<LOG2N>();
-  auto kern = clifford_bwd_kernel<LOG2N, ROWK>;
+  auto kern = clifford_bwd_kernel<LOG2N, ROWK, FAST>;
   int grid = 0;
   const long long work = (p.rows + Pl::GROUPS - 1) / Pl::GROUPS;
   if (int rc = persistent_grid(kern, Pl::THREADS, smem, work, &grid)) return rc;

@@ -521,13 +521,14 @@ struct BwdRowSrc {
 };
 
 // Element k of the backward: returns dL/dtheta_k, accumulates / stores dL/dkappa_k.
-template <bool ROWK, class RowGrad>
+// SAVED: the launcher guarantees the RNG forward's saved draws (src.tps != null): the injected-draw path is compiled out.
+template <bool ROWK, class RowGrad, bool SAVED = false>
 __device__ __forceinline__ float clifford_bwd_element(const CliffordBwdParams& p, const BwdRowSrc& src, long long row,
                                                       long long prow, int k, cplx Gk, RowGrad& bc, float inv_d,
                                                       float& dk) {
   const long long idx = row * p.d + k;
   float tp, s;
-  if (src.tps) {
+  if (SAVED || src.tps) {
     const float ts = src.tps[k];
     tp = fabsf(ts);
     s = (ts < 0.f) ? -1.0f : 1.0f;
@@ -537,7 +538,7 @@ __device__ __forceinline__ float clifford_bwd_element(const CliffordBwdParams& p
   }
   const CirclePhase ph = circle_phase(tp, s);       // identical arithmetic to the forward
   float sl, cl;
-  if (src.tps) sincos_any<true>(src.loc[k], sl, cl);
+  if (SAVED || src.tps) sincos_any<true>(src.loc[k], sl, cl);
   else sincos_any<false>(src.loc[k], sl, cl);
   const cplx x = make_float2(fmaf(cl, ph.c, -sl * ph.s), fmaf(sl, ph.c, cl * ph.s));
   // dL/dtheta_k = -(2/n) Im(X_k conj(G_k)), 2/n = 1/d
@@ -563,7 +564,9 @@ constexpr size_t clifford_bwd_smem_bytes() {
          Pl::GROUPS;
 }
 
-template <int LOG2N, bool ROWK>
+// FAST: saved draws + TMA-staged element inputs (the training path: backward of a device-RNG rsample with 16-byte
+// aligned rows); the injected-draw and unstaged paths are compiled out.
+template <int LOG2N, bool ROWK, bool FAST = false>
 __global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS, (FftPlan<LOG2N>::THREADS <= 128 ? clifford_bwd_min_blocks<LOG2N>() : 1))
 clifford_bwd_kernel(const CliffordBwdParams p, const cplx* __restrict__ tw) {
   using Pl = FftPlan<LOG2N>;
@@ -580,8 +583,8 @@ clifford_bwd_kernel(const CliffordBwdParams p, const cplx* __restrict__ tw) {
   float* rowconst = scratch + 32;
   uint64_t* bar = reinterpret_cast<uint64_t*>(after_stage + (sizeof(cplx) * Pl::XCH + sizeof(float) * kScratch) * (size_t)G) + group;
   const long long stride = (long long)gridDim.x * G;
-  const bool staged = p.staged != 0;
-  const bool saved = p.tp_signed != nullptr;
+  const bool staged = FAST ? true : (p.staged != 0);
+  const bool saved = FAST ? true : (p.tp_signed != nullptr);
 
   // bulk copies of one row's element inputs (thread 0 of the group); they land while grad_z is transformed
   auto issue = [&](long long row) {
@@ -645,7 +648,7 @@ clifford_bwd_kernel(const CliffordBwdParams p, const cplx* __restrict__ tw) {
       const int k = t + e * T;
       float dk = 0.f;
       if (valid && k != 0) {
-        clifford_bwd_element<ROWK>(p, src, row, prow, k, xch[pad16(k)], bc, 1.0f / (float)d, dk);
+        clifford_bwd_element<ROWK, BetaGradRowShared, FAST>(p, src, row, prow, k, xch[pad16(k)], bc, 1.0f / (float)d, dk);
       } else if (valid) {
         stg_stream1(p.dloc + row * d, 0.0f);
         if (!ROWK) stg_stream1(p.dkappa + row * d, 0.0f);
