@@ -9,14 +9,17 @@ namespace {
 
 constexpr size_t kGenericSmemLimit = 200 * 1024;
 
-template <int LOG2N, bool ROWK>
+template <int LOG2N, bool ROWK, bool FWD_ONLY = false>
 int launch_lp_fast(const CliffordLogProbParams& p, cudaStream_t st) {
+  if constexpr (ROWK && !FWD_ONLY) {
+    if (!p.dlp_dF && !p.dlp_dloc && !p.dlp_dkappa) return launch_lp_fast<LOG2N, ROWK, true>(p, st);   // evaluation
+  }
   using Pl = FftPlan<LOG2N>;
   const cplx* tw = device_twiddles();
   if (!tw) return kCudaError;
   const size_t smem = sizeof(cplx) * Pl::XCH * Pl::GROUPS + sizeof(float) * 32 * Pl::GROUPS + sizeof(float2) * kLpConstCache * Pl::GROUPS +
                       sizeof(float) * Pl::N * Pl::GROUPS;
-  auto kern = clifford_log_prob_kernel<LOG2N, ROWK>;
+  auto kern = clifford_log_prob_kernel<LOG2N, ROWK, FWD_ONLY>;
   int grid = 0;
   const long long work = (p.rows + Pl::GROUPS - 1) / Pl::GROUPS;
   if (int rc = persistent_grid(kern, Pl::THREADS, smem, work, &grid)) return rc;

@@ -682,7 +682,8 @@ struct CliffordLogProbParams {
   int d;
 };
 
-template <bool ROWK>
+// FWD_ONLY: the launcher guarantees no gradient outputs were requested (evaluation): their code is compiled out.
+template <bool ROWK, bool FWD_ONLY = false>
 __device__ __forceinline__ void clifford_lp_element(const CliffordLogProbParams& p, long long row, long long prow, int k,
                                                     cplx Fk, float loc_k, float kap, float logc, float dlogc, float& acc,
                                                     float& dk_acc) {
@@ -706,7 +707,7 @@ __device__ __forceinline__ void clifford_lp_element(const CliffordLogProbParams&
   const float dot = fminf(fmaxf(dot_raw, -1.0f + kEps), 1.0f - kEps);
   const float l1p = log1pf(dot);
   acc += logc + kap * l1p;
-  if (p.dlp_dF) {
+  if (!FWD_ONLY && p.dlp_dF) {
     // d/dF of kappa log1p(u_hat(F) . m), m = (cos loc, sin loc): kappa / (1 + dot) * (m - dot u_hat) / |F|
     float2 gF = make_float2(0.f, 0.f);
     if (mag2 > 0.f && dot_raw >= -1.0f + kEps && dot_raw <= 1.0f - kEps) {
@@ -715,7 +716,7 @@ __device__ __forceinline__ void clifford_lp_element(const CliffordLogProbParams&
     }
     reinterpret_cast<float2*>(p.dlp_dF)[row * p.d + k] = gF;
   }
-  if (p.dlp_dloc) {
+  if (!FWD_ONLY && p.dlp_dloc) {
     // d dot / d loc = -sin(loc) cos(a) + cos(loc) sin(a); zero where the clamp is active
     const bool inside = (dot_raw >= -1.0f + kEps) && (dot_raw <= 1.0f - kEps);
     const float ddot = inside ? fmaf(cl, sa, -sl * ca) : 0.0f;
@@ -727,7 +728,7 @@ __device__ __forceinline__ void clifford_lp_element(const CliffordLogProbParams&
 
 constexpr int kLpConstCache = 256;   // rows per group whose log-normaliser constants are precomputed
 
-template <int LOG2N, bool ROWK>
+template <int LOG2N, bool ROWK, bool FWD_ONLY = false>
 __global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS, (FftPlan<LOG2N>::THREADS <= 128 ? 4 : 1))
 clifford_log_prob_kernel(const CliffordLogProbParams p, const cplx* __restrict__ tw) {
   using Pl = FftPlan<LOG2N>;
@@ -790,11 +791,11 @@ clifford_log_prob_kernel(const CliffordLogProbParams p, const cplx* __restrict__
 #pragma unroll 2
     for (int e = 0; e < E; ++e) {
       const int k = t + e * T;
-      if (valid) clifford_lp_element<ROWK>(p, row, prow, k, xch[pad16(k)], locs[k], kap_row, logc, dlogc, acc, dk_acc);
+      if (valid) clifford_lp_element<ROWK, FWD_ONLY>(p, row, prow, k, xch[pad16(k)], locs[k], kap_row, logc, dlogc, acc, dk_acc);
     }
     const float tot = group_sum<LOG2N>(acc, scratch, t);
     float dk_tot = 0.f;
-    if (ROWK && p.dlp_dloc) dk_tot = group_sum<LOG2N>(dk_acc, scratch, t);
+    if (!FWD_ONLY && ROWK && p.dlp_dloc) dk_tot = group_sum<LOG2N>(dk_acc, scratch, t);
     if (valid && t == 0) {
       p.log_prob[row] = tot;
       if (ROWK && p.dlp_dkappa) p.dlp_dkappa[row] = dk_tot;
