@@ -236,6 +236,110 @@ sphere_rsample_kernel(const SphereParams p) {
 }
 
 // Backward: grad_z -> dloc (rows, D), dkappa (rows).
+// Register-resident variant for D <= 128 K (K = 1..8; the reference's latents are D = 512 / 513): one warp per row, lane
+// `lane` owns the element groups q = lane + 32 kq (4 consecutive elements each, the unit one Philox call serves).  The
+// loc row is loaded ONCE with all loads in flight together (the two-pass kernel above re-reads it and stashes the normals
+// in the output row: `long_scoreboard` 52 % of its stalls), the normals stay in registers, z is written once, and the
+// compile-time trip counts remove most of the per-element index arithmetic (IMAD/IADD3/LEA were 35 % of its instructions).
+template <int FAMILY, int K>
+__global__ void __launch_bounds__(256)
+sphere_rsample_reg_kernel(const SphereParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int D = p.D;
+  // A warp owns rows warp, warp + nwarps, ...; it takes them 32 at a time so that the vMF mixture coordinates (Wood's
+  // fp64 rejection sampler) of a batch are drawn by 32 lanes in parallel, one row each, instead of redundantly by every
+  // lane for one row (that was 37 % of the vMF kernel).  With fewer than 32 rows per warp the idle lanes simply skip.
+  for (long long base = warp; base < p.rows; base += 32 * nwarps) {
+  float w_l = 0.f, dw_l = 0.f;      // lane j: scalar draw of the batch's j-th row (vMF: w, dw/dkappa; PS: t')
+  {
+    const long long rj = base + (long long)lane * nwarps;
+    if (rj < p.rows) {
+      const float kapj = __ldg(p.kappa + rj % p.loc_rows);
+      if (FAMILY == kFamilyVMF) {
+        const WoodDraw wd = vmf_draw_w(p, rj, kapj);
+        w_l = wd.w;
+        dw_l = wd.dw_dkappa;
+      } else if (p.tprime) {
+        w_l = p.tprime[rj];
+      } else {
+        // t' = X / (X + Y), X ~ Gamma((D-1)/2 + kappa + eps), Y ~ Gamma((D-1)/2): same streams as the two-pass kernel
+        const float half = 0.5f * (float)(D - 1);
+        PhiloxKey k = p.key;
+        k.stream = 4;
+        const float x = gamma_draw_float(half + (kapj + 1e-7f), k, (uint64_t)(rj * 2));
+        const float y = gamma_draw_float(half, k, (uint64_t)(rj * 2 + 1));
+        w_l = fminf(fmaxf(x / (x + y), 1.17549435e-38f), 1.0f - 5.9604645e-8f);
+      }
+    }
+  }
+  for (int jr = 0; jr < 32; ++jr) {
+    const long long row = base + (long long)jr * nwarps;
+    if (row >= p.rows) break;
+    const long long prow = row % p.loc_rows;
+    const float* lr = p.loc + prow * D;
+    float u[K][4], g[K][4] = {};
+#pragma unroll
+    for (int kq = 0; kq < K; ++kq) {
+      const int i0 = 4 * (lane + 32 * kq);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) u[kq][j] = (i0 + j < D) ? __ldg(lr + i0 + j) : 0.0f;
+    }
+    // scalar coordinate t (drawn above for the whole batch)
+    float t, save0, save1 = 0.f;
+    if (FAMILY == kFamilyPS) {
+      const float tp = __shfl_sync(0xffffffffu, w_l, jr);
+      t = 2.0f * tp - 1.0f;
+      save0 = tp;
+    } else {
+      t = __shfl_sync(0xffffffffu, w_l, jr);
+      save0 = t;
+      save1 = __shfl_sync(0xffffffffu, dw_l, jr);
+    }
+    // tangent normals and the three reductions; u = e1 - loc; slots past D (and the scalar slot 0) hold zeros
+    float sgg = 0.f, suu = 0.f, sgu = 0.f;
+#pragma unroll
+    for (int kq = 0; kq < K; ++kq) {
+      const int q = lane + 32 * kq, i0 = 4 * q;
+      if (i0 < D) normals4(p, row, q, 0, g[kq]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = i0 + j;
+        const bool in = i < D;
+        u[kq][j] = in ? ((i == 0 ? 1.0f : 0.0f) - u[kq][j]) : 0.0f;
+        g[kq][j] = (in && i > 0) ? g[kq][j] : 0.0f;
+        suu = fmaf(u[kq][j], u[kq][j], suu);
+        sgg = fmaf(g[kq][j], g[kq][j], sgg);
+        sgu = fmaf(g[kq][j], u[kq][j], sgu);
+      }
+    }
+    sgg = warp_sum(sgg); suu = warp_sum(suu); sgu = warp_sum(sgu);
+    const float sq = sqrtf(fmaxf(1.0f - t * t, p.clamp_eps));
+    const float cg = sq / (sqrtf(sgg) + p.norm_eps);           // y_i = cg * g_i, i >= 1
+    const float un = sqrtf(suu);
+    const float iu = 1.0f / (un + p.house_eps);
+    const float u0 = __shfl_sync(0xffffffffu, u[0][0], 0);     // 1 - loc_0
+    const float ydotu = (t * u0 + cg * sgu) * iu;               // y . u_hat
+    const float c2 = 2.0f * ydotu * iu;
+    float* zr = p.z + row * D;
+#pragma unroll
+    for (int kq = 0; kq < K; ++kq) {
+      const int i0 = 4 * (lane + 32 * kq);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = i0 + j;
+        if (i < D) {
+          const float y = (i == 0) ? t : cg * g[kq][j];
+          zr[i] = fmaf(-c2, u[kq][j], y);                      // z = y - 2 (y.u_hat) u_hat
+        }
+      }
+    }
+    if (p.save && lane == 0) { p.save[2 * row] = save0; p.save[2 * row + 1] = save1; }
+  }
+  }
+}
+
 template <int FAMILY>
 __global__ void __launch_bounds__(256)
 sphere_rsample_bwd_kernel(const SphereParams p) {
