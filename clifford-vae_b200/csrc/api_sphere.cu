@@ -26,6 +26,17 @@ int launch_sphere_rsample(const SphereParams& p, cudaStream_t st, const char* wh
   }
   return check_launch(what);
 }
+template <int FAMILY>
+int launch_sphere_rsample_bwd(const SphereParams& p, cudaStream_t st, const char* what) {
+  const int grid = row_warp_grid(p.rows);
+  switch ((p.D + 127) / 128) {
+#define CVB_CASE(KK) case KK: sphere_rsample_bwd_reg_kernel<FAMILY, KK><<<grid, 256, 0, st>>>(p); break;
+    CVB_CASE(1) CVB_CASE(2) CVB_CASE(3) CVB_CASE(4) CVB_CASE(5) CVB_CASE(6) CVB_CASE(7) CVB_CASE(8)
+#undef CVB_CASE
+    default: sphere_rsample_bwd_kernel<FAMILY><<<grid, 256, 0, st>>>(p);
+  }
+  return check_launch(what);
+}
 }  // namespace
 
 extern "C" {
@@ -54,8 +65,7 @@ int cvb_powerspherical_rsample_backward(const float* grad_z, const float* loc, c
   p.loc = loc; p.kappa = kappa; p.loc_rows = loc_rows; p.tprime = tprime; p.gnoise = gnoise; p.g_pitch = D - 1;
   p.g_off = 0; p.save = const_cast<float*>(save); p.grad_z = grad_z; p.dloc = dloc; p.dkappa = dkappa; p.rows = rows;
   p.D = D; p.norm_eps = 1e-7f; p.clamp_eps = 1e-7f; p.house_eps = 1e-7f; p.key = make_key(seed, offset, 0);
-  sphere_rsample_bwd_kernel<kFamilyPS><<<row_warp_grid(rows), 256, 0, (cudaStream_t)stream>>>(p);
-  return check_launch("sphere_rsample_bwd_kernel<PS>");
+  return launch_sphere_rsample_bwd<kFamilyPS>(p, (cudaStream_t)stream, "sphere_rsample_bwd_kernel<PS>");
 }
 
 int cvb_powerspherical_log_prob(const float* value, const float* loc, const float* kappa, long long loc_rows,
@@ -113,8 +123,7 @@ int cvb_vmf_rsample_backward(const float* grad_z, const float* loc, const float*
   p.loc = loc; p.kappa = kappa; p.loc_rows = loc_rows; p.gnoise = gnoise; p.g_pitch = D; p.g_off = 1;
   p.save = const_cast<float*>(save); p.grad_z = grad_z; p.dloc = dloc; p.dkappa = dkappa; p.rows = rows; p.D = D;
   p.norm_eps = 0.0f; p.clamp_eps = 1e-10f; p.house_eps = 1e-5f; p.key = make_key(seed, offset, 0);
-  sphere_rsample_bwd_kernel<kFamilyVMF><<<row_warp_grid(rows), 256, 0, (cudaStream_t)stream>>>(p);
-  return check_launch("sphere_rsample_bwd_kernel<VMF>");
+  return launch_sphere_rsample_bwd<kFamilyVMF>(p, (cudaStream_t)stream, "sphere_rsample_bwd_kernel<VMF>");
 }
 
 int cvb_vmf_entropy_lognorm(const float* kappa, long long rows, int D, float* entropy, float* log_norm, float* dentropy,

@@ -425,6 +425,114 @@ sphere_rsample_bwd_kernel(const SphereParams p) {
   }
 }
 
+// Register-resident backward (D <= 128 K), same structure as sphere_rsample_reg_kernel: loc and grad_z are read once with
+// all loads in flight, the replayed normals stay in registers, dloc is written once, and the per-row scalar tail (the
+// implicit Beta gradient for PowerSpherical, fp32 + the fp64 saddle branch) is evaluated for 32 rows in parallel lanes
+// instead of on lane 0 of every row.
+template <int FAMILY, int K>
+__global__ void __launch_bounds__(256)
+sphere_rsample_bwd_reg_kernel(const SphereParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int D = p.D;
+  for (long long base = warp; base < p.rows; base += 32 * nwarps) {
+    // lane j: saved scalars of the batch's j-th row
+    const long long rj = base + (long long)lane * nwarps;
+    float s0_l = 0.f, s1_l = 0.f, gt_l = 0.f;
+    if (rj < p.rows) {
+      if (FAMILY == kFamilyPS) {
+        s0_l = p.tprime ? p.tprime[rj] : p.save[2 * rj];
+      } else {
+        s0_l = p.save[2 * rj];
+        s1_l = p.save[2 * rj + 1];
+      }
+    }
+    for (int jr = 0; jr < 32; ++jr) {
+      const long long row = base + (long long)jr * nwarps;
+      if (row >= p.rows) break;
+      const long long prow = row % p.loc_rows;
+      const float* lr = p.loc + prow * D;
+      const float* gzr = p.grad_z + row * D;
+      float u[K][4], gz[K][4], g[K][4] = {};
+#pragma unroll
+      for (int kq = 0; kq < K; ++kq) {
+        const int i0 = 4 * (lane + 32 * kq);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const bool in = i0 + j < D;
+          u[kq][j] = in ? __ldg(lr + i0 + j) : 0.0f;
+          gz[kq][j] = in ? ldg_stream1(gzr + i0 + j) : 0.0f;
+        }
+      }
+      const float s0 = __shfl_sync(0xffffffffu, s0_l, jr);
+      const float t = (FAMILY == kFamilyPS) ? 2.0f * s0 - 1.0f : s0;
+      float sgg = 0.f, suu = 0.f, sgu = 0.f, sug = 0.f, szg = 0.f;
+#pragma unroll
+      for (int kq = 0; kq < K; ++kq) {
+        const int q = lane + 32 * kq, i0 = 4 * q;
+        if (i0 < D) normals4(p, row, q, 0, g[kq]);       // replays the forward's draws from the counter-based generator
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int i = i0 + j;
+          const bool in = i < D;
+          u[kq][j] = in ? ((i == 0 ? 1.0f : 0.0f) - u[kq][j]) : 0.0f;
+          g[kq][j] = (in && i > 0) ? g[kq][j] : 0.0f;
+          suu = fmaf(u[kq][j], u[kq][j], suu);
+          sug = fmaf(u[kq][j], gz[kq][j], sug);
+          sgg = fmaf(g[kq][j], g[kq][j], sgg);
+          sgu = fmaf(g[kq][j], u[kq][j], sgu);
+          szg = fmaf(gz[kq][j], g[kq][j], szg);
+        }
+      }
+      sgg = warp_sum(sgg); suu = warp_sum(suu); sgu = warp_sum(sgu); sug = warp_sum(sug); szg = warp_sum(szg);
+      const float om = 1.0f - t * t;
+      const float sq = sqrtf(fmaxf(om, p.clamp_eps));
+      const float ng = sqrtf(sgg) + p.norm_eps;
+      const float cg = sq / ng;
+      const float un = sqrtf(suu);
+      const float ne = un + p.house_eps;
+      const float u0 = __shfl_sync(0xffffffffu, u[0][0], 0);      // 1 - loc_0
+      const float gz0 = __shfl_sync(0xffffffffu, gz[0][0], 0);
+      const float a = sug / ne;                                   // grad_z . u_hat
+      const float b = (t * u0 + cg * sgu) / ne;                   // y . u_hat
+      const float gy0 = gz0 - 2.0f * a * u0 / ne;
+      const float s_gv = (szg - 2.0f * a * sgu / ne) / ng;        // grad_y[1:] . v
+      const float dsq = (om > p.clamp_eps) ? (-t / sq) : 0.0f;
+      const float gt = gy0 + dsq * s_gv;
+      if (lane == jr) gt_l = gt;
+      // dloc_i = 2 (a y_i + b gz_i)/ne - u_i 4ab / (un ne)
+      const float k2 = (un > 0.f) ? 4.0f * a * b / (un * ne) : 0.0f;
+      const float ca = 2.0f * a / ne, cb = 2.0f * b / ne;
+      float* dl = p.dloc + row * D;
+#pragma unroll
+      for (int kq = 0; kq < K; ++kq) {
+        const int i0 = 4 * (lane + 32 * kq);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int i = i0 + j;
+          if (i < D) {
+            const float y = (i == 0) ? t : cg * g[kq][j];
+            dl[i] = fmaf(ca, y, fmaf(cb, gz[kq][j], -u[kq][j] * k2));
+          }
+        }
+      }
+    }
+    // scalar tails of the batch, one row per lane
+    if (rj < p.rows) {
+      float dk;
+      if (FAMILY == kFamilyPS) {
+        const float half = 0.5f * (float)(D - 1);
+        const BetaGradConsts bc(half + (__ldg(p.kappa + rj % p.loc_rows) + 1e-7f), half);
+        dk = 2.0f * gt_l * dirichlet_grad_one(s0_l, bc) * (1.0f - s0_l);
+      } else {
+        dk = gt_l * s1_l;
+      }
+      p.dkappa[rj] = dk;
+    }
+  }
+}
+
 // PowerSpherical.log_prob (clifford.py:198-202): lp = logC(kappa) + kappa log1p(clamp(loc . x)).
 // Optional outputs for the backward: coef (rows) = kappa / (1 + dot) inside the clamp else 0
 // (d lp / d loc = coef * value, d lp / d value = coef * loc) and dlp_dkappa (rows).

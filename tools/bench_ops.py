@@ -106,3 +106,20 @@ if what in ("iwae", "all"):
             ms = timeit(fn)
             print(f"iwae {name:28s} B={B:6d} S={S:3d} d={d:5d} {ms:8.3f} ms {rows/(ms*1e-3):.3e} samples/s")
         del loc, z, lp
+if what in ("sphere_bwd", "all"):
+    for fam in ("ps", "vmf"):
+        B, D = 1 << 18, 513
+        loc = torch.nn.functional.normalize(torch.randn(B, D, device=dev), dim=-1); kap = torch.rand(B, device=dev) * 9.2 + 0.8
+        z = torch.empty(B, D, device=dev); save = torch.empty(B, 2, device=dev)
+        gz = torch.randn(B, D, device=dev); dloc = torch.empty(B, D, device=dev); dk = torch.empty(B, device=dev)
+        if fam == "ps":
+            lib.cvb_powerspherical_rsample(loc.data_ptr(), kap.data_ptr(), B, None, None, 3, 0, z.data_ptr(), save.data_ptr(), B, D, st)
+            f = lambda: lib.cvb_powerspherical_rsample_backward(gz.data_ptr(), loc.data_ptr(), kap.data_ptr(), B, None, None, save.data_ptr(), 3, 0,
+                                                                dloc.data_ptr(), dk.data_ptr(), B, D, st)
+        else:
+            lib.cvb_vmf_rsample(loc.data_ptr(), kap.data_ptr(), B, None, None, 0, None, 3, 0, z.data_ptr(), save.data_ptr(), B, D, st)
+            f = lambda: lib.cvb_vmf_rsample_backward(gz.data_ptr(), loc.data_ptr(), kap.data_ptr(), B, None, save.data_ptr(), 3, 0,
+                                                     dloc.data_ptr(), dk.data_ptr(), B, D, st)
+        ms = timeit(f)
+        gb = B * (12 * D + 12) / (ms * 1e-3) / 1e9
+        print(f"{fam} rsample bwd B={B} D={D} {ms:8.3f} ms {B/(ms*1e-3):.3e} rows/s {gb:7.1f} GB/s {100*gb/PEAK:5.1f}% (12D+12 B/row)")
