@@ -1,5 +1,6 @@
 // Host-side launch plumbing shared by the api_*.cu translation units.
 #pragma once
+#include <cstdlib>
 #include <cstdio>
 #include <atomic>
 #include "common.cuh"
@@ -63,6 +64,8 @@ inline int persistent_grid(Kernel kernel, int threads, size_t smem, long long wo
     set_last_error("kernel does not fit on an SM (threads=%d smem=%zu)", threads, smem);
     return kUnsupported;
   }
+  static const int cap = getenv("CVB_MAX_CTAS_PER_SM") ? atoi(getenv("CVB_MAX_CTAS_PER_SM")) : 0;   // tuning knob
+  if (cap > 0 && per_sm > cap) per_sm = cap;
   long long g = (long long)sm_count() * per_sm;
   if (g > work_ctas) g = work_ctas;
   if (g < 1) g = 1;
