@@ -76,13 +76,13 @@ int cvb_vsa_depth_chain_cosine(const float* vecs, float* out, long long trials, 
 
 int cvb_vsa_invert(const float* a, float* out, long long rows, int d, void* stream) {
   CVB_REQUIRE(a && out && rows > 0 && d >= 1, kBadArgument, "cvb_vsa_invert: bad arguments");
-  invert_kernel<<<ew_grid(rows * d, 256), 256, 0, (cudaStream_t)stream>>>(a, out, rows, d);
+  invert_kernel<<<ew_grid(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(a, out, rows, d);
   return check_launch("invert_kernel");
 }
 
 int cvb_vsa_permute(const float* v, const long long* perm, float* out, long long rows, int d, int inverse, void* stream) {
   CVB_REQUIRE(v && perm && out && rows > 0 && d >= 1, kBadArgument, "cvb_vsa_permute: bad arguments");
-  permute_kernel<<<ew_grid(rows * d, 256), 256, 0, (cudaStream_t)stream>>>(v, perm, out, rows, d, inverse);
+  permute_kernel<<<ew_grid(rows * 256, 256), 256, 0, (cudaStream_t)stream>>>(v, perm, out, rows, d, inverse);
   return check_launch("permute_kernel");
 }
 
@@ -128,7 +128,8 @@ int cvb_vsa_cosine_backward(const float* a, const float* b, const float* grad_ou
 
 int cvb_vsa_normalize(const float* x, float* out, long long rows, int d, void* stream) {
   CVB_REQUIRE(x && out && rows > 0 && d >= 1, kBadArgument, "cvb_vsa_normalize: bad arguments");
-  normalize_kernel<<<ew_grid(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(x, out, rows, d);
+  const int vec4 = (d % 4 == 0) && aligned(x, 16) && aligned(out, 16);
+  normalize_kernel<<<ew_grid(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(x, out, rows, d, vec4);
   return check_launch("normalize_kernel");
 }
 

@@ -299,25 +299,33 @@ bind_generic_kernel(const BindParams p, int d) {
 
 // ---- elementwise / reduction VSA helpers --------------------------------------------------------
 // invert (vsa.py:49-53): out[r, j] = a[r, (d - j) mod d]
-static __global__ void invert_kernel(const float* __restrict__ a, float* __restrict__ out, long long rows, int d) {
-  const long long total = rows * d;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / d;
-    const int j = (int)(i - r * d);
-    out[i] = a[r * d + (j == 0 ? 0 : d - j)];
+// one warp per row: no per-element 64-bit division
+static __global__ void __launch_bounds__(256)
+invert_kernel(const float* __restrict__ a, float* __restrict__ out, long long rows, int d) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long row = warp; row < rows; row += nwarps) {
+    const float* ar = a + row * (long long)d;
+    float* orow = out + row * (long long)d;
+#pragma unroll 4
+    for (int j = lane; j < d; j += 32) stg_stream1(orow + j, ldg_stream1(ar + (j == 0 ? 0 : d - j)));
   }
 }
 
 // permute (vsa.py:82-84): out[r, j] = v[r, perm[j]];  unpermute (:87-90): out[r, perm[j]] = v[r, j]
 static __global__ void permute_kernel(const float* __restrict__ v, const long long* __restrict__ perm, float* __restrict__ out,
                                long long rows, int d, int inverse) {
-  const long long total = rows * d;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / d;
-    const int j = (int)(i - r * d);
-    const long long pj = perm[j];
-    if (inverse) out[r * d + pj] = v[i];
-    else out[i] = v[r * d + pj];
+  // one CTA per row: the 256 threads gather from the same (L1-resident) row; no per-element 64-bit division
+  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+    const float* vr = v + row * (long long)d;
+    float* orow = out + row * (long long)d;
+#pragma unroll 4
+    for (int j = threadIdx.x; j < d; j += blockDim.x) {
+      const int pj = (int)__ldg(perm + j);
+      if (inverse) orow[pj] = vr[j];
+      else orow[j] = vr[pj];
+    }
   }
 }
 
@@ -420,17 +428,31 @@ cosine_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, cons
 
 // normalize_vectors (vsa.py:39-40): x / max(||x||, 1e-12); backward dx = (g - y (y.g)) / max(||x||, eps)
 static __global__ void __launch_bounds__(256)
-normalize_kernel(const float* __restrict__ x, float* __restrict__ out, long long rows, int d) {
+normalize_kernel(const float* __restrict__ x, float* __restrict__ out, long long rows, int d, int vec4) {
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   for (long long row = warp; row < rows; row += nwarps) {
     const float* xr = x + row * (long long)d;
+    float* orow = out + row * (long long)d;
     float ss = 0.f;
+    if (vec4) {
+      // rows are 16-byte aligned and d % 4 == 0: 128-bit accesses (the second pass hits L1 / L2)
+      const float4* x4 = reinterpret_cast<const float4*>(xr);
+      float4* o4 = reinterpret_cast<float4*>(orow);
+      const int d4 = d >> 2;
+#pragma unroll 4
+      for (int i = lane; i < d4; i += 32) { const float4 v = x4[i]; ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w; }
+      ss = warp_sum(ss);
+      const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll 4
+      for (int i = lane; i < d4; i += 32) { const float4 v = x4[i]; o4[i] = make_float4(v.x * inv, v.y * inv, v.z * inv, v.w * inv); }
+      continue;
+    }
     for (int i = lane; i < d; i += 32) { const float v = xr[i]; ss += v * v; }
     ss = warp_sum(ss);
     const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
-    for (int i = lane; i < d; i += 32) out[row * (long long)d + i] = xr[i] * inv;
+    for (int i = lane; i < d; i += 32) orow[i] = xr[i] * inv;
   }
 }
 static __global__ void __launch_bounds__(256)

@@ -123,3 +123,20 @@ if what in ("sphere_bwd", "all"):
         ms = timeit(f)
         gb = B * (12 * D + 12) / (ms * 1e-3) / 1e9
         print(f"{fam} rsample bwd B={B} D={D} {ms:8.3f} ms {B/(ms*1e-3):.3e} rows/s {gb:7.1f} GB/s {100*gb/PEAK:5.1f}% (12D+12 B/row)")
+if what in ("vsa_small", "all"):
+    for dd in (1024, 4096):
+        N = (1 << 30) // (8 * dd)
+        a = torch.randn(N, dd, device=dev); b = torch.randn(N, dd, device=dev); o = torch.empty(N, dd, device=dev); r = torch.empty(N, device=dev)
+        ws_bytes = lib.cvb_vsa_bundle_workspace_bytes(N, dd)
+        ws = torch.empty(max(int(ws_bytes), 4) // 4 + 1, device=dev); od = torch.empty(dd, device=dev)
+        perm = torch.randperm(dd, device=dev)
+        for name, fn, byts in (
+                ("cosine", lambda: lib.cvb_vsa_cosine(a.data_ptr(), b.data_ptr(), r.data_ptr(), N, N, N, dd, st), N * (8 * dd + 4)),
+                ("normalize", lambda: lib.cvb_vsa_normalize(a.data_ptr(), o.data_ptr(), N, dd, st), N * 8 * dd),
+                ("invert", lambda: lib.cvb_vsa_invert(a.data_ptr(), o.data_ptr(), N, dd, st), N * 8 * dd),
+                ("permute", lambda: lib.cvb_vsa_permute(a.data_ptr(), perm.data_ptr(), o.data_ptr(), N, dd, 0, st), N * 8 * dd),
+                ("bundle", lambda: lib.cvb_vsa_bundle(a.data_ptr(), od.data_ptr(), N, dd, 1.0, ws.data_ptr(), st), N * 4 * dd)):
+            ms = timeit(fn)
+            gb = byts / (ms * 1e-3) / 1e9
+            print(f"{name:10s} d={dd:5d} N={N:7d} {ms:8.3f} ms {gb:7.1f} GB/s {100*gb/PEAK:5.1f}%")
+        del a, b, o
