@@ -112,15 +112,16 @@ def test_ks_device_samplers_vs_reference(golden_ks):
             assert pval > 1e-3, ("vmf", D, col, pval)
 
 
+@pytest.mark.parametrize("B,D", [(64, 513), (40, 5), (33, 128), (35, 129), (70, 300), (20, 1024), (9, 1025), (6, 2051)])
 @pytest.mark.parametrize("family", ["ps", "vmf"])
-def test_rng_mode_backward_consistency(family):
+def test_rng_mode_backward_consistency(family, B, D):
     """RNG mode: the backward replays the tangent normals from Philox; check it against autograd of
-    the oracle fed the realised sample's own decomposition."""
+    the oracle fed the realised sample's own decomposition.  D <= 1024 runs the register-resident kernels (every
+    K = ceil(D / 128) boundary), larger D the two-pass kernels; B > 32 exercises the 32-row scalar batches."""
     from oracle import latent_oracle as O
     from dists.clifford import PowerSpherical
     from hyperspherical_vae.distributions import VonMisesFisher
     torch.manual_seed(9)
-    B, D = 64, 513
     loc = torch.nn.functional.normalize(torch.randn(B, D, device=DEV), dim=-1).requires_grad_()
     if family == "ps":
         kap = (torch.rand(B, device=DEV) * 9 + 0.8).requires_grad_()
