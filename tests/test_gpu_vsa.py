@@ -218,3 +218,36 @@ def test_c4_full_size_2pow20_vectors():
     s = vsa.bundle(ab, normalize=True)
     assert s.shape == (d,) and torch.isfinite(s).all()
     assert rel_err(s.cpu(), (ab.double().sum(0) / N ** 0.5).cpu()) < 1e-5
+
+
+def test_indexing_beyond_2_31_elements():
+    """Row offsets are 64-bit: tensors with more than 2^31 elements (C4 sizes: 2^20 vectors at d up to 16384 per GPU)
+    round-trip in their LAST rows too.  ~26 GB of device memory."""
+    from utils import vsa
+    from dists.clifford import CliffordPowerSphericalDistribution
+    if torch.cuda.get_device_properties(0).total_memory < 60 * 2 ** 30:
+        pytest.skip("needs ~26 GB of device memory")
+    torch.manual_seed(8)
+    N, d = (1 << 18) + 3, 8192                       # 2.15e9 elements per operand
+    a = vsa.hrr_init(N, d, device=DEV)
+    key = vsa.unitary_init(1, d, device=DEV)
+    assert a.numel() > 2 ** 31 and float(a[-1].abs().max()) > 0 and float(a[N // 2].abs().max()) > 0
+    bound = vsa.bind(a, key)
+    rec = vsa.unbind(bound, key)
+    for sl in (slice(0, 4), slice(N // 2, N // 2 + 4), slice(N - 4, N)):
+        assert float((rec[sl] - a[sl]).abs().max()) < 1e-3 * float(a[sl].abs().max())
+    cs = vsa.similarity(rec, a)
+    assert cs.shape == (N,) and float((cs - 1).abs().max()) < 1e-4
+    del bound, rec, cs, a
+    torch.cuda.empty_cache()
+    B, dl = (1 << 19) + 1, 2048                      # z: 2.15e9 elements
+    loc = torch.randn(B, dl, device=DEV)
+    kap = torch.rand(B, 1, device=DEV) * 5 + 0.2
+    q = CliffordPowerSphericalDistribution(loc, kap, validate_args=False)
+    z = q.rsample()
+    assert z.numel() > 2 ** 31
+    for sl in (slice(0, 8), slice(B - 8, B)):
+        F = torch.fft.rfft(z[sl].double(), dim=-1)
+        assert float((F.abs() - 1).abs().max()) < 5e-5 and float((z[sl].norm(dim=-1) - 1).abs().max()) < 1e-5
+    kl = torch.distributions.kl.kl_divergence(q, __import__("dists.clifford", fromlist=["x"]).CliffordTorusUniform(dl, device=DEV))
+    assert kl.shape == (B,) and torch.isfinite(kl).all() and float(kl.min()) > -1e-3
