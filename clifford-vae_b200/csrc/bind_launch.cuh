@@ -10,7 +10,7 @@ namespace cvb {
 template <int LOG2N, int MODE>
 int launch_bind_fast(const BindParams& p_in, cudaStream_t st) {
   BindParams p = p_in;
-  using Pl = FftPlan<LOG2N>;
+  using Pl = WideFftPlan<LOG2N>;
   const cplx* tw = device_twiddles();
   if (!tw) return kCudaError;
   // CVB_BIND_VARIANT (experiments): "staged" (TMA-staged rows) or "direct" (plain loads); default by size

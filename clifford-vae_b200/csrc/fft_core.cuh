@@ -15,11 +15,18 @@
 
 namespace cvb {
 
-template <int LOG2N>
-struct FftPlan {
-  static_assert(LOG2N >= 4 && LOG2N <= 13, "fast path covers N = 16 .. 8192 complex points");
+// LOGE = log2(points per thread).  The default plan keeps 16 points per thread for every N >= 256; the bind kernels use
+// 32 points per thread at N = 8192 (radix 32 x 32 x 8 on 256 threads): with 16 points that size needs 512 threads, which
+// caps the kernel at 128 registers per thread (it spilled) and costs a fourth pass.  (The Clifford kernels at N = 8192
+// were measured 11-24 % SLOWER on the wide plan -- their sampling loops want the extra warps -- so it is opt-in.)
+constexpr int default_loge(int log2n) { return (log2n >= 8) ? 4 : (log2n >= 6 ? 3 : 2); }
+
+template <int LOG2N_, int LOGE_>
+struct FftPlanT {
+  static_assert(LOG2N_ >= 4 && LOG2N_ <= 13, "fast path covers N = 16 .. 8192 complex points");
+  static constexpr int LOG2N = LOG2N_;
   static constexpr int N = 1 << LOG2N;
-  static constexpr int LOGE = (LOG2N >= 8) ? 4 : (LOG2N >= 6 ? 3 : 2);
+  static constexpr int LOGE = LOGE_;
   static constexpr int E = 1 << LOGE;              // points per thread
   static constexpr int T = N / E;                  // threads per FFT
   static constexpr int LOGT = LOG2N - LOGE;
@@ -27,13 +34,16 @@ struct FftPlan {
   static constexpr int THREADS = (T >= 128) ? T : 128;   // CTA size
   static constexpr int GROUPS = THREADS / T;       // FFTs processed side by side in one CTA
 };
+template <int LOG2N>
+using FftPlan = FftPlanT<LOG2N, default_loge(LOG2N)>;
+template <int LOG2N>
+using WideFftPlan = FftPlanT<LOG2N, (LOG2N >= 13) ? 5 : default_loge(LOG2N)>;
 
 // Barrier among the T threads that own one FFT.  A group of <= 32 threads is (part of) one warp:
 // __syncwarp; a group that is a proper part of the CTA uses its own named barrier, so the groups of a
 // CTA run independently; a group that is the whole CTA uses __syncthreads.
-template <int LOG2N>
-__device__ __forceinline__ void group_sync() {
-  using Pl = FftPlan<LOG2N>;
+template <class Pl>
+__device__ __forceinline__ void group_sync_p() {
   if constexpr (Pl::T <= 32) {
     __syncwarp();
   } else if constexpr (Pl::T < Pl::THREADS) {
@@ -42,6 +52,8 @@ __device__ __forceinline__ void group_sync() {
     __syncthreads();
   }
 }
+template <int LOG2N>
+__device__ __forceinline__ void group_sync() { group_sync_p<FftPlan<LOG2N>>(); }
 
 // ---- small in-register DFTs (natural order in, natural order out) ---------------------------
 template <bool INV>
@@ -126,6 +138,35 @@ struct Dft<16, INV> {
   }
 };
 
+template <bool INV>
+struct Dft<32, INV> {
+  // decimation in time over two 16-point transforms: X[k] = E[k] + W32^k O[k], X[k + 16] = E[k] - W32^k O[k]
+  static __device__ __forceinline__ void run(cplx (&u)[32]) {
+    constexpr float c[16] = {1.0f, 0.98078528040323044913f, 0.92387953251128675613f, 0.83146961230254523708f,
+                             0.70710678118654752440f, 0.55557023301960222474f, 0.38268343236508977173f, 0.19509032201612826785f,
+                             0.0f, -0.19509032201612826785f, -0.38268343236508977173f, -0.55557023301960222474f,
+                             -0.70710678118654752440f, -0.83146961230254523708f, -0.92387953251128675613f, -0.98078528040323044913f};
+    constexpr float s[16] = {0.0f, 0.19509032201612826785f, 0.38268343236508977173f, 0.55557023301960222474f,
+                             0.70710678118654752440f, 0.83146961230254523708f, 0.92387953251128675613f, 0.98078528040323044913f,
+                             1.0f, 0.98078528040323044913f, 0.92387953251128675613f, 0.83146961230254523708f,
+                             0.70710678118654752440f, 0.55557023301960222474f, 0.38268343236508977173f, 0.19509032201612826785f};
+    cplx ev[16], od[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { ev[i] = u[2 * i]; od[i] = u[2 * i + 1]; }
+    Dft<16, INV>::run(ev);
+    Dft<16, INV>::run(od);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      cplx o;
+      if (k == 0) o = od[0];
+      else if (k == 8) o = INV ? cmul_i(od[8]) : cmul_mi(od[8]);
+      else o = rot<INV>(od[k], c[k], s[k]);
+      u[k] = cadd(ev[k], o);
+      u[k + 16] = csub(ev[k], o);
+    }
+  }
+};
+
 // u[r] *= w1^r, r = 1..R-1 (powers built by squaring / one extra multiply: depth <= 2 log2 R)
 template <int R>
 __device__ __forceinline__ void apply_twiddle_powers(cplx (&u)[R], cplx w1) {
@@ -144,15 +185,14 @@ __device__ __forceinline__ void apply_twiddle_powers(cplx (&u)[R], cplx w1) {
   for (int i = 1; i < R; ++i) u[i] = cmul(u[i], w[i]);
 }
 
-template <int LOG2N, int P, bool INV>
-__device__ __forceinline__ void fft_pass(cplx (&v)[FftPlan<LOG2N>::E], cplx* xch, const int t,
-                                         const cplx* __restrict__ tw) {
-  using Pl = FftPlan<LOG2N>;
+template <class Pl, int P, bool INV>
+__device__ __forceinline__ void fft_pass_p(cplx (&v)[Pl::E], cplx* xch, const int t, const cplx* __restrict__ tw) {
+  constexpr int LOG2N = Pl::LOG2N;
   constexpr int LOGNS = P * Pl::LOGE;
   constexpr int LOGR = (LOG2N - LOGNS) < Pl::LOGE ? (LOG2N - LOGNS) : Pl::LOGE;
   constexpr int R = 1 << LOGR, Q = Pl::E / R, NS = 1 << LOGNS;
   constexpr bool LAST = (LOGNS + LOGR == LOG2N);
-  if (!LAST) group_sync<LOG2N>();               // earlier readers of xch are done
+  if (!LAST) group_sync_p<Pl>();                // earlier readers of xch are done
 #pragma unroll
   for (int q = 0; q < Q; ++q) {
     cplx u[R];
@@ -176,18 +216,22 @@ __device__ __forceinline__ void fft_pass(cplx (&v)[FftPlan<LOG2N>::E], cplx* xch
     }
   }
   if constexpr (!LAST) {
-    group_sync<LOG2N>();
+    group_sync_p<Pl>();
 #pragma unroll
     for (int e = 0; e < Pl::E; ++e) v[e] = xch[pad16(t + e * Pl::T)];
-    fft_pass<LOG2N, P + 1, INV>(v, xch, t, tw);
+    fft_pass_p<Pl, P + 1, INV>(v, xch, t, tw);
   }
 }
 
 // In: v[e] = x[t + e T].  Out: v[e] = X[t + e T], X[k] = sum_j x[j] exp(-+ 2 pi i j k / N) (unnormalised).
+template <class Pl, bool INV>
+__device__ __forceinline__ void fft_run_p(cplx (&v)[Pl::E], cplx* xch, int t, const cplx* __restrict__ tw) {
+  fft_pass_p<Pl, 0, INV>(v, xch, t, tw);
+}
 template <int LOG2N, bool INV>
 __device__ __forceinline__ void fft_run(cplx (&v)[FftPlan<LOG2N>::E], cplx* xch, int t,
                                         const cplx* __restrict__ tw) {
-  fft_pass<LOG2N, 0, INV>(v, xch, t, tw);
+  fft_pass_p<FftPlan<LOG2N>, 0, INV>(v, xch, t, tw);
 }
 
 // R2C untangle.  In: v = Z = FFT_N(z), z[m] = x[2m] + i x[2m+1] of a real row of length n = 2N.

@@ -61,14 +61,14 @@ __device__ __forceinline__ cplx bind_op_unscaled(int mode, cplx a, cplx b) {
 // next row's HBM read overlaps this row's passes; otherwise plain coalesced 64-bit loads.
 template <int LOG2N, int STAGED>
 constexpr size_t bind_v3_smem_bytes() {
-  using Pl = FftPlan<LOG2N>;
+  using Pl = WideFftPlan<LOG2N>;
   return (sizeof(cplx) * (Pl::XCH + Pl::N + (STAGED == 2 ? Pl::N : 0)) + 3 * sizeof(uint64_t)) * Pl::GROUPS;
 }
 
 template <int LOG2N, int MODE, int STAGED>
-__global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS, (FftPlan<LOG2N>::THREADS <= 128 ? CVB_BIND_MINB : (FftPlan<LOG2N>::THREADS <= 256 ? 2 : 1)))
+__global__ void __launch_bounds__(WideFftPlan<LOG2N>::THREADS, (WideFftPlan<LOG2N>::THREADS <= 128 ? CVB_BIND_MINB : ((WideFftPlan<LOG2N>::THREADS <= 256 && WideFftPlan<LOG2N>::E <= 16) ? 2 : 1)))
 bind_v3_kernel(const BindParams p, const cplx* __restrict__ tw) {
-  using Pl = FftPlan<LOG2N>;
+  using Pl = WideFftPlan<LOG2N>;
   constexpr int N = Pl::N, T = Pl::T, E = Pl::E, G = Pl::GROUPS;
   constexpr uint32_t kRowBytes = 2u * N * sizeof(float);
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -118,7 +118,7 @@ bind_v3_kernel(const BindParams p, const cplx* __restrict__ tw) {
 #pragma unroll
       for (int e = 0; e < E; ++e) v[e] = valid ? ldg_stream2(ar + t + e * T) : make_float2(0.f, 0.f);
     }
-    fft_run<LOG2N, false>(v, xch, t, tw);      // (STAGED: its barriers order every thread's stage read before the park write)
+    fft_run_p<Pl, false>(v, xch, t, tw);      // (STAGED: its barriers order every thread's stage read before the park write)
     const long long next_row = dynamic ? (long long)*next_slot + stride : row + stride;   // visible after the barriers above
     const bool next_valid = next_row < p.rows;
 #pragma unroll
@@ -133,16 +133,16 @@ bind_v3_kernel(const BindParams p, const cplx* __restrict__ tw) {
 #pragma unroll
       for (int e = 0; e < E; ++e) v[e] = valid ? ldg_stream2(br + t + e * T) : make_float2(1.f, 0.f);
     }
-    fft_run<LOG2N, false>(v, xch, t, tw);
+    fft_run_p<Pl, false>(v, xch, t, tw);
     if (STAGED == 2 && t == 0 && next_valid) {   // every thread has read stage_b (barriers inside fft_run)
       mbar_expect_tx(&bars[1], kRowBytes);
       tma_load_1d(stage_b, p.b + (next_row % p.b_rows) * (2LL * N), kRowBytes, &bars[1]);
     }
     // ---- one partner exchange: untangle a and b, pointwise op, re-pack for the inverse transform
-    group_sync<LOG2N>();
+    group_sync_p<Pl>();
 #pragma unroll
     for (int e = 0; e < E; ++e) xch[pad16(t + e * T)] = v[e];
-    group_sync<LOG2N>();
+    group_sync_p<Pl>();
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       const int k = t + e * T, kp = (N - k) & (N - 1);
@@ -163,13 +163,13 @@ bind_v3_kernel(const BindParams p, const cplx* __restrict__ tw) {
     }
     if (STAGED) {
       fence_proxy_async();                       // parked-spectrum accesses before the next TMA write
-      group_sync<LOG2N>();
+      group_sync_p<Pl>();
       if (t == 0 && next_valid) {
         mbar_expect_tx(&bars[0], kRowBytes);
         tma_load_1d(park, p.a + (next_row % p.a_rows) * (2LL * N), kRowBytes, &bars[0]);
       }
     }
-    fft_run<LOG2N, true>(v, xch, t, tw);        // begins with a barrier: partner reads are complete
+    fft_run_p<Pl, true>(v, xch, t, tw);        // begins with a barrier: partner reads are complete
     if (valid) {
       float2* o = reinterpret_cast<float2*>(p.out + row * (2LL * N));
 #pragma unroll
