@@ -18,7 +18,8 @@ namespace cvb {
 // LOGE = log2(points per thread).  The default plan keeps 16 points per thread for every N >= 256; the bind kernels use
 // 32 points per thread at N = 8192 (radix 32 x 32 x 8 on 256 threads): with 16 points that size needs 512 threads, which
 // caps the kernel at 128 registers per thread (it spilled) and costs a fourth pass.  (The Clifford kernels at N = 8192
-// were measured 11-24 % SLOWER on the wide plan -- their sampling loops want the extra warps -- so it is opt-in.)
+// were measured 11-24 % SLOWER on the wide plan -- their sampling loops want the extra warps -- so it is opt-in; a
+// two-pass 32 x 32 plan for bind at N = 1024 was also measured: 43.9 % vs 47.1 % of the HBM roofline, not adopted.)
 constexpr int default_loge(int log2n) { return (log2n >= 8) ? 4 : (log2n >= 6 ? 3 : 2); }
 
 template <int LOG2N_, int LOGE_>
