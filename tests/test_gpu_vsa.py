@@ -251,3 +251,37 @@ def test_indexing_beyond_2_31_elements():
         assert float((F.abs() - 1).abs().max()) < 5e-5 and float((z[sl].norm(dim=-1) - 1).abs().max()) < 1e-5
     kl = torch.distributions.kl.kl_divergence(q, __import__("dists.clifford", fromlist=["x"]).CliffordTorusUniform(dl, device=DEV))
     assert kl.shape == (B,) and torch.isfinite(kl).all() and float(kl.min()) > -1e-3
+
+
+def test_kernels_are_cuda_graph_capturable():
+    """The entry points neither allocate nor synchronise, so a chain of them records into a CUDA graph and replays
+    with new input contents (only the device-RNG samplers bake their (seed, offset) into the graph)."""
+    from utils import vsa
+    from dists.clifford import CliffordPowerSphericalDistribution
+    torch.manual_seed(12)
+    N, d = 64, 1024
+    a = vsa.hrr_init(N, d, device=DEV)
+    key = vsa.unitary_init(N, d, device=DEV)
+    loc = torch.randn(N, d // 2, device=DEV)
+    kap = torch.rand(N, 1, device=DEV) * 4 + 0.3
+    q = CliffordPowerSphericalDistribution(loc, kap, validate_args=False)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s), torch.no_grad():
+        for _ in range(2):                                # warm-up outside capture (lazy init, occupancy cache)
+            rec = vsa.unbind(vsa.bind(a, key), key)
+            cs = vsa.similarity(rec, a)
+            lp = q.log_prob(rec)
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.no_grad(), torch.cuda.graph(g):
+        rec = vsa.unbind(vsa.bind(a, key), key)
+        cs = vsa.similarity(rec, a)
+        lp = q.log_prob(rec)
+    a.copy_(vsa.hrr_init(N, d, device=DEV))               # new contents, same buffers
+    g.replay()
+    torch.cuda.synchronize()
+    assert float((rec - a).abs().max()) < 1e-3 * float(a.abs().max())
+    assert float((cs - 1).abs().max()) < 1e-4
+    with torch.no_grad():
+        assert rel_err(lp.cpu(), q.log_prob(rec.clone()).cpu()) < 1e-6
