@@ -221,9 +221,9 @@ class CliffordPowerSphericalDistribution(CliffordTorusDistribution):
         return z.reshape(out_shape).to(self.dtype)
 
     def rsample_bind(self, other, sample_shape=torch.Size(), return_sample=True, _base_draws=None):
-        """Extension (not in the reference): draw z and return bind(z, other) from ONE kernel.  The sample's
-        spectrum is the unit phasors themselves, so binding it costs one forward FFT of `other` and one inverse
-        FFT, and z is never re-read.  `other`: (2d,), (1, 2d) or sample_shape + batch_shape + (2d,).  Forward only
+        """Extension (not in the reference): draw z and return bind(z, other); with return_sample=False from ONE
+        kernel.  The sample's spectrum is the unit phasors themselves, so binding it costs one forward FFT of `other`
+        and one inverse FFT, and z is never materialised.  `other`: (2d,), (1, 2d) or sample_shape + batch_shape + (2d,).  Forward only
         (under autograd use rsample() and utils.vsa.bind).  Returns (z, bound), or bound if return_sample=False."""
         from . import vsa
         sample_shape = torch.Size(sample_shape)
@@ -231,7 +231,9 @@ class CliffordPowerSphericalDistribution(CliffordTorusDistribution):
         d = self.orig_dim
         n = _numel(sample_shape)
         out_shape = tuple(sample_shape) + tuple(self.batch_shape) + (2 * d,)
-        fast = kap2.shape[-1] == 1 and d >= 16 and d <= 8192 and (d & (d - 1)) == 0
+        # the one-kernel path pays off when z itself is not wanted (its inverse FFT and 8d bytes of writes are skipped:
+        # 12-17 % faster than rsample + bind); with z written the two specialised kernels are faster than the fused one
+        fast = (not return_sample) and kap2.shape[-1] == 1 and d >= 16 and d <= 8192 and (d & (d - 1)) == 0
         if not fast:
             z = self.rsample(sample_shape, _base_draws=_base_draws)
             bound = vsa.bind(z, other)

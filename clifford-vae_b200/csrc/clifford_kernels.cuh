@@ -20,8 +20,12 @@
 // backward: 5 resident CTAs help at d = 2048 (+7 %), hurt at d = 1024 (-5 %); log_prob: 4 is best at every size
 template <int LOG2N>
 constexpr int clifford_bwd_min_blocks() { return LOG2N == 11 ? 5 : 4; }
-template <int LOG2N>
-constexpr int clifford_fwd_min_blocks() { return LOG2N == 10 ? 4 : CVB_FWD_MINB; }
+#ifndef CVB_FWD_BIND_MINB
+#define CVB_FWD_BIND_MINB 3
+#endif
+// the fused-bind variant carries a second set of transforms: it needs ~150 registers (it spilled at 4-5 CTAs / SM)
+template <int LOG2N, bool BIND = false>
+constexpr int clifford_fwd_min_blocks() { return BIND ? CVB_FWD_BIND_MINB : (LOG2N == 10 ? 4 : CVB_FWD_MINB); }
 
 namespace cvb {
 
@@ -235,7 +239,7 @@ constexpr size_t clifford_fwd_smem_bytes() {
 // predicated-off instructions of the optional outputs and the global-memory input path are compiled out (+8 %).
 // (Also assuming the dynamic schedule / always-valid rows was measured: +2 % at d = 512 / 1024, -2 % at d = 2048.)
 template <int LOG2N, int MODE, bool ROWK, bool BIND = false, bool LEAN = false>
-__global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS, (FftPlan<LOG2N>::THREADS <= 128 ? clifford_fwd_min_blocks<LOG2N>() : 1))
+__global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS, (FftPlan<LOG2N>::THREADS <= 128 ? clifford_fwd_min_blocks<LOG2N, BIND>() : 1))
 clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw) {
   using Pl = FftPlan<LOG2N>;
   constexpr int d = Pl::N, T = Pl::T, E = Pl::E, G = Pl::GROUPS;

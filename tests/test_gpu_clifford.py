@@ -312,6 +312,15 @@ def test_fused_rsample_bind_matches_separate_ops(golden_clifford, name):
     from utils import vsa
     z3, b3 = q.rsample_bind(roles.to(DEV), torch.Size(sshape))
     assert rel_err(b3.cpu(), vsa.bind(z3, roles.to(DEV)).cpu()) < 2e-5
+    # the fused kernel's own z output (the Python layer prefers two kernels when z is wanted; the C ABI offers both)
+    d = c["loc"].shape[-1]
+    if d >= 16 and d & (d - 1) == 0:
+        from clifford_b200 import ops
+        n = int(np.prod(sshape)) if sshape else 1
+        z4, b4, _ = ops.clifford_rsample_bind(T(c["loc"]), T(c["kappa"]), roles.reshape(-1, 2 * d).to(DEV), n,
+                                              (T(c["tprime"]).reshape(-1, d), T(c["g"]).reshape(-1, d)), True)
+        assert rel_err(z4.cpu(), zref.reshape(-1, 2 * d)) < 1e-5
+        assert rel_err(b4.cpu(), O.bind(zref, roles).reshape(-1, 2 * d)) < 2e-5
 
 
 def test_extreme_concentrations_are_stable():
