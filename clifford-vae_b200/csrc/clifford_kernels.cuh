@@ -141,7 +141,7 @@ __device__ __forceinline__ RowSrc global_row_src(const CliffordFwdParams& p, lon
   return s;
 }
 
-// e^{i theta_k} for bin k (1 <= k <= d-1) of `row`.  For kPsRng a rejected first Marsaglia-Tsang
+// e^{i theta_k} for bin k (1 <= k <= d-1) of `row`.  For kPsRng a rejected first half-angle envelope
 // proposal returns false (the caller queues k and finishes it with clifford_phasor_retry).
 template <int MODE, bool ROWK>
 __device__ __forceinline__ bool clifford_phasor(const CliffordFwdParams& p, const RowSrc& src, long long row,
