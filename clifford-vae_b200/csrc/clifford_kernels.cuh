@@ -17,9 +17,9 @@
 #ifndef CVB_FWD_MINB
 #define CVB_FWD_MINB 5
 #endif
-// backward: 5 resident CTAs help at d = 2048 (+7 %), hurt at d = 1024 (-5 %); log_prob: 4 is best at every size
+// backward: 5 resident CTAs help at d = 2048 (+7 %) and d = 512 (+6 %), hurt at d = 1024 (-2 %); log_prob: 4 is best at every size
 template <int LOG2N>
-constexpr int clifford_bwd_min_blocks() { return LOG2N == 11 ? 5 : 4; }
+constexpr int clifford_bwd_min_blocks() { return LOG2N == 10 ? 4 : 5; }
 #ifndef CVB_FWD_BIND_MINB
 #define CVB_FWD_BIND_MINB 3
 #endif
