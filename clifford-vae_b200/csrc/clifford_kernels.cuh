@@ -733,7 +733,7 @@ __device__ __forceinline__ void clifford_lp_element(const CliffordLogProbParams&
 constexpr int kLpConstCache = 256;   // rows per group whose log-normaliser constants are precomputed
 
 template <int LOG2N, bool ROWK, bool FWD_ONLY = false>
-__global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS, (FftPlan<LOG2N>::THREADS <= 128 ? 4 : 1))
+__global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS, (FftPlan<LOG2N>::THREADS <= 128 ? ((FWD_ONLY && LOG2N <= 9) ? 5 : 4) : 1))
 clifford_log_prob_kernel(const CliffordLogProbParams p, const cplx* __restrict__ tw) {
   using Pl = FftPlan<LOG2N>;
   constexpr int d = Pl::N, T = Pl::T, E = Pl::E, G = Pl::GROUPS;
