@@ -20,6 +20,15 @@ int launch_fwd_fast(const CliffordFwdParams& p, cudaStream_t st) {
   int grid = 0;
   const long long work = (p.rows + Pl::GROUPS - 1) / Pl::GROUPS;
   if (int rc = persistent_grid(kern, Pl::THREADS, smem, work, &grid)) return rc;
+  if constexpr (LEAN) {
+    // 7 resident CTAs / SM win 2-3 % once a CTA loops over >= 8 rows (and for single-row grids), but the longer row
+    // latency costs 1-2 % when a CTA only gets 3-5 rows (B = 4096 at d = 2048): fall back to 6 there (measured sweep)
+    const int sms = sm_count();
+    if (grid == sms * 7) {
+      const double rows_per_cta = (double)work / (double)grid;
+      if (rows_per_cta > 2.0 && rows_per_cta < 6.0) grid = sms * 6;
+    }
+  }
   static const bool static_sched = getenv("CVB_STATIC_SCHEDULE") != nullptr;
   const bool dynamic = !static_sched && work > grid;                         // dynamic rows only when CTAs loop
   if constexpr (MODE == kPsRng && ROWK && !LEAN) {

@@ -24,8 +24,13 @@ constexpr int clifford_bwd_min_blocks() { return LOG2N == 10 ? 4 : 5; }
 #define CVB_FWD_BIND_MINB 3
 #endif
 // the fused-bind variant carries a second set of transforms: it needs ~150 registers (it spilled at 4-5 CTAs / SM)
-template <int LOG2N, bool BIND = false>
-constexpr int clifford_fwd_min_blocks() { return BIND ? CVB_FWD_BIND_MINB : (LOG2N == 10 ? 4 : CVB_FWD_MINB); }
+#ifndef CVB_FWD_LEAN_MINB
+#define CVB_FWD_LEAN_MINB 7
+#endif
+template <int LOG2N, bool BIND = false, bool LEAN = false>
+constexpr int clifford_fwd_min_blocks() {
+  return BIND ? CVB_FWD_BIND_MINB : ((LEAN && LOG2N == 11) ? CVB_FWD_LEAN_MINB : (LOG2N == 10 ? 4 : CVB_FWD_MINB));
+}
 
 namespace cvb {
 
@@ -222,12 +227,13 @@ __device__ __forceinline__ void clifford_row_entropy(const CliffordFwdParams& p,
 
 // Shared memory per group: exchange buffer (XCH cplx) | retry queue (N ints) | up to 3 staged input
 // rows (N floats each) ; then per group one mbarrier and one queue counter.
+typedef unsigned short QueueIndex;   // retry-queue entries are bin indices < N <= 8192
 constexpr int kLpSlots = 16;   // per-warp partial sums of the fused log_prob (groups of up to 512 threads)
 constexpr int clifford_fwd_stages(int mode) { return mode == kPsInjected ? 3 : ((mode == kPsRng || mode == kPhases) ? 1 : 0); }
 template <int LOG2N, int MODE, bool BIND = false>
 constexpr size_t clifford_fwd_smem_bytes() {
   using Pl = FftPlan<LOG2N>;
-  return (sizeof(cplx) * Pl::XCH + sizeof(int) * Pl::N + sizeof(float) * Pl::N * clifford_fwd_stages(MODE) +
+  return (sizeof(cplx) * Pl::XCH + sizeof(QueueIndex) * Pl::N + sizeof(float) * Pl::N * clifford_fwd_stages(MODE) +
           (BIND ? sizeof(cplx) * Pl::N : 0)) * Pl::GROUPS +
          (sizeof(uint64_t) + sizeof(int) * 2 + sizeof(float) * kLpSlots) * Pl::GROUPS;
 }
@@ -239,7 +245,7 @@ constexpr size_t clifford_fwd_smem_bytes() {
 // predicated-off instructions of the optional outputs and the global-memory input path are compiled out (+8 %).
 // (Also assuming the dynamic schedule / always-valid rows was measured: +2 % at d = 512 / 1024, -2 % at d = 2048.)
 template <int LOG2N, int MODE, bool ROWK, bool BIND = false, bool LEAN = false>
-__global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS, (FftPlan<LOG2N>::THREADS <= 128 ? clifford_fwd_min_blocks<LOG2N, BIND>() : 1))
+__global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS, (FftPlan<LOG2N>::THREADS <= 128 ? clifford_fwd_min_blocks<LOG2N, BIND, LEAN>() : 1))
 clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw) {
   using Pl = FftPlan<LOG2N>;
   constexpr int d = Pl::N, T = Pl::T, E = Pl::E, G = Pl::GROUPS;
@@ -251,11 +257,11 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw) {
   float* stage = reinterpret_cast<float*>(smem_raw) + (size_t)group * NST * d;
   unsigned char* after_stage = smem_raw + sizeof(float) * (size_t)G * NST * d;
   cplx* xch = reinterpret_cast<cplx*>(after_stage) + (size_t)group * Pl::XCH;
-  int* queue = reinterpret_cast<int*>(after_stage + sizeof(cplx) * (size_t)G * Pl::XCH) + (size_t)group * d;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(after_stage + (sizeof(cplx) * Pl::XCH + sizeof(int) * d) * (size_t)G) + group;
-  int* qcount = reinterpret_cast<int*>(after_stage + (sizeof(cplx) * Pl::XCH + sizeof(int) * d + sizeof(uint64_t)) * (size_t)G) + 2 * group;
-  float* lps = reinterpret_cast<float*>(after_stage + (sizeof(cplx) * Pl::XCH + sizeof(int) * d + sizeof(uint64_t) + 2 * sizeof(int)) * (size_t)G) + kLpSlots * group;
-  cplx* spec = reinterpret_cast<cplx*>(after_stage + (sizeof(cplx) * Pl::XCH + sizeof(int) * d + sizeof(uint64_t) + 2 * sizeof(int) + kLpSlots * sizeof(float)) * (size_t)G) + (size_t)group * d;   // BIND only
+  QueueIndex* queue = reinterpret_cast<QueueIndex*>(after_stage + sizeof(cplx) * (size_t)G * Pl::XCH) + (size_t)group * d;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(after_stage + (sizeof(cplx) * Pl::XCH + sizeof(QueueIndex) * d) * (size_t)G) + group;
+  int* qcount = reinterpret_cast<int*>(after_stage + (sizeof(cplx) * Pl::XCH + sizeof(QueueIndex) * d + sizeof(uint64_t)) * (size_t)G) + 2 * group;
+  float* lps = reinterpret_cast<float*>(after_stage + (sizeof(cplx) * Pl::XCH + sizeof(QueueIndex) * d + sizeof(uint64_t) + 2 * sizeof(int)) * (size_t)G) + kLpSlots * group;
+  cplx* spec = reinterpret_cast<cplx*>(after_stage + (sizeof(cplx) * Pl::XCH + sizeof(QueueIndex) * d + sizeof(uint64_t) + 2 * sizeof(int) + kLpSlots * sizeof(float)) * (size_t)G) + (size_t)group * d;   // BIND only
   constexpr bool PS = (MODE == kPsInjected || MODE == kPsRng);
   const long long stride = (long long)gridDim.x * G;
   const bool staged = LEAN ? true : (NST > 0 && p.staged);   // LEAN implies TMA-staged inputs (16-byte aligned rows)
@@ -382,13 +388,13 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw) {
         while (rej_mask) {
           const int e = __ffs(rej_mask) - 1;
           rej_mask &= rej_mask - 1;
-          queue[pos++] = t + e * T;
+          queue[pos++] = (QueueIndex)(t + e * T);
         }
       } else {
         while (rej_mask) {
           const int e = __ffs(rej_mask) - 1;
           rej_mask &= rej_mask - 1;
-          queue[atomicAdd(qcount, 1)] = t + e * T;
+          queue[atomicAdd(qcount, 1)] = (QueueIndex)(t + e * T);
         }
       }
     } else if (MODE == kUniformRng || MODE == kUnitaryRng) {
