@@ -15,14 +15,18 @@ from ._lib import check, ptr, stream_ptr
 BIND_MUL, BIND_MUL_CONJ, BIND_DIV, BIND_DIV_CONJ, BIND_NEG_MUL_CONJ = range(5)
 
 
-def _launch(name, *args):
-    """Call a C-ABI launcher on the device of its first tensor pointer's owner (set by _prep/_dev).
-    Launches over zero rows are skipped (the outputs are already-empty tensors, like the reference)."""
-    lib = _lib.load()
-    if _EMPTY[0]:
+def _launch(name, dev, *args, skip=False):
+    """Call a C-ABI launcher on device `dev` (a torch.device of one of the call's own tensors) and on that
+    device's current stream.  Nothing is remembered between calls: forward and backward (which autograd may run on
+    another thread, after any number of unrelated ops) each pass their own device and emptiness.
+    skip=True (a launch over zero rows / zero-length vectors) returns without launching: the outputs are
+    already-empty tensors, like the reference."""
+    if skip:
         return
-    dev = _CUR_DEV[0]
-    if dev is not None and dev.index is not None and dev.index != torch.cuda.current_device():
+    lib = _lib.load()
+    dev = torch.device(dev)
+    _lib.ensure_device(dev)
+    if dev.index is not None and dev.index != torch.cuda.current_device():
         with torch.cuda.device(dev):
             rc = getattr(lib, name)(*args, torch.cuda.current_stream().cuda_stream)
     else:
@@ -30,8 +34,8 @@ def _launch(name, *args):
     check(rc, name)
 
 
-_CUR_DEV = [None]
-_EMPTY = [False]
+def _any_empty(*tensors) -> bool:
+    return any(t is not None and t.numel() == 0 for t in tensors)
 
 
 def _f32c(t: torch.Tensor) -> torch.Tensor:
@@ -42,10 +46,9 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
 
 
 def _prep(*tensors):
+    """Check that all tensors live on one CUDA device (initialising the library there).  Returns (lib, device)."""
     dev = tensors[0].device
     _lib.ensure_device(dev)
-    _CUR_DEV[0] = dev
-    _EMPTY[0] = any(t is not None and t.numel() == 0 for t in tensors)
     for t in tensors[1:]:
         if t is not None and t.device != dev:
             raise _lib.CliffordB200Error(f"tensors on different devices: {dev} vs {t.device}")
@@ -86,13 +89,13 @@ class CliffordPSRsample(torch.autograd.Function):
         if draws is None:
             tp = g = None
             tp_signed = torch.empty(rows, d, device=dev, dtype=torch.float32) if need_grad else None
-            seed, off = _lib.next_rng(_CUR_DEV[0])
+            seed, off = _lib.next_rng(dev)
         else:
             tp, g = (_f32c(t.reshape(rows, d)) for t in draws)
             tp_signed = None
             seed, off = 0, 0
-        _launch("cvb_clifford_ps_rsample", ptr(loc_c), ptr(kap_c), krs, kes, B, ptr(tp), ptr(g), seed, off, ptr(z),
-                                          ptr(tp_signed), ptr(ent), None, ptr(dent), rows, d)
+        _launch("cvb_clifford_ps_rsample", dev, ptr(loc_c), ptr(kap_c), krs, kes, B, ptr(tp), ptr(g), seed, off, ptr(z),
+                ptr(tp_signed), ptr(ent), None, ptr(dent), rows, d, skip=rows == 0 or d == 0)
         ctx.save_for_backward(loc_c, kap_c, tp, g, tp_signed, dent)
         ctx.meta = (B, d, rows, n_samples, krs, kes, tuple(kappa.shape))
         if ent is None:
@@ -108,8 +111,8 @@ class CliffordPSRsample(torch.autograd.Function):
             gz = _f32c(grad_z)
             dloc_rows = torch.empty(rows, d, device=gz.device, dtype=torch.float32)
             dk_rows = torch.empty((rows,) if kes == 0 else (rows, d), device=gz.device, dtype=torch.float32)
-            _launch("cvb_clifford_ps_rsample_backward", ptr(gz), ptr(loc_c), ptr(kap_c), krs, kes, B, ptr(tp), ptr(g),
-                                                       ptr(tp_signed), ptr(dloc_rows), ptr(dk_rows), rows, d)
+            _launch("cvb_clifford_ps_rsample_backward", gz.device, ptr(gz), ptr(loc_c), ptr(kap_c), krs, kes, B, ptr(tp),
+                    ptr(g), ptr(tp_signed), ptr(dloc_rows), ptr(dk_rows), rows, d, skip=rows == 0 or d == 0)
             if n_samples > 1:
                 dloc_rows = dloc_rows.view(n_samples, B, d).sum(0)
                 dk_rows = dk_rows.view(n_samples, B, -1).sum(0) if kes else dk_rows.view(n_samples, B).sum(0)
@@ -140,12 +143,12 @@ def clifford_rsample_bind(loc, kappa, other, n_samples=1, draws=None, want_sampl
     ent = torch.empty(B, device=dev, dtype=torch.float32) if n_samples == 1 else None
     if draws is None:
         tp = g = None
-        seed, off = _lib.next_rng(_CUR_DEV[0])
+        seed, off = _lib.next_rng(dev)
     else:
         tp, g = (_f32c(t.reshape(rows, d)) for t in draws)
         seed, off = 0, 0
-    _launch("cvb_clifford_ps_rsample_bind", ptr(loc_c), ptr(kap_c), B, ptr(tp), ptr(g), seed, off, ptr(oth_c),
-            oth_c.shape[0], ptr(z), ptr(bound), ptr(ent), None, None, rows, d)
+    _launch("cvb_clifford_ps_rsample_bind", dev, ptr(loc_c), ptr(kap_c), B, ptr(tp), ptr(g), seed, off, ptr(oth_c),
+            oth_c.shape[0], ptr(z), ptr(bound), ptr(ent), None, None, rows, d, skip=rows == 0 or d == 0)
     return z, bound, ent
 
 
@@ -164,12 +167,12 @@ def clifford_rsample_log_prob(loc, kappa, n_samples=1, draws=None):
     ent = torch.empty(B, device=dev, dtype=torch.float32) if n_samples == 1 else None
     if draws is None:
         tp = g = None
-        seed, off = _lib.next_rng(_CUR_DEV[0])
+        seed, off = _lib.next_rng(dev)
     else:
         tp, g = (_f32c(t.reshape(rows, d)) for t in draws)
         seed, off = 0, 0
-    _launch("cvb_clifford_ps_rsample_log_prob", ptr(loc_c), ptr(kap_c), B, ptr(tp), ptr(g), seed, off, ptr(z), ptr(lp),
-            ptr(ent), None, rows, d)
+    _launch("cvb_clifford_ps_rsample_log_prob", dev, ptr(loc_c), ptr(kap_c), B, ptr(tp), ptr(g), seed, off, ptr(z),
+            ptr(lp), ptr(ent), None, rows, d, skip=rows == 0 or d == 0)
     return z, lp, ent
 
 
@@ -188,8 +191,8 @@ class PSEntropy(torch.autograd.Function):
             B = kap_c.shape[0]
         ent = torch.empty(B, device=dev, dtype=torch.float32)
         dent = torch.empty((B,) if kes == 0 else (B, d), device=dev, dtype=torch.float32)
-        _launch("cvb_ps_entropy_kl", ptr(kap_c), krs, kes, B, d, float(half_dm1), 1 if torus else 0, 0.0, ptr(ent),
-                                    None, ptr(dent))
+        _launch("cvb_ps_entropy_kl", dev, ptr(kap_c), krs, kes, B, d, float(half_dm1), 1 if torus else 0, 0.0, ptr(ent),
+                None, ptr(dent), skip=B == 0)
         ctx.save_for_backward(dent)
         ctx.kshape = tuple(kappa.shape)
         ctx.kes = kes
@@ -219,8 +222,8 @@ class CliffordPSLogProb(torch.autograd.Function):
         dl = torch.empty(rows, d, device=dev, dtype=torch.float32) if need else None
         dk = torch.empty((rows,) if kes == 0 else (rows, d), device=dev, dtype=torch.float32) if need else None
         dF = torch.empty(rows, d, 2, device=dev, dtype=torch.float32) if ctx.needs_input_grad[0] else None
-        _launch("cvb_clifford_ps_log_prob", ptr(val_c), ptr(loc_c), ptr(kap_c), krs, kes, B, ptr(lp), ptr(dl), ptr(dk),
-                ptr(dF), rows, d)
+        _launch("cvb_clifford_ps_log_prob", dev, ptr(val_c), ptr(loc_c), ptr(kap_c), krs, kes, B, ptr(lp), ptr(dl),
+                ptr(dk), ptr(dF), rows, d, skip=rows == 0 or d == 0)
         ctx.save_for_backward(dl, dk, dF)
         ctx.meta = (B, d, rows, kes, tuple(kappa.shape))
         return lp
@@ -233,11 +236,9 @@ class CliffordPSLogProb(torch.autograd.Function):
         g = grad.reshape(rows)
         dval = dloc = dkap = None
         if dF is not None:
-            _CUR_DEV[0] = g.device
-            _EMPTY[0] = rows == 0
             h = (g[:, None, None] * dF).contiguous()
             dval = torch.empty(rows, 2 * d, device=g.device, dtype=torch.float32)
-            _launch("cvb_clifford_spectrum_adjoint", ptr(h), ptr(dval), rows, d)
+            _launch("cvb_clifford_spectrum_adjoint", g.device, ptr(h), ptr(dval), rows, d, skip=rows == 0 or d == 0)
         if dl is not None:
             dloc = (g[:, None] * dl).view(S, B, d).sum(0)
             dkap = ((g * dk).view(S, B).sum(0) if kes == 0 else (g[:, None] * dk).view(S, B, d).sum(0)).reshape(kshape)
@@ -248,14 +249,14 @@ def clifford_phases_to_vector(phases, scale, rows, d, device):
     """phases (rows, d) * scale -> (rows, 2d); phases None draws U[0,1) on the device."""
     _lib.ensure_device(torch.device(device))
     z = torch.empty(rows, 2 * d, device=device, dtype=torch.float32)
-    _CUR_DEV[0] = z.device
+    dev = z.device
     if phases is None:
-        seed, off = _lib.next_rng(_CUR_DEV[0])
+        seed, off = _lib.next_rng(dev)
         ph = None
     else:
         ph, seed, off = _f32c(phases.reshape(rows, d)), 0, 0
-    with torch.cuda.device(z.device):
-        _launch("cvb_clifford_phases_to_vector", ptr(ph), float(scale), seed, off, ptr(z), rows, d)
+    _launch("cvb_clifford_phases_to_vector", dev, ptr(ph), float(scale), seed, off, ptr(z), rows, d,
+            skip=rows == 0 or d == 0)
     return z
 
 
@@ -264,7 +265,8 @@ def clifford_phases_to_vector(phases, scale, rows, d, device):
 # =================================================================================================
 def _bind_raw(a2, b2, rows, d, mode):
     out = torch.empty(rows, d, device=a2.device, dtype=torch.float32)
-    _launch("cvb_vsa_bind", ptr(a2), ptr(b2), ptr(out), rows, a2.shape[0], b2.shape[0], d, mode)
+    _launch("cvb_vsa_bind", out.device, ptr(a2), ptr(b2), ptr(out), rows, a2.shape[0], b2.shape[0], d, mode,
+            skip=_any_empty(a2, b2, out))
     return out
 
 
@@ -346,7 +348,7 @@ def invert(a):
     d = a.shape[-1]
     a2 = _f32c(a).reshape(-1, d)
     out = torch.empty_like(a2)
-    _launch("cvb_vsa_invert", ptr(a2), ptr(out), a2.shape[0], d)
+    _launch("cvb_vsa_invert", dev, ptr(a2), ptr(out), a2.shape[0], d, skip=_any_empty(a2))
     return out.reshape(a.shape)
 
 
@@ -368,7 +370,7 @@ def permute(v, perm, inverse):
     v2 = _f32c(v).reshape(-1, d)
     pm = perm.to(torch.int64).contiguous()
     out = torch.empty_like(v2)
-    _launch("cvb_vsa_permute", ptr(v2), ptr(pm), ptr(out), v2.shape[0], d, 1 if inverse else 0)
+    _launch("cvb_vsa_permute", dev, ptr(v2), ptr(pm), ptr(out), v2.shape[0], d, 1 if inverse else 0, skip=_any_empty(v2))
     return out.reshape(v.shape)
 
 
@@ -395,7 +397,9 @@ class Bundle(torch.autograd.Function):
         v2 = _f32c(vectors).reshape(k, d)
         out = torch.empty(d, device=dev, dtype=torch.float32)
         ws = torch.empty(max(int(lib.cvb_vsa_bundle_workspace_bytes(k, d)) // 4, 1), device=dev, dtype=torch.float32)
-        _launch("cvb_vsa_bundle", ptr(v2), ptr(out), k, d, float(scale), ptr(ws))
+        if k == 0:
+            out.zero_()           # an empty stack sums to zero (torch.sum over an empty dim)
+        _launch("cvb_vsa_bundle", dev, ptr(v2), ptr(out), k, d, float(scale), ptr(ws), skip=_any_empty(v2))
         ctx.meta = (tuple(vectors.shape), float(scale))
         return out.reshape(inner)
 
@@ -412,7 +416,10 @@ class Cosine(torch.autograd.Function):
         a2, b2, rows, out_shape = _flatten_pair(a, b)
         d = out_shape[-1]
         out = torch.empty(rows, device=dev, dtype=torch.float32)
-        _launch("cvb_vsa_cosine", ptr(a2), ptr(b2), ptr(out), rows, a2.shape[0], b2.shape[0], d)
+        if d == 0:
+            out.zero_()
+        _launch("cvb_vsa_cosine", dev, ptr(a2), ptr(b2), ptr(out), rows, a2.shape[0], b2.shape[0], d,
+                skip=_any_empty(a2, b2, out))
         ctx.save_for_backward(a2, b2)
         ctx.meta = (rows, out_shape, tuple(a.shape), tuple(b.shape))
         return out.reshape(out_shape[:-1])
@@ -425,7 +432,8 @@ class Cosine(torch.autograd.Function):
         g = _f32c(grad).reshape(rows)
         da = torch.empty(rows, d, device=g.device, dtype=torch.float32) if ctx.needs_input_grad[0] else None
         db = torch.empty(rows, d, device=g.device, dtype=torch.float32) if ctx.needs_input_grad[1] else None
-        _launch("cvb_vsa_cosine_backward", ptr(a2), ptr(b2), ptr(g), ptr(da), ptr(db), rows, a2.shape[0], b2.shape[0], d)
+        _launch("cvb_vsa_cosine_backward", g.device, ptr(a2), ptr(b2), ptr(g), ptr(da), ptr(db), rows, a2.shape[0],
+                b2.shape[0], d, skip=_any_empty(a2, b2, g))
         if da is not None:
             da = _reduce_to(da, ashape, out_shape)
         if db is not None:
@@ -440,7 +448,7 @@ class Normalize(torch.autograd.Function):
         d = x.shape[-1]
         x2 = _f32c(x).reshape(-1, d)
         out = torch.empty_like(x2)
-        _launch("cvb_vsa_normalize", ptr(x2), ptr(out), x2.shape[0], d)
+        _launch("cvb_vsa_normalize", dev, ptr(x2), ptr(out), x2.shape[0], d, skip=_any_empty(x2))
         ctx.save_for_backward(x2)
         ctx.shape = tuple(x.shape)
         return out.reshape(x.shape)
@@ -450,7 +458,8 @@ class Normalize(torch.autograd.Function):
         (x2,) = ctx.saved_tensors
         g = _f32c(grad).reshape(x2.shape)
         dx = torch.empty_like(x2)
-        _launch("cvb_vsa_normalize_backward", ptr(x2), ptr(g), ptr(dx), x2.shape[0], x2.shape[1])
+        _launch("cvb_vsa_normalize_backward", g.device, ptr(x2), ptr(g), ptr(dx), x2.shape[0], x2.shape[1],
+                skip=_any_empty(x2))
         return dx.reshape(ctx.shape)
 
 
@@ -458,10 +467,9 @@ def hrr_init(n, d, device):
     dev = torch.device(device)
     _lib.ensure_device(dev)
     out = torch.empty(n, d, device=dev, dtype=torch.float32)
-    _CUR_DEV[0] = out.device
-    seed, off = _lib.next_rng(_CUR_DEV[0])
-    with torch.cuda.device(out.device):
-        _launch("cvb_vsa_hrr_init", ptr(out), n, d, seed, off)
+    dev = out.device
+    seed, off = _lib.next_rng(dev)
+    _launch("cvb_vsa_hrr_init", dev, ptr(out), n, d, seed, off, skip=out.numel() == 0)
     return out
 
 
@@ -469,10 +477,9 @@ def unitary_init(n, d, device, eps):
     dev = torch.device(device)
     _lib.ensure_device(dev)
     out = torch.empty(n, d, device=dev, dtype=torch.float32)
-    _CUR_DEV[0] = out.device
-    seed, off = _lib.next_rng(_CUR_DEV[0])
-    with torch.cuda.device(out.device):
-        _launch("cvb_vsa_unitary_init", ptr(out), n, d, float(eps), seed, off)
+    dev = out.device
+    seed, off = _lib.next_rng(dev)
+    _launch("cvb_vsa_unitary_init", dev, ptr(out), n, d, float(eps), seed, off, skip=out.numel() == 0)
     return out
 
 
@@ -483,13 +490,13 @@ def sphere_uniform_rsample(rows, D, device, norm_eps, gnoise=None):
     dev = torch.device(device)
     _lib.ensure_device(dev)
     z = torch.empty(rows, D, device=dev, dtype=torch.float32)
-    _CUR_DEV[0] = z.device
+    dev = z.device
     if gnoise is None:
-        seed, off = _lib.next_rng(_CUR_DEV[0])
+        seed, off = _lib.next_rng(dev)
         g = None
     else:
         g, seed, off = _f32c(gnoise.reshape(rows, D)), 0, 0
-    _launch("cvb_sphere_uniform_rsample", ptr(g), seed, off, ptr(z), rows, D, float(norm_eps))
+    _launch("cvb_sphere_uniform_rsample", dev, ptr(g), seed, off, ptr(z), rows, D, float(norm_eps), skip=z.numel() == 0)
     return z
 
 
@@ -506,13 +513,13 @@ class PowerSphericalRsample(torch.autograd.Function):
         if draws is None:
             tp = g = None
             save = torch.empty(rows, 2, device=dev, dtype=torch.float32)
-            seed, off = _lib.next_rng(_CUR_DEV[0])
+            seed, off = _lib.next_rng(dev)
         else:
             tp = _f32c(draws[0].reshape(rows))
             g = _f32c(draws[1].reshape(rows, D - 1))
             save, seed, off = None, 0, 0
-        _launch("cvb_powerspherical_rsample", ptr(loc_c), ptr(kap_c), B, ptr(tp), ptr(g), seed, off, ptr(z), ptr(save),
-                rows, D)
+        _launch("cvb_powerspherical_rsample", dev, ptr(loc_c), ptr(kap_c), B, ptr(tp), ptr(g), seed, off, ptr(z),
+                ptr(save), rows, D, skip=z.numel() == 0)
         ctx.save_for_backward(loc_c, kap_c, tp, g, save)
         ctx.meta = (B, D, rows, n_samples, seed, off, tuple(kappa.shape))
         return z
@@ -522,11 +529,10 @@ class PowerSphericalRsample(torch.autograd.Function):
         loc_c, kap_c, tp, g, save = ctx.saved_tensors
         B, D, rows, n_samples, seed, off, kshape = ctx.meta
         gz = _f32c(grad_z).reshape(rows, D)
-        _CUR_DEV[0] = gz.device
         dloc = torch.empty(rows, D, device=gz.device, dtype=torch.float32)
         dk = torch.empty(rows, device=gz.device, dtype=torch.float32)
-        _launch("cvb_powerspherical_rsample_backward", ptr(gz), ptr(loc_c), ptr(kap_c), B, ptr(tp), ptr(g), ptr(save),
-                seed, off, ptr(dloc), ptr(dk), rows, D)
+        _launch("cvb_powerspherical_rsample_backward", gz.device, ptr(gz), ptr(loc_c), ptr(kap_c), B, ptr(tp), ptr(g),
+                ptr(save), seed, off, ptr(dloc), ptr(dk), rows, D, skip=gz.numel() == 0)
         if n_samples > 1:
             dloc = dloc.view(n_samples, B, D).sum(0)
             dk = dk.view(n_samples, B).sum(0)
@@ -544,8 +550,8 @@ class PowerSphericalLogProb(torch.autograd.Function):
         need = any(ctx.needs_input_grad)
         coef = torch.empty(rows, device=dev, dtype=torch.float32) if need else None
         dk = torch.empty(rows, device=dev, dtype=torch.float32) if need else None
-        _launch("cvb_powerspherical_log_prob", ptr(val_c), ptr(loc_c), ptr(kap_c), B, ptr(lp), ptr(coef), ptr(dk),
-                rows, D)
+        _launch("cvb_powerspherical_log_prob", dev, ptr(val_c), ptr(loc_c), ptr(kap_c), B, ptr(lp), ptr(coef), ptr(dk),
+                rows, D, skip=val_c.numel() == 0)
         ctx.save_for_backward(val_c, loc_c, coef, dk)
         ctx.meta = (B, D, rows, tuple(kappa.shape))
         return lp
@@ -569,7 +575,7 @@ class PSLogNormalizer(torch.autograd.Function):
         k = _f32c(kappa.reshape(-1))
         ln = torch.empty_like(k)
         dln = torch.empty_like(k)
-        _launch("cvb_ps_log_normalizer", ptr(k), k.numel(), (dim - 1) / 2, ptr(ln), ptr(dln))
+        _launch("cvb_ps_log_normalizer", dev, ptr(k), k.numel(), (dim - 1) / 2, ptr(ln), ptr(dln), skip=k.numel() == 0)
         ctx.save_for_backward(dln)
         ctx.kshape = tuple(kappa.shape)
         return ln.reshape(kappa.shape)
@@ -595,7 +601,7 @@ class VMFRsample(torch.autograd.Function):
         if draws is None:
             e = u = g = None
             R = 0
-            seed, off = _lib.next_rng(_CUR_DEV[0])
+            seed, off = _lib.next_rng(dev)
         else:
             e, u, g = draws
             u = u.to(torch.float64).reshape(-1, rows).contiguous()
@@ -603,8 +609,8 @@ class VMFRsample(torch.autograd.Function):
             R = u.shape[0]
             g = _f32c(g.reshape(rows, D))
             seed, off = 0, 0
-        _launch("cvb_vmf_rsample", ptr(loc_c), ptr(kap_c), B, ptr(e), ptr(u), R, ptr(g), seed, off, ptr(z), ptr(save),
-                rows, D)
+        _launch("cvb_vmf_rsample", dev, ptr(loc_c), ptr(kap_c), B, ptr(e), ptr(u), R, ptr(g), seed, off, ptr(z), ptr(save),
+                rows, D, skip=z.numel() == 0)
         ctx.save_for_backward(loc_c, kap_c, g, save)
         ctx.meta = (B, D, rows, n_samples, seed, off, tuple(kappa.shape))
         return z
@@ -614,11 +620,10 @@ class VMFRsample(torch.autograd.Function):
         loc_c, kap_c, g, save = ctx.saved_tensors
         B, D, rows, n_samples, seed, off, kshape = ctx.meta
         gz = _f32c(grad_z).reshape(rows, D)
-        _CUR_DEV[0] = gz.device
         dloc = torch.empty(rows, D, device=gz.device, dtype=torch.float32)
         dk = torch.empty(rows, device=gz.device, dtype=torch.float32)
-        _launch("cvb_vmf_rsample_backward", ptr(gz), ptr(loc_c), ptr(kap_c), B, ptr(g), ptr(save), seed, off, ptr(dloc),
-                ptr(dk), rows, D)
+        _launch("cvb_vmf_rsample_backward", gz.device, ptr(gz), ptr(loc_c), ptr(kap_c), B, ptr(g), ptr(save), seed, off,
+                ptr(dloc), ptr(dk), rows, D, skip=gz.numel() == 0)
         if n_samples > 1:
             dloc = dloc.view(n_samples, B, D).sum(0)
             dk = dk.view(n_samples, B).sum(0)
@@ -633,7 +638,8 @@ class VMFEntropyLogNorm(torch.autograd.Function):
         lib, dev = _prep(kappa)
         k = _f32c(kappa.reshape(-1))
         ent, ln, dent, dln = (torch.empty_like(k) for _ in range(4))
-        _launch("cvb_vmf_entropy_lognorm", ptr(k), k.numel(), D, ptr(ent), ptr(ln), ptr(dent), ptr(dln))
+        _launch("cvb_vmf_entropy_lognorm", dev, ptr(k), k.numel(), D, ptr(ent), ptr(ln), ptr(dent), ptr(dln),
+                skip=k.numel() == 0)
         ctx.save_for_backward(dent, dln)
         ctx.kshape = tuple(kappa.shape)
         return ent, ln

@@ -1,0 +1,172 @@
+"""GPU: the reference-facing boundary -- harness entry points under the reference's names (utils/vsa.py:99-630)
+against the oracle loops, CPU-argument staging, and launch-state hygiene (an op over an empty tensor or on another
+thread between a forward and its backward must not disturb the backward)."""
+import threading
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def test_reference_named_entry_points_run_and_keep_the_result_contract():
+    from utils import vsa
+    torch.manual_seed(0)
+    r = vsa.test_bundle_capacity(d=512, n_items=200, k_range=[2, 40], n_trials=8, device=DEV)
+    assert set(r) == {"k", "accuracy", "std"} and r["k"] == [2, 40] and r["accuracy"][0] == 1.0
+    assert 0.5 < r["accuracy"][1] <= 1.0
+    # the reference's default device is "cpu" and drivers pass CPU item memories: both run on the GPU here
+    mem = torch.randn(300, 1024) / 32.0
+    r = vsa.test_binding_unbinding_pairs(d=1024, n_items=300, k_range=[2, 6], n_trials=6, item_memory=mem)
+    assert r["k"] == [2, 6] and r["accuracy"][0] > 0.9 and len(r["std"]) == 2
+    r = vsa.test_binding_unbinding_pairs(d=1024, n_items=300, k_range=[2], n_trials=4, device=DEV, item_memory=mem,
+                                         use_braiding=True, bind_with_random=False, unbind_method="†", plot=True)
+    assert r["accuracy"][0] > 0.9
+    with pytest.raises(ValueError):
+        vsa.test_binding_unbinding_pairs(d=64, n_items=20, k_range=[2], n_trials=1, device=DEV, unbind_method="x")
+    r = vsa.test_per_class_bundle_capacity_k_items(d=256, n_items=100, n_classes=5, items_per_class=2, device=DEV)
+    assert r["avg_similarity_matrix"].shape == (10, 10) and r["n_bundles"] == 10
+    assert np.allclose(np.diag(r["avg_similarity_matrix"]), 1.0, atol=1e-5)
+    assert (r["std_similarity_matrix"] == 0).all()
+    # a class without enough items -> the reference's early-out dict
+    lab = torch.zeros(10, dtype=torch.long)
+    r = vsa.test_per_class_bundle_capacity_k_items(d=64, n_items=10, n_classes=1, items_per_class=20,
+                                                   item_memory=torch.randn(10, 64), labels=lab)
+    assert r == {"avg_similarity_matrix": None}
+
+
+@pytest.mark.parametrize("braid,per_class", [(False, False), (True, False), (True, True)])
+def test_per_class_similarity_matches_oracle_loops(braid, per_class):
+    from oracle import latent_oracle as O
+    from utils import vsa
+    torch.manual_seed(7)
+    n_items, d, n_classes, ipc = 60, 128, 4, 3
+    mem = torch.randn(n_items, d)
+    labels = torch.randint(0, n_classes, (n_items,))
+    perms = (torch.stack([torch.randperm(d) for _ in range(n_classes)]) if per_class else
+             torch.stack([torch.randperm(d) for _ in range(n_items)])) if braid else None
+    got = vsa.test_per_class_bundle_capacity_k_items(
+        d=d, n_items=n_items, n_classes=n_classes, items_per_class=ipc, n_trials=2, device=DEV, item_memory=mem,
+        labels=labels, use_braiding=braid, per_class_braid=per_class,
+        _perms=None if perms is None else perms.to(DEV))
+    # utils/vsa.py:431-513 restated with the oracle ops
+    items = O.normalize_vectors(mem)
+    if braid:
+        items = torch.stack([O.permute_vector(items[i], perms[int(labels[i])] if per_class else perms[i])
+                             for i in range(n_items)])
+    sel = []
+    for c in torch.unique(labels).tolist()[:n_classes]:
+        idx = torch.where(labels == c)[0]
+        assert len(idx) >= ipc
+        sel += idx[:ipc].tolist()
+    B = items[sel]
+    ref = np.stack([O.similarity(B[i].unsqueeze(0), B).numpy() for i in range(len(sel))])
+    assert got["n_bundles"] == n_classes * ipc and got["items_per_class"] == ipc
+    assert np.abs(got["avg_similarity_matrix"] - ref).max() < 1e-5
+
+
+def test_cpu_arguments_are_staged_to_the_gpu_and_returned_home():
+    """utils/vsa.py:266-267,278 and wandb_utils.py:165 hand the ops CPU tensors: computed on the GPU, returned on CPU."""
+    from clifford_b200 import _lib
+    from oracle import latent_oracle as O
+    from utils import vsa
+    torch.manual_seed(1)
+    a, b = torch.randn(5, 256) / 16, torch.randn(5, 256) / 16
+    n0 = _lib.launch_count()
+    ab = vsa.bind(a, b)
+    assert ab.device.type == "cpu" and _lib.launch_count() > n0
+    assert rel_err(ab, O.bind(a, b)) < 1e-5
+    assert rel_err(vsa.unbind(ab, b.to(DEV), "†"), O.unbind(ab, b, "†")) < 2e-3
+    assert vsa.unbind(ab, b.to(DEV)).device.type == "cpu"
+    s = vsa.similarity(a[0], b.to(DEV))
+    assert s.device.type == "cpu" and rel_err(s, O.similarity(a[0], b)) < 1e-5
+    s = vsa.similarity(a.to(DEV), b)
+    assert s.device.type == "cuda"
+    h = vsa.hrr_init(7, 64)
+    u = vsa.unitary_init(7, 64)
+    assert h.device.type == "cpu" and u.device.type == "cpu"
+    assert float((torch.fft.rfft(u).abs() - 1).abs().max()) < 1e-4
+    assert vsa.normalize_vectors(a).device.type == "cpu" and vsa.bundle(a).device.type == "cpu"
+    assert vsa.invert(a).device.type == "cpu"
+    perm = torch.randperm(256)
+    assert torch.equal(vsa.unpermute_vector(vsa.permute_vector(a, perm), perm), a)
+    ag = a.clone().requires_grad_()
+    vsa.bind(ag, b).sum().backward()                       # autograd flows through the staging copies
+    assert ag.grad is not None and ag.grad.device.type == "cpu"
+
+
+def test_backward_is_not_disturbed_by_an_intervening_empty_op(golden_clifford):
+    """Round-1 defect: launch state lived in module globals set by forward; an op over an empty tensor between a
+    forward and its backward made the backward skip its launch and return uninitialised memory."""
+    from dists.clifford import CliffordPowerSphericalDistribution
+    from oracle import latent_oracle as O
+    from utils import vsa
+    torch.manual_seed(2)
+    B, d = 6, 64
+    loc = torch.randn(B, d)
+    kap = torch.rand(B, 1) * 4 + 0.2
+    tp = torch.distributions.Beta(0.5 + kap + 1e-7, torch.tensor(0.5)).sample((d,)).squeeze(-1).T.contiguous()
+    g = torch.randn(B, d)
+    w = torch.randn(B, 2 * d)
+    loc_r, kap_r = loc.clone().requires_grad_(), kap.clone().requires_grad_()
+    (O.clifford_ps_rsample(loc_r, kap_r, tp, g) * w).sum().backward()
+
+    loc_g, kap_g = loc.to(DEV).requires_grad_(), kap.to(DEV).requires_grad_()
+    z = CliffordPowerSphericalDistribution(loc_g, kap_g).rsample(_base_draws=(tp.to(DEV), g.to(DEV)))
+    a = torch.randn(4, 128, device=DEV, requires_grad=True)
+    b = torch.randn(4, 128, device=DEV)
+    ab = vsa.bind(a, b)
+    # ops over empty tensors between the forwards and the backwards
+    e = torch.empty(0, 128, device=DEV)
+    assert vsa.bind(e, e).shape == (0, 128)
+    assert vsa.similarity(e, e).shape == (0,)
+    assert vsa.normalize_vectors(e).shape == (0, 128)
+    h = vsa.hrr_init(3, 32, device=DEV)                    # and a generator right after them
+    assert float(h.abs().max()) > 0 and torch.isfinite(h).all()
+    (z * w.to(DEV)).sum().backward()
+    assert rel_err(loc_g.grad.cpu(), loc_r.grad) < 2e-5
+    assert rel_err(kap_g.grad.cpu(), kap_r.grad) < 3e-4
+    ab.sum().backward()
+    ref = torch.fft.irfft(torch.fft.rfft(torch.ones(4, 128, dtype=torch.float64)) *
+                          torch.fft.rfft(b.double().cpu()).conj(), n=128)
+    assert rel_err(a.grad.cpu(), ref) < 1e-5
+
+
+def test_ops_from_two_threads_do_not_share_launch_state():
+    """Autograd runs backward on its own thread; user threads may interleave ops over empty and non-empty tensors."""
+    from utils import vsa
+    torch.manual_seed(3)
+    d = 256
+    a = torch.randn(64, d, device=DEV)
+    b = torch.randn(64, d, device=DEV)
+    ref = torch.fft.irfft(torch.fft.rfft(a.double()) * torch.fft.rfft(b.double()), n=d).cpu()
+    stop = threading.Event()
+    errs = []
+
+    def empties():
+        e = torch.empty(0, d, device=DEV)
+        while not stop.is_set():
+            try:
+                vsa.bind(e, e)
+                vsa.similarity(e, e)
+            except Exception as ex:                        # pragma: no cover
+                errs.append(ex)
+                return
+
+    t = threading.Thread(target=empties)
+    t.start()
+    try:
+        for _ in range(200):
+            ar = a.clone().requires_grad_()
+            out = vsa.bind(ar, b)
+            out.sum().backward()
+            assert rel_err(out.detach().cpu(), ref) < 1e-5
+            assert float(ar.grad.abs().max()) > 0 and torch.isfinite(ar.grad).all()
+    finally:
+        stop.set()
+        t.join()
+    assert not errs
