@@ -8,7 +8,8 @@ quoted on): per step and per GPU, B = 4096 rows of the Clifford-torus latent at 
   2. vsa.bind(z, roles) with per-row roles (B, 4096)  [reference utils/vsa.py:43-46]
 `value` = samples/s with inputs resident in HBM (two rotating buffer sets, 2 x 224 MB > 126 MB L2);
 `e2e` = the same step through the reference-named Python API with HOST (pinned) inputs/outputs.
-`--impl reference` times the CPU restatement of the reference's torch path (oracle/) instead.
+`--impl reference` times the reference's OWN classes on the host cores (staged copy under oracle/_ref, see
+oracle/stage_reference.py; falls back to the oracle port only when no copy of the reference is available).
 """
 from __future__ import annotations
 
@@ -100,37 +101,70 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle's restatement of the reference's torch CPU path
+# reference arm / cpu baseline: the reference's own torch CPU path (oracle/_ref), else the oracle port
 # --------------------------------------------------------------------------------------------------
-def cpu_step(torch, O, rows, loc, kap, roles):
-    """One pass of the same step on the host: draws + rsample + KL + bind (reference call sequence:
-    Beta.rsample then randn, dists/clifford.py:295-308; kl :325-327; bind utils/vsa.py:43-46)."""
-    d = loc.shape[1]
-    alpha = 0.5 + kap + 1e-7
-    tprime = torch.distributions.Beta(alpha.expand(rows, d), torch.full((rows, d), 0.5)).sample()
-    g = torch.randn(rows, d)
-    z = O.clifford_ps_rsample(loc, kap, tprime, g)
-    kl = O.clifford_ps_kl(kap.expand(rows, d))
-    out = O.bind(z, roles)
-    return out, kl
+REF_ROWS = 1024     # bounded sample of the 4096-row step (the reference runs at ~1e3 samples/s on 16 host threads)
 
 
-def cpu_timing(rows, reps):
-    import torch
+def make_cpu_step(torch):
+    """-> (step(loc, kap, roles) -> (bound, kl), kind, description).  kind "reference": the reference's classes,
+    imported unmodified (dists/clifford.py:295-327 rsample + kl_divergence, utils/vsa.py:43-46 bind), constructed the
+    way its conv VAE does (cnn/models.py:226-231: concentration expanded to loc's shape).  kind "port": the oracle
+    restatement, used only when neither /root/reference nor oracle/_ref exists."""
+    from oracle import reference_loader as RL
+    ref = RL.load()
+    if ref is not None:
+        C, V = ref.clifford, ref.vsa
+        prior = C.CliffordTorusUniform(D_LAT)
+
+        def step(loc, kap, roles):
+            q = C.CliffordPowerSphericalDistribution(loc, kap.expand_as(loc))
+            z = q.rsample()
+            kl = torch.distributions.kl.kl_divergence(q, prior)
+            return V.bind(z, roles), kl
+        return step, "reference", f"the reference's own classes ({ref.kind} copy), torch {torch.__version__} CPU"
+
     from oracle import latent_oracle as O
-    torch.set_num_threads(os.cpu_count() or 1)
+
+    def step(loc, kap, roles):
+        rows, d = loc.shape
+        alpha = 0.5 + kap + 1e-7
+        tprime = torch.distributions.Beta(alpha.expand(rows, d), torch.full((rows, d), 0.5)).sample()
+        g = torch.randn(rows, d)
+        z = O.clifford_ps_rsample(loc, kap, tprime, g)
+        kl = O.clifford_ps_kl(kap.expand(rows, d))
+        return O.bind(z, roles), kl
+    return step, "port", f"oracle port of the reference's torch CPU path, torch {torch.__version__} CPU"
+
+
+def cpu_inputs(torch, rows):
     torch.manual_seed(0)
     loc = torch.randn(rows, D_LAT)
     kap = torch.rand(rows, 1) * 9.87 + 0.13
     roles = torch.randn(rows, N_VEC) / math.sqrt(N_VEC)
+    return loc, kap, roles
+
+
+def cpu_timing(rows, reps):
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    step, kind, desc = make_cpu_step(torch)
+    loc, kap, roles = cpu_inputs(torch, rows)
     with torch.no_grad():
-        cpu_step(torch, O, rows, loc, kap, roles)          # warm-up
+        step(loc, kap, roles)          # warm-up
         ts = []
         for _ in range(reps):
             t0 = time.perf_counter()
-            cpu_step(torch, O, rows, loc, kap, roles)
+            step(loc, kap, roles)
             ts.append(time.perf_counter() - t0)
-    return rows / statistics.median(ts), torch.get_num_threads(), ts
+    return rows / statistics.median(ts), torch.get_num_threads(), ts, kind, desc
+
+
+def bench_config():
+    """`config` of both arms (identical keys and values: same workload, same shapes)."""
+    return {"workload": WORKLOAD, "rows_per_gpu": B_ROWS, "d": D_LAT,
+            "rng": "b200 arm: Philox4x32-10 on the device; reference arm: torch CPU generator",
+            "l2": "b200 arm: inputs rotate over 2 buffer sets of 224 MB (> 126 MB L2)"}
 
 
 def run_reference(args):
@@ -138,28 +172,25 @@ def run_reference(args):
     if rank != 0:
         return 0
     import torch
-    from oracle import latent_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
-    rows = 128       # bounded sample of the 4096-row step
-    torch.manual_seed(0)
-    loc = torch.randn(rows, D_LAT)
-    kap = torch.rand(rows, 1) * 9.87 + 0.13
-    roles = torch.randn(rows, N_VEC) / math.sqrt(N_VEC)
+    step, kind, desc = make_cpu_step(torch)
+    rows = REF_ROWS
+    loc, kap, roles = cpu_inputs(torch, rows)
     with torch.no_grad():
         for _ in range(args.warmup):
-            cpu_step(torch, O, rows, loc, kap, roles)
+            step(loc, kap, roles)
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            cpu_step(torch, O, rows, loc, kap, roles)
+            step(loc, kap, roles)
         dt = time.perf_counter() - t0
     val = rows * args.steps / dt
-    sample = f"{rows} of the {B_ROWS} rows per step (same d={D_LAT}), torch {torch.__version__} CPU"
+    sample = f"{rows} of the {B_ROWS} rows per step (same d={D_LAT}); {desc}"
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "config": bench_config(),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -319,8 +350,7 @@ def run_gpu(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "rows_per_gpu": B, "d": d, "rng": "philox4x32-10 on device",
-                       "l2": f"inputs rotate over {NSETS} buffer sets of 224 MB (> 126 MB L2)"},
+            "config": bench_config(),
             "roofline": {"bound": "hbm", "kernel": dom["name"], "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": load_traffic(dom["name"]), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": dom["bytes"], "ms_per_launch": dom["ms"]},
@@ -337,10 +367,10 @@ def run_gpu(args):
             "gpu_launches": int(launches), "clocks": clk,
         }
         if world == 1 and not args.no_cpu_baseline:
-            v, cores, ts = cpu_timing(2048, 5)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"2048 of the {B} rows (same d={d}), median of 5 passes "
-                                              f"({sum(ts):.1f} s CPU), oracle port of the reference's torch CPU path"}
+            v, cores, ts, kind, desc = cpu_timing(REF_ROWS, 5)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+                                    "sample": f"{REF_ROWS} of the {B} rows (same d={d}), median of 5 passes "
+                                              f"({sum(ts):.1f} s CPU); {desc}"}
         if vae is not None:
             line["vae_train_step"] = vae
         if world == 1:
@@ -351,23 +381,70 @@ def run_gpu(args):
     return 0
 
 
-def vae_train_leg(torch, dev, world, rank, local, steps=8, warmup=3):
-    """Second half of BASELINE.json's metric: the C3 training step (conv VAE on 3x32x32 inputs, Clifford latent d=2048,
-    batch 4096 per GPU, L1 + KL, AdamW, clip 1.0; cnn/cifar10_train.py:62-121) with the latent drop-in classes, data
-    parallel over NCCL when world > 1.  Every rank runs it (DDP all-reduce); returns steps/s as max-over-ranks time."""
+def vae_train_leg(torch, dev, world, rank, local, steps=8, warmup=3, compare_reference_dists=True):
+    """Second half of BASELINE.json's metric: the C3 training step of the reference's OWN model -- `cnn.models.VAE(
+    latent_dim=2048, in_channels=3, distribution="clifford", device, recon_loss_type="l1")` (cnn/models.py:134-315,
+    18.4 M parameters), loaded unmodified from the staged copy under oracle/_ref with `dists.clifford` resolved to the
+    drop-in classes -- run the way cnn/cifar10_train.py:62-77 runs it (zero_grad, forward, compute_loss, backward,
+    clip_grad_norm_ 1.0, AdamW lr 3e-4 step; the per-step .item() logging left out), batch 4096 per GPU, synthetic
+    U(-1,1) 3x32x32 inputs, DistributedDataParallel over NCCL when world > 1.  Every rank runs it; the time is the
+    max over ranks.  At world == 1 the same step is also timed with the reference's own distribution classes on the
+    GPU (eager PyTorch + cuFFT): the "reference on cuda" comparator of BASELINE.md.  Falls back to the stand-in conv
+    VAE of examples/train_vae_ddp.py only when no copy of the reference is available."""
+    import torch.distributed as dist
+    import torch.nn as nn
     import importlib.util
     spec = importlib.util.spec_from_file_location("train_vae_ddp", os.path.join(ROOT, "examples", "train_vae_ddp.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
-    torch.manual_seed(1234 + rank)
+    from oracle import reference_loader as RL
+    ref = RL.load()
     batch = 4096
-    step = mod.make_training_step("conv", "clifford", D_LAT, batch, dev, world, local)
+    torch.manual_seed(1234 + rank)
+
+    def reference_model_step(models_mod):
+        model = models_mod.VAE(latent_dim=D_LAT, in_channels=3, distribution="clifford", device=dev, recon_loss_type="l1")
+        net = nn.parallel.DistributedDataParallel(model, device_ids=[local]) if world > 1 else model
+        opt = torch.optim.AdamW(net.parameters(), lr=3e-4)
+        x = torch.rand(batch, 3, 32, 32, device=dev) * 2 - 1
+
+        def step():
+            opt.zero_grad()
+            x_recon, q_z, p_z, _ = net(x)
+            losses = model.compute_loss(x, x_recon, q_z, p_z, 1.0)
+            losses["total_loss"].backward()
+            torch.nn.utils.clip_grad_norm_(net.parameters(), 1.0)
+            opt.step()
+            return losses["total_loss"]
+        return step, sum(p.numel() for p in model.parameters())
+
+    out = {"batch_per_gpu": batch, "n_gpus": world, "parallelism": f"ddp{world}" if world > 1 else "single",
+           "steps": steps, "warmup": warmup}
+    if ref is not None:
+        step, nparam = reference_model_step(RL.models(ref, "cnn"))
+        out["model"] = (f"reference cnn.models.VAE(latent_dim={D_LAT}, in_channels=3, distribution='clifford', "
+                        f"recon_loss_type='l1') [{ref.kind} copy, unmodified], {nparam} parameters, AdamW lr 3e-4, clip 1.0; "
+                        "dists.clifford = drop-in kernels")
+    else:
+        step = mod.make_training_step("conv", "clifford", D_LAT, batch, dev, world, local)
+        out["model"] = "stand-in conv VAE (examples/train_vae_ddp.py): no copy of the reference available"
     ms, loss = mod.time_training_steps(step, steps, warmup, dev, world)
+    out.update({"ms_per_step": ms, "steps_per_s": 1e3 / ms, "samples_per_s": world * batch * 1e3 / ms, "loss": loss})
     del step
     torch.cuda.empty_cache()
-    return {"model": "conv VAE 3x32x32, Clifford latent d=2048 (z 4096), AdamW, clip 1.0", "batch_per_gpu": batch,
-            "n_gpus": world, "parallelism": f"ddp{world}" if world > 1 else "single", "steps": steps, "warmup": warmup,
-            "ms_per_step": ms, "steps_per_s": 1e3 / ms, "samples_per_s": world * batch * 1e3 / ms, "loss": loss}
+    if ref is not None and world == 1 and compare_reference_dists:
+        try:
+            step, _ = reference_model_step(RL.models(ref, "cnn", ref.clifford))
+            ms_r, loss_r = mod.time_training_steps(step, max(3, steps // 2), 2, dev, world)
+            out["reference_on_cuda"] = {"what": "same model and step with the reference's own dists/clifford.py classes "
+                                                "on the GPU (eager PyTorch, cuFFT, torch._sample_dirichlet)",
+                                        "ms_per_step": ms_r, "steps_per_s": 1e3 / ms_r, "loss": loss_r,
+                                        "speedup_of_drop_in": ms_r / ms}
+            del step
+        except Exception as e:          # the comparator must never take the bench line down
+            out["reference_on_cuda"] = {"error": f"{type(e).__name__}: {e}"[:200]}
+        torch.cuda.empty_cache()
+    return out
 
 
 def extras(torch, lib, dev, st, peak, full=False):

@@ -15,7 +15,7 @@ from torch.distributions import Distribution, constraints
 from torch.distributions.kl import register_kl
 from torch.distributions.utils import broadcast_all
 
-from . import ops
+from . import ops, testing
 
 _LOG_2PI = math.log(2 * math.pi)
 
@@ -55,7 +55,8 @@ class HypersphericalUniform(Distribution):
     def entropy(self):
         if self.dim <= 0:
             return torch.tensor(float("inf"), device=self.device, dtype=self.dtype)
-        return torch.full((1,), -self._log_density(), device=self.device, dtype=self.dtype)
+        # 0-d like the reference (-log_prob(zeros(1)) indexes the event dim away, dists/clifford.py:118-121)
+        return torch.full((), -self._log_density(), device=self.device, dtype=self.dtype)
 
 
 class PowerSpherical(Distribution):
@@ -82,6 +83,8 @@ class PowerSpherical(Distribution):
         sample_shape = torch.Size(sample_shape)
         loc2, kap = self._flat()
         n = _numel(sample_shape)
+        if _base_draws is None:
+            _base_draws = testing.take()
         z = ops.PowerSphericalRsample.apply(loc2, kap, n, _base_draws)
         return z.reshape(tuple(sample_shape) + tuple(self.batch_shape) + (self.dim,)).to(self.loc.dtype)
 
@@ -203,6 +206,8 @@ class CliffordPowerSphericalDistribution(CliffordTorusDistribution):
         n = _numel(sample_shape)
         d = self.orig_dim
         out_shape = tuple(sample_shape) + tuple(self.batch_shape) + (2 * d,)
+        if _base_draws is None:
+            _base_draws = testing.take()
         no_grad = not (torch.is_grad_enabled() and (loc2.requires_grad or kap2.requires_grad))
         if (no_grad and len(sample_shape) > 0 and kap2.shape[-1] == 1 and 16 <= d <= 8192 and (d & (d - 1)) == 0
                 and loc2.shape[0] > 0 and n > 0):
@@ -259,8 +264,14 @@ class CliffordPowerSphericalDistribution(CliffordTorusDistribution):
         return lp.reshape(lead).to(self.dtype)
 
     def entropy(self):
-        if self._fused_entropy is not None:
-            return self._fused_entropy.to(self.dtype)
+        cached = self._fused_entropy
+        if cached is not None:
+            # a value cached by a no-grad rsample (evaluation path) carries no graph: recompute when the caller now
+            # wants d entropy / d kappa
+            stale = (torch.is_grad_enabled() and self._kappa.requires_grad and cached.grad_fn is None
+                     and not cached.requires_grad)
+            if not stale:
+                return cached.to(self.dtype)
         _, kap2 = self._flat()
         ent = ops.PSEntropy.apply(kap2, self.orig_dim, 0.5, True)
         return ent.reshape(self.batch_shape).to(self.dtype)

@@ -10,7 +10,7 @@ import math
 import torch
 from torch.distributions.kl import register_kl
 
-from . import ops
+from . import ops, testing
 
 
 class HypersphericalUniform(torch.distributions.Distribution):
@@ -100,6 +100,8 @@ class VonMisesFisher(torch.distributions.Distribution):
         n = 1
         for s in shape:
             n *= int(s)
+        if _base_draws is None:
+            _base_draws = testing.take()
         z = ops.VMFRsample.apply(loc2, kap, n, _base_draws)
         return z.reshape(tuple(shape) + tuple(self.loc.shape)).type(self.dtype)
 

@@ -322,6 +322,7 @@ def main():
     gen_special()
     gen_ks(rc, VMF)
     gen_vae_step()
+    gen_conv_vae_step()
 
 
 def gen_vae_step():
@@ -361,10 +362,46 @@ def gen_vae_step():
     print("vae_step.npz", len(out), "arrays")
 
 
+def gen_conv_vae_step():
+    """One training-loss evaluation of the reference's conv VAE (cnn/models.py:134-315; the C3 model at a small latent)
+    with seeded weights, seeded synthetic inputs and RECORDED latent draws: loss terms and parameter gradients."""
+    sys.path.insert(0, REF)
+    from cnn.models import VAE
+    out = {}
+    for dist_name, latent_dim in (("clifford", 64), ("powerspherical", 33)):
+        torch.manual_seed(777 + latent_dim)
+        model = VAE(latent_dim=latent_dim, in_channels=3, distribution=dist_name, device="cpu", recon_loss_type="l1")
+        x = torch.rand(4, 3, 32, 32) * 2 - 1
+        with Recorder() as r:
+            x_recon, q_z, p_z, mu = model(x)
+            losses = model.compute_loss(x, x_recon, q_z, p_z, 1.0)
+        losses["total_loss"].backward()
+        c = {"x": np_(x), "recon": np_(losses["recon_loss"]), "kl": np_(losses["kld_loss"]),
+             "total": np_(losses["total_loss"]), "entropy": np_(losses["entropy"]), "mu": np_(mu),
+             "x_recon": np_(x_recon)}
+        c["tprime"] = np_(r.get("beta_rsample")[0])
+        g = r.get("randn")[0]
+        c["g"] = np_(g.squeeze(-1) if dist_name == "clifford" else g)
+        for name, prm in model.named_parameters():
+            c["grad_norm/" + name] = np.float64(prm.grad.norm().item())
+        c["grad/encoder.fc_concentration.weight"] = np_(model.encoder.fc_concentration.weight.grad)
+        c["grad/encoder.fc_mu.bias"] = np_(model.encoder.fc_mu.bias.grad)
+        c["grad/decoder.fc.bias"] = np_(model.decoder.fc.bias.grad)
+        c["param_checksum"] = np.float64(sum(p.double().sum().item() for p in model.parameters()))
+        for k, v in c.items():
+            out[f"{dist_name}/{k}"] = v
+    np.savez_compressed(os.path.join(OUT, "conv_vae_step.npz"), **out)
+    print("conv_vae_step.npz", len(out), "arrays")
+
+
 if __name__ == "__main__":
     if os.environ.get("GEN_ONLY") == "vae_step":      # regenerate just this fixture
         os.makedirs(OUT, exist_ok=True)
         _import_reference()
         gen_vae_step()
+    elif os.environ.get("GEN_ONLY") == "conv_vae_step":
+        os.makedirs(OUT, exist_ok=True)
+        _import_reference()
+        gen_conv_vae_step()
     else:
         main()
