@@ -20,20 +20,31 @@ enum Status : int {
 
 typedef float2 cplx;
 
+// Complex arithmetic on (re, im) pairs with sm_100's packed fp32 instructions (FADD2 / FMUL2 / FFMA2).  A complex
+// add is ONE instruction and a complex multiply TWO: ptxas folds the lane swap, the per-lane sign and the scalar
+// broadcast of the expressions below into operand modifiers (R.F32x2.LO_HI, .NP, R.F32), so no MOV is emitted.  The
+// fp32 pipes retire the same number of lane operations as the scalar forms (measured, tools/microbench/
+// packed_fp32_throughput.cu: 124 lane-ops / SM / clk either way) -- what halves is the issue-slot count.
+// Rounding is identical to the scalar fmaf forms these replace.
+__device__ __forceinline__ cplx cadd(cplx a, cplx b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ cplx csub(cplx a, cplx b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
 __device__ __forceinline__ cplx cmul(cplx a, cplx b) {
-  return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+  // (a.x b.x - a.y b.y, a.x b.y + a.y b.x) = b * a.x + swap(b) * (-a.y, a.y)
+  return __ffma2_rn(b, make_float2(a.x, a.x), __fmul2_rn(make_float2(b.y, b.x), make_float2(-a.y, a.y)));
 }
-// a * conj(b)
+// a * conj(b) = a * b.x + swap(a) * (b.y, -b.y)
 __device__ __forceinline__ cplx cmulc(cplx a, cplx b) {
-  return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
+  return __ffma2_rn(a, make_float2(b.x, b.x), __fmul2_rn(make_float2(a.y, a.x), make_float2(b.y, -b.y)));
 }
-__device__ __forceinline__ cplx cadd(cplx a, cplx b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ cplx csub(cplx a, cplx b) { return make_float2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ cplx cconj(cplx a) { return make_float2(a.x, -a.y); }
-__device__ __forceinline__ cplx cscale(cplx a, float s) { return make_float2(a.x * s, a.y * s); }
-// multiply by +i / -i
+__device__ __forceinline__ cplx cscale(cplx a, float s) { return __fmul2_rn(a, make_float2(s, s)); }
+// s * (a + b), s * a + b
+__device__ __forceinline__ cplx cadd_scaled(cplx a, cplx b, float s) { return __fmul2_rn(__fadd2_rn(a, b), make_float2(s, s)); }
+__device__ __forceinline__ cplx caxpy(float s, cplx a, cplx b) { return __ffma2_rn(a, make_float2(s, s), b); }
+// multiply by +i / -i (a lane swap with one sign: folded into the consumer's operand modifiers)
 __device__ __forceinline__ cplx cmul_i(cplx a) { return make_float2(-a.y, a.x); }
 __device__ __forceinline__ cplx cmul_mi(cplx a) { return make_float2(a.y, -a.x); }
+__device__ __forceinline__ float cabs2(cplx a) { return fmaf(a.x, a.x, a.y * a.y); }
 
 // Shared-memory exchange buffers hold complex values as float2 with one pad slot every 16
 // entries: stride-R (R = 2..16) writes of the first Stockham pass and the contiguous reads of

@@ -78,8 +78,9 @@ __device__ __forceinline__ void dft4(cplx& a0, cplx& a1, cplx& a2, cplx& a3) {
 // z * exp(-+ i*phi) with (c, s) = (cos phi, sin phi): forward uses exp(-i phi)
 template <bool INV>
 __device__ __forceinline__ cplx rot(cplx z, float c, float s) {
-  return INV ? make_float2(fmaf(z.x, c, -z.y * s), fmaf(z.x, s, z.y * c))
-             : make_float2(fmaf(z.x, c, z.y * s), fmaf(z.y, c, -z.x * s));
+  // z * c + swap(z) * (-+s, +-s): two packed instructions
+  return INV ? __ffma2_rn(z, make_float2(c, c), __fmul2_rn(make_float2(z.y, z.x), make_float2(-s, s)))
+             : __ffma2_rn(z, make_float2(c, c), __fmul2_rn(make_float2(z.y, z.x), make_float2(s, -s)));
 }
 
 template <int R, bool INV>
@@ -178,8 +179,7 @@ __device__ __forceinline__ void apply_twiddle_powers(cplx (&u)[R], cplx w1) {
     if (i & 1) {
       w[i] = cmul(w[i - 1], w1);
     } else {
-      cplx h = w[i >> 1];
-      w[i] = make_float2(fmaf(h.x, h.x, -h.y * h.y), 2.0f * h.x * h.y);
+      w[i] = cmul(w[i >> 1], w[i >> 1]);
     }
   }
 #pragma unroll
@@ -256,7 +256,7 @@ __device__ __forceinline__ float r2c_untangle(cplx (&v)[FftPlan<LOG2N>::E], cplx
     const cplx w = __ldg(&tw[twiddle_offset(LOG2N) + k]);   // exp(-2 pi i k / n)
     const cplx s = cadd(z, zp), d = csub(z, zp);
     const cplx wd = cmul_mi(cmul(w, d));                                 // -i w (z - zp)
-    v[e] = make_float2(0.5f * (s.x + wd.x), 0.5f * (s.y + wd.y));
+    v[e] = cadd_scaled(s, wd, 0.5f);
   }
   return nyq;
 }
@@ -283,7 +283,7 @@ __device__ __forceinline__ void c2r_pretangle(cplx (&v)[FftPlan<LOG2N>::E], floa
     const cplx w = cconj(__ldg(&tw[twiddle_offset(LOG2N) + k]));   // exp(+2 pi i k / n)
     const cplx s = cadd(x, xp), d = csub(x, xp);
     const cplx wd = cmul_i(cmul(w, d));                                       // +i w (x - xp)
-    v[e] = make_float2(scale * (s.x + wd.x), scale * (s.y + wd.y));
+    v[e] = cadd_scaled(s, wd, scale);
   }
 }
 
@@ -303,7 +303,7 @@ __device__ __forceinline__ void c2r_pretangle_load(cplx (&v)[FftPlan<LOG2N>::E],
     const cplx w = cconj(__ldg(&tw[twiddle_offset(LOG2N) + k]));   // exp(+2 pi i k / n)
     const cplx s = cadd(x, xp), d = csub(x, xp);
     const cplx wd = cmul_i(cmul(w, d));
-    v[e] = make_float2(scale * (s.x + wd.x), scale * (s.y + wd.y));
+    v[e] = cadd_scaled(s, wd, scale);
   }
 }
 

@@ -159,7 +159,7 @@ bind_v3_kernel(const BindParams p, const cplx* __restrict__ tw) {
       const cplx Pk = bind_op_unscaled(MODE, Ak, Bk), Pkpc = cconj(bind_op_unscaled(MODE, Akp, Bkp));
       const cplx s = cadd(Pk, Pkpc), d = cmul_i(cmul(cconj(w), csub(Pk, Pkpc)));
       constexpr float fold = (MODE == kBindDiv || MODE == kBindDivConj) ? scale : 0.25f * scale;
-      v[e] = make_float2(fold * (s.x + d.x), fold * (s.y + d.y));
+      v[e] = cadd_scaled(s, d, fold);
     }
     if (STAGED) {
       fence_proxy_async();                       // parked-spectrum accesses before the next TMA write

@@ -63,7 +63,7 @@ def test_reference_mlp_vae_loss_unchanged_on_drop_ins(dist_name, z_dim):
     with injected_draws(draws):
         res = mv.vae_loss(model, x, beta=1.0, return_dict=True)
     res["total"].backward()
-    assert _lib.launch_count() - n0 >= 3          # sampler, entropy/KL, backward ran in libclifford_b200.so
+    assert _lib.launch_count() - n0 >= 2          # sampler (+ fused entropy / KL) and backward ran in libclifford_b200.so
     assert abs(float(res["recon"]) - float(c["recon"])) < 2e-5 * abs(float(c["recon"]))
     assert abs(float(res["kl"]) - float(c["kl"])) < 2e-5 * max(1.0, abs(float(c["kl"])), abs(float(c["entropy"])))
     assert abs(float(res["entropy"]) - float(c["entropy"])) < 2e-5 * max(1.0, abs(float(c["entropy"])))
