@@ -57,6 +57,7 @@ _SIGNATURES = {
     "cvb_vmf_rsample": ([_f, _f, _ll, _f, _f, _i, _f, _ull, _ull, _f, _f, _ll, _i, _f], _i),
     "cvb_vmf_rsample_backward": ([_f, _f, _f, _ll, _f, _f, _ull, _ull, _f, _f, _ll, _i, _f], _i),
     "cvb_vmf_entropy_lognorm": ([_f, _ll, _i, _f, _f, _f, _f, _f], _i),
+    "cvb_ps_halfangle_icdf_table": ([_f, _ll, _f, _f, _f], _i),
     "cvb_philox_fill": ([_f, _ll, _ull, _ull, _f], _i),
 }
 

@@ -14,7 +14,8 @@ template <int LOG2N, int MODE, bool ROWK, bool LEAN = false>
 int launch_fwd_fast(const CliffordFwdParams& p, cudaStream_t st) {
   using Pl = FftPlan<LOG2N>;
   const cplx* tw = device_twiddles();
-  if (!tw) return kCudaError;
+  const float2* icdf = device_icdf_table();
+  if (!tw || !icdf) return kCudaError;
   const size_t smem = clifford_fwd_smem_bytes<LOG2N, MODE>();
   auto kern = clifford_fwd_kernel<LOG2N, MODE, ROWK, false, LEAN>;
   int grid = 0;
@@ -37,7 +38,7 @@ int launch_fwd_fast(const CliffordFwdParams& p, cudaStream_t st) {
   }
   CliffordFwdParams q = p;
   q.sched = dynamic ? next_sched_slot() : nullptr;
-  kern<<<grid, Pl::THREADS, smem, st>>>(q, tw);
+  kern<<<grid, Pl::THREADS, smem, st>>>(q, tw, icdf);
   return check_launch("clifford_fwd_kernel");
 }
 
@@ -45,7 +46,8 @@ template <int LOG2N, int MODE>
 int launch_fwd_bind(const CliffordFwdParams& p, cudaStream_t st) {
   using Pl = FftPlan<LOG2N>;
   const cplx* tw = device_twiddles();
-  if (!tw) return kCudaError;
+  const float2* icdf = device_icdf_table();
+  if (!tw || !icdf) return kCudaError;
   const size_t smem = clifford_fwd_smem_bytes<LOG2N, MODE, true>();
   auto kern = clifford_fwd_kernel<LOG2N, MODE, true, true>;
   int grid = 0;
@@ -54,7 +56,7 @@ int launch_fwd_bind(const CliffordFwdParams& p, cudaStream_t st) {
   CliffordFwdParams q = p;
   static const bool static_sched = getenv("CVB_STATIC_SCHEDULE") != nullptr;
   q.sched = (!static_sched && work > grid) ? next_sched_slot() : nullptr;
-  kern<<<grid, Pl::THREADS, smem, st>>>(q, tw);
+  kern<<<grid, Pl::THREADS, smem, st>>>(q, tw, icdf);
   return check_launch("clifford_fwd_kernel<bind>");
 }
 

@@ -6,6 +6,7 @@
 #include <unordered_map>
 #include <vector>
 #include "launch.cuh"
+#include "icdf_table.cuh"
 #include "../../include/clifford_b200.h"
 
 namespace cvb {
@@ -19,6 +20,102 @@ static int* g_sched[64] = {nullptr};
 static std::atomic<unsigned> g_sched_seq{0};
 constexpr int kSchedSlots = 64;
 static std::unordered_map<const void*, int> g_occ;
+static const float2* g_icdf[64] = {nullptr};
+static std::vector<float2> g_icdf_host;
+
+// ---- host construction of the half-angle inverse-CDF table (icdf_table.cuh), double precision ----------------
+// regularised incomplete beta I_x(a, b) by the modified Lentz continued fraction; xc = 1 - x passed separately so
+// that both ends keep their relative accuracy
+static double beta_cf(double a, double b, double x) {
+  const double tiny = 1e-300, eps = 1e-16;
+  const double qab = a + b, qap = a + 1.0, qam = a - 1.0;
+  double c = 1.0, d = 1.0 - qab * x / qap;
+  if (fabs(d) < tiny) d = tiny;
+  d = 1.0 / d;
+  double h = d;
+  for (int m = 1; m <= 2000; ++m) {
+    const int m2 = 2 * m;
+    double aa = m * (b - m) * x / ((qam + m2) * (a + m2));
+    d = 1.0 + aa * d; if (fabs(d) < tiny) d = tiny;
+    c = 1.0 + aa / c; if (fabs(c) < tiny) c = tiny;
+    d = 1.0 / d; h *= d * c;
+    aa = -(a + m) * (qab + m) * x / ((a + m2) * (qap + m2));
+    d = 1.0 + aa * d; if (fabs(d) < tiny) d = tiny;
+    c = 1.0 + aa / c; if (fabs(c) < tiny) c = tiny;
+    d = 1.0 / d;
+    const double del = d * c;
+    h *= del;
+    if (fabs(del - 1.0) < eps) break;
+  }
+  return h;
+}
+// (I_x(a, b), 1 - I_x(a, b)) with x + xc = 1
+static void beta_inc(double a, double b, double x, double xc, double* lower, double* upper) {
+  if (x <= 0.0) { *lower = 0.0; *upper = 1.0; return; }
+  if (xc <= 0.0) { *lower = 1.0; *upper = 0.0; return; }
+  const double lbt = lgamma(a + b) - lgamma(a) - lgamma(b) + a * log(x) + b * log(xc);
+  if (x < (a + 1.0) / (a + b + 2.0)) {
+    *lower = exp(lbt) * beta_cf(a, b, x) / a;
+    *upper = 1.0 - *lower;
+  } else {
+    *upper = exp(lbt) * beta_cf(b, a, xc) / b;
+    *lower = 1.0 - *upper;
+  }
+}
+
+static void build_icdf_host(std::vector<float2>& out) {
+  const double half_pi = 1.57079632679489661923;
+  out.assign(kIcdfTableEntries, make_float2(0.f, 0.f));
+  for (int ki = 0; ki < kIcdfKappaNodes; ++ki) {
+    const double kap = expm1((double)kIcdfQMax * ki / (kIcdfKappaNodes - 1));
+    const double a = kap + 0.5, p = 2.0 * kap + 1.0;
+    const double Z = exp(log(0.5 * sqrt(3.14159265358979323846)) + lgamma(kap + 0.5) - lgamma(kap + 1.0));   // int_0^{pi/2} cos^{2k}
+    float2* row = out.data() + (size_t)ki * kIcdfRowStride;
+    double prev = half_pi;
+    for (int j = 0; j <= kIcdfCells; ++j) {
+      const double s = (double)j / kIcdfCells;
+      double psi, dpsi;
+      if (j == 0) {
+        psi = half_pi; dpsi = -pow(p * Z, 1.0 / p);
+      } else if (j == kIcdfCells) {
+        psi = 0.0; dpsi = -p * Z;
+      } else {
+        // solve tail(psi) = P(|psi'| > psi) = I_{cos^2 psi}(k + 1/2, 1/2) = s^p: safeguarded Newton on log tail
+        const double lv = p * log(s);
+        double lo = 0.0, hi = prev;                     // H is decreasing in s
+        psi = 0.5 * (lo + hi);
+        for (int it = 0; it < 200; ++it) {
+          const double cs = cos(psi), sn = sin(psi);
+          double low, up;
+          beta_inc(a, 0.5, cs * cs, sn * sn, &low, &up);
+          const double f = log(low) - lv;               // decreasing in psi
+          if (f > 0.0) lo = psi; else hi = psi;
+          if (hi - lo < 1e-15 * half_pi) break;
+          // d log(tail) / d psi = -g / tail, g = cos^{2k} / Z
+          const double g = exp(2.0 * kap * log(fmax(cs, 1e-300))) / Z;
+          double nxt = psi + f * low / g;
+          if (!(nxt > lo && nxt < hi)) nxt = 0.5 * (lo + hi);
+          if (fabs(nxt - psi) < 1e-15) { psi = nxt; break; }
+          psi = nxt;
+        }
+        const double g = exp(2.0 * kap * log(cos(psi))) / Z;
+        dpsi = -p * exp((p - 1.0) * log(s)) / g;
+        prev = psi;
+      }
+      row[j] = make_float2((float)psi, (float)(dpsi / kIcdfCells));
+    }
+    row[kIcdfCells + 1] = row[kIcdfCells];          // padding entry (never interpolated)
+  }
+}
+
+const float2* device_icdf_table() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || !g_icdf[dev]) {
+    set_last_error("cvb_init() has not been called on the current device");
+    return nullptr;
+  }
+  return g_icdf[dev];
+}
 
 void set_last_error(const char* fmt, ...) {
   va_list ap;
@@ -102,9 +199,35 @@ int cvb_init(void) {
   int* sched = nullptr;
   CVB_CUDA(cudaMalloc(&sched, sizeof(int) * 2 * kSchedSlots));
   CVB_CUDA(cudaMemset(sched, 0, sizeof(int) * 2 * kSchedSlots));
+  if (g_icdf_host.empty()) build_icdf_host(g_icdf_host);
+  float2* icdf = nullptr;
+  CVB_CUDA(cudaMalloc(&icdf, sizeof(float2) * kIcdfTableEntries));
+  {
+    std::vector<float2> dev_copy(g_icdf_host);      // the device samples the phase phi = 2 psi directly
+    for (auto& e : dev_copy) { e.x *= 2.0f; e.y *= 2.0f; }
+    CVB_CUDA(cudaMemcpy(icdf, dev_copy.data(), sizeof(float2) * kIcdfTableEntries, cudaMemcpyHostToDevice));
+  }
+  g_icdf[dev] = icdf;
   g_sched[dev] = sched;
   g_tw[dev] = dptr;
   g_sms[dev] = prop.multiProcessorCount;
+  return kOk;
+}
+
+// Host-only: the half-angle inverse-CDF table the device samplers interpolate (icdf_table.cuh); no GPU needed.
+int cvb_ps_halfangle_icdf_table(float* out, long long capacity_floats, int* n_kappa, int* n_nodes, float* kappa_max) {
+  if (n_kappa) *n_kappa = kIcdfKappaNodes;
+  if (n_nodes) *n_nodes = kIcdfCells + 1;
+  if (kappa_max) *kappa_max = kIcdfKappaMax;
+  if (!out) return kOk;
+  const long long need = 2LL * kIcdfKappaNodes * (kIcdfCells + 1);
+  CVB_REQUIRE(capacity_floats >= need, kBadArgument, "cvb_ps_halfangle_icdf_table: need room for %lld floats", need);
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_icdf_host.empty()) build_icdf_host(g_icdf_host);
+  }
+  for (int ki = 0; ki < kIcdfKappaNodes; ++ki)       // drop the row padding
+    memcpy(out + 2LL * ki * (kIcdfCells + 1), g_icdf_host.data() + (size_t)ki * kIcdfRowStride, sizeof(float2) * (kIcdfCells + 1));
   return kOk;
 }
 

@@ -11,6 +11,7 @@
 #include "fft_core.cuh"
 #include "tma.cuh"
 #include "rng.cuh"
+#include "icdf_table.cuh"
 #include "special.cuh"
 // Minimum resident CTAs per SM requested for the forward kernel's 128-thread configurations (register cap 102 at 5).
 // Measured on B200 (device RNG, >= 1 GiB per launch): 5 beats 4 by 2-4 % at d = 512 / 2048 and loses 2 % at d = 1024.
@@ -230,11 +231,15 @@ __device__ __forceinline__ void clifford_row_entropy(const CliffordFwdParams& p,
 typedef unsigned short QueueIndex;   // retry-queue entries are bin indices < N <= 8192
 constexpr int kLpSlots = 16;   // per-warp partial sums of the fused log_prob (groups of up to 512 threads)
 constexpr int clifford_fwd_stages(int mode) { return mode == kPsInjected ? 3 : ((mode == kPsRng || mode == kPhases) ? 1 : 0); }
+// Device-RNG rows with one concentration <= kIcdfKappaMax are sampled through the row's inverse-CDF table
+// (icdf_table.cuh) when the row is long enough to amortise building it (d >= 512: 256 cells by >= 32 threads).
+template <int LOG2N, int MODE>
+constexpr bool clifford_fwd_has_icdf() { return MODE == kPsRng && LOG2N >= 9; }
 template <int LOG2N, int MODE, bool BIND = false>
 constexpr size_t clifford_fwd_smem_bytes() {
   using Pl = FftPlan<LOG2N>;
   return (sizeof(cplx) * Pl::XCH + sizeof(QueueIndex) * Pl::N + sizeof(float) * Pl::N * clifford_fwd_stages(MODE) +
-          (BIND ? sizeof(cplx) * Pl::N : 0)) * Pl::GROUPS +
+          (BIND ? sizeof(cplx) * Pl::N : 0) + (clifford_fwd_has_icdf<LOG2N, MODE>() ? sizeof(float4) * kIcdfCells : 0)) * Pl::GROUPS +
          (sizeof(uint64_t) + sizeof(int) * 2 + sizeof(float) * kLpSlots) * Pl::GROUPS;
 }
 
@@ -246,10 +251,11 @@ constexpr size_t clifford_fwd_smem_bytes() {
 // (Also assuming the dynamic schedule / always-valid rows was measured: +2 % at d = 512 / 1024, -2 % at d = 2048.)
 template <int LOG2N, int MODE, bool ROWK, bool BIND = false, bool LEAN = false>
 __global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS, (FftPlan<LOG2N>::THREADS <= 128 ? clifford_fwd_min_blocks<LOG2N, BIND, LEAN>() : 1))
-clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw) {
+clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw, const float2* __restrict__ icdf) {
   using Pl = FftPlan<LOG2N>;
   constexpr int d = Pl::N, T = Pl::T, E = Pl::E, G = Pl::GROUPS;
   constexpr int NST = clifford_fwd_stages(MODE);
+  constexpr bool ICDF = clifford_fwd_has_icdf<LOG2N, MODE>() && ROWK;
   constexpr uint32_t kRowBytes = d * sizeof(float);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int group = threadIdx.x / T, t = threadIdx.x % T;
@@ -262,6 +268,8 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw) {
   int* qcount = reinterpret_cast<int*>(after_stage + (sizeof(cplx) * Pl::XCH + sizeof(QueueIndex) * d + sizeof(uint64_t)) * (size_t)G) + 2 * group;
   float* lps = reinterpret_cast<float*>(after_stage + (sizeof(cplx) * Pl::XCH + sizeof(QueueIndex) * d + sizeof(uint64_t) + 2 * sizeof(int)) * (size_t)G) + kLpSlots * group;
   cplx* spec = reinterpret_cast<cplx*>(after_stage + (sizeof(cplx) * Pl::XCH + sizeof(QueueIndex) * d + sizeof(uint64_t) + 2 * sizeof(int) + kLpSlots * sizeof(float)) * (size_t)G) + (size_t)group * d;   // BIND only
+  // row inverse-CDF cells (16-byte aligned: every block before it is a multiple of 16 bytes per CTA)
+  float4* cells = reinterpret_cast<float4*>(after_stage + (sizeof(cplx) * Pl::XCH + sizeof(QueueIndex) * d + sizeof(uint64_t) + 2 * sizeof(int) + kLpSlots * sizeof(float) + (BIND ? sizeof(cplx) * d : 0)) * (size_t)G) + (size_t)group * kIcdfCells;
   constexpr bool PS = (MODE == kPsInjected || MODE == kPsRng);
   const long long stride = (long long)gridDim.x * G;
   const bool staged = LEAN ? true : (NST > 0 && p.staged);   // LEAN implies TMA-staged inputs (16-byte aligned rows)
@@ -288,6 +296,13 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw) {
   __syncthreads();
   const long long first_row = (long long)blockIdx.x * G + group;
   if (staged && t == 0 && first_row < p.rows) issue(first_row);
+  // a row is table-sampled when its concentration is inside the table's range; the cells of the first row are built
+  // here, those of every later row right after the previous row's sampling phase (their loads overlap its FFT)
+  auto icdf_row_ok = [&](float kap) { return kap + kEps <= kIcdfKappaMax; };
+  if (ICDF && first_row < p.rows) {
+    const float k0 = __ldg(p.kappa + (first_row % p.loc_rows) * p.kappa_row_stride);
+    if (icdf_row_ok(k0)) icdf_build_row(cells, k0 + kEps, icdf, t, T);
+  }
 
   // Prologue: the closed-form row entropy / KL / dH/dkappa (fp64 special functions) of every row this
   // group will process, one row per thread, so the per-row loop carries no serial fp64 chain.
@@ -338,7 +353,38 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw) {
       }
     };
     // phase 1: phasors of the half spectrum into the exchange buffer (lightly unrolled: small code, some ILP)
-    if (MODE == kPsRng) {
+    const bool table_row = ICDF && icdf_row_ok(kap_row);      // uniform over the group
+    if (ICDF && table_row) {
+      // device RNG through the row's inverse-CDF cells: one Philox call per FOUR circles, no rejection, no queue
+      const uint64_t quad_base = (uint64_t)row * (uint64_t)(d / 4) + (uint64_t)t * (E / 4);
+      PhiloxKey pkey = p.key;
+      pkey.stream = 10;
+      const float inv_p = __frcp_rn(fmaf(2.0f, kap_row + kEps, 1.0f));
+#pragma unroll 2
+      for (int e = 0; e < E; e += 4) {
+        const uint4 r = philox_draw(pkey, quad_base + (e >> 2), 0);
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = t + (e + j) * T;
+          // phi = s max(|phi|, sqrt(eps)): the reference's atan2(s sqrt(max(1 - t^2, eps)), t) (clifford.py:44-48) never
+          // returns a phase below sqrt(eps); theta = loc + phi needs ONE sincos instead of sincos(loc), cos/sin(phi)
+          // and a complex multiply
+          const float aphi = fminf(fmaxf(icdf_sample_phi(cells, inv_p, w[j]), 3.16227766e-4f), 3.14127642f);   // [sqrt(eps), pi - sqrt(eps)]
+          const float phi = __uint_as_float(__float_as_uint(aphi) | (w[j] & 0x80000000u));
+          cplx x = make_float2(1.0f, 0.0f);
+          if (valid && k != 0) {
+            if ((!LEAN && p.tp_signed) || want_lp) {
+              const float tpj = icdf_tprime(aphi);
+              if (!LEAN && p.tp_signed) stg_stream1(p.tp_signed + row * d + k, __uint_as_float(__float_as_uint(tpj) | (w[j] & 0x80000000u)));
+              if (want_lp) lp_acc += circle_log_half_1pt<true>(tpj);
+            }
+            sincos_any<true>(src.loc[k] + phi, x.y, x.x);
+          }
+          xch[pad16(k)] = x;
+        }
+      }
+    } else if (MODE == kPsRng) {
       // device RNG: one Philox call + one Box-Muller per PAIR of bins (one envelope proposal each);
       // rejected proposals are queued and finished in phase 1b
       const uint64_t pair_base = (uint64_t)row * (uint64_t)(d / 2) + (uint64_t)t * (E / 2);
@@ -446,7 +492,9 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw) {
     if (MODE == kPsInjected && want_lp) lp_reduce();
     group_sync<LOG2N>();
     if (MODE == kPsInjected && want_lp) lp_emit();
-    if (MODE == kPsRng) {
+    if (ICDF && table_row) {
+      if (want_lp) { lp_reduce(); group_sync<LOG2N>(); lp_emit(); }
+    } else if (MODE == kPsRng) {
       // phase 1b: rejected proposals, spread evenly over the group's threads
       const int nq = *qcount;
 #pragma unroll 1
@@ -463,6 +511,11 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw) {
     }
     // every thread is done with the staged inputs: fetch the next row's while this one is transformed
     if (staged && t == 0 && next_row < p.rows) issue(next_row);
+    if (ICDF && next_row < p.rows) {
+      // ... and with this row's cells: build the next row's (the loop-top barrier orders them before its sampling)
+      const float kn = __ldg(p.kappa + (next_row % p.loc_rows) * p.kappa_row_stride);
+      if (icdf_row_ok(kn)) icdf_build_row(cells, kn + kEps, icdf, t, T);
+    }
     // phase 2: Hermitian half spectrum -> packed complex spectrum -> inverse FFT -> real row
     cplx v[E];
     if (BIND) {

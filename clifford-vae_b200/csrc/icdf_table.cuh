@@ -1,0 +1,89 @@
+// Inverse-CDF table of the power-spherical half-angle on one circle (row-scalar concentration).
+//
+// t' ~ Beta(1/2 + k, 1/2) (reference dists/clifford.py:124-134 with dim = 2) is cos^2(psi) for a half-angle
+// |psi| in [0, pi/2] with density ~ cos^{2k}(psi).  With v uniform in (0, 1] and p = 2k + 1,
+//     |psi| = H_k(s),   s = v^{1/p},   H_k(s) = G_k^{-1}(1 - s^p),   G_k = CDF of |psi|,
+// and H_k is smooth on [0, 1] for every k (the substitution s = v^{1/p} removes the (pi/2 - psi)^{2k+1} tail
+// singularity of the plain inverse CDF): cubic Hermite interpolation on a uniform s-grid of 256 cells reproduces the
+// CDF to < 1e-6 for k <= 10 and < 6e-5 for k <= 32 (tests/test_icdf_table.py, against SciPy's betaincinv).  H_k is
+// also smooth in k: the library holds H and dH/ds on 64 concentration nodes uniform in log1p(k) over [0, 32] (built in
+// double precision on the host at cvb_init), and a row's table is a 4-point Lagrange interpolation between them.
+// One circle then costs one uniform word + log2/exp2 + one table cell + 3 FMAs instead of an envelope rejection test
+// with a retry queue.  (The DEVICE copy of the table stores the phase 2H and its slope: phi = 2 psi is what the sampler
+// adds to loc; the host copy exported through cvb_ps_halfangle_icdf_table holds H itself.)  Rows with k > 32 (and per-element concentrations) keep the exact rejection sampler (rng.cuh).
+#pragma once
+#include "common.cuh"
+
+namespace cvb {
+
+constexpr int kIcdfKappaNodes = 64;
+constexpr int kIcdfCells = 256;                       // s-cells per concentration node (nodes = cells + 1)
+constexpr float kIcdfKappaMax = 32.0f;
+constexpr float kIcdfQMax = 3.49650756146648f;        // log1p(32)
+constexpr int kIcdfRowStride = kIcdfCells + 2;        // nodes per concentration row, padded to a multiple of 16 bytes
+constexpr int kIcdfTableEntries = kIcdfKappaNodes * kIcdfRowStride;     // float2 (H, dH/ds / cells)
+
+// per-device copy of the table (nullptr + error set before cvb_init)
+const float2* device_icdf_table();
+
+#ifdef __CUDACC__
+// Build one row's cell polynomials psi(tau) = c.x + tau (c.y + tau (c.z + tau c.w)) in shared memory (kIcdfCells
+// float4); called by the T threads of a group (t = 0..T-1), followed by the caller's group barrier.
+__device__ __forceinline__ void icdf_build_row(float4* cell, float kappa, const float2* __restrict__ table, int t, int T) {
+  const float x = log1pf(kappa) * ((float)(kIcdfKappaNodes - 1) / kIcdfQMax);
+  int i = (int)x;
+  i = i < 1 ? 1 : (i > kIcdfKappaNodes - 3 ? kIcdfKappaNodes - 3 : i);
+  const float u = x - (float)i;                        // in [-1, 2] at the ends of the node range
+  const float w0 = -u * (u - 1.0f) * (u - 2.0f) * (1.0f / 6.0f);
+  const float w1 = (u + 1.0f) * (u - 1.0f) * (u - 2.0f) * 0.5f;
+  const float w2 = -(u + 1.0f) * u * (u - 2.0f) * 0.5f;
+  const float w3 = (u + 1.0f) * u * (u - 1.0f) * (1.0f / 6.0f);
+  // thread t builds cells 2t', 2t'+1 from nodes 2t' .. 2t'+2: one 128-bit + one 64-bit load per concentration row
+  const float2* r0 = table + (size_t)(i - 1) * kIcdfRowStride;
+  for (int j = 2 * t; j < kIcdfCells; j += 2 * T) {
+    float2 n0 = make_float2(0.f, 0.f), n1 = n0, n2 = n0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float w = q == 0 ? w0 : (q == 1 ? w1 : (q == 2 ? w2 : w3));
+      const float4 a = __ldg(reinterpret_cast<const float4*>(r0 + (size_t)q * kIcdfRowStride + j));
+      const float2 b = __ldg(r0 + (size_t)q * kIcdfRowStride + j + 2);
+      n0.x = fmaf(w, a.x, n0.x); n0.y = fmaf(w, a.y, n0.y);
+      n1.x = fmaf(w, a.z, n1.x); n1.y = fmaf(w, a.w, n1.y);
+      n2.x = fmaf(w, b.x, n2.x); n2.y = fmaf(w, b.y, n2.y);
+    }
+    const float d0 = n1.x - n0.x, d1 = n2.x - n1.x;
+    cell[j] = make_float4(n0.x, n0.y, 3.0f * d0 - 2.0f * n0.y - n1.y, -2.0f * d0 + n0.y + n1.y);
+    cell[j + 1] = make_float4(n1.x, n1.y, 3.0f * d1 - 2.0f * n1.y - n2.y, -2.0f * d1 + n1.y + n2.y);
+  }
+}
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+__device__ __forceinline__ float fast_log2(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// One circle from one 32-bit word: bits 7..30 -> v in (0, 1]; returns the phase magnitude |phi| = 2 |psi| in [0, pi]
+// (the device table stores 2 H).  inv_p = 1 / (2k + 1).  Bit 31 of the word is the circle's sign draw.
+__device__ __forceinline__ float icdf_sample_phi(const float4* cell, float inv_p, uint32_t w) {
+  const float v = (float)(((w >> 7) & 0xFFFFFFu) + 1u) * 0x1p-24f;
+  const float x = fast_exp2(fast_log2(v) * inv_p) * (float)kIcdfCells;
+  int j = (int)x;
+  j = j > kIcdfCells - 1 ? kIcdfCells - 1 : j;
+  const float tau = x - (float)j;
+  const float4 c = cell[j];
+  return fmaf(fmaf(fmaf(c.w, tau, c.z), tau, c.y), tau, c.x);
+}
+// t' = cos^2(psi) = (1 + cos phi) / 2 in torch's Beta clamp range, like the exact sampler
+__device__ __forceinline__ float icdf_tprime(float phi) {
+  return fminf(fmaxf(fmaf(0.5f, __cosf(phi), 0.5f), 1.17549435e-38f), 1.0f - 5.9604645e-8f);
+}
+#endif
+
+}  // namespace cvb

@@ -138,16 +138,18 @@ bind_v3_kernel(const BindParams p, const cplx* __restrict__ tw) {
       mbar_expect_tx(&bars[1], kRowBytes);
       tma_load_1d(stage_b, p.b + (next_row % p.b_rows) * (2LL * N), kRowBytes, &bars[1]);
     }
-    // ---- one partner exchange: untangle a and b, pointwise op, re-pack for the inverse transform
+    // ---- one partner exchange: untangle a and b, pointwise op, re-pack for the inverse transform.
+    // Bins k and N-k share every intermediate (V[k] = c (s + d), V[N-k] = c conj(s - d)), so each pair is formed ONCE,
+    // by the thread that owns k < N/2 (its points e < E/2); the partner value V[N-k] goes back through the parked row
+    // (the slot this thread just consumed), and every thread re-reads its upper-half points after one barrier.
     group_sync_p<Pl>();
 #pragma unroll
     for (int e = 0; e < E; ++e) xch[pad16(t + e * T)] = v[e];
     group_sync_p<Pl>();
-#pragma unroll
-    for (int e = 0; e < E; ++e) {
-      const int k = t + e * T, kp = (N - k) & (N - 1);
+    constexpr float fold = (MODE == kBindDiv || MODE == kBindDivConj) ? scale : 0.25f * scale;
+    auto pair = [&](int k, int kp, cplx zb, cplx& vk, cplx& vkp) {
       const cplx za = park[k], zap = cconj(park[kp]);
-      const cplx zb = v[e], zbp = cconj(xch[pad16(kp)]);
+      const cplx zbp = cconj(xch[pad16(kp)]);
       const cplx w = __ldg(&tw[twiddle_offset(LOG2N) + k]);    // exp(-2 pi i k / n)
       // bins k and N-k of the real FFTs (X[N-k] uses W^(N-k) = -conj(W^k)); factor 1/2 each
       const cplx sa = cadd(za, zap), da = cmul_mi(cmul(w, csub(za, zap)));
@@ -158,9 +160,24 @@ bind_v3_kernel(const BindParams p, const cplx* __restrict__ tw) {
       const cplx Bk = cadd(sb, db), Bkp = cconj(csub(sb, db));
       const cplx Pk = bind_op_unscaled(MODE, Ak, Bk), Pkpc = cconj(bind_op_unscaled(MODE, Akp, Bkp));
       const cplx s = cadd(Pk, Pkpc), d = cmul_i(cmul(cconj(w), csub(Pk, Pkpc)));
-      constexpr float fold = (MODE == kBindDiv || MODE == kBindDivConj) ? scale : 0.25f * scale;
-      v[e] = cadd_scaled(s, d, fold);
+      vk = cadd_scaled(s, d, fold);
+      vkp = cconj(cscale(csub(s, d), fold));
+    };
+#pragma unroll
+    for (int e = 0; e < E / 2; ++e) {
+      const int k = t + e * T, kp = (N - k) & (N - 1);
+      cplx vkp;
+      pair(k, kp, v[e], v[e], vkp);
+      if (kp != k) park[kp] = vkp;               // k = 0 pairs the DC / Nyquist bins inside one slot
     }
+    if (t == 0) {                                // k = N/2 is its own partner
+      cplx vk, vkp;
+      pair(N / 2, N / 2, v[E / 2], vk, vkp);
+      park[N / 2] = vk;
+    }
+    group_sync_p<Pl>();
+#pragma unroll
+    for (int e = E / 2; e < E; ++e) v[e] = park[t + e * T];
     if (STAGED) {
       fence_proxy_async();                       // parked-spectrum accesses before the next TMA write
       group_sync_p<Pl>();

@@ -190,6 +190,14 @@ CVB_API int cvb_vmf_rsample_backward(const float* grad_z, const float* loc, cons
 CVB_API int cvb_vmf_entropy_lognorm(const float* kappa, long long rows, int D, float* entropy, float* log_norm,
                                     float* dentropy, float* dlog_norm, void* stream);
 
+/* ---- host-only: the inverse-CDF table behind the device sampler of dists/clifford.py:124-134's Beta(1/2 + kappa, 1/2)
+ * draw for row-scalar concentrations <= *kappa_max (csrc/icdf_table.cuh).  Layout: [n_kappa][n_nodes][2] floats =
+ * (H, dH/ds / (n_nodes - 1)) with concentration node i at kappa_i = expm1(log1p(kappa_max) * i / (n_kappa - 1)) and
+ * s-node j at s = j / (n_nodes - 1); |psi| = H(s), s = v^(1 / (2 kappa + 1)), t' = cos^2(psi).  out may be NULL to
+ * query the sizes only.  Needs no GPU (the CPU test checks it against SciPy's betaincinv). */
+CVB_API int cvb_ps_halfangle_icdf_table(float* out, long long capacity_floats, int* n_kappa, int* n_nodes,
+                                        float* kappa_max);
+
 /* ---- test hook: raw Philox4x32-10 words, out[4*i .. 4*i+3] = philox(counter = (i, 0, 0, offset)) --- */
 CVB_API int cvb_philox_fill(unsigned int* out, long long n_vec4, unsigned long long seed, unsigned long long offset,
                     void* stream);

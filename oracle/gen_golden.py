@@ -323,6 +323,7 @@ def main():
     gen_ks(rc, VMF)
     gen_vae_step()
     gen_conv_vae_step()
+    gen_ks_extra(rc)
 
 
 def gen_vae_step():
@@ -362,6 +363,21 @@ def gen_vae_step():
     print("vae_step.npz", len(out), "arrays")
 
 
+def gen_ks_extra(rc):
+    """Reference-class phase samples at the concentrations the round-2 sampler tests add (0.001, 0.13, 100)."""
+    out = {}
+    torch.manual_seed(4321)
+    n = 8192
+    for kap in (0.001, 0.13, 100.0):
+        loc = torch.zeros(n, 2)
+        q = rc.CliffordPowerSphericalDistribution(loc, torch.full((n, 1), kap))
+        z = q.rsample()
+        th = torch.angle(torch.fft.fft(z, dim=-1)[:, 1])
+        out[f"clifford_phi_k{kap}"] = np.sort(np_(th))
+    np.savez_compressed(os.path.join(OUT, "ks_samples_extra.npz"), **out)
+    print("ks_samples_extra.npz", len(out), "arrays")
+
+
 def gen_conv_vae_step():
     """One training-loss evaluation of the reference's conv VAE (cnn/models.py:134-315; the C3 model at a small latent)
     with seeded weights, seeded synthetic inputs and RECORDED latent draws: loss terms and parameter gradients."""
@@ -399,6 +415,9 @@ if __name__ == "__main__":
         os.makedirs(OUT, exist_ok=True)
         _import_reference()
         gen_vae_step()
+    elif os.environ.get("GEN_ONLY") == "ks_extra":
+        os.makedirs(OUT, exist_ok=True)
+        gen_ks_extra(_import_reference()[0])
     elif os.environ.get("GEN_ONLY") == "conv_vae_step":
         os.makedirs(OUT, exist_ok=True)
         _import_reference()

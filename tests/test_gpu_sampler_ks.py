@@ -1,0 +1,84 @@
+"""GPU: distribution of the on-device Clifford phase sampler at the sizes that take the inverse-CDF table path
+(d >= 512, one concentration per row <= 32; csrc/icdf_table.cuh) and the exact rejection path (larger concentrations):
+one-sample KS of >= 2^20 device draws against the analytic law of the reference's draw -- phi = +-acos(2 t' - 1),
+t' ~ Beta(1/2 + k, 1/2) (dists/clifford.py:124-134, :295-301), with its sqrt(eps) phase clamp (:44-48) -- and two-sample
+KS against samples drawn from the reference class itself (tests/golden/ks_samples*.npz)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _phase_cdf(phi, k):
+    """CDF of the phase on (-pi, pi): 1/2 +- G(|phi| / 2) / 2 with G(psi) = 1 - I_{cos^2 psi}(k + 1/2, 1/2)."""
+    from scipy.special import betainc
+    g = 1.0 - betainc(k + 0.5, 0.5, np.cos(np.abs(phi) / 2) ** 2)
+    return 0.5 + 0.5 * np.sign(phi) * g
+
+
+def _device_phases(k, rows, d):
+    from dists.clifford import CliffordPowerSphericalDistribution
+    loc = torch.zeros(rows, d, device=DEV)
+    q = CliffordPowerSphericalDistribution(loc, torch.full((rows, 1), k, device=DEV), validate_args=False)
+    z = q.rsample()
+    return torch.angle(torch.fft.rfft(z.double(), dim=-1)[:, 1:d]).cpu().numpy()      # (rows, d-1) phases, loc = 0
+
+
+@pytest.mark.parametrize("k", [1e-3, 0.13, 1.0, 10.0, 31.0, 100.0])
+def test_one_sample_ks_against_the_analytic_law(k):
+    torch.manual_seed(int(k * 1000) + 5)
+    d, rows = 512, 2112                                   # 2112 * 511 = 1,079,232 >= 2^20 draws
+    th = _device_phases(k, rows, d).reshape(-1)
+    n = th.size
+    assert n >= 1 << 20
+    x = np.sort(th)
+    F = _phase_cdf(x, k)
+    i = np.arange(1, n + 1)
+    D = max(np.max(i / n - F), np.max(F - (i - 1) / n))
+    # the reference never returns |phi| < sqrt(eps) (clamped to +-sqrt(eps)): that mass sits on two atoms
+    atom = _phase_cdf(np.array([3.16227766e-4]), k)[0] - 0.5
+    crit = 1.95 / np.sqrt(n)                              # alpha = 0.001
+    assert D < crit + atom, (k, D, crit, atom)
+    assert np.abs(th).min() >= 3.0e-4 and np.abs(th).max() <= np.pi
+    # signs are fair and independent of the magnitude
+    assert abs(np.mean(th > 0) - 0.5) < 4 / np.sqrt(n)
+    assert abs(np.corrcoef(np.abs(th[::2][: n // 2 - 1]), np.abs(th[1::2][: n // 2 - 1]))[0, 1]) < 5e-3
+
+
+@pytest.mark.parametrize("k,fname", [(0.001, "ks_samples_extra.npz"), (0.13, "ks_samples_extra.npz"),
+                                     (100.0, "ks_samples_extra.npz"), (0.1, "ks_samples.npz"), (1.0, "ks_samples.npz"),
+                                     (10.0, "ks_samples.npz")])
+def test_two_sample_ks_against_reference_class_samples(k, fname):
+    from scipy.stats import ks_2samp
+    ref = np.load(os.path.join(GOLDEN, fname))[f"clifford_phi_k{k}"]
+    torch.manual_seed(11)
+    th = _device_phases(k, 64, 512)
+    for col in (0, 255, 510):                             # single circles across rows ...
+        stat, pval = ks_2samp(th[:, col], ref)
+        assert pval > 1e-3, (k, col, stat, pval)
+    stat, pval = ks_2samp(th.reshape(-1)[:8192], ref)     # ... and across circles of the same rows
+    assert pval > 1e-3, (k, stat, pval)
+
+
+def test_rows_with_different_concentrations_use_their_own_table():
+    """Consecutive rows switch between table rows (k <= 32) and exact rows (k > 32) inside one launch."""
+    from dists.clifford import CliffordPowerSphericalDistribution
+    torch.manual_seed(3)
+    ks = torch.tensor([0.05, 40.0, 2.0, 0.5, 64.0, 9.0, 31.9, 32.1], device=DEV).repeat(96)[:, None]
+    rows, d = ks.shape[0], 1024
+    z = CliffordPowerSphericalDistribution(torch.zeros(rows, d, device=DEV), ks, validate_args=False).rsample()
+    th = torch.angle(torch.fft.rfft(z.double(), dim=-1)[:, 1:d]).cpu().numpy()
+    for j, k in enumerate(ks[:8, 0].tolist()):
+        x = np.sort(th[j::8].reshape(-1))
+        n = x.size
+        F = _phase_cdf(x, k)
+        i = np.arange(1, n + 1)
+        D = max(np.max(i / n - F), np.max(F - (i - 1) / n))
+        atom = _phase_cdf(np.array([3.16227766e-4]), k)[0] - 0.5
+        assert D < 1.95 / np.sqrt(n) + atom, (k, D)
