@@ -40,11 +40,15 @@ BYTES_RSAMPLE = 12 * D_LAT + 8
 BYTES_BIND = 12 * N_VEC
 
 
+TRAFFIC_FILE = "profiles/r02_traffic.json"
+
+
 def load_traffic(kernel_name):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
-    ncu --set full capture of this bench (profiles/r01_traffic.json), or None."""
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel.  ncu cannot run inside the timed
+    bench, so the figure comes from the committed `ncu --set full` capture of this very command (profiles/README.md,
+    regenerated with the kernels it describes); None when the file has no entry for the kernel."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+        with open(os.path.join(ROOT, TRAFFIC_FILE)) as f:
             t = json.load(f)
         for k, v in t.items():
             if kernel_name.startswith(k):
@@ -270,76 +274,87 @@ def run_gpu(args):
     ms_bind = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
 
     # ---- e2e: reference-named Python API, host (pinned) buffers in and out ------------------------
+    # One packed pinned buffer per direction: [loc | kappa | roles] in (one H2D copy per step), [bound | kl] out (one
+    # D2H copy per step); the device tensors the API sees are views of the packed device buffers.
     from dists.clifford import CliffordPowerSphericalDistribution, CliffordTorusUniform
     from utils import vsa
-    h_loc = torch.randn(B, d).pin_memory()
-    h_kap = (torch.rand(B, 1) * 9.87 + 0.13).pin_memory()
-    h_roles = (torch.randn(B, n) / math.sqrt(n)).pin_memory()
-    h_out = torch.empty(B, n).pin_memory()
-    h_kl = torch.empty(B).pin_memory()
+    n_in, n_out = B * d + B + B * n, B * n + B
+    h_in = torch.empty(n_in).pin_memory()
+    h_in[:B * d].normal_()
+    h_in[B * d:B * d + B].uniform_(0.13, 10.0)
+    h_in[B * d + B:].normal_().mul_(1.0 / math.sqrt(n))
+    h_out = torch.empty(n_out).pin_memory()
     prior = CliffordTorusUniform(d, device=dev)
 
     # Double-buffered pipeline: copy-in (H2D), compute, copy-out (D2H) on three streams, two device buffer
     # sets; every step still moves its own inputs from pinned host memory and its own results back.
     s_in, s_cmp, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
-    dbuf = [dict(loc=torch.empty(B, d, device=dev), kap=torch.empty(B, 1, device=dev), roles=torch.empty(B, n, device=dev),
-                 ev_in=torch.cuda.Event(), ev_cmp=torch.cuda.Event(), ev_out=torch.cuda.Event(), out=None, kl=None)
-            for _ in range(2)]
+    dbuf = [dict(inp=torch.empty(n_in, device=dev), out=torch.empty(n_out, device=dev),
+                 ev_in=torch.cuda.Event(), ev_cmp=torch.cuda.Event(), ev_out=torch.cuda.Event()) for _ in range(2)]
 
-    def e2e_step(i):
+    def e2e_step(i, compute=True):
         b = dbuf[i % 2]
         with torch.no_grad():
             with torch.cuda.stream(s_in):
                 s_in.wait_event(b["ev_cmp"])                  # the compute that last read this set is done
-                b["loc"].copy_(h_loc, non_blocking=True)
-                b["kap"].copy_(h_kap, non_blocking=True)
-                b["roles"].copy_(h_roles, non_blocking=True)
+                b["inp"].copy_(h_in, non_blocking=True)
                 b["ev_in"].record(s_in)
             with torch.cuda.stream(s_cmp):
                 s_cmp.wait_event(b["ev_in"])
                 s_cmp.wait_event(b["ev_out"])                 # the previous outputs of this set were copied out
-                q = CliffordPowerSphericalDistribution(b["loc"], b["kap"], validate_args=False)
-                z = q.rsample()
-                b["kl"] = torch.distributions.kl.kl_divergence(q, prior)
-                b["out"] = vsa.bind(z, b["roles"])
+                if compute:
+                    loc_v = b["inp"][:B * d].view(B, d)
+                    kap_v = b["inp"][B * d:B * d + B].view(B, 1)
+                    roles_v = b["inp"][B * d + B:].view(B, n)
+                    q = CliffordPowerSphericalDistribution(loc_v, kap_v, validate_args=False)
+                    z = q.rsample()
+                    kl = torch.distributions.kl.kl_divergence(q, prior)
+                    bound = vsa.bind(z, roles_v)
+                    b["out"][:B * n].view(B, n).copy_(bound)      # the API allocates its result; gather it next to kl
+                    b["out"][B * n:].copy_(kl)
                 b["ev_cmp"].record(s_cmp)
             with torch.cuda.stream(s_out):
                 s_out.wait_event(b["ev_cmp"])
                 h_out.copy_(b["out"], non_blocking=True)
-                h_kl.copy_(b["kl"], non_blocking=True)
-                b["out"].record_stream(s_out)
-                b["kl"].record_stream(s_out)
                 b["ev_out"].record(s_out)
 
     def e2e_drain():
         s_in.synchronize(); s_cmp.synchronize(); s_out.synchronize()
 
+    def e2e_time(steps, compute):
+        for i in range(4):
+            e2e_step(i, compute)
+        e2e_drain()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        s_in.wait_event(e0); s_cmp.wait_event(e0); s_out.wait_event(e0)
+        for i in range(steps):
+            e2e_step(i, compute)
+        e2e_drain()
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1)
+
     e2e_steps = max(3, min(args.steps, 20))
-    for i in range(4):
-        e2e_step(i)
-    e2e_drain()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    s_in.wait_event(e0); s_cmp.wait_event(e0); s_out.wait_event(e0)
-    for i in range(e2e_steps):
-        e2e_step(i)
-    e2e_drain()
-    e1.record()
-    barrier()
-    ms_e2e = e0.elapsed_time(e1)
+    ms_e2e = e2e_time(e2e_steps, True)
+    # the link ceiling on this box: the same two copies per step (full duplex) with no kernel in between
+    ms_link = e2e_time(e2e_steps, False)
     clk = clocks.stop() if rank == 0 else None
 
     vae = None if args.no_vae_step else vae_train_leg(torch, dev, world, rank, local)
+    peak, peak_src = load_peaks()
+    other = None
+    if not args.no_other_configs:
+        other = reduce_legs(torch, dist, config_legs(torch, lib, dev, st, world), dev, world, peak)
 
     # max over ranks
     if world > 1:
-        t = torch.tensor([ms_total, ms_e2e, ms_rs, ms_bind], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms_total, ms_e2e, ms_rs, ms_bind, ms_link], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, ms_e2e, ms_rs, ms_bind = (float(x) for x in t.tolist())
+        ms_total, ms_e2e, ms_rs, ms_bind, ms_link = (float(x) for x in t.tolist())
 
     if rank == 0:
-        peak, peak_src = load_peaks()
         value = world * B * args.steps / (ms_total * 1e-3)
         e2e_val = world * B * e2e_steps / (ms_e2e * 1e-3)
         k_rs = {"name": "clifford_fwd_kernel<11,PsRng,rowk>", "ms": ms_rs, "bytes": B * BYTES_RSAMPLE}
@@ -352,7 +367,9 @@ def run_gpu(args):
             "dtype": "f32", "data": "synthetic",
             "config": bench_config(),
             "roofline": {"bound": "hbm", "kernel": dom["name"], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": load_traffic(dom["name"]), "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": load_traffic(dom["name"]),
+                         "traffic_source": f"{TRAFFIC_FILE}: static, from the committed ncu --set full capture of this command",
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": dom["bytes"], "ms_per_launch": dom["ms"]},
             "kernels": {
                 "rsample_kl": {"ms": ms_rs, "GBps": k_rs["bytes"] / (ms_rs * 1e-3) / 1e9,
@@ -360,10 +377,16 @@ def run_gpu(args):
                 "bind": {"ms": ms_bind, "GBps": k_bd["bytes"] / (ms_bind * 1e-3) / 1e9,
                          "frac": k_bd["bytes"] / (ms_bind * 1e-3) / 1e9 / peak}},
             "e2e": {"value": e2e_val, "unit": UNIT, "steps": e2e_steps,
-                    "h2d_bytes_per_step": world * (h_loc.numel() + h_kap.numel() + h_roles.numel()) * 4,
-                    "d2h_bytes_per_step": world * (h_out.numel() + h_kl.numel()) * 4,
+                    "h2d_bytes_per_step": world * n_in * 4, "d2h_bytes_per_step": world * n_out * 4,
                     "api": "dists.clifford.CliffordPowerSphericalDistribution.rsample + kl_divergence + utils.vsa.bind",
-                    "pipeline": "double-buffered: H2D / compute / D2H on three streams"},
+                    "pipeline": "double-buffered: one packed H2D copy [loc|kappa|roles], compute, one packed D2H copy "
+                                "[bound|kl] per step on three streams",
+                    "link_ceiling": {"value": world * B * e2e_steps / (ms_link * 1e-3), "unit": UNIT,
+                                     "h2d_GBps_per_gpu": n_in * 4 * e2e_steps / (ms_link * 1e-3) / 1e9,
+                                     "d2h_GBps_per_gpu": n_out * 4 * e2e_steps / (ms_link * 1e-3) / 1e9,
+                                     "what": "the same pinned copies per step with no kernel between them, all ranks at once "
+                                             "(max over ranks): what the host link of this box allows"},
+                    "frac_of_link_ceiling": ms_link / ms_e2e},
             "gpu_launches": int(launches), "clocks": clk,
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -373,8 +396,8 @@ def run_gpu(args):
                                               f"({sum(ts):.1f} s CPU); {desc}"}
         if vae is not None:
             line["vae_train_step"] = vae
-        if world == 1:
-            line["other_configs"] = extras(torch, lib, dev, st, peak, full=args.extras)
+        if other is not None:
+            line["other_configs"] = other
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -447,13 +470,18 @@ def vae_train_leg(torch, dev, world, rank, local, steps=8, warmup=3, compare_ref
     return out
 
 
-def extras(torch, lib, dev, st, peak, full=False):
-    """Per-op throughput at the other BASELINE shapes (context for the headline, not bench lines):
-    C1 Clifford B=128 d=512, C2 PowerSpherical / vMF B=1024 D=513, C4 bind sweep (~1 GiB per launch)."""
-    out = {}
+def config_legs(torch, lib, dev, st, world):
+    """The other BASELINE.json configurations at their stated sizes, every rank on its own shard (weak scaling, no
+    data-path collective); returns [(name, info dict, local ms)], the caller reduces the times with MAX over ranks.
+      C1  Clifford rsample+KL  B=128  d=512 (one launch)          C2  PowerSpherical / vMF rsample+KL  B=1024  D=513
+      C3  rsample backward and log_prob at B=4096 d=2048          C4  bind / unbind sweep, 2^20 vectors per GPU, d=1024..16384
+      C5  depth-1..32 bind -> reverse unbind -> cosine, d=8192, 512 trials per depth per GPU (fused chain kernel)"""
+    from clifford_b200 import harness
+    from utils import vsa
+    legs = []
 
-    def timeit(fn, reps=10):
-        for _ in range(3):
+    def timeit(fn, reps, warm=2):
+        for _ in range(warm):
             fn()
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -464,46 +492,140 @@ def extras(torch, lib, dev, st, peak, full=False):
         torch.cuda.synchronize()
         return a.elapsed_time(b) / reps
 
-    for dd in ((1024, 4096, 16384) if not full else (1024, 2048, 4096, 8192, 16384)):
-        N = (1 << 30) // (12 * dd)
-        a = torch.randn(N, dd, device=dev)
-        b = torch.randn(N, dd, device=dev)
-        o = torch.empty(N, dd, device=dev)
-        ms = timeit(lambda: lib.cvb_vsa_bind(a.data_ptr(), b.data_ptr(), o.data_ptr(), N, N, N, dd, 0, st))
-        gb = N * 12 * dd / (ms * 1e-3) / 1e9
-        out[f"C4_bind_d{dd}"] = {"vectors": N, "ms": ms, "vec_per_s": N / (ms * 1e-3), "GBps": gb, "frac": gb / peak}
+    # ---- C4: 2^20 vectors per GPU, streamed in chunks of <= 12 GiB working set (d = 16384 would need 192 GiB at once)
+    NV = 1 << 20
+    for dd in (1024, 2048, 4096, 8192, 16384):
+        chunk = min(NV, (12 << 30) // (12 * dd))
+        chunk = 1 << (chunk.bit_length() - 1)
+        a = torch.randn(chunk, dd, device=dev)
+        b = torch.randn(chunk, dd, device=dev)
+        o = torch.empty(chunk, dd, device=dev)
+        nchunks = NV // chunk
+        modes = (("bind", 0), ("unbind_inv", 1), ("unbind_deconv", 2)) if dd in (1024, 4096, 16384) else (("bind", 0),)
+        for opname, mode in modes:
+            def run(mode=mode):
+                for _ in range(nchunks):
+                    lib.cvb_vsa_bind(a.data_ptr(), b.data_ptr(), o.data_ptr(), chunk, chunk, chunk, dd, mode, st)
+            ms = timeit(run, reps=2, warm=1)
+            legs.append((f"C4_{opname}_d{dd}", {"vectors_per_gpu": NV, "chunk": chunk, "unit": "vec/s", "units": NV,
+                                                "bytes_per_unit": 12 * dd}, ms))
+        if dd == 4096:
+            out1 = torch.empty(chunk, device=dev)
+            ms = timeit(lambda: [lib.cvb_vsa_cosine(a.data_ptr(), b.data_ptr(), out1.data_ptr(), chunk, chunk, chunk, dd, st)
+                                 for _ in range(nchunks)], reps=2, warm=1)
+            legs.append((f"C4_similarity_d{dd}", {"vectors_per_gpu": NV, "chunk": chunk, "unit": "pairs/s", "units": NV,
+                                                  "bytes_per_unit": 8 * dd + 4}, ms))
+            ws = torch.empty(max(int(lib.cvb_vsa_bundle_workspace_bytes(chunk, dd)) // 4, 1), device=dev)
+            outv = torch.empty(dd, device=dev)
+            ms = timeit(lambda: [lib.cvb_vsa_bundle(a.data_ptr(), outv.data_ptr(), chunk, dd, 1.0, ws.data_ptr(), st)
+                                 for _ in range(nchunks)], reps=2, warm=1)
+            legs.append((f"C4_bundle_d{dd}", {"vectors_per_gpu": NV, "chunk": chunk, "unit": "vec/s", "units": NV,
+                                              "bytes_per_unit": 4 * dd}, ms))
+            del out1, ws, outv
         del a, b, o
-    for name, B, d in (("C1_clifford_rsample_kl_B128_d512", 128, 512), ("clifford_rsample_kl_B65536_d2048", 65536, 2048)):
-        loc = torch.randn(B, d, device=dev)
-        kap = torch.rand(B, device=dev) * 9.87 + 0.13
-        z = torch.empty(B, 2 * d, device=dev)
-        kl = torch.empty(B, device=dev)
-        ms = timeit(lambda: lib.cvb_clifford_ps_rsample(loc.data_ptr(), kap.data_ptr(), 1, 0, B, None, None, 7, 0,
-                                                        z.data_ptr(), None, None, kl.data_ptr(), None, B, d, st))
-        gb = B * (12 * d + 8) / (ms * 1e-3) / 1e9
-        out[name] = {"rows": B, "d": d, "ms": ms, "samples_per_s": B / (ms * 1e-3), "GBps": gb, "frac": gb / peak}
-        del loc, z
-    B, D = 1024, 513
-    loc = torch.nn.functional.normalize(torch.randn(B, D, device=dev), dim=-1)
-    kap = torch.rand(B, device=dev) * 9.2 + 0.8
-    z = torch.empty(B, D, device=dev)
-    save = torch.empty(B, 2, device=dev)
-    ent = torch.empty(B, device=dev)
-    kl = torch.empty(B, device=dev)
+    torch.cuda.empty_cache()
+
+    # ---- C3: the rest of the training path at the headline shape
+    B, d = B_ROWS, D_LAT
+    loc = torch.randn(B, d, device=dev)
+    kap = torch.rand(B, device=dev) * 9.87 + 0.13
+    z = torch.empty(B, 2 * d, device=dev)
+    tps = torch.empty(B, d, device=dev)
+    gz = torch.randn(B, 2 * d, device=dev)
+    dloc = torch.empty(B, d, device=dev)
+    dk = torch.empty(B, device=dev)
+    lp = torch.empty(B, device=dev)
+    lib.cvb_clifford_ps_rsample(loc.data_ptr(), kap.data_ptr(), 1, 0, B, None, None, 7, 0, z.data_ptr(), tps.data_ptr(),
+                                None, None, None, B, d, st)
+    flush = torch.empty(64 << 20, device=dev)          # 256 MB > L2: written between repetitions
+
+    def with_flush(fn):
+        def run():
+            flush.zero_()
+            fn()
+        return run
+    ms_flush = timeit(lambda: flush.zero_(), reps=10)
+    ms = timeit(with_flush(lambda: lib.cvb_clifford_ps_rsample_backward(
+        gz.data_ptr(), loc.data_ptr(), kap.data_ptr(), 1, 0, B, None, None, tps.data_ptr(), dloc.data_ptr(),
+        dk.data_ptr(), B, d, st)), reps=10) - ms_flush
+    legs.append(("C3_rsample_backward_B4096_d2048", {"rows": B, "unit": "samples/s", "units": B, "bytes_per_unit": 20 * d + 8,
+                                                     "l2": "256 MB flush between repetitions (its time subtracted)"}, ms))
+    ms = timeit(with_flush(lambda: lib.cvb_clifford_ps_log_prob(
+        z.data_ptr(), loc.data_ptr(), kap.data_ptr(), 1, 0, B, lp.data_ptr(), None, None, None, B, d, st)), reps=10) - ms_flush
+    legs.append(("C3_log_prob_B4096_d2048", {"rows": B, "unit": "samples/s", "units": B, "bytes_per_unit": 12 * d + 8,
+                                             "l2": "256 MB flush between repetitions (its time subtracted)"}, ms))
+    del loc, z, tps, gz, dloc
+
+    # ---- C1 / C2: launch-latency-sized configurations
+    B1, d1 = 128, 512
+    loc = torch.randn(B1, d1, device=dev)
+    kap1 = torch.rand(B1, device=dev) * 9.97 + 0.03
+    z = torch.empty(B1, 2 * d1, device=dev)
+    kl = torch.empty(B1, device=dev)
+    ms = timeit(lambda: lib.cvb_clifford_ps_rsample(loc.data_ptr(), kap1.data_ptr(), 1, 0, B1, None, None, 7, 0, z.data_ptr(),
+                                                    None, None, kl.data_ptr(), None, B1, d1, st), reps=50)
+    legs.append(("C1_clifford_rsample_kl_B128_d512", {"rows": B1, "unit": "samples/s", "units": B1,
+                                                      "bytes_per_unit": 12 * d1 + 8, "launches_per_step": 1}, ms))
+    B2, D2 = 1024, 513
+    loc = torch.nn.functional.normalize(torch.randn(B2, D2, device=dev), dim=-1)
+    kap2 = torch.rand(B2, device=dev) * 9.2 + 0.8
+    z = torch.empty(B2, D2, device=dev)
+    save = torch.empty(B2, 2, device=dev)
+    ent = torch.empty(B2, device=dev)
+    kl = torch.empty(B2, device=dev)
 
     def ps_step():
-        lib.cvb_powerspherical_rsample(loc.data_ptr(), kap.data_ptr(), B, None, None, 3, 0, z.data_ptr(), save.data_ptr(), B, D, st)
-        lib.cvb_ps_entropy_kl(kap.data_ptr(), 1, 0, B, D, (D - 1) / 2, 0, 0.0, ent.data_ptr(), kl.data_ptr(), None, st)
+        lib.cvb_powerspherical_rsample(loc.data_ptr(), kap2.data_ptr(), B2, None, None, 3, 0, z.data_ptr(), save.data_ptr(), B2, D2, st)
+        lib.cvb_ps_entropy_kl(kap2.data_ptr(), 1, 0, B2, D2, (D2 - 1) / 2, 0, 0.0, ent.data_ptr(), kl.data_ptr(), None, st)
 
     def vmf_step():
-        lib.cvb_vmf_rsample(loc.data_ptr(), kap.data_ptr(), B, None, None, 0, None, 3, 0, z.data_ptr(), save.data_ptr(), B, D, st)
-        lib.cvb_vmf_entropy_lognorm(kap.data_ptr(), B, D, ent.data_ptr(), None, None, None, st)
+        lib.cvb_vmf_rsample(loc.data_ptr(), kap2.data_ptr(), B2, None, None, 0, None, 3, 0, z.data_ptr(), save.data_ptr(), B2, D2, st)
+        lib.cvb_vmf_entropy_lognorm(kap2.data_ptr(), B2, D2, ent.data_ptr(), None, None, None, st)
 
     for name, fn in (("C2_powerspherical_rsample_kl_B1024_D513", ps_step), ("C2_vmf_rsample_kl_B1024_D513", vmf_step)):
         ms = timeit(fn, reps=50)
-        gb = B * (8 * D + 8) / (ms * 1e-3) / 1e9
-        out[name] = {"rows": B, "D": D, "ms": ms, "samples_per_s": B / (ms * 1e-3), "GBps": gb, "frac": gb / peak,
-                     "note": "4 MB per launch: launch-latency bound at this batch"}
+        legs.append((name, {"rows": B2, "unit": "samples/s", "units": B2, "bytes_per_unit": 8 * D2 + 8,
+                            "launches_per_step": 2, "note": "4 MB per step: launch-latency bound at this batch"}, ms))
+
+    # ---- C5: depth 1..32 at d = 8192, 512 trials per depth per GPU, whole chain + cosine in one kernel per depth
+    d5, T5, depths = 8192, 512, list(range(1, 33))
+    pool = vsa.normalize_vectors(vsa.unitary_init(T5 * 33, d5, device=dev))
+
+    def c5():
+        sims = []
+        for m in depths:
+            sims.append(harness.binding_depth_cell_fused(pool[:T5 * (m + 1)].view(T5, m + 1, d5)).mean())
+        return torch.stack(sims)
+    sims = c5()
+    ms = timeit(c5, reps=2, warm=1)
+    ops = T5 * sum(2 * m for m in depths)
+    legs.append(("C5_depth_1_32_d8192", {"trials_per_depth_per_gpu": T5, "unit": "bind+unbind ops/s", "units": ops,
+                                         "bytes_per_unit": None, "algorithmic_bytes": sum(4 * d5 * (m + 1) * T5 for m in depths),
+                                         "min_similarity_unitary_keys": float(sims.min())}, ms))
+    return legs
+
+
+def reduce_legs(torch, dist, legs, dev, world, peak):
+    """MAX over ranks of every leg's time; aggregate throughput = world * units / time."""
+    t = torch.tensor([ms for _, _, ms in legs], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    out = {}
+    for (name, info, _), ms in zip(legs, t.tolist()):
+        e = dict(info)
+        units = e.pop("units")
+        e["ms"] = ms
+        e["n_gpus"] = world
+        e["per_s"] = world * units / (ms * 1e-3)
+        if e.get("bytes_per_unit"):
+            gb = units * e["bytes_per_unit"] / (ms * 1e-3) / 1e9
+            e["GBps_per_gpu"] = gb
+            e["frac"] = gb / peak
+        elif e.get("algorithmic_bytes"):
+            gb = e["algorithmic_bytes"] / (ms * 1e-3) / 1e9
+            e["GBps_per_gpu"] = gb
+            e["frac"] = gb / peak
+        out[name] = e
     return out
 
 
@@ -513,7 +635,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--extras", action="store_true", help="time the full bind sweep in other_configs")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the C1/C2/C3-bwd/C4/C5 legs (other_configs)")
     ap.add_argument("--no-vae-step", action="store_true", help="skip the C3 VAE training-step leg (vae_train_step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
