@@ -405,3 +405,36 @@ def test_fused_sample_log_prob_device_rng_and_cache_rules():
     assert q3._sample_log_prob is None and z3.requires_grad
     (gl,) = torch.autograd.grad(q3.log_prob(z3.detach()).sum(), [loc_g])
     assert torch.isfinite(gl).all() and float(gl.abs().max()) > 0
+
+
+def test_full_size_values_c3_injected_draws_vs_oracle():
+    """BASELINE config 3 latent shape (B=4096, d=2048), VALUES not only invariants: the kernel and the CPU oracle are fed
+    the same recorded Beta / sign draws; sample, KL, and the backward (closed form of SURVEY 8(a), checked against
+    autograd in tests/test_oracle_vs_golden.py) are compared over all 4096 x 4096 outputs."""
+    from dists.clifford import CliffordPowerSphericalDistribution, CliffordTorusUniform
+    from oracle import latent_oracle as O
+    torch.manual_seed(2048)
+    B, d = 4096, 2048
+    loc = torch.randn(B, d)
+    kap = torch.rand(B, 1) * 9.87 + 0.13
+    tprime = torch.distributions.Beta((0.5 + kap + 1e-7).expand(B, d), torch.full((B, d), 0.5)).sample()
+    g = torch.randn(B, d)
+    gz = torch.randn(B, 2 * d)
+    loc_g, kap_g = loc.to(DEV).requires_grad_(), kap.to(DEV).requires_grad_()
+    q = CliffordPowerSphericalDistribution(loc_g, kap_g, validate_args=False)
+    z = q.rsample(_base_draws=(tprime.to(DEV), g.to(DEV)))
+    kl = torch.distributions.kl.kl_divergence(q, CliffordTorusUniform(d, device=DEV))
+    dloc, dkap = torch.autograd.grad((z * gz.to(DEV)).sum(), [loc_g, kap_g])
+    with torch.no_grad():
+        zo = O.clifford_ps_rsample(loc, kap, tprime, g)
+        klo = O.clifford_ps_kl(kap.expand(B, d))
+        dth, dk_el = O.clifford_ps_rsample_backward(loc, kap, tprime, g, gz)
+    assert rel_err(z.detach().cpu(), zo) < 1e-5
+    assert float((z.detach().cpu() - zo).abs().max()) < 2e-7 + 1e-5 * float(zo.abs().max())
+    assert float((kl.detach().cpu() - klo).abs().max()) < 1e-5 * (d - 1) * math.log(2 * math.pi)
+    assert rel_err(dloc.cpu()[:, 1:], dth[:, 1:]) < 1e-5
+    # row sums of 2047 cancelling terms: the ORACLE (fp32 torch ops) is the less accurate side here, see
+    # tests/test_gpu_fp64_truth.py; compare on the scale of the row's absolute sum
+    dk_ref = dk_el[:, 1:].double().sum(-1, keepdim=True)
+    scale = dk_el[:, 1:].double().abs().sum(-1, keepdim=True)
+    assert float(((dkap.cpu().double() - dk_ref).abs() / scale).max()) < 1e-5
