@@ -136,10 +136,13 @@ class CliffordTorusUniform(Distribution):
 class CliffordTorusDistribution(Distribution):
     """Product of von Mises distributions on the torus (reference dists/clifford.py:245-278).
 
-    Kept for the isinstance / KL-registry relations.  The reference's own ``rsample`` raises an
-    AssertionError for generic angles (its Hermitian-symmetry assert at :274 uses the wrong flip), so
-    no driver uses it; here it raises NotImplementedError.  ``entropy`` is evaluated with
-    torch.special.i0e/i1e (off the hot path).
+    ``rsample`` draws the von Mises phases on the device (Best & Fisher rejection, the algorithm of
+    torch.distributions.VonMises.sample that the reference calls at :262) and maps them through the same Hermitian
+    spectrum -> inverse FFT kernel as the other samplers.  Like the reference's VonMises draw it is NOT reparameterised
+    (no gradient reaches loc / concentration).  The reference's own method never gets that far: its Hermitian-symmetry
+    assert (:274) compares against the wrong flip and raises for generic angles, so no driver uses it
+    (scripts/sample_viz.py:55-64 restates the sampler inline); this is the working version of what it computes.
+    ``entropy`` is evaluated with torch.special.i0e/i1e exactly as the reference does (off the hot path).
     """
 
     arg_constraints: Dict[str, constraints.Constraint] = {}
@@ -153,9 +156,16 @@ class CliffordTorusDistribution(Distribution):
                          validate_args=validate_args)
 
     def rsample(self, sample_shape=torch.Size()):
-        raise NotImplementedError(
-            "CliffordTorusDistribution (von Mises) sampling is unusable in the reference (AssertionError at "
-            "dists/clifford.py:274); use CliffordPowerSphericalDistribution")
+        sample_shape = torch.Size(sample_shape)
+        d = self.orig_dim
+        n = _numel(sample_shape)
+        raw = self._raw_concentration
+        if torch.is_tensor(raw) and raw.dim() >= 1 and raw.shape[-1] == 1 and d != 1:
+            kap = raw.expand(tuple(self.batch_shape) + (1,)).reshape(-1, 1)
+        else:
+            kap = self.concentration.reshape(-1, d)
+        z = ops.clifford_vm_rsample(self.loc.reshape(-1, d), kap, n)
+        return z.reshape(tuple(sample_shape) + tuple(self.batch_shape) + (2 * d,)).to(self.loc.dtype)
 
     def entropy(self):
         k = self.concentration

@@ -245,6 +245,21 @@ class CliffordPSLogProb(torch.autograd.Function):
         return dval, dloc, dkap
 
 
+def clifford_vm_rsample(loc, kappa, n_samples=1):
+    """z (n_samples * B, 2d) of the von Mises torus distribution (dists/clifford.py:261-275): phases loc + VonMises(0, kappa)
+    drawn on the device, then the Hermitian-spectrum inverse FFT.  loc (B, d), kappa (B, 1) | (B, d).  No autograd."""
+    lib, dev = _prep(loc, kappa)
+    B, d = loc.shape
+    rows = B * n_samples
+    loc_c = _f32c(loc.detach())
+    kap_c, krs, kes = _kappa_layout(kappa.detach(), d)
+    z = torch.empty(rows, 2 * d, device=dev, dtype=torch.float32)
+    seed, off = _lib.next_rng(dev)
+    _launch("cvb_clifford_vm_rsample", dev, ptr(loc_c), ptr(kap_c), krs, kes, B, seed, off, ptr(z), rows, d,
+            skip=rows == 0 or d == 0)
+    return z
+
+
 def clifford_phases_to_vector(phases, scale, rows, d, device):
     """phases (rows, d) * scale -> (rows, 2d); phases None draws U[0,1) on the device."""
     _lib.ensure_device(torch.device(device))

@@ -150,6 +150,19 @@ int cvb_clifford_phases_to_vector(const float* phases, float phase_scale, unsign
   return phases ? dispatch_fwd<kPhases, true>(p, st) : dispatch_fwd<kUniformRng, true>(p, st);
 }
 
+// CliffordTorusDistribution.rsample (dists/clifford.py:261-275): von Mises phases -> Hermitian phasors -> C2R iFFT
+int cvb_clifford_vm_rsample(const float* loc, const float* kappa, long long kappa_row_stride, int kappa_el_stride,
+                            long long loc_rows, unsigned long long seed, unsigned long long offset, float* z,
+                            long long rows, int d, void* stream) {
+  CVB_REQUIRE(loc && kappa && z, kBadArgument, "cvb_clifford_vm_rsample: null pointer");
+  CVB_REQUIRE(rows > 0 && d >= 1 && loc_rows > 0, kBadArgument, "cvb_clifford_vm_rsample: rows=%lld d=%d loc_rows=%lld", rows, d, loc_rows);
+  CliffordFwdParams p{};
+  p.loc = loc; p.kappa = kappa; p.kappa_row_stride = kappa_row_stride; p.kappa_el_stride = kappa_el_stride;
+  p.loc_rows = (int)loc_rows; p.z = z; p.rows = rows; p.d = d; p.n = 2 * d;
+  p.key = make_key(seed, offset, 3);
+  return dispatch_fwd<kVonMisesRng, false>(p, (cudaStream_t)stream);
+}
+
 // fused sample + entropy/KL + bind with a second vector (one concentration per row; power-of-two d in [16, 8192])
 int cvb_clifford_ps_rsample_bind(const float* loc, const float* kappa, long long loc_rows, const float* tprime,
                                  const float* gnoise, unsigned long long seed, unsigned long long offset, const float* b,

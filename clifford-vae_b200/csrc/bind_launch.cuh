@@ -41,6 +41,20 @@ int launch_bind_fast(const BindParams& p_in, cudaStream_t st) {
   return check_launch("bind_v3_kernel<direct>");
 }
 
+template <int LOG2N, int MODE>
+int launch_bind_pad(const BindParams& p, int d, cudaStream_t st) {
+  using Pl = WideFftPlan<LOG2N>;
+  const cplx* tw = device_twiddles();
+  if (!tw) return kCudaError;
+  const size_t smem = bind_pad_smem_bytes<LOG2N>();
+  auto kern = bind_pad_kernel<LOG2N, MODE>;
+  const long long work = (p.rows + Pl::GROUPS - 1) / Pl::GROUPS;
+  int grid = 0;
+  if (int rc = persistent_grid(kern, Pl::THREADS, smem, work, &grid)) return rc;
+  kern<<<grid, Pl::THREADS, smem, st>>>(p, d, tw);
+  return check_launch("bind_pad_kernel");
+}
+
 template <int MODE>
 int dispatch_bind(const BindParams& p, int d, cudaStream_t st) {
   const bool fast = is_pow2(d) && d >= 32 && d <= 16384 && aligned(p.a, 8) && aligned(p.b, 8) && aligned(p.out, 8);
@@ -50,6 +64,20 @@ int dispatch_bind(const BindParams& p, int d, cudaStream_t st) {
       CVB_CASE(4) CVB_CASE(5) CVB_CASE(6) CVB_CASE(7) CVB_CASE(8) CVB_CASE(9) CVB_CASE(10) CVB_CASE(11) CVB_CASE(12)
       CVB_CASE(13)
 #undef CVB_CASE
+    }
+  }
+  // any other length: the bilinear modes fold a zero-padded power-of-two convolution (bind_pad_kernel) once the
+  // O(d^2) direct DFT would cost more (d > 48); the quotient modes need the true length-d spectrum (direct DFT)
+  static const bool no_pad = getenv("CVB_BIND_NO_PAD") != nullptr;      // A/B switch for tools/bench_small_dims.py
+  if constexpr (MODE == kBindMul || MODE == kBindMulConj || MODE == kBindNegMulConj) {
+    if (d > 48 && d <= 8192 && !no_pad) {
+      int log2m = 1;
+      while ((1 << log2m) < 2 * d) ++log2m;
+      switch (log2m - 1) {
+#define CVB_CASE(L) case L: return launch_bind_pad<L, MODE>(p, d, st);
+        CVB_CASE(6) CVB_CASE(7) CVB_CASE(8) CVB_CASE(9) CVB_CASE(10) CVB_CASE(11) CVB_CASE(12) CVB_CASE(13)
+#undef CVB_CASE
+      }
     }
   }
   const size_t smem = sizeof(cplx) * d + sizeof(float) * (2 * d + 2) + sizeof(cplx) * (d / 2 + 1);

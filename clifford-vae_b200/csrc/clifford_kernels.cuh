@@ -42,6 +42,7 @@ enum CliffordMode : int {
   kUniformRng = 3,   // theta = 2 pi U
   kUnitaryRng = 4,   // theta = sign * pi * (eps + a (1 - 2 eps))   (utils/vsa.py:15-36)
   kSpectrum = 5,     // X_k = phase_scale * H[row, k] given as complex (rows, d): adjoint of the truncated real FFT
+  kVonMisesRng = 6,  // theta = loc + VonMises(0, kappa) draw  (CliffordTorusDistribution, dists/clifford.py:261-275)
 };
 
 struct CliffordFwdParams {
@@ -130,6 +131,29 @@ __device__ __forceinline__ cplx ps_phasor(float tp, float sgn, float loc) {
   return make_float2(fmaf(cl, pc, -sl * psn), fmaf(sl, pc, cl * psn));
 }
 
+// One von Mises(0, kappa) draw by Best & Fisher's wrapped-Cauchy rejection, in double like the sampler the reference
+// calls (torch/distributions/von_mises.py:93-190 `_rejection_sample` + `_proposal_r` with its small-kappa Taylor
+// branch); acceptance >= 0.66.  Not reparameterised (VonMises has no rsample): no backward.
+__device__ __forceinline__ float von_mises_draw(float kappa_f, const PhiloxKey& key, uint64_t elem) {
+  const double kap = (double)kappa_f;
+  const double tau = 1.0 + sqrt(1.0 + 4.0 * kap * kap);
+  const double rho = (tau - sqrt(2.0 * tau)) / (2.0 * kap);
+  const double r = (kap < 1e-5) ? (1.0 / kap + kap) : (1.0 + rho * rho) / (2.0 * rho);
+  double x = 0.0;
+  for (uint32_t attempt = 0; attempt < 1024; ++attempt) {
+    const uint4 w = philox_draw(key, elem, attempt);
+    const double u1 = (double)u01_open1(w.x), u2 = (double)u01_open0(w.y);
+    const double z = cospi(u1);
+    const double f = (1.0 + r * z) / (r + z);
+    const double c = kap * (r - f);
+    if ((c * (2.0 - c) - u2 > 0.0) || (log(c / u2) + 1.0 - c >= 0.0)) {
+      x = ((w.z & 0x80000000u) ? -1.0 : 1.0) * acos(fmin(fmax(f, -1.0), 1.0));
+      break;
+    }
+  }
+  return (float)x;
+}
+
 // Per-row input pointers, indexed by the bin k: either the global rows or their staged copies in
 // shared memory (generic loads serve both).
 struct RowSrc {
@@ -168,6 +192,14 @@ __device__ __forceinline__ bool clifford_phasor(const CliffordFwdParams& p, cons
     return true;
   }
   float th;
+  if (MODE == kVonMisesRng) {
+    const float kap = __ldg(p.kappa + prow * p.kappa_row_stride + (long long)k * p.kappa_el_stride);
+    PhiloxKey vkey = p.key;
+    vkey.stream = 11;
+    th = src.loc[k] + von_mises_draw(kap, vkey, (uint64_t)idx);
+    sincosf(th, &out.y, &out.x);
+    return true;
+  }
   if (MODE == kSpectrum) {
     const float2 hv = reinterpret_cast<const float2*>(src.phases)[k];
     out = make_float2(p.phase_scale * hv.x, p.phase_scale * hv.y);

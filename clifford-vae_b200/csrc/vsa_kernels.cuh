@@ -65,6 +65,31 @@ constexpr size_t bind_v3_smem_bytes() {
   return (sizeof(cplx) * (Pl::XCH + Pl::N + (STAGED == 2 ? Pl::N : 0)) + 3 * sizeof(uint64_t)) * Pl::GROUPS;
 }
 
+// Bins k and kp = N-k of the product spectrum, re-packed for the inverse half-length transform: from the parked
+// Z_a (park[]), the exchanged Z_b (xch[], padded layout) and this thread's own zb = Z_b[k].  V[k] = c (s + d),
+// V[N-k] = c conj(s - d).
+template <int LOG2N, int MODE>
+__device__ __forceinline__ void bind_pair(const cplx* park, const cplx* xch, const cplx* __restrict__ tw, int k, int kp,
+                                          cplx zb, cplx& vk, cplx& vkp) {
+  constexpr int N = 1 << LOG2N;
+  constexpr float scale = 1.0f / (2.0f * N);
+  constexpr float fold = (MODE == kBindDiv || MODE == kBindDivConj) ? scale : 0.25f * scale;
+  const cplx za = park[k], zap = cconj(park[kp]);
+  const cplx zbp = cconj(xch[pad16(kp)]);
+  const cplx w = __ldg(&tw[twiddle_offset(LOG2N) + k]);    // exp(-2 pi i k / n)
+  // bins k and N-k of the real FFTs (X[N-k] uses W^(N-k) = -conj(W^k)); factor 1/2 each
+  const cplx sa = cadd(za, zap), da = cmul_mi(cmul(w, csub(za, zap)));
+  const cplx sb = cadd(zb, zbp), db = cmul_mi(cmul(w, csub(zb, zbp)));
+  // A = (sa +- da)/2, B = (sb +- db)/2: the halves are folded into one final constant -- the bilinear modes
+  // pick up 1/4; for the quotient modes they cancel (only the 1e-12 regulariser has to be doubled to match)
+  const cplx Ak = cadd(sa, da), Akp = cconj(csub(sa, da));
+  const cplx Bk = cadd(sb, db), Bkp = cconj(csub(sb, db));
+  const cplx Pk = bind_op_unscaled(MODE, Ak, Bk), Pkpc = cconj(bind_op_unscaled(MODE, Akp, Bkp));
+  const cplx s = cadd(Pk, Pkpc), d = cmul_i(cmul(cconj(w), csub(Pk, Pkpc)));
+  vk = cadd_scaled(s, d, fold);
+  vkp = cconj(cscale(csub(s, d), fold));
+}
+
 template <int LOG2N, int MODE, int STAGED>
 __global__ void __launch_bounds__(WideFftPlan<LOG2N>::THREADS, (WideFftPlan<LOG2N>::THREADS <= 128 ? (WideFftPlan<LOG2N>::E > 16 ? 2 : CVB_BIND_MINB) : ((WideFftPlan<LOG2N>::THREADS <= 256 && WideFftPlan<LOG2N>::E <= 16) ? 2 : 1)))
 bind_v3_kernel(const BindParams p, const cplx* __restrict__ tw) {
@@ -146,23 +171,7 @@ bind_v3_kernel(const BindParams p, const cplx* __restrict__ tw) {
 #pragma unroll
     for (int e = 0; e < E; ++e) xch[pad16(t + e * T)] = v[e];
     group_sync_p<Pl>();
-    constexpr float fold = (MODE == kBindDiv || MODE == kBindDivConj) ? scale : 0.25f * scale;
-    auto pair = [&](int k, int kp, cplx zb, cplx& vk, cplx& vkp) {
-      const cplx za = park[k], zap = cconj(park[kp]);
-      const cplx zbp = cconj(xch[pad16(kp)]);
-      const cplx w = __ldg(&tw[twiddle_offset(LOG2N) + k]);    // exp(-2 pi i k / n)
-      // bins k and N-k of the real FFTs (X[N-k] uses W^(N-k) = -conj(W^k)); factor 1/2 each
-      const cplx sa = cadd(za, zap), da = cmul_mi(cmul(w, csub(za, zap)));
-      const cplx sb = cadd(zb, zbp), db = cmul_mi(cmul(w, csub(zb, zbp)));
-      // A = (sa +- da)/2, B = (sb +- db)/2: the halves are folded into one final constant -- the bilinear modes
-      // pick up 1/4; for the quotient modes they cancel (only the 1e-12 regulariser has to be doubled to match)
-      const cplx Ak = cadd(sa, da), Akp = cconj(csub(sa, da));
-      const cplx Bk = cadd(sb, db), Bkp = cconj(csub(sb, db));
-      const cplx Pk = bind_op_unscaled(MODE, Ak, Bk), Pkpc = cconj(bind_op_unscaled(MODE, Akp, Bkp));
-      const cplx s = cadd(Pk, Pkpc), d = cmul_i(cmul(cconj(w), csub(Pk, Pkpc)));
-      vk = cadd_scaled(s, d, fold);
-      vkp = cconj(cscale(csub(s, d), fold));
-    };
+    auto pair = [&](int k, int kp, cplx zb, cplx& vk, cplx& vkp) { bind_pair<LOG2N, MODE>(park, xch, tw, k, kp, zb, vk, vkp); };
 #pragma unroll
     for (int e = 0; e < E / 2; ++e) {
       const int k = t + e * T, kp = (N - k) & (N - 1);
@@ -196,6 +205,82 @@ bind_v3_kernel(const BindParams p, const cplx* __restrict__ tw) {
   }
   if (dynamic && t == 0) {
     if (atomicAdd(p.sched + 1, 1) == (int)stride - 1) { p.sched[0] = 0; p.sched[1] = 0; }
+  }
+}
+
+// ---- any-length bind / unbind("inv") through the power-of-two kernel's machinery -----------------------------------
+// A circular convolution of length n is the linear convolution folded once: out[i] = c[i] + c[i + n], c = a * b zero-
+// padded to M >= 2n (power of two); the circular correlation of unbind("inv") folds the negative lags,
+// out[i] = c[i] + c[M + i - n].  Rows of any length n (odd, 513, 144, 484 ... -- the reference's PowerSpherical / vMF
+// latents and heat-map dimensions) therefore cost one pass of the fused FFT pipeline at M instead of an O(n^2) direct
+// DFT.  Rows are only 4-byte aligned: scalar coalesced loads / stores.  LOG2N = log2(M / 2).
+template <int LOG2N>
+constexpr size_t bind_pad_smem_bytes() {
+  using Pl = WideFftPlan<LOG2N>;
+  return sizeof(cplx) * (Pl::XCH + Pl::N) * Pl::GROUPS;
+}
+
+template <int LOG2N, int MODE>
+__global__ void __launch_bounds__(WideFftPlan<LOG2N>::THREADS, (WideFftPlan<LOG2N>::THREADS <= 128 ? (WideFftPlan<LOG2N>::E > 16 ? 2 : 4) : ((WideFftPlan<LOG2N>::THREADS <= 256 && WideFftPlan<LOG2N>::E <= 16) ? 2 : 1)))
+bind_pad_kernel(const BindParams p, int n, const cplx* __restrict__ tw) {
+  using Pl = WideFftPlan<LOG2N>;
+  constexpr int N = Pl::N, T = Pl::T, E = Pl::E, G = Pl::GROUPS, M = 2 * N;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int group = threadIdx.x / T, t = threadIdx.x % T;
+  cplx* park = reinterpret_cast<cplx*>(smem_raw) + (size_t)group * N;
+  cplx* xch = reinterpret_cast<cplx*>(smem_raw) + (size_t)G * N + (size_t)group * Pl::XCH;
+  const long long stride = (long long)gridDim.x * G;
+  for (long long base = (long long)blockIdx.x * G; base < p.rows; base += stride) {   // trip counts uniform over the CTA
+    const long long row = base + group;
+    const bool valid = row < p.rows;
+    cplx v[E];
+    auto load_padded = [&](const float* src) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const int i0 = 2 * (t + e * T);
+        v[e] = make_float2((valid && i0 < n) ? ldg_stream1(src + i0) : 0.0f, (valid && i0 + 1 < n) ? ldg_stream1(src + i0 + 1) : 0.0f);
+      }
+    };
+    load_padded(p.a + (valid ? row % p.a_rows : 0) * (long long)n);
+    fft_run_p<Pl, false>(v, xch, t, tw);
+#pragma unroll
+    for (int e = 0; e < E; ++e) park[t + e * T] = v[e];
+    load_padded(p.b + (valid ? row % p.b_rows : 0) * (long long)n);
+    fft_run_p<Pl, false>(v, xch, t, tw);
+    group_sync_p<Pl>();
+#pragma unroll
+    for (int e = 0; e < E; ++e) xch[pad16(t + e * T)] = v[e];
+    group_sync_p<Pl>();
+#pragma unroll
+    for (int e = 0; e < E / 2; ++e) {
+      const int k = t + e * T, kp = (N - k) & (N - 1);
+      cplx vkp;
+      bind_pair<LOG2N, MODE>(park, xch, tw, k, kp, v[e], v[e], vkp);
+      if (kp != k) park[kp] = vkp;
+    }
+    if (t == 0) {
+      cplx vk, vkp;
+      bind_pair<LOG2N, MODE>(park, xch, tw, N / 2, N / 2, v[E / 2], vk, vkp);
+      park[N / 2] = vk;
+    }
+    group_sync_p<Pl>();
+#pragma unroll
+    for (int e = E / 2; e < E; ++e) v[e] = park[t + e * T];
+    fft_run_p<Pl, true>(v, xch, t, tw);
+    // fold: the M real samples c[2m], c[2m+1] go to the parked buffer (as floats), then out[i] = c[i] + c[partner(i)]
+    group_sync_p<Pl>();
+#pragma unroll
+    for (int e = 0; e < E; ++e) park[t + e * T] = v[e];
+    group_sync_p<Pl>();
+    if (valid) {
+      const float* c = reinterpret_cast<const float*>(park);
+      float* o = p.out + row * (long long)n;
+      for (int i = t; i < n; i += T) {
+        const int j = (MODE == kBindMul) ? i + n : M + i - n;
+        stg_stream1(o + i, c[i] + c[j]);          // (the NegMulConj sign is already in the product spectrum)
+      }
+    }
+    group_sync_p<Pl>();            // the parked samples are consumed before the next row parks its spectrum
   }
 }
 

@@ -107,6 +107,16 @@ CVB_API int cvb_ps_entropy_kl(const float* kappa, long long kappa_row_stride, in
                       double half_dm1, int torus, double prior_entropy, float* entropy, float* kl, float* dentropy,
                       void* stream);
 
+/* CliffordTorusDistribution.rsample (dists/clifford.py:261-275; scripts/sample_viz.py:55-64 restates it): phases
+ * theta = loc + VonMises(0, kappa) drawn on the device with Best & Fisher's rejection (the algorithm behind
+ * torch.distributions.VonMises.sample, which the reference calls at :262), then the same Hermitian spectrum -> C2R
+ * inverse FFT.  kappa addressed like cvb_clifford_ps_rsample's.  Not reparameterised (no backward), like the
+ * reference.  (The reference's own method stops at its Hermitian-symmetry assert, :274; this entry point is the
+ * working version of what it computes.) */
+CVB_API int cvb_clifford_vm_rsample(const float* loc, const float* kappa, long long kappa_row_stride, int kappa_el_stride,
+                                    long long loc_rows, unsigned long long seed, unsigned long long offset, float* z,
+                                    long long rows, int d, void* stream);
+
 /* CliffordTorusUniform.rsample (dists/clifford.py:228-236) and the shared "phases -> real vector with
  * unit-magnitude spectrum" map.  phases (rows, d) are multiplied by phase_scale (2*pi for uniform u);
  * phases == NULL draws u on the device.  z (rows, 2d). */

@@ -82,3 +82,36 @@ def test_rows_with_different_concentrations_use_their_own_table():
         D = max(np.max(i / n - F), np.max(F - (i - 1) / n))
         atom = _phase_cdf(np.array([3.16227766e-4]), k)[0] - 0.5
         assert D < 1.95 / np.sqrt(n) + atom, (k, D)
+
+
+@pytest.mark.parametrize("d", [16, 512, 20])
+def test_von_mises_torus_distribution_sampling(d):
+    """CliffordTorusDistribution.rsample (dists/clifford.py:261-275): every circle's phase is loc + VonMises(0, kappa);
+    one-sample KS against scipy's von Mises CDF, unit-modulus spectrum, per-element and row-scalar concentrations."""
+    from scipy.stats import vonmises
+    from dists.clifford import CliffordTorusDistribution, CliffordTorusUniform
+    torch.manual_seed(d)
+    rows = 4096 if d <= 20 else 512
+    for k in (0.05, 2.0, 30.0):
+        loc = torch.full((rows, d), 0.3, device=DEV)
+        q = CliffordTorusDistribution(loc, torch.full((rows, 1), k, device=DEV))
+        z = q.rsample()
+        assert z.shape == (rows, 2 * d) and q.batch_shape == (rows,) and q.event_shape == (2 * d,)
+        F = torch.fft.rfft(z.double(), dim=-1)
+        assert float((F.abs() - 1).abs().max()) < 2e-5
+        th = (torch.angle(F[:, 1:d]) - 0.3).cpu().numpy().reshape(-1)
+        th = (th + np.pi) % (2 * np.pi) - np.pi
+        x = np.sort(th)
+        n = x.size
+        Fx = vonmises.cdf(x, k)
+        i = np.arange(1, n + 1)
+        D = max(np.max(i / n - Fx), np.max(Fx - (i - 1) / n))
+        assert D < 1.95 / np.sqrt(n), (k, D)
+    # per-element concentrations, sample_shape, KL registration with the uniform prior
+    kap = torch.rand(rows, d, device=DEV) * 5 + 0.1
+    q = CliffordTorusDistribution(torch.zeros(rows, d, device=DEV), kap)
+    z = q.rsample(torch.Size([2]))
+    assert z.shape == (2, rows, 2 * d)
+    assert float((torch.fft.rfft(z.double(), dim=-1).abs() - 1).abs().max()) < 2e-5
+    kl = torch.distributions.kl.kl_divergence(q, CliffordTorusUniform(d, device=DEV))
+    assert kl.shape == (rows,) and bool((kl > 0).all())
