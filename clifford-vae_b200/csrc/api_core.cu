@@ -19,7 +19,13 @@ static int g_sms[64] = {0};
 static int* g_sched[64] = {nullptr};
 static std::atomic<unsigned> g_sched_seq{0};
 constexpr int kSchedSlots = 64;
-static std::unordered_map<const void*, int> g_occ;
+static std::unordered_map<unsigned long long, int> g_occ;   // (device, kernel) -> resident CTAs per SM
+static unsigned long long occ_key(const void* kernel) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  // the dynamic-smem opt-in (cudaFuncSetAttribute) and the occupancy answer are per device: key them so
+  return (unsigned long long)reinterpret_cast<uintptr_t>(kernel) * 64ull + (unsigned long long)(dev & 63);
+}
 static const float2* g_icdf[64] = {nullptr};
 static std::vector<float2> g_icdf_host;
 
@@ -151,13 +157,13 @@ int sm_count() {
 
 int cached_ctas_per_sm(const void* kernel, int, size_t, bool* found) {
   std::lock_guard<std::mutex> lk(g_mu);
-  auto it = g_occ.find(kernel);
+  auto it = g_occ.find(occ_key(kernel));
   *found = it != g_occ.end();
   return *found ? it->second : 0;
 }
 void store_ctas_per_sm(const void* kernel, int per_sm) {
   std::lock_guard<std::mutex> lk(g_mu);
-  g_occ[kernel] = per_sm;
+  g_occ[occ_key(kernel)] = per_sm;
 }
 
 __global__ void philox_fill_kernel(uint4* out, long long n, PhiloxKey key) {

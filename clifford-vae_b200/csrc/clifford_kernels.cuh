@@ -432,7 +432,10 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw, cons
           h1 = HalfAngle(__ldg(p.kappa + prow * p.kappa_row_stride + (long long)k1 * p.kappa_el_stride) + kEps);
         }
         float tp[2], sg[2];
-        const uint32_t acc = half_angle_pair(h0, h1, philox_draw(pkey, pair_base + (e >> 1), 0), tp, sg);
+        const uint4 r1 = philox_draw(pkey, pair_base + (e >> 1), 0);
+        uint4 r2 = r1;
+        if (!ROWK && ((h0.sigma > 0.f) != (h1.sigma > 0.f))) r2 = philox_draw(pkey, pair_base + (e >> 1), 0x80u);   // mixed regimes
+        const uint32_t acc = half_angle_pair(h0, h1, r1, r2, tp, sg);
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           const int k = j ? k1 : k0;

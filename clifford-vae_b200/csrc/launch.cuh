@@ -46,7 +46,8 @@ inline int check_launch(const char* what) {
 }
 
 // Persistent grid: min(work CTAs, SMs x resident CTAs per SM).  Opts in to > 48 KB dynamic smem.
-// The occupancy answer is cached per kernel (one device per process is the deployment model).
+// The occupancy answer and the > 48 KB opt-in are cached per (device, kernel): a second device in the same process
+// gets its own cudaFuncSetAttribute call.
 int cached_ctas_per_sm(const void* kernel, int threads, size_t smem, bool* found);
 void store_ctas_per_sm(const void* kernel, int per_sm);
 

@@ -126,14 +126,26 @@ __device__ __forceinline__ bool half_angle_try(const HalfAngle& h, uint4 r, floa
 }
 // One Philox result serves TWO elements with one proposal each (a rejected one is queued):
 // element j in {0, 1} of the pair gets (t', sign) and returns its acceptance in bit j.
-__device__ __forceinline__ uint32_t half_angle_pair(const HalfAngle& h0, const HalfAngle& h1, uint4 r, float (&tp)[2],
-                                                    float (&sign)[2]) {
+// `r2`: a SECOND, independent Philox result, used only in the mixed case (one bin in the normal regime, the other in
+// the uniform one -- per-element concentrations straddling 1/pi): there the normal proposal depends on both r.x and r.y
+// through the Box-Muller pair, so the uniform bin draws its proposal and accept word from r2 instead of re-using r.y
+// (which made the two circles' proposals dependent).  Callers pass r2 = r when both bins share a regime.
+__device__ __forceinline__ uint32_t half_angle_pair(const HalfAngle& h0, const HalfAngle& h1, uint4 r, uint4 r2,
+                                                    float (&tp)[2], float (&sign)[2]) {
   float p0, p1;
-  uint32_t u0, u1;
+  uint32_t u0 = r.z, u1 = r.w;
   const float2 nn = box_muller(r.x, r.y);
-  p0 = (h0.sigma > 0.f) ? nn.x * h0.sigma : (u01_open1(r.x) - 0.5f) * 3.14159265358979f;
-  p1 = (h1.sigma > 0.f) ? nn.y * h1.sigma : (u01_open1(r.y) - 0.5f) * 3.14159265358979f;
-  u0 = r.z; u1 = r.w;
+  const bool n0 = h0.sigma > 0.f, n1 = h1.sigma > 0.f;
+  if (n0 == n1) {
+    p0 = n0 ? nn.x * h0.sigma : (u01_open1(r.x) - 0.5f) * 3.14159265358979f;
+    p1 = n1 ? nn.y * h1.sigma : (u01_open1(r.y) - 0.5f) * 3.14159265358979f;
+  } else if (n0) {
+    p0 = nn.x * h0.sigma;
+    p1 = (u01_open1(r2.x) - 0.5f) * 3.14159265358979f; u1 = r2.y;
+  } else {
+    p1 = nn.y * h1.sigma;
+    p0 = (u01_open1(r2.x) - 0.5f) * 3.14159265358979f; u0 = r2.y;
+  }
   const bool a0 = half_angle_accept(h0, p0, u0), a1 = half_angle_accept(h1, p1, u1);
   const float c0 = __cosf(p0), c1 = __cosf(p1);
   tp[0] = fminf(fmaxf(c0 * c0, 1.17549435e-38f), 1.0f - 5.9604645e-8f);

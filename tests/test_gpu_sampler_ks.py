@@ -115,3 +115,34 @@ def test_von_mises_torus_distribution_sampling(d):
     assert float((torch.fft.rfft(z.double(), dim=-1).abs() - 1).abs().max()) < 2e-5
     kl = torch.distributions.kl.kl_divergence(q, CliffordTorusUniform(d, device=DEV))
     assert kl.shape == (rows,) and bool((kl > 0).all())
+
+
+@pytest.mark.parametrize("d", [16, 512])
+def test_per_element_concentrations_straddling_the_envelope_switch(d):
+    """with per-element concentrations on both sides of 1/pi (Gaussian vs uniform envelope) two circles that
+    share one Philox result must still get independent proposals: marginals by KS, pairs by correlation."""
+    from dists.clifford import CliffordPowerSphericalDistribution
+    torch.manual_seed(5)
+    rows = 1 << 15 if d == 16 else 2048
+    kap = torch.where(torch.arange(d, device=DEV) % 2 == 0, 0.2, 0.5).expand(rows, d).contiguous()
+    if d == 512:      # pairs are (k, k + 32) there: alternate in blocks of 32
+        kap = torch.where((torch.arange(d, device=DEV) // 32) % 2 == 0, 0.2, 0.5).expand(rows, d).contiguous()
+    q = CliffordPowerSphericalDistribution(torch.zeros(rows, d, device=DEV), kap, validate_args=False)
+    th = torch.angle(torch.fft.rfft(q.rsample().double(), dim=-1)[:, :d]).cpu().numpy()
+    kv = kap[0].cpu().numpy()
+    for k in (0.2, 0.5):
+        x = np.sort(th[:, (kv == k) & (np.arange(d) > 0)].reshape(-1))
+        n = x.size
+        F = _phase_cdf(x, float(np.float32(k)))
+        i = np.arange(1, n + 1)
+        D = max(np.max(i / n - F), np.max(F - (i - 1) / n))
+        atom = _phase_cdf(np.array([3.16227766e-4]), k)[0] - 0.5
+        assert D < 1.95 / np.sqrt(n) + atom, (k, D)
+    step = 1 if d == 16 else 32
+    # per column pair (k, k + step) -- the two circles that share a Philox result -- after removing the column means
+    # (the two columns have different concentrations, hence different mean |phi|)
+    a, b = np.abs(th[:, 2:d - step:1]), np.abs(th[:, 2 + step:d:1])
+    a = (a - a.mean(0)) / a.std(0)
+    b = (b - b.mean(0)) / b.std(0)
+    c = (a * b).mean(0)                                   # one correlation coefficient per pair, sd 1 / sqrt(rows)
+    assert abs(c.mean()) < 5 / np.sqrt(a.size) and np.abs(c).max() < 6 / np.sqrt(rows), (c.mean(), np.abs(c).max())
