@@ -270,6 +270,26 @@ def run_gpu(args):
     barrier()
     launches = _lib.launch_count() - l0
     ms_total = t_start.elapsed_time(t_end)
+
+    # the same outputs (z, KL, bound) from ONE launch (cvb_clifford_ps_rsample_bind: the sample's spectrum is known, so the
+    # bind needs two transforms instead of three and z is not re-read) -- reported beside the headline, not as it
+    def fused_step(i):
+        s = sets[i % NSETS]
+        rc = lib.cvb_clifford_ps_rsample_bind(s["loc"].data_ptr(), s["kap"].data_ptr(), B, None, None, seed, i,
+                                              s["roles"].data_ptr(), B, s["z"].data_ptr(), s["out"].data_ptr(),
+                                              s["ent"].data_ptr(), s["kl"].data_ptr(), None, B, d, st)
+        if rc:
+            raise RuntimeError(lib.cvb_last_error_string().decode())
+    for i in range(3):
+        fused_step(i)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(args.steps):
+        fused_step(i)
+    f1.record()
+    barrier()
+    ms_fused = f0.elapsed_time(f1) / args.steps
     ms_rs = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
     ms_bind = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
 
@@ -350,9 +370,9 @@ def run_gpu(args):
 
     # max over ranks
     if world > 1:
-        t = torch.tensor([ms_total, ms_e2e, ms_rs, ms_bind, ms_link], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms_total, ms_e2e, ms_rs, ms_bind, ms_link, ms_fused], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, ms_e2e, ms_rs, ms_bind, ms_link = (float(x) for x in t.tolist())
+        ms_total, ms_e2e, ms_rs, ms_bind, ms_link, ms_fused = (float(x) for x in t.tolist())
 
     if rank == 0:
         value = world * B * args.steps / (ms_total * 1e-3)
@@ -375,7 +395,12 @@ def run_gpu(args):
                 "rsample_kl": {"ms": ms_rs, "GBps": k_rs["bytes"] / (ms_rs * 1e-3) / 1e9,
                                "frac": k_rs["bytes"] / (ms_rs * 1e-3) / 1e9 / peak},
                 "bind": {"ms": ms_bind, "GBps": k_bd["bytes"] / (ms_bind * 1e-3) / 1e9,
-                         "frac": k_bd["bytes"] / (ms_bind * 1e-3) / 1e9 / peak}},
+                         "frac": k_bd["bytes"] / (ms_bind * 1e-3) / 1e9 / peak},
+                "fused_one_launch_variant": {
+                    "what": "cvb_clifford_ps_rsample_bind: z, KL and bind(z, roles) from one kernel (28d+12 B per row)",
+                    "ms": ms_fused, "samples_per_s": world * B / (ms_fused * 1e-3),
+                    "GBps": B * (28 * d + 12) / (ms_fused * 1e-3) / 1e9,
+                    "frac": B * (28 * d + 12) / (ms_fused * 1e-3) / 1e9 / peak}},
             "e2e": {"value": e2e_val, "unit": UNIT, "steps": e2e_steps,
                     "h2d_bytes_per_step": world * n_in * 4, "d2h_bytes_per_step": world * n_out * 4,
                     "api": "dists.clifford.CliffordPowerSphericalDistribution.rsample + kl_divergence + utils.vsa.bind",

@@ -573,10 +573,40 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw, cons
 #pragma unroll
       for (int e = 0; e < E; ++e) v[e] = valid ? ldg_stream2(br + t + e * T) : make_float2(0.f, 0.f);
       fft_run<LOG2N, false>(v, xch, t, tw);
-      const float r_nyq = r2c_untangle<LOG2N>(v, xch, t, tw);
+      // One partner exchange: bins k and N-k of R = rfft(b) from Z_b[k], Z_b[N-k]; P = S * R with the sample's own
+      // phasors S (spec[]; S[0] = S[N] = 1); both re-packed values V[k] = c (s + q), V[N-k] = c conj(s - q) for the inverse
+      // half-length transform.  Each pair is formed once, by the owner of k < N/2; the partner value returns through
+      // spec[N-k] (the slot this thread just consumed).
+      group_sync<LOG2N>();
 #pragma unroll
-      for (int e = 0; e < E; ++e) v[e] = cmul(spec[t + e * T], v[e]);
-      c2r_pretangle<LOG2N>(v, r_nyq, xch, t, tw);
+      for (int e = 0; e < E; ++e) xch[pad16(t + e * T)] = v[e];
+      group_sync<LOG2N>();
+      auto pair = [&](int k, int kp, cplx zb, cplx& vk, cplx& vkp) {
+        constexpr float fold = 0.5f / (2.0f * d);
+        const cplx zbp = cconj(xch[pad16(kp)]);
+        const cplx w = __ldg(&tw[twiddle_offset(LOG2N) + k]);
+        const cplx sb = cadd(zb, zbp), db = cmul_mi(cmul(w, csub(zb, zbp)));
+        const cplx Bk = cadd(sb, db), Bkp = cconj(csub(sb, db));             // 2 R[k], 2 R[N-k]
+        const cplx Pk = cmul(spec[k], Bk), Pkpc = cconj(cmul(spec[kp], Bkp));
+        const cplx s = cadd(Pk, Pkpc), q = cmul_i(cmul(cconj(w), csub(Pk, Pkpc)));
+        vk = cadd_scaled(s, q, fold);
+        vkp = cconj(cscale(csub(s, q), fold));
+      };
+#pragma unroll
+      for (int e = 0; e < E / 2; ++e) {
+        const int k = t + e * T, kp = (d - k) & (d - 1);
+        cplx vkp;
+        pair(k, kp, v[e], v[e], vkp);
+        if (kp != k) spec[kp] = vkp;
+      }
+      if (t == 0) {
+        cplx vk, vkp;
+        pair(d / 2, d / 2, v[E / 2], vk, vkp);
+        spec[d / 2] = vk;
+      }
+      group_sync<LOG2N>();
+#pragma unroll
+      for (int e = E / 2; e < E; ++e) v[e] = spec[t + e * T];
       fft_run<LOG2N, true>(v, xch, t, tw);
       if (valid) {
         float2* orow = reinterpret_cast<float2*>(p.bind_out + row * (2LL * d));
