@@ -583,12 +583,12 @@ def config_legs(torch, lib, dev, st, world):
 
     # ---- C1 / C2: launch-latency-sized configurations
     B1, d1 = 128, 512
-    loc = torch.randn(B1, d1, device=dev)
+    loc1 = torch.randn(B1, d1, device=dev)
     kap1 = torch.rand(B1, device=dev) * 9.97 + 0.03
-    z = torch.empty(B1, 2 * d1, device=dev)
-    kl = torch.empty(B1, device=dev)
-    ms = timeit(lambda: lib.cvb_clifford_ps_rsample(loc.data_ptr(), kap1.data_ptr(), 1, 0, B1, None, None, 7, 0, z.data_ptr(),
-                                                    None, None, kl.data_ptr(), None, B1, d1, st), reps=50)
+    z1 = torch.empty(B1, 2 * d1, device=dev)
+    kl1 = torch.empty(B1, device=dev)
+    ms = timeit(lambda: lib.cvb_clifford_ps_rsample(loc1.data_ptr(), kap1.data_ptr(), 1, 0, B1, None, None, 7, 0, z1.data_ptr(),
+                                                    None, None, kl1.data_ptr(), None, B1, d1, st), reps=50)
     legs.append(("C1_clifford_rsample_kl_B128_d512", {"rows": B1, "unit": "samples/s", "units": B1,
                                                       "bytes_per_unit": 12 * d1 + 8, "launches_per_step": 1}, ms))
     B2, D2 = 1024, 513
@@ -611,6 +611,46 @@ def config_legs(torch, lib, dev, st, world):
         ms = timeit(fn, reps=50)
         legs.append((name, {"rows": B2, "unit": "samples/s", "units": B2, "bytes_per_unit": 8 * D2 + 8,
                             "launches_per_step": 2, "note": "4 MB per step: launch-latency bound at this batch"}, ms))
+
+    # the same C1 / C2 steps captured once in a CUDA graph and replayed (device-resident Philox launch counter, so every
+    # replay draws a fresh stream: cvb_set_rng_device_counter)
+    ctr = torch.zeros(1, dtype=torch.int64, device=dev)
+    lib.cvb_set_rng_device_counter(ctr.data_ptr())
+
+    def cur():
+        return torch.cuda.current_stream().cuda_stream
+
+    def g_c1():
+        ctr.add_(1)
+        lib.cvb_clifford_ps_rsample(loc1.data_ptr(), kap1.data_ptr(), 1, 0, B1, None, None, 7, 0, z1.data_ptr(), None, None,
+                                    kl1.data_ptr(), None, B1, d1, cur())
+
+    def g_ps():
+        ctr.add_(1)
+        lib.cvb_powerspherical_rsample(loc.data_ptr(), kap2.data_ptr(), B2, None, None, 3, 0, z.data_ptr(), save.data_ptr(), B2, D2, cur())
+        lib.cvb_ps_entropy_kl(kap2.data_ptr(), 1, 0, B2, D2, (D2 - 1) / 2, 0, 0.0, ent.data_ptr(), kl.data_ptr(), None, cur())
+
+    def g_vmf():
+        ctr.add_(1)
+        lib.cvb_vmf_rsample(loc.data_ptr(), kap2.data_ptr(), B2, None, None, 0, None, 3, 0, z.data_ptr(), save.data_ptr(), B2, D2, cur())
+        lib.cvb_vmf_entropy_lognorm(kap2.data_ptr(), B2, D2, ent.data_ptr(), None, None, None, cur())
+
+    for name, fn, rows, bpu in (("C1_clifford_rsample_kl_B128_d512_graph", g_c1, B1, 12 * d1 + 8),
+                                ("C2_powerspherical_rsample_kl_B1024_D513_graph", g_ps, B2, 8 * D2 + 8),
+                                ("C2_vmf_rsample_kl_B1024_D513_graph", g_vmf, B2, 8 * D2 + 8)):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            fn()
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for _ in range(10):                 # ten steps per replay: the replay launch cost is amortised like a training loop's
+                fn()
+        ms = timeit(graph.replay, reps=20) / 10
+        legs.append((name, {"rows": rows, "unit": "samples/s", "units": rows, "bytes_per_unit": bpu,
+                            "note": "CUDA graph of 10 steps replayed; fresh draws per replay"}, ms))
+    lib.cvb_set_rng_device_counter(None)
 
     # ---- C5: depth 1..32 at d = 8192, 512 trials per depth per GPU, whole chain + cosine in one kernel per depth
     d5, T5, depths = 8192, 512, list(range(1, 33))

@@ -58,6 +58,7 @@ _SIGNATURES = {
     "cvb_vmf_rsample": ([_f, _f, _ll, _f, _f, _i, _f, _ull, _ull, _f, _f, _ll, _i, _f], _i),
     "cvb_vmf_rsample_backward": ([_f, _f, _f, _ll, _f, _f, _ull, _ull, _f, _f, _ll, _i, _f], _i),
     "cvb_vmf_entropy_lognorm": ([_f, _ll, _i, _f, _f, _f, _f, _f], _i),
+    "cvb_set_rng_device_counter": ([_f], _i),
     "cvb_ps_halfangle_icdf_table": ([_f, _ll, _f, _f, _f], _i),
     "cvb_philox_fill": ([_f, _ll, _ull, _ull, _f], _i),
 }
@@ -140,6 +141,16 @@ def _rank_mix(seed: int) -> int:
     return seed & 0xFFFFFFFFFFFFFFFF
 
 
+_graph_counters: dict[int, torch.Tensor] = {}      # device index -> int64 launch counter kept for CUDA-graph capture
+
+
+def _capturing() -> bool:
+    try:
+        return torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
+    except Exception:
+        return False
+
+
 def next_rng(device=None):
     """(seed, offset) for the next kernel that draws on the device.
 
@@ -148,11 +159,36 @@ def next_rng(device=None):
     re-seeding restarts the stream and our draws interleave consistently with torch's.  The seed is
     xor-ed with the distributed rank so DDP ranks draw disjoint streams.  Without a device (CPU unit
     tests of the host logic) a process-local call counter stands in for the offset.
+
+    Under CUDA-graph capture the host values are frozen into the graph, so a device-resident launch counter is
+    registered with the library (cvb_set_rng_device_counter) and bumped by a captured `counter += 1` right here --
+    i.e. once per sampling launch, before it -- which gives every replay of the graph a fresh stream.  Outside capture
+    the counter is cleared again (host offsets only).
     """
     global _rng_seed, _rng_offset
     if device is not None and torch.device(device).type == "cuda":
         dev = torch.device(device)
         idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        lib = load()
+        if _capturing():
+            ctr = _graph_counters.get(idx)
+            if ctr is None:
+                raise CliffordB200Error(
+                    "sampling inside CUDA-graph capture needs clifford_b200._lib.enable_graph_rng(device) to be called "
+                    "BEFORE the capture starts (it allocates the device-resident launch counter)")
+            with torch.cuda.device(idx):
+                lib.cvb_set_rng_device_counter(ctr.data_ptr())
+            ctr.add_(1)                                     # captured: runs on every replay
+            _graph_counters[-idx - 1] = ctr                 # mark: registered, clear it at the next eager call
+            seed = _rank_mix(torch.initial_seed())
+            # a per-capture host constant keeps distinct captured launches apart; torch's generator state cannot be
+            # advanced from inside a capture without registering it with the graph
+            _rng_offset += 1
+            return seed, (1 << 40) + _rng_offset
+        if (-idx - 1) in _graph_counters:                   # leaving capture mode: back to host offsets only
+            with torch.cuda.device(idx):
+                lib.cvb_set_rng_device_counter(None)
+            del _graph_counters[-idx - 1]
         gen = torch.cuda.default_generators[idx]
         off = gen.get_offset()
         gen.set_offset(off + 4)
@@ -163,3 +199,14 @@ def next_rng(device=None):
     off = _rng_offset
     _rng_offset += 1
     return seed, off
+
+
+def enable_graph_rng(device) -> torch.Tensor:
+    """Allocate (once per device) the device-resident launch counter that lets the samplers be captured in a CUDA
+    graph with fresh draws per replay.  Call before `torch.cuda.graph(...)` / `CUDAGraph.capture_begin()`."""
+    dev = torch.device(device)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    ensure_device(torch.device("cuda", idx))
+    if idx not in _graph_counters:
+        _graph_counters[idx] = torch.zeros(1, dtype=torch.int64, device=torch.device("cuda", idx))
+    return _graph_counters[idx]

@@ -27,6 +27,7 @@ static unsigned long long occ_key(const void* kernel) {
   return (unsigned long long)reinterpret_cast<uintptr_t>(kernel) * 64ull + (unsigned long long)(dev & 63);
 }
 static const float2* g_icdf[64] = {nullptr};
+static const unsigned long long* g_rng_ctr[64] = {nullptr};
 static std::vector<float2> g_icdf_host;
 
 // ---- host construction of the half-angle inverse-CDF table (icdf_table.cuh), double precision ----------------
@@ -139,6 +140,12 @@ const cplx* device_twiddles() {
   return g_tw[dev];
 }
 
+const unsigned long long* rng_device_counter() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  return g_rng_ctr[dev];
+}
+
 int* next_sched_slot() {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || !g_sched[dev]) return nullptr;
@@ -220,6 +227,18 @@ int cvb_init(void) {
   return kOk;
 }
 
+// Register (or clear, with NULL) a device-resident 64-bit launch counter for the CURRENT device: every sampling kernel
+// launched afterwards adds it to its Philox offset.  The library only reads it; the caller increments it on the stream
+// (e.g. a captured `counter += 1`) after each sampling launch, which is what makes the samplers replayable inside a
+// CUDA graph with fresh draws per replay.
+int cvb_set_rng_device_counter(const unsigned long long* counter) {
+  int dev = 0;
+  CVB_CUDA(cudaGetDevice(&dev));
+  CVB_REQUIRE(dev >= 0 && dev < 64, kUnsupported, "device ordinal %d out of range", dev);
+  g_rng_ctr[dev] = counter;
+  return kOk;
+}
+
 // Host-only: the half-angle inverse-CDF table the device samplers interpolate (icdf_table.cuh); no GPU needed.
 int cvb_ps_halfangle_icdf_table(float* out, long long capacity_floats, int* n_kappa, int* n_nodes, float* kappa_max) {
   if (n_kappa) *n_kappa = kIcdfKappaNodes;
@@ -242,6 +261,7 @@ int cvb_philox_fill(unsigned int* out, long long n_vec4, unsigned long long seed
   CVB_REQUIRE(out && n_vec4 > 0, kBadArgument, "cvb_philox_fill: bad arguments");
   PhiloxKey key = make_key(seed, 0, 0);
   key.offset = (uint32_t)offset;
+  key.dev_counter = nullptr;          // the known-answer test hook is addressed by (seed, offset) alone
   philox_fill_kernel<<<148, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<uint4*>(out), n_vec4, key);
   return check_launch("philox_fill_kernel");
 }

@@ -10,6 +10,10 @@ struct PhiloxKey {
   uint32_t k0, k1;     // seed
   uint32_t offset;     // per-call offset (host increments it for every launch that draws)
   uint32_t stream;     // which variate family inside a call (0 = gamma proposals, 1 = normals ...)
+  // Optional device-resident launch counter added to `offset` (cvb_set_rng_device_counter): under CUDA-graph capture
+  // the host-chosen offset is frozen into the graph, so the caller keeps a counter in device memory and bumps it with a
+  // captured kernel after every sampling launch -- each replay then draws a fresh stream.  nullptr: host offset only.
+  const unsigned long long* dev_counter;
 };
 
 __host__ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
@@ -29,7 +33,9 @@ __host__ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, ui
 
 // counter layout: (element lo, element hi, attempt | stream << 24, call offset)
 __device__ __forceinline__ uint4 philox_draw(const PhiloxKey& key, uint64_t elem, uint32_t attempt) {
-  return philox4x32_10(make_uint4((uint32_t)elem, (uint32_t)(elem >> 32), attempt | (key.stream << 24), key.offset),
+  uint32_t off = key.offset;
+  if (key.dev_counter) off += (uint32_t)__ldg(key.dev_counter) * 0x9E3779B9u;   // uniform branch on a kernel parameter
+  return philox4x32_10(make_uint4((uint32_t)elem, (uint32_t)(elem >> 32), attempt | (key.stream << 24), off),
                        key.k0, key.k1);
 }
 

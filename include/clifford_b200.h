@@ -200,6 +200,12 @@ CVB_API int cvb_vmf_rsample_backward(const float* grad_z, const float* loc, cons
 CVB_API int cvb_vmf_entropy_lognorm(const float* kappa, long long rows, int D, float* entropy, float* log_norm,
                                     float* dentropy, float* dlog_norm, void* stream);
 
+/* ---- CUDA-graph capture of the samplers.  (seed, offset) are kernel arguments chosen on the host, so a captured graph
+ * would replay the same draws.  Register a device-resident 64-bit counter for the current device (NULL clears it): every
+ * sampling kernel launched afterwards mixes it into its Philox offset.  The library only READS it; the caller bumps it
+ * on the stream after each sampling launch (inside the capture), so every replay draws a fresh stream. */
+CVB_API int cvb_set_rng_device_counter(const unsigned long long* counter);
+
 /* ---- host-only: the inverse-CDF table behind the device sampler of dists/clifford.py:124-134's Beta(1/2 + kappa, 1/2)
  * draw for row-scalar concentrations <= *kappa_max (csrc/icdf_table.cuh).  Layout: [n_kappa][n_nodes][2] floats =
  * (H, dH/ds / (n_nodes - 1)) with concentration node i at kappa_i = expm1(log1p(kappa_max) * i / (n_kappa - 1)) and

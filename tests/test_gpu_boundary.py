@@ -170,3 +170,62 @@ def test_ops_from_two_threads_do_not_share_launch_state():
         stop.set()
         t.join()
     assert not errs
+
+
+def test_samplers_inside_a_cuda_graph_draw_fresh_streams_on_every_replay():
+    """(seed, offset) are host-chosen kernel arguments, so a captured graph used to replay the same
+    draws.  With the device-resident launch counter (cvb_set_rng_device_counter, _lib.enable_graph_rng) every replay of
+    a captured rsample + KL + bind step yields new samples of the right law."""
+    from clifford_b200 import _lib
+    from dists.clifford import CliffordPowerSphericalDistribution, CliffordTorusUniform, PowerSpherical
+    from utils import vsa
+    torch.manual_seed(0)
+    B, d = 256, 512
+    loc = torch.zeros(B, d, device=DEV)
+    kap = torch.full((B, 1), 2.0, device=DEV)
+    roles = vsa.unitary_init(B, 2 * d, device=DEV)
+    ploc = torch.nn.functional.normalize(torch.randn(B, 33, device=DEV), dim=-1)
+    pk = torch.full((B,), 5.0, device=DEV)
+    _lib.enable_graph_rng(DEV)
+    prior = CliffordTorusUniform(d, device=DEV)
+
+    def step():
+        q = CliffordPowerSphericalDistribution(loc, kap, validate_args=False)
+        z = q.rsample()
+        kl = torch.distributions.kl.kl_divergence(q, prior)
+        return z, kl, vsa.bind(z, roles), PowerSpherical(ploc, pk).rsample()
+
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(2):
+            step()                                          # warm-up outside capture (allocator, cvb_init)
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        z, kl, bound, zs = step()
+    outs = []
+    for _ in range(3):
+        g.replay()
+        torch.cuda.synchronize()
+        outs.append((z.clone(), bound.clone(), zs.clone()))
+        assert float((z.norm(dim=-1) - 1).abs().max()) < 2e-5
+        assert float((torch.fft.rfft(z.double(), dim=-1).abs() - 1).abs().max()) < 2e-5
+        rec = vsa.unbind(bound, roles)
+        assert float((rec - z).abs().max()) < 1e-4
+        assert float((zs.norm(dim=-1) - 1).abs().max()) < 1e-5
+    for i in range(3):
+        for j in range(i + 1, 3):
+            assert float((outs[i][0] - outs[j][0]).abs().max()) > 1e-2       # different draws on every replay
+            assert float((outs[i][2] - outs[j][2]).abs().max()) > 1e-2
+    # the law is unchanged: KS of the pooled phases of the three replays
+    from test_gpu_sampler_ks import _phase_cdf
+    th = torch.cat([torch.angle(torch.fft.rfft(o[0].double(), dim=-1)[:, 1:d]).reshape(-1) for o in outs]).cpu().numpy()
+    x = np.sort(th)
+    n = x.size
+    F = _phase_cdf(x, 2.0)
+    i = np.arange(1, n + 1)
+    assert max(np.max(i / n - F), np.max(F - (i - 1) / n)) < 1.95 / np.sqrt(n) + 2e-4
+    # eager sampling afterwards still works and differs from the graph's draws
+    z2 = CliffordPowerSphericalDistribution(loc, kap, validate_args=False).rsample()
+    assert float((z2 - outs[-1][0]).abs().max()) > 1e-2
