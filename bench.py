@@ -599,18 +599,19 @@ def config_legs(torch, lib, dev, st, world):
     ent = torch.empty(B2, device=dev)
     kl = torch.empty(B2, device=dev)
 
+    # rsample fused with entropy / KL: ONE launch per step (round 1: sampler + entropy kernel)
     def ps_step():
-        lib.cvb_powerspherical_rsample(loc.data_ptr(), kap2.data_ptr(), B2, None, None, 3, 0, z.data_ptr(), save.data_ptr(), B2, D2, st)
-        lib.cvb_ps_entropy_kl(kap2.data_ptr(), 1, 0, B2, D2, (D2 - 1) / 2, 0, 0.0, ent.data_ptr(), kl.data_ptr(), None, st)
+        lib.cvb_powerspherical_rsample_kl(loc.data_ptr(), kap2.data_ptr(), B2, None, None, 3, 0, z.data_ptr(), save.data_ptr(),
+                                          ent.data_ptr(), kl.data_ptr(), None, B2, D2, st)
 
     def vmf_step():
-        lib.cvb_vmf_rsample(loc.data_ptr(), kap2.data_ptr(), B2, None, None, 0, None, 3, 0, z.data_ptr(), save.data_ptr(), B2, D2, st)
-        lib.cvb_vmf_entropy_lognorm(kap2.data_ptr(), B2, D2, ent.data_ptr(), None, None, None, st)
+        lib.cvb_vmf_rsample_kl(loc.data_ptr(), kap2.data_ptr(), B2, None, None, 0, None, 3, 0, z.data_ptr(), save.data_ptr(),
+                               ent.data_ptr(), kl.data_ptr(), None, None, None, B2, D2, st)
 
     for name, fn in (("C2_powerspherical_rsample_kl_B1024_D513", ps_step), ("C2_vmf_rsample_kl_B1024_D513", vmf_step)):
         ms = timeit(fn, reps=50)
         legs.append((name, {"rows": B2, "unit": "samples/s", "units": B2, "bytes_per_unit": 8 * D2 + 8,
-                            "launches_per_step": 2, "note": "4 MB per step: launch-latency bound at this batch"}, ms))
+                            "launches_per_step": 1, "note": "4 MB per step: launch-latency bound at this batch"}, ms))
 
     # the same C1 / C2 steps captured once in a CUDA graph and replayed (device-resident Philox launch counter, so every
     # replay draws a fresh stream: cvb_set_rng_device_counter)
@@ -627,13 +628,13 @@ def config_legs(torch, lib, dev, st, world):
 
     def g_ps():
         ctr.add_(1)
-        lib.cvb_powerspherical_rsample(loc.data_ptr(), kap2.data_ptr(), B2, None, None, 3, 0, z.data_ptr(), save.data_ptr(), B2, D2, cur())
-        lib.cvb_ps_entropy_kl(kap2.data_ptr(), 1, 0, B2, D2, (D2 - 1) / 2, 0, 0.0, ent.data_ptr(), kl.data_ptr(), None, cur())
+        lib.cvb_powerspherical_rsample_kl(loc.data_ptr(), kap2.data_ptr(), B2, None, None, 3, 0, z.data_ptr(), save.data_ptr(),
+                                          ent.data_ptr(), kl.data_ptr(), None, B2, D2, cur())
 
     def g_vmf():
         ctr.add_(1)
-        lib.cvb_vmf_rsample(loc.data_ptr(), kap2.data_ptr(), B2, None, None, 0, None, 3, 0, z.data_ptr(), save.data_ptr(), B2, D2, cur())
-        lib.cvb_vmf_entropy_lognorm(kap2.data_ptr(), B2, D2, ent.data_ptr(), None, None, None, cur())
+        lib.cvb_vmf_rsample_kl(loc.data_ptr(), kap2.data_ptr(), B2, None, None, 0, None, 3, 0, z.data_ptr(), save.data_ptr(),
+                               ent.data_ptr(), kl.data_ptr(), None, None, None, B2, D2, cur())
 
     for name, fn, rows, bpu in (("C1_clifford_rsample_kl_B128_d512_graph", g_c1, B1, 12 * d1 + 8),
                                 ("C2_powerspherical_rsample_kl_B1024_D513_graph", g_ps, B2, 8 * D2 + 8),

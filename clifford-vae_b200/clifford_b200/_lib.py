@@ -51,11 +51,13 @@ _SIGNATURES = {
     "cvb_vsa_hrr_init": ([_f, _ll, _i, _ull, _ull, _f], _i),
     "cvb_vsa_unitary_init": ([_f, _ll, _i, _fl, _ull, _ull, _f], _i),
     "cvb_powerspherical_rsample": ([_f, _f, _ll, _f, _f, _ull, _ull, _f, _f, _ll, _i, _f], _i),
+    "cvb_powerspherical_rsample_kl": ([_f, _f, _ll, _f, _f, _ull, _ull, _f, _f, _f, _f, _f, _ll, _i, _f], _i),
     "cvb_powerspherical_rsample_backward": ([_f, _f, _f, _ll, _f, _f, _f, _ull, _ull, _f, _f, _ll, _i, _f], _i),
     "cvb_powerspherical_log_prob": ([_f, _f, _f, _ll, _f, _f, _f, _ll, _i, _f], _i),
     "cvb_ps_log_normalizer": ([_f, _ll, _db, _f, _f, _f], _i),
     "cvb_sphere_uniform_rsample": ([_f, _ull, _ull, _f, _ll, _i, _fl, _f], _i),
     "cvb_vmf_rsample": ([_f, _f, _ll, _f, _f, _i, _f, _ull, _ull, _f, _f, _ll, _i, _f], _i),
+    "cvb_vmf_rsample_kl": ([_f, _f, _ll, _f, _f, _i, _f, _ull, _ull, _f, _f, _f, _f, _f, _f, _f, _ll, _i, _f], _i),
     "cvb_vmf_rsample_backward": ([_f, _f, _f, _ll, _f, _f, _ull, _ull, _f, _f, _ll, _i, _f], _i),
     "cvb_vmf_entropy_lognorm": ([_f, _ll, _i, _f, _f, _f, _f, _f], _i),
     "cvb_set_rng_device_counter": ([_f], _i),

@@ -72,6 +72,7 @@ class PowerSpherical(Distribution):
     def __init__(self, loc, scale, validate_args=None):
         self.loc, self.scale = loc, scale
         self.dim = loc.shape[-1]
+        self._fused_entropy = None
         super().__init__(batch_shape=scale.shape, event_shape=torch.Size([self.dim]), validate_args=False)
 
     def _flat(self):
@@ -85,7 +86,9 @@ class PowerSpherical(Distribution):
         n = _numel(sample_shape)
         if _base_draws is None:
             _base_draws = testing.take()
-        z = ops.PowerSphericalRsample.apply(loc2, kap, n, _base_draws)
+        z, ent, dent = ops.PowerSphericalRsample.apply(loc2, kap, n, _base_draws)
+        if ent.numel():                                             # same launch; entropy() / kl_divergence reuse it
+            self._fused_entropy = ops.row_scalar(self.scale, ent, dent).reshape(self.scale.shape)
         return z.reshape(tuple(sample_shape) + tuple(self.batch_shape) + (self.dim,)).to(self.loc.dtype)
 
     def sample(self, sample_shape=torch.Size()):
@@ -105,6 +108,12 @@ class PowerSpherical(Distribution):
         return lp.reshape(lead).to(self.loc.dtype)
 
     def entropy(self):
+        cached = self._fused_entropy
+        if cached is not None:
+            stale = (torch.is_grad_enabled() and torch.is_tensor(self.scale) and self.scale.requires_grad
+                     and cached.grad_fn is None and not cached.requires_grad)
+            if not stale:
+                return cached.to(self.loc.dtype)
         ent = ops.PSEntropy.apply(self.scale, 1, (self.dim - 1) / 2, False)
         return ent.reshape(self.scale.shape).to(self.loc.dtype)
 
@@ -230,9 +239,9 @@ class CliffordPowerSphericalDistribution(CliffordTorusDistribution):
             z = z.reshape(out_shape).to(self.dtype)
             self._sample_log_prob = (weakref.ref(z), z._version, lp.reshape(out_shape[:-1]))
             return z
-        z, ent = ops.CliffordPSRsample.apply(loc2, kap2, n, _base_draws, True)
+        z, ent, dent = ops.CliffordPSRsample.apply(loc2, kap2, n, _base_draws, True)
         if ent.numel():
-            self._fused_entropy = ent.reshape(self.batch_shape)
+            self._fused_entropy = ops.row_scalar(kap2, ent, dent).reshape(self.batch_shape)
         return z.reshape(out_shape).to(self.dtype)
 
     def rsample_bind(self, other, sample_shape=torch.Size(), return_sample=True, _base_draws=None):

@@ -64,6 +64,32 @@ def _kappa_layout(kappa: torch.Tensor, d: int):
     return k, d, 1
 
 
+class RowScalarOfKappa(torch.autograd.Function):
+    """A per-row scalar (entropy, log-normaliser) that a sampler launch already produced, re-attached to the graph as a
+    function of the concentration: forward hands back the precomputed value, backward multiplies by the derivative the
+    same launch produced.  Its own autograd node (own saved tensors), so the sample and the entropy / KL can be
+    differentiated in separate backward passes, like the reference's independent graphs."""
+
+    @staticmethod
+    def forward(ctx, kappa, box):
+        value, dvalue = box              # plain tensors made inside the sampler's forward (not inputs of this node)
+        ctx.save_for_backward(dvalue)
+        ctx.kshape = tuple(kappa.shape)
+        return value
+
+    @staticmethod
+    def backward(ctx, grad):
+        (dvalue,) = ctx.saved_tensors
+        return (grad.reshape(-1) * dvalue.reshape(-1)).reshape(ctx.kshape), None
+
+
+def row_scalar(kappa, value, dvalue):
+    """value as a differentiable function of kappa when that is wanted, else the bare value."""
+    if torch.is_grad_enabled() and torch.is_tensor(kappa) and kappa.requires_grad:
+        return RowScalarOfKappa.apply(kappa, (value, dvalue))
+    return value
+
+
 # =================================================================================================
 # Clifford torus
 # =================================================================================================
@@ -71,7 +97,8 @@ class CliffordPSRsample(torch.autograd.Function):
     """z, entropy = f(loc (B,d), kappa (B,1)|(B,d)); rows = n_samples * B.
 
     draws: None (device Philox) or (tprime, g) each (n_samples*B, d) -- parity mode.
-    Returns (z (rows, 2d), entropy (B,) or None-like empty when kappa is per element).
+    Returns (z (rows, 2d), entropy (B,), d entropy / d kappa (B,)); the last two are plain values (empty when kappa is per
+    element or n_samples > 1) that the distribution re-attaches to kappa with row_scalar().
     """
 
     @staticmethod
@@ -96,15 +123,16 @@ class CliffordPSRsample(torch.autograd.Function):
             seed, off = 0, 0
         _launch("cvb_clifford_ps_rsample", dev, ptr(loc_c), ptr(kap_c), krs, kes, B, ptr(tp), ptr(g), seed, off, ptr(z),
                 ptr(tp_signed), ptr(ent), None, ptr(dent), rows, d, skip=rows == 0 or d == 0)
-        ctx.save_for_backward(loc_c, kap_c, tp, g, tp_signed, dent)
+        ctx.save_for_backward(loc_c, kap_c, tp, g, tp_signed)
         ctx.meta = (B, d, rows, n_samples, krs, kes, tuple(kappa.shape))
         if ent is None:
-            ent = z.new_empty(0)
-        return z, ent
+            ent, dent = z.new_empty(0), z.new_empty(0)
+        ctx.mark_non_differentiable(ent, dent)      # re-attached to kappa by row_scalar(): its own autograd node
+        return z, ent, dent
 
     @staticmethod
-    def backward(ctx, grad_z, grad_ent):
-        loc_c, kap_c, tp, g, tp_signed, dent = ctx.saved_tensors
+    def backward(ctx, grad_z, grad_ent, grad_dent):
+        loc_c, kap_c, tp, g, tp_signed = ctx.saved_tensors
         B, d, rows, n_samples, krs, kes, kshape = ctx.meta
         dloc = dkap = None
         if grad_z is not None:
@@ -118,9 +146,6 @@ class CliffordPSRsample(torch.autograd.Function):
                 dk_rows = dk_rows.view(n_samples, B, -1).sum(0) if kes else dk_rows.view(n_samples, B).sum(0)
             dloc = dloc_rows
             dkap = dk_rows.reshape(kshape)
-        if dent is not None and grad_ent is not None and grad_ent.numel():
-            de = (grad_ent * dent).reshape(kshape)
-            dkap = de if dkap is None else dkap + de
         if dloc is None and ctx.needs_input_grad[0]:
             dloc = torch.zeros_like(loc_c)
         return dloc, dkap, None, None, None
@@ -516,7 +541,9 @@ def sphere_uniform_rsample(rows, D, device, norm_eps, gnoise=None):
 
 
 class PowerSphericalRsample(torch.autograd.Function):
-    """z (n*B, D) = PowerSpherical(loc (B,D), kappa (B,)).rsample; draws None or (tprime (rows,), g (rows, D-1))."""
+    """(z (n*B, D), entropy (B,), d entropy / d kappa (B,)) = PowerSpherical(loc (B,D), kappa (B,)).rsample fused with
+    .entropy() in ONE launch (the training step evaluates both, mnist/mlp_vae.py:110-129); the two row scalars are plain
+    values re-attached to kappa by row_scalar().  draws None or (tprime (rows,), g (rows, D-1))."""
 
     @staticmethod
     def forward(ctx, loc, kappa, n_samples, draws):
@@ -525,6 +552,8 @@ class PowerSphericalRsample(torch.autograd.Function):
         rows = B * n_samples
         loc_c, kap_c = _f32c(loc), _f32c(kappa.reshape(-1))
         z = torch.empty(rows, D, device=dev, dtype=torch.float32)
+        ent = torch.empty(B, device=dev, dtype=torch.float32)
+        dent = torch.empty(B, device=dev, dtype=torch.float32)
         if draws is None:
             tp = g = None
             save = torch.empty(rows, 2, device=dev, dtype=torch.float32)
@@ -533,25 +562,30 @@ class PowerSphericalRsample(torch.autograd.Function):
             tp = _f32c(draws[0].reshape(rows))
             g = _f32c(draws[1].reshape(rows, D - 1))
             save, seed, off = None, 0, 0
-        _launch("cvb_powerspherical_rsample", dev, ptr(loc_c), ptr(kap_c), B, ptr(tp), ptr(g), seed, off, ptr(z),
-                ptr(save), rows, D, skip=z.numel() == 0)
+        _launch("cvb_powerspherical_rsample_kl", dev, ptr(loc_c), ptr(kap_c), B, ptr(tp), ptr(g), seed, off, ptr(z),
+                ptr(save), ptr(ent), None, ptr(dent), rows, D, skip=z.numel() == 0)
         ctx.save_for_backward(loc_c, kap_c, tp, g, save)
         ctx.meta = (B, D, rows, n_samples, seed, off, tuple(kappa.shape))
-        return z
+        ctx.mark_non_differentiable(ent, dent)
+        return z, ent, dent
 
     @staticmethod
-    def backward(ctx, grad_z):
+    def backward(ctx, grad_z, grad_ent, grad_dent):
         loc_c, kap_c, tp, g, save = ctx.saved_tensors
         B, D, rows, n_samples, seed, off, kshape = ctx.meta
-        gz = _f32c(grad_z).reshape(rows, D)
-        dloc = torch.empty(rows, D, device=gz.device, dtype=torch.float32)
-        dk = torch.empty(rows, device=gz.device, dtype=torch.float32)
-        _launch("cvb_powerspherical_rsample_backward", gz.device, ptr(gz), ptr(loc_c), ptr(kap_c), B, ptr(tp), ptr(g),
-                ptr(save), seed, off, ptr(dloc), ptr(dk), rows, D, skip=gz.numel() == 0)
-        if n_samples > 1:
-            dloc = dloc.view(n_samples, B, D).sum(0)
-            dk = dk.view(n_samples, B).sum(0)
-        return dloc, dk.reshape(kshape), None, None
+        dloc = dk = None
+        if grad_z is not None:
+            gz = _f32c(grad_z).reshape(rows, D)
+            dloc = torch.empty(rows, D, device=gz.device, dtype=torch.float32)
+            dk = torch.empty(rows, device=gz.device, dtype=torch.float32)
+            _launch("cvb_powerspherical_rsample_backward", gz.device, ptr(gz), ptr(loc_c), ptr(kap_c), B, ptr(tp), ptr(g),
+                    ptr(save), seed, off, ptr(dloc), ptr(dk), rows, D, skip=gz.numel() == 0)
+            if n_samples > 1:
+                dloc = dloc.view(n_samples, B, D).sum(0)
+                dk = dk.view(n_samples, B).sum(0)
+        if dloc is None and ctx.needs_input_grad[0]:
+            dloc = torch.zeros_like(loc_c)
+        return dloc, (None if dk is None else dk.reshape(kshape)), None, None
 
 
 class PowerSphericalLogProb(torch.autograd.Function):
@@ -602,7 +636,9 @@ class PSLogNormalizer(torch.autograd.Function):
 
 
 class VMFRsample(torch.autograd.Function):
-    """z (rows, D) = VonMisesFisher(loc (B,D), kappa (B,1)).rsample.
+    """(z (rows, D), entropy, log_norm, d entropy / d kappa, d log_norm / d kappa (B,) each) = VonMisesFisher(loc (B,D),
+    kappa (B,1)).rsample fused with the row's entropy and log-normaliser (von_mises_fisher.py:183-212) in ONE launch; the
+    row scalars are plain values re-attached to kappa by row_scalar().
     draws: None or (e_rounds (R, rows) f64 | None for D == 3, u_rounds (R, rows) f64, g (rows, D))."""
 
     @staticmethod
@@ -613,6 +649,7 @@ class VMFRsample(torch.autograd.Function):
         loc_c, kap_c = _f32c(loc), _f32c(kappa.reshape(-1))
         z = torch.empty(rows, D, device=dev, dtype=torch.float32)
         save = torch.empty(rows, 2, device=dev, dtype=torch.float32)
+        ent, ln, dent, dln = (torch.empty(B, device=dev, dtype=torch.float32) for _ in range(4))
         if draws is None:
             e = u = g = None
             R = 0
@@ -624,25 +661,30 @@ class VMFRsample(torch.autograd.Function):
             R = u.shape[0]
             g = _f32c(g.reshape(rows, D))
             seed, off = 0, 0
-        _launch("cvb_vmf_rsample", dev, ptr(loc_c), ptr(kap_c), B, ptr(e), ptr(u), R, ptr(g), seed, off, ptr(z), ptr(save),
-                rows, D, skip=z.numel() == 0)
+        _launch("cvb_vmf_rsample_kl", dev, ptr(loc_c), ptr(kap_c), B, ptr(e), ptr(u), R, ptr(g), seed, off, ptr(z), ptr(save),
+                ptr(ent), None, ptr(dent), ptr(ln), ptr(dln), rows, D, skip=z.numel() == 0)
         ctx.save_for_backward(loc_c, kap_c, g, save)
         ctx.meta = (B, D, rows, n_samples, seed, off, tuple(kappa.shape))
-        return z
+        ctx.mark_non_differentiable(ent, ln, dent, dln)
+        return z, ent, ln, dent, dln
 
     @staticmethod
-    def backward(ctx, grad_z):
+    def backward(ctx, grad_z, *unused):
         loc_c, kap_c, g, save = ctx.saved_tensors
         B, D, rows, n_samples, seed, off, kshape = ctx.meta
-        gz = _f32c(grad_z).reshape(rows, D)
-        dloc = torch.empty(rows, D, device=gz.device, dtype=torch.float32)
-        dk = torch.empty(rows, device=gz.device, dtype=torch.float32)
-        _launch("cvb_vmf_rsample_backward", gz.device, ptr(gz), ptr(loc_c), ptr(kap_c), B, ptr(g), ptr(save), seed, off,
-                ptr(dloc), ptr(dk), rows, D, skip=gz.numel() == 0)
-        if n_samples > 1:
-            dloc = dloc.view(n_samples, B, D).sum(0)
-            dk = dk.view(n_samples, B).sum(0)
-        return dloc, dk.reshape(kshape), None, None
+        dloc = dk = None
+        if grad_z is not None:
+            gz = _f32c(grad_z).reshape(rows, D)
+            dloc = torch.empty(rows, D, device=gz.device, dtype=torch.float32)
+            dk = torch.empty(rows, device=gz.device, dtype=torch.float32)
+            _launch("cvb_vmf_rsample_backward", gz.device, ptr(gz), ptr(loc_c), ptr(kap_c), B, ptr(g), ptr(save), seed, off,
+                    ptr(dloc), ptr(dk), rows, D, skip=gz.numel() == 0)
+            if n_samples > 1:
+                dloc = dloc.view(n_samples, B, D).sum(0)
+                dk = dk.view(n_samples, B).sum(0)
+        if dloc is None and ctx.needs_input_grad[0]:
+            dloc = torch.zeros_like(loc_c)
+        return dloc, (None if dk is None else dk.reshape(kshape)), None, None
 
 
 class VMFEntropyLogNorm(torch.autograd.Function):

@@ -76,6 +76,7 @@ class VonMisesFisher(torch.distributions.Distribution):
         self.device = loc.device
         self._m = loc.shape[-1]
         self.k = k
+        self._fused = None
         super().__init__(self.loc.size(), validate_args=validate_args)   # batch_shape quirk kept (:44)
 
     @property
@@ -102,10 +103,19 @@ class VonMisesFisher(torch.distributions.Distribution):
             n *= int(s)
         if _base_draws is None:
             _base_draws = testing.take()
-        z = ops.VMFRsample.apply(loc2, kap, n, _base_draws)
+        z, ent, ln, dent, dln = ops.VMFRsample.apply(loc2, kap, n, _base_draws)
+        if ent.numel() and tuple(self.scale.shape) == tuple(self.loc.shape[:-1]) + (1,):
+            shp = self.scale.shape[:-1]                     # same launch: entropy() / KL / log_prob reuse the row scalars
+            self._fused = (ops.row_scalar(self.scale, ent, dent).reshape(shp), ops.row_scalar(self.scale, ln, dln).reshape(shp))
         return z.reshape(tuple(shape) + tuple(self.loc.shape)).type(self.dtype)
 
     def _ent_ln(self):
+        cached = self._fused
+        if cached is not None:
+            stale = (torch.is_grad_enabled() and self.scale.requires_grad and cached[0].grad_fn is None
+                     and not cached[0].requires_grad)
+            if not stale:
+                return cached
         ent, ln = ops.VMFEntropyLogNorm.apply(self.scale, self._m)
         shp = self.scale.shape[:-1]
         return ent.reshape(shp), ln.reshape(shp)

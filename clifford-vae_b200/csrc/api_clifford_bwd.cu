@@ -23,7 +23,7 @@ int launch_bwd_fast(const CliffordBwdParams& p, cudaStream_t st) {
   int grid = 0;
   const long long work = (p.rows + Pl::GROUPS - 1) / Pl::GROUPS;
   if (int rc = persistent_grid(kern, Pl::THREADS, smem, work, &grid)) return rc;
-  kern<<<grid, Pl::THREADS, smem, st>>>(p, tw);
+  launch_pdl(kern, grid, Pl::THREADS, smem, st, p, tw);
   return check_launch("clifford_bwd_kernel");
 }
 

@@ -38,7 +38,7 @@ int launch_fwd_fast(const CliffordFwdParams& p, cudaStream_t st) {
   }
   CliffordFwdParams q = p;
   q.sched = dynamic ? next_sched_slot() : nullptr;
-  kern<<<grid, Pl::THREADS, smem, st>>>(q, tw, icdf);
+  launch_pdl(kern, grid, Pl::THREADS, smem, st, q, tw, icdf);
   return check_launch("clifford_fwd_kernel");
 }
 
@@ -56,7 +56,7 @@ int launch_fwd_bind(const CliffordFwdParams& p, cudaStream_t st) {
   CliffordFwdParams q = p;
   static const bool static_sched = getenv("CVB_STATIC_SCHEDULE") != nullptr;
   q.sched = (!static_sched && work > grid) ? next_sched_slot() : nullptr;
-  kern<<<grid, Pl::THREADS, smem, st>>>(q, tw, icdf);
+  launch_pdl(kern, grid, Pl::THREADS, smem, st, q, tw, icdf);
   return check_launch("clifford_fwd_kernel<bind>");
 }
 

@@ -53,6 +53,24 @@ int cvb_powerspherical_rsample(const float* loc, const float* kappa, long long l
   return launch_sphere_rsample<kFamilyPS>(p, (cudaStream_t)stream, "sphere_rsample_kernel<PS>");
 }
 
+// rsample fused with entropy() / KL to the uniform prior (dists/clifford.py:204-212, :335-337): one launch for the
+// training step's latent terms.  entropy / kl / dentropy: (loc_rows), each optional.
+int cvb_powerspherical_rsample_kl(const float* loc, const float* kappa, long long loc_rows, const float* tprime,
+                                  const float* gnoise, unsigned long long seed, unsigned long long offset, float* z,
+                                  float* save, float* entropy, float* kl, float* dentropy, long long rows, int D,
+                                  void* stream) {
+  CVB_REQUIRE(loc && kappa && z && rows > 0 && loc_rows > 0 && D >= 2, kBadArgument, "cvb_powerspherical_rsample_kl: bad arguments");
+  CVB_REQUIRE((tprime == nullptr) == (gnoise == nullptr), kBadArgument, "cvb_powerspherical_rsample_kl: give both tprime and gnoise or neither");
+  SphereParams p{};
+  p.loc = loc; p.kappa = kappa; p.loc_rows = loc_rows; p.tprime = tprime; p.gnoise = gnoise; p.g_pitch = D - 1;
+  p.g_off = 0; p.z = z; p.save = save; p.rows = rows; p.D = D; p.norm_eps = 1e-7f; p.clamp_eps = 1e-7f;
+  p.house_eps = 1e-7f; p.key = make_key(seed, offset, 0);
+  p.entropy = entropy; p.kl = kl; p.dentropy = dentropy;
+  // HypersphericalUniform.entropy (dists/clifford.py:109-121): ln 2 + (D/2) ln pi - lgamma(D/2)
+  p.prior_entropy = 0.69314718055994530942 + 0.5 * (double)D * 1.14472988584940017414 - lgamma(0.5 * (double)D);
+  return launch_sphere_rsample<kFamilyPS>(p, (cudaStream_t)stream, "sphere_rsample_kernel<PS,kl>");
+}
+
 int cvb_powerspherical_rsample_backward(const float* grad_z, const float* loc, const float* kappa, long long loc_rows,
                                         const float* tprime, const float* gnoise, const float* save,
                                         unsigned long long seed, unsigned long long offset, float* dloc, float* dkappa,
@@ -112,6 +130,28 @@ int cvb_vmf_rsample(const float* loc, const float* kappa, long long loc_rows, co
   p.n_rounds = n_rounds; p.gnoise = gnoise; p.g_pitch = D; p.g_off = 1; p.z = z; p.save = save; p.rows = rows; p.D = D;
   p.norm_eps = 0.0f; p.clamp_eps = 1e-10f; p.house_eps = 1e-5f; p.key = make_key(seed, offset, 0);
   return launch_sphere_rsample<kFamilyVMF>(p, (cudaStream_t)stream, "sphere_rsample_kernel<VMF>");
+}
+
+// rsample fused with entropy / KL to the uniform prior / log-normaliser (von_mises_fisher.py:183-217): one launch.
+int cvb_vmf_rsample_kl(const float* loc, const float* kappa, long long loc_rows, const double* e_rounds,
+                       const double* u_rounds, int n_rounds, const float* gnoise, unsigned long long seed,
+                       unsigned long long offset, float* z, float* save, float* entropy, float* kl, float* dentropy,
+                       float* log_norm, float* dlog_norm, long long rows, int D, void* stream) {
+  CVB_REQUIRE(loc && kappa && z && rows > 0 && loc_rows > 0 && D >= 2, kBadArgument, "cvb_vmf_rsample_kl: bad arguments");
+  const bool injected = gnoise != nullptr;
+  if (injected) {
+    CVB_REQUIRE(u_rounds && n_rounds >= 1 && (D == 3 || e_rounds), kBadArgument, "cvb_vmf_rsample_kl: injected mode needs e_rounds/u_rounds");
+  } else {
+    CVB_REQUIRE(!e_rounds && !u_rounds, kBadArgument, "cvb_vmf_rsample_kl: give all injected draws or none");
+  }
+  SphereParams p{};
+  p.loc = loc; p.kappa = kappa; p.loc_rows = loc_rows; p.e_rounds = e_rounds; p.u_rounds = u_rounds;
+  p.n_rounds = n_rounds; p.gnoise = gnoise; p.g_pitch = D; p.g_off = 1; p.z = z; p.save = save; p.rows = rows; p.D = D;
+  p.norm_eps = 0.0f; p.clamp_eps = 1e-10f; p.house_eps = 1e-5f; p.key = make_key(seed, offset, 0);
+  p.entropy = entropy; p.kl = kl; p.dentropy = dentropy; p.log_norm = log_norm; p.dlog_norm = dlog_norm;
+  // vMF HypersphericalUniform.entropy (hyperspherical_uniform.py:48-54) in fp32 like the reference's tensor
+  p.prior_entropy = (double)(float)(0.69314718055994530942 + 0.5 * (double)D * 1.14472988584940017414 - lgamma(0.5 * (double)D));
+  return launch_sphere_rsample<kFamilyVMF>(p, (cudaStream_t)stream, "sphere_rsample_kernel<VMF,kl>");
 }
 
 int cvb_vmf_rsample_backward(const float* grad_z, const float* loc, const float* kappa, long long loc_rows,

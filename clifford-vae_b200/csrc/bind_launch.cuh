@@ -29,7 +29,7 @@ int launch_bind_fast(const BindParams& p_in, cudaStream_t st) {
       auto kern = bind_v3_kernel<LOG2N, MODE, 2>;
       if (int rc = persistent_grid(kern, Pl::THREADS, smem, work, &grid)) return rc;
       p.sched = (!static_sched && work > grid) ? next_sched_slot() : nullptr;
-    kern<<<grid, Pl::THREADS, smem, st>>>(p, tw);
+    launch_pdl(kern, grid, Pl::THREADS, smem, st, p, tw);
       return check_launch("bind_v3_kernel<staged ab>");
     }
   }
@@ -37,7 +37,7 @@ int launch_bind_fast(const BindParams& p_in, cudaStream_t st) {
   auto kern = bind_v3_kernel<LOG2N, MODE, 0>;
   if (int rc = persistent_grid(kern, Pl::THREADS, smem, work, &grid)) return rc;
   p.sched = (!static_sched && work > grid) ? next_sched_slot() : nullptr;
-  kern<<<grid, Pl::THREADS, smem, st>>>(p, tw);
+  launch_pdl(kern, grid, Pl::THREADS, smem, st, p, tw);
   return check_launch("bind_v3_kernel<direct>");
 }
 

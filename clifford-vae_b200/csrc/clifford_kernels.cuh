@@ -284,6 +284,7 @@ constexpr size_t clifford_fwd_smem_bytes() {
 template <int LOG2N, int MODE, bool ROWK, bool BIND = false, bool LEAN = false>
 __global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS, (FftPlan<LOG2N>::THREADS <= 128 ? clifford_fwd_min_blocks<LOG2N, BIND, LEAN>() : 1))
 clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw, const float2* __restrict__ icdf) {
+  pdl_wait_and_release();
   using Pl = FftPlan<LOG2N>;
   constexpr int d = Pl::N, T = Pl::T, E = Pl::E, G = Pl::GROUPS;
   constexpr int NST = clifford_fwd_stages(MODE);
@@ -697,6 +698,7 @@ constexpr size_t clifford_bwd_smem_bytes() {
 template <int LOG2N, bool ROWK, bool FAST = false>
 __global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS, (FftPlan<LOG2N>::THREADS <= 128 ? clifford_bwd_min_blocks<LOG2N>() : 1))
 clifford_bwd_kernel(const CliffordBwdParams p, const cplx* __restrict__ tw) {
+  pdl_wait_and_release();
   using Pl = FftPlan<LOG2N>;
   constexpr int d = Pl::N, T = Pl::T, E = Pl::E, G = Pl::GROUPS;
   constexpr uint32_t kRowBytes = d * sizeof(float);
@@ -859,6 +861,7 @@ constexpr int kLpConstCache = 256;   // rows per group whose log-normaliser cons
 template <int LOG2N, bool ROWK, bool FWD_ONLY = false>
 __global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS, (FftPlan<LOG2N>::THREADS <= 128 ? ((FWD_ONLY && LOG2N <= 9) ? 5 : 4) : 1))
 clifford_log_prob_kernel(const CliffordLogProbParams p, const cplx* __restrict__ tw) {
+  pdl_wait_and_release();
   using Pl = FftPlan<LOG2N>;
   constexpr int d = Pl::N, T = Pl::T, E = Pl::E, G = Pl::GROUPS;
   extern __shared__ cplx smem[];

@@ -77,6 +77,13 @@ __device__ __forceinline__ void stg_stream1(float* p, float v) {
   asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 
+// Programmatic dependent launch: wait for the preceding kernel on the stream (no-op when launched without the attribute),
+// then let the NEXT kernel start becoming resident as this one's CTAs retire.
+__device__ __forceinline__ void pdl_wait_and_release() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // single-instruction MUFU.SQRT (max relative error 2^-23); sqrtf() expands to a refinement sequence
 __device__ __forceinline__ float fast_sqrt(float x) {
   float r;

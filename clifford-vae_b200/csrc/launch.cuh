@@ -87,6 +87,26 @@ inline PhiloxKey make_key(unsigned long long seed, unsigned long long offset, ui
   return k;
 }
 
+// Programmatic dependent launch (sm_90+): the kernel is allowed to become resident while its predecessor on the stream
+// drains; it blocks at pdl_wait() (griddepcontrol.wait) -- its first statement, before any global access to caller data --
+// until the predecessor has completed and flushed.  That removes the launch / scheduling gap between the back-to-back
+// kernels of a step (sampler -> bind -> sampler ...).  CVB_NO_PDL=1 restores plain launches (A/B switch).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int threads, size_t smem, cudaStream_t st, Args... args) {
+  static const bool no_pdl = getenv("CVB_NO_PDL") != nullptr;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = no_pdl ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 inline bool is_pow2(long long x) { return x > 0 && (x & (x - 1)) == 0; }
 inline int ilog2(long long x) { int l = 0; while ((1LL << l) < x) ++l; return l; }
 inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }

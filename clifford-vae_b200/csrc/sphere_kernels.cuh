@@ -33,6 +33,13 @@ struct SphereParams {
   long long rows;
   int D;
   float norm_eps, clamp_eps, house_eps;
+  // fused row scalars of the first sample of every parameter row (row < loc_rows), all optional:
+  float* entropy;            // (loc_rows)
+  float* kl;                 // (loc_rows): prior_entropy - entropy
+  float* dentropy;           // (loc_rows): d entropy / d kappa
+  float* log_norm;           // (loc_rows)  vMF only
+  float* dlog_norm;          // (loc_rows)  vMF only
+  double prior_entropy;
   PhiloxKey key;
 };
 
@@ -135,6 +142,67 @@ __device__ __forceinline__ WoodDraw vmf_draw_w(const SphereParams& p, long long 
 }
 
 // One warp per row.  FAMILY kFamilyUniform: z = g / (||g|| + norm_eps) with D tangent components.
+// vMF entropy (:183-191) / log-normaliser (:200-212) and kappa-derivatives, one thread per row, fp64.
+// Reproduces the reference's log(ive + 1e-20) (ive underflows to 0 for large orders) and its Bessel-
+// ratio bound ive_fraction_approx2 (ops/ive.py:63-79).
+__device__ __forceinline__ void bessel_ratio_bound(double v, double z, double a, double& B, double& dB) {
+  const double lam = v + (a - 1.0) / 2.0;
+  const double r = sqrt(fmax(lam * lam + z * z, 1e-20));
+  const double delta = (v - 0.5) + lam / (2.0 * r);
+  const double ddelta = -lam * z / (2.0 * r * r * r);
+  const double S = fmax(sqrt(delta * delta + z * z), 1e-20);
+  const double dS = (delta * ddelta + z) / S;
+  const double den = delta + S;
+  B = z / den;
+  dB = (den - z * (ddelta + dS)) / (den * den);
+}
+struct VmfRowScalars { float entropy, log_norm, dentropy, dlog_norm; };
+__device__ __forceinline__ VmfRowScalars vmf_row_scalars(double k, int D) {
+  const double m2 = 0.5 * (double)D, v = m2 - 1.0;
+  const double live = log_ive(v, k);
+  const double ive = exp(live);
+  const double lval = log(ive + 1e-20);
+  const double ln = -(v * log(k) - m2 * 1.83787706640934548356 - (k + lval));
+  // d ive/dk = ive(v-1) - ive(v) (v + k)/k   (ops/ive.py:29-34)
+  double im1;   // ive(v - 1, k); orders below zero only occur for m = 2 (I_{-1} = I_1) and m = 3 (closed form)
+  if (v >= 1.0) im1 = exp(log_ive(v - 1.0, k));
+  else if (v == 0.0) im1 = exp(log_ive(1.0, k));
+  else im1 = sqrt(2.0 / (3.14159265358979323846 * k)) * 0.5 * (1.0 + exp(-2.0 * k));
+  const double dive = im1 - ive * (v + k) / k;
+  const double dlval = dive / (ive + 1e-20);
+  const double dln = -(v / k - (1.0 + dlval));
+  const float ln_f = (float)ln;
+  double B0, dB0, B2, dB2;
+  bessel_ratio_bound(m2, k, 0.0, B0, dB0);
+  bessel_ratio_bound(m2, k, 2.0, B2, dB2);
+  const double frac = 0.5 * (B0 + B2), dfrac = 0.5 * (dB0 + dB2);
+  VmfRowScalars r;
+  r.log_norm = ln_f;
+  r.dlog_norm = (float)dln;
+  r.entropy = (float)(-k * frac + (double)ln_f);
+  r.dentropy = (float)(-frac - k * dfrac + dln);
+  return r;
+}
+
+// Fused row scalars (entropy / KL / their kappa-derivatives) of parameter row `prow`, written by ONE lane.
+template <int FAMILY>
+__device__ __forceinline__ void sphere_row_scalars(const SphereParams& p, long long prow) {
+  const double kap = (double)__ldg(p.kappa + prow);
+  if (FAMILY == kFamilyVMF) {
+    const VmfRowScalars r = vmf_row_scalars(kap, p.D);
+    if (p.entropy) p.entropy[prow] = r.entropy;
+    if (p.kl) p.kl[prow] = (float)(p.prior_entropy - (double)r.entropy);
+    if (p.dentropy) p.dentropy[prow] = r.dentropy;
+    if (p.log_norm) p.log_norm[prow] = r.log_norm;
+    if (p.dlog_norm) p.dlog_norm[prow] = r.dlog_norm;
+  } else {
+    const PsConsts c = ps_consts(kap, 0.5 * (double)(p.D - 1));
+    if (p.entropy) p.entropy[prow] = (float)c.entropy;
+    if (p.kl) p.kl[prow] = (float)(p.prior_entropy - c.entropy);
+    if (p.dentropy) p.dentropy[prow] = (float)c.dentropy;
+  }
+}
+
 template <int FAMILY>
 __global__ void __launch_bounds__(256)
 sphere_rsample_kernel(const SphereParams p) {
@@ -144,6 +212,8 @@ sphere_rsample_kernel(const SphereParams p) {
   const int D = p.D;
   for (long long row = warp; row < p.rows; row += nwarps) {
     float* zr = p.z + row * D;
+    if (FAMILY != kFamilyUniform && (p.entropy || p.kl || p.dentropy || p.log_norm) && row < p.loc_rows && lane == 31)
+      sphere_row_scalars<FAMILY>(p, row);
     if (FAMILY == kFamilyUniform) {
       float ss = 0.f;
       for (int q = lane; 4 * q < D; q += 32) {
@@ -253,6 +323,12 @@ sphere_rsample_reg_kernel(const SphereParams p) {
   // lane for one row (that was 37 % of the vMF kernel).  With fewer than 32 rows per warp the idle lanes simply skip.
   for (long long base = warp; base < p.rows; base += 32 * nwarps) {
   float w_l = 0.f, dw_l = 0.f;      // lane j: scalar draw of the batch's j-th row (vMF: w, dw/dkappa; PS: t')
+  if (FAMILY != kFamilyUniform && (p.entropy || p.kl || p.dentropy || p.log_norm)) {
+    // fused entropy / KL of the batch's rows: lane (j + 16) % 32 takes row j, so that with a single row per warp (small
+    // batches) the fp64 chain runs on lane 16 while lane 0 draws -- the two divergent paths interleave
+    const long long re = base + (long long)((lane + 16) & 31) * nwarps;
+    if (re < p.rows && re < p.loc_rows) sphere_row_scalars<FAMILY>(p, re);
+  }
   {
     const long long rj = base + (long long)lane * nwarps;
     if (rj < p.rows) {
@@ -576,46 +652,14 @@ static __global__ void ps_log_normalizer_kernel(const float* kappa, long long ro
   }
 }
 
-// vMF entropy (:183-191) / log-normaliser (:200-212) and kappa-derivatives, one thread per row, fp64.
-// Reproduces the reference's log(ive + 1e-20) (ive underflows to 0 for large orders) and its Bessel-
-// ratio bound ive_fraction_approx2 (ops/ive.py:63-79).
-__device__ __forceinline__ void bessel_ratio_bound(double v, double z, double a, double& B, double& dB) {
-  const double lam = v + (a - 1.0) / 2.0;
-  const double r = sqrt(fmax(lam * lam + z * z, 1e-20));
-  const double delta = (v - 0.5) + lam / (2.0 * r);
-  const double ddelta = -lam * z / (2.0 * r * r * r);
-  const double S = fmax(sqrt(delta * delta + z * z), 1e-20);
-  const double dS = (delta * ddelta + z) / S;
-  const double den = delta + S;
-  B = z / den;
-  dB = (den - z * (ddelta + dS)) / (den * den);
-}
 static __global__ void vmf_entropy_kernel(const float* kappa, long long rows, int D, float* entropy, float* log_norm,
                                           float* dentropy, float* dlog_norm) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (long long)gridDim.x * blockDim.x) {
-    const double k = (double)kappa[i];
-    const double m2 = 0.5 * (double)D, v = m2 - 1.0;
-    const double live = log_ive(v, k);
-    const double ive = exp(live);
-    const double lval = log(ive + 1e-20);
-    const double ln = -(v * log(k) - m2 * 1.83787706640934548356 - (k + lval));
-    // d ive/dk = ive(v-1) - ive(v) (v + k)/k   (ops/ive.py:29-34)
-    double im1;   // ive(v - 1, k); orders below zero only occur for m = 2 (I_{-1} = I_1) and m = 3 (closed form)
-    if (v >= 1.0) im1 = exp(log_ive(v - 1.0, k));
-    else if (v == 0.0) im1 = exp(log_ive(1.0, k));
-    else im1 = sqrt(2.0 / (3.14159265358979323846 * k)) * 0.5 * (1.0 + exp(-2.0 * k));
-    const double dive = im1 - ive * (v + k) / k;
-    const double dlval = dive / (ive + 1e-20);
-    const double dln = -(v / k - (1.0 + dlval));
-    const float ln_f = (float)ln;
-    double B0, dB0, B2, dB2;
-    bessel_ratio_bound(m2, k, 0.0, B0, dB0);
-    bessel_ratio_bound(m2, k, 2.0, B2, dB2);
-    const double frac = 0.5 * (B0 + B2), dfrac = 0.5 * (dB0 + dB2);
-    if (log_norm) log_norm[i] = ln_f;
-    if (dlog_norm) dlog_norm[i] = (float)dln;
-    if (entropy) entropy[i] = (float)(-k * frac + (double)ln_f);
-    if (dentropy) dentropy[i] = (float)(-frac - k * dfrac + dln);
+    const VmfRowScalars r = vmf_row_scalars((double)kappa[i], D);
+    if (log_norm) log_norm[i] = r.log_norm;
+    if (dlog_norm) dlog_norm[i] = r.dlog_norm;
+    if (entropy) entropy[i] = r.entropy;
+    if (dentropy) dentropy[i] = r.dentropy;
   }
 }
 

@@ -93,6 +93,7 @@ __device__ __forceinline__ void bind_pair(const cplx* park, const cplx* xch, con
 template <int LOG2N, int MODE, int STAGED>
 __global__ void __launch_bounds__(WideFftPlan<LOG2N>::THREADS, (WideFftPlan<LOG2N>::THREADS <= 128 ? (WideFftPlan<LOG2N>::E > 16 ? 2 : CVB_BIND_MINB) : ((WideFftPlan<LOG2N>::THREADS <= 256 && WideFftPlan<LOG2N>::E <= 16) ? 2 : 1)))
 bind_v3_kernel(const BindParams p, const cplx* __restrict__ tw) {
+  pdl_wait_and_release();
   using Pl = WideFftPlan<LOG2N>;
   constexpr int N = Pl::N, T = Pl::T, E = Pl::E, G = Pl::GROUPS;
   constexpr uint32_t kRowBytes = 2u * N * sizeof(float);

@@ -165,6 +165,12 @@ CVB_API int cvb_powerspherical_rsample(const float* loc, const float* kappa, lon
 /* Backward: grad_z (rows, D) -> dloc (rows, D), dkappa (rows).  Injected mode: pass the same tprime /
  * gnoise; RNG mode: pass save from the forward and the same (seed, offset) -- the tangent normals are
  * replayed from the counter-based generator instead of being stored. */
+/* The same sampler fused with entropy() / KL to HypersphericalUniform (dists/clifford.py:204-212, :335-337): ONE launch
+ * for the latent terms of a training step (BASELINE config 2).  entropy / kl / dentropy: (loc_rows), each may be NULL. */
+CVB_API int cvb_powerspherical_rsample_kl(const float* loc, const float* kappa, long long loc_rows, const float* tprime,
+                                          const float* gnoise, unsigned long long seed, unsigned long long offset,
+                                          float* z, float* save, float* entropy, float* kl, float* dentropy,
+                                          long long rows, int D, void* stream);
 CVB_API int cvb_powerspherical_rsample_backward(const float* grad_z, const float* loc, const float* kappa,
                                                 long long loc_rows, const float* tprime, const float* gnoise,
                                                 const float* save, unsigned long long seed, unsigned long long offset,
@@ -191,6 +197,12 @@ CVB_API int cvb_sphere_uniform_rsample(const float* gnoise, unsigned long long s
 CVB_API int cvb_vmf_rsample(const float* loc, const float* kappa, long long loc_rows, const double* e_rounds,
                             const double* u_rounds, int n_rounds, const float* gnoise, unsigned long long seed,
                             unsigned long long offset, float* z, float* save, long long rows, int D, void* stream);
+/* cvb_vmf_rsample fused with entropy / KL to the uniform prior / log-normaliser and their kappa-derivatives
+ * (von_mises_fisher.py:183-217): one launch; the five row outputs are (loc_rows) and optional. */
+CVB_API int cvb_vmf_rsample_kl(const float* loc, const float* kappa, long long loc_rows, const double* e_rounds,
+                               const double* u_rounds, int n_rounds, const float* gnoise, unsigned long long seed,
+                               unsigned long long offset, float* z, float* save, float* entropy, float* kl,
+                               float* dentropy, float* log_norm, float* dlog_norm, long long rows, int D, void* stream);
 CVB_API int cvb_vmf_rsample_backward(const float* grad_z, const float* loc, const float* kappa, long long loc_rows,
                                      const float* gnoise, const float* save, unsigned long long seed,
                                      unsigned long long offset, float* dloc, float* dkappa, long long rows, int D,

@@ -136,7 +136,7 @@ def test_rng_mode_invariants_and_backward_vs_oracle(B, d):
     torch.manual_seed(d + B)
     loc = (torch.randn(B, d, device=DEV) * 2).requires_grad_()
     kap = (torch.rand(B, 1, device=DEV) * 9.9 + 0.03).requires_grad_()
-    z, _ = ops.CliffordPSRsample.apply(loc, kap, 1, None, True)
+    z, _, _ = ops.CliffordPSRsample.apply(loc, kap, 1, None, True)
     F = torch.fft.rfft(z.detach().double(), dim=-1)
     assert float((F.abs() - 1).abs().max()) < 2e-5
     assert float((z.detach().double().norm(dim=-1) - 1).abs().max()) < 1e-5

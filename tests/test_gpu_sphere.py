@@ -157,3 +157,48 @@ def test_rng_mode_backward_consistency(family, B, D):
     dlo, dko = torch.autograd.grad((zo * gz.cpu()).sum(), [loc_c, kap_c])
     assert rel_err(dloc.cpu(), dlo) < 1e-4
     assert rel_err(dkap.cpu(), dko) < 2e-3
+
+
+@pytest.mark.parametrize("family", ["powerspherical", "vmf"])
+def test_fused_row_scalars_one_launch_and_separate_backward_passes(family, golden_ps, golden_vmf):
+    """rsample produces entropy (and the vMF log-normaliser) in the SAME launch; they are separate autograd nodes, so the
+    sample and the KL can be differentiated in two backward passes (like the reference's independent graphs) or in one."""
+    from clifford_b200 import _lib
+    from dists.clifford import PowerSpherical, HypersphericalUniform
+    from hyperspherical_vae.distributions import VonMisesFisher
+    from hyperspherical_vae.distributions.hyperspherical_uniform import HypersphericalUniform as VMFUniform
+    torch.manual_seed(0)
+    B, D = 64, 33
+    loc = torch.nn.functional.normalize(torch.randn(B, D, device=DEV), dim=-1).requires_grad_()
+    if family == "powerspherical":
+        kap = (torch.rand(B, device=DEV) * 8 + 0.5).requires_grad_()
+        make = lambda: (PowerSpherical(loc, kap), HypersphericalUniform(D, device=DEV))
+    else:
+        kap = (torch.rand(B, 1, device=DEV) * 8 + 0.5).requires_grad_()
+        make = lambda: (VonMisesFisher(loc, kap), VMFUniform(D - 1, device=DEV))
+    q, p = make()
+    n0 = _lib.launch_count()
+    z = q.rsample()
+    kl = torch.distributions.kl.kl_divergence(q, p)
+    ent = q.entropy()
+    assert _lib.launch_count() - n0 == 1                        # sampler + entropy + KL: one kernel
+    w = torch.randn_like(z)
+    (g1,) = torch.autograd.grad((z * w).sum(), [kap], retain_graph=False)
+    (g2,) = torch.autograd.grad(kl.sum(), [kap])               # second, independent backward pass
+    # against the unfused evaluation of the same quantities
+    q2, p2 = make()
+    kl2 = torch.distributions.kl.kl_divergence(q2, p2)         # no rsample before: the stand-alone entropy kernel
+    (g2_ref,) = torch.autograd.grad(kl2.sum(), [kap])
+    assert rel_err(kl.detach().cpu(), kl2.detach().cpu()) < 1e-6 and rel_err(g2.cpu(), g2_ref.cpu()) < 1e-6
+    assert rel_err(ent.detach().cpu(), q2.entropy().detach().cpu()) < 1e-6
+    assert torch.isfinite(g1).all() and float(g1.abs().max()) > 0
+    # one joint backward equals the sum
+    q3, p3 = make()
+    torch.manual_seed(1)
+    z3 = q3.rsample()
+    loss = (z3 * w).sum() + torch.distributions.kl.kl_divergence(q3, p3).sum()
+    (g3,) = torch.autograd.grad(loss, [kap])
+    torch.manual_seed(1)
+    q4, _ = make()
+    (g4,) = torch.autograd.grad((q4.rsample() * w).sum(), [kap])
+    assert rel_err(g3.cpu(), (g4 + g2_ref).cpu()) < 1e-5

@@ -26,7 +26,7 @@ def timeit(fn, reps=20):
 
 d = 2048
 n = 2 * d
-for B in (1024, 2048, 4096, 8192, 16384, 32768):
+for B in (148, 592, 1184, 2048, 4096, 8192, 16384, 32768):
     loc = torch.randn(B, d, device=dev); kap = torch.rand(B, device=dev) * 9.87 + 0.13
     z = torch.empty(B, n, device=dev); kl = torch.empty(B, device=dev)
     roles = torch.randn(B, n, device=dev) / n ** 0.5; out = torch.empty(B, n, device=dev)
