@@ -580,11 +580,11 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw, cons
       // spec[N-k] (the slot this thread just consumed).
       group_sync<LOG2N>();
 #pragma unroll
-      for (int e = 0; e < E; ++e) xch[pad16(t + e * T)] = v[e];
+      for (int e = E / 2; e < E; ++e) xch[pad16(t + e * T)] = v[e];      // partners only ever read bins > N/2
       group_sync<LOG2N>();
       auto pair = [&](int k, int kp, cplx zb, cplx& vk, cplx& vkp) {
         constexpr float fold = 0.5f / (2.0f * d);
-        const cplx zbp = cconj(xch[pad16(kp)]);
+        const cplx zbp = cconj(kp == k ? zb : xch[pad16(kp)]);
         const cplx w = __ldg(&tw[twiddle_offset(LOG2N) + k]);
         const cplx sb = cadd(zb, zbp), db = cmul_mi(cmul(w, csub(zb, zbp)));
         const cplx Bk = cadd(sb, db), Bkp = cconj(csub(sb, db));             // 2 R[k], 2 R[N-k]

@@ -75,7 +75,8 @@ __device__ __forceinline__ void bind_pair(const cplx* park, const cplx* xch, con
   constexpr float scale = 1.0f / (2.0f * N);
   constexpr float fold = (MODE == kBindDiv || MODE == kBindDivConj) ? scale : 0.25f * scale;
   const cplx za = park[k], zap = cconj(park[kp]);
-  const cplx zbp = cconj(xch[pad16(kp)]);
+  // self-paired bins (k = 0: DC / Nyquist, k = N/2) pair the thread's own value; only upper-half bins are exchanged
+  const cplx zbp = cconj(kp == k ? zb : xch[pad16(kp)]);
   const cplx w = __ldg(&tw[twiddle_offset(LOG2N) + k]);    // exp(-2 pi i k / n)
   // bins k and N-k of the real FFTs (X[N-k] uses W^(N-k) = -conj(W^k)); factor 1/2 each
   const cplx sa = cadd(za, zap), da = cmul_mi(cmul(w, csub(za, zap)));
@@ -170,7 +171,7 @@ bind_v3_kernel(const BindParams p, const cplx* __restrict__ tw) {
     // (the slot this thread just consumed), and every thread re-reads its upper-half points after one barrier.
     group_sync_p<Pl>();
 #pragma unroll
-    for (int e = 0; e < E; ++e) xch[pad16(t + e * T)] = v[e];
+    for (int e = E / 2; e < E; ++e) xch[pad16(t + e * T)] = v[e];      // partners only ever read bins > N/2
     group_sync_p<Pl>();
     auto pair = [&](int k, int kp, cplx zb, cplx& vk, cplx& vkp) { bind_pair<LOG2N, MODE>(park, xch, tw, k, kp, zb, vk, vkp); };
 #pragma unroll
@@ -250,7 +251,7 @@ bind_pad_kernel(const BindParams p, int n, const cplx* __restrict__ tw) {
     fft_run_p<Pl, false>(v, xch, t, tw);
     group_sync_p<Pl>();
 #pragma unroll
-    for (int e = 0; e < E; ++e) xch[pad16(t + e * T)] = v[e];
+    for (int e = E / 2; e < E; ++e) xch[pad16(t + e * T)] = v[e];
     group_sync_p<Pl>();
 #pragma unroll
     for (int e = 0; e < E / 2; ++e) {
