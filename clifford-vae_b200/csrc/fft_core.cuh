@@ -22,7 +22,7 @@ namespace cvb {
 // two-pass 32 x 32 plan for bind at N = 1024 was also measured: 43.9 % vs 47.1 % of the HBM roofline, not adopted.)
 constexpr int default_loge(int log2n) { return (log2n >= 8) ? 4 : (log2n >= 6 ? 3 : 2); }
 
-template <int LOG2N_, int LOGE_>
+template <int LOG2N_, int LOGE_, int MINTHREADS_ = 128>
 struct FftPlanT {
   static_assert(LOG2N_ >= 4 && LOG2N_ <= 13, "fast path covers N = 16 .. 8192 complex points");
   static constexpr int LOG2N = LOG2N_;
@@ -32,7 +32,7 @@ struct FftPlanT {
   static constexpr int T = N / E;                  // threads per FFT
   static constexpr int LOGT = LOG2N - LOGE;
   static constexpr int XCH = pad16(N) + 2;         // float2 slots in one exchange buffer (index N usable)
-  static constexpr int THREADS = (T >= 128) ? T : 128;   // CTA size
+  static constexpr int THREADS = (T >= MINTHREADS_) ? T : MINTHREADS_;   // CTA size
   static constexpr int GROUPS = THREADS / T;       // FFTs processed side by side in one CTA
 };
 template <int LOG2N>
@@ -169,9 +169,86 @@ struct Dft<32, INV> {
   }
 };
 
+
+// 64-point DFT as 8 x 8 (decimation n = n1 + 8 n2, k = 8 k1 + k2): used by the 64-points-per-thread plans (one warp per
+// 2048-point transform, ONE shared-memory exchange per transform instead of two).
+template <bool INV>
+struct Dft<64, INV> {
+  static __device__ __forceinline__ void run(cplx (&u)[64]) {
+    // cos / sin of 2 pi m / 64, m = 0 .. 15 (first quadrant; the rest by symmetry)
+    constexpr float C[17] = {1.0f, 0.99518472667219688624f, 0.98078528040323044913f, 0.95694033573220886494f,
+                             0.92387953251128675613f, 0.88192126434835502971f, 0.83146961230254523708f, 0.77301045336273696081f,
+                             0.70710678118654752440f, 0.63439328416364549822f, 0.55557023301960222474f, 0.47139673682599764856f,
+                             0.38268343236508977173f, 0.29028467725446236764f, 0.19509032201612826785f, 0.09801714032956060199f, 0.0f};
+    // stage 1: for each n1, DFT-8 over n2 of x[n1 + 8 n2] -> Y[n1][k2] left at slot n1 + 8 k2
+#pragma unroll
+    for (int n1 = 0; n1 < 8; ++n1) {
+      cplx w[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) w[j] = u[n1 + 8 * j];
+      Dft<8, INV>::run(w);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) u[n1 + 8 * j] = w[j];
+    }
+    // stage 2: Y[n1][k2] *= W64^(n1 k2)
+#pragma unroll
+    for (int n1 = 1; n1 < 8; ++n1) {
+#pragma unroll
+      for (int k2 = 1; k2 < 8; ++k2) {
+        const int m = n1 * k2;              // 1 .. 49
+        const int q = m >> 4, r = m & 15;   // quadrant, offset: angle = (16 q + r) 2 pi / 64
+        // cos / sin of the first-quadrant offset, then rotate by q quarter turns
+        const float c0 = C[r], s0 = C[16 - r];
+        const float c = (q == 0) ? c0 : (q == 1) ? -s0 : (q == 2) ? -c0 : s0;
+        const float sn = (q == 0) ? s0 : (q == 1) ? c0 : (q == 2) ? -s0 : -c0;
+        cplx& z = u[n1 + 8 * k2];
+        if (r == 0) {
+          z = (q == 1) ? (INV ? cmul_i(z) : cmul_mi(z)) : (q == 2) ? make_float2(-z.x, -z.y) : (INV ? cmul_mi(z) : cmul_i(z));
+        } else {
+          z = rot<INV>(z, c, sn);
+        }
+      }
+    }
+    // stage 3: for each k2, DFT-8 over n1 -> X[8 k1 + k2] left at slot k1 + 8 k2
+#pragma unroll
+    for (int k2 = 0; k2 < 8; ++k2) {
+      cplx w[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) w[j] = u[8 * k2 + j];
+      Dft<8, INV>::run(w);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) u[8 * k2 + j] = w[j];
+    }
+    // 8 x 8 register transpose (renaming only after unrolling): slot k1 + 8 k2 holds X[8 k1 + k2]
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+#pragma unroll
+      for (int b = a + 1; b < 8; ++b) {
+        const cplx tmp = u[a + 8 * b];
+        u[a + 8 * b] = u[b + 8 * a];
+        u[b + 8 * a] = tmp;
+      }
+    }
+  }
+};
+
 // u[r] *= w1^r, r = 1..R-1 (powers built by squaring / one extra multiply: depth <= 2 log2 R)
 template <int R>
 __device__ __forceinline__ void apply_twiddle_powers(cplx (&u)[R], cplx w1) {
+  if constexpr (R > 16) {
+    // streaming form for the wide butterflies: w^r = w^(r-1) w, re-anchored by squaring at every power of two
+    // (w^2, w^4, ... are the only powers kept live) so the chain's round-off stays at a few ulp
+    cplx pw = w1, cur = w1;              // pw: last power-of-two power; cur: w^(r-1)
+#pragma unroll
+    for (int i = 1; i < R; ++i) {
+      if (i > 1) {
+        if ((i & (i - 1)) == 0) { pw = cmul(pw, pw); cur = pw; }
+        else cur = cmul(cur, w1);
+      }
+      u[i] = cmul(u[i], cur);
+    }
+    return;
+  }
   cplx w[R];
   w[1] = w1;
 #pragma unroll
