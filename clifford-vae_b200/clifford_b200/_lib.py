@@ -60,6 +60,12 @@ _SIGNATURES = {
     "cvb_vmf_rsample_kl": ([_f, _f, _ll, _f, _f, _i, _f, _ull, _ull, _f, _f, _f, _f, _f, _f, _f, _ll, _i, _f], _i),
     "cvb_vmf_rsample_backward": ([_f, _f, _f, _ll, _f, _f, _ull, _ull, _f, _f, _ll, _i, _f], _i),
     "cvb_vmf_entropy_lognorm": ([_f, _ll, _i, _f, _f, _f, _f, _f], _i),
+    "cvb_clifford_ps_rsample_head": ([_f, _f, _ll, _fl, _fl, _f, _f, _ull, _ull, _f, _f, _f, _f, _f, _ll, _i, _f], _i),
+    "cvb_clifford_ps_rsample_backward_head": ([_f, _f, _f, _ll, _fl, _fl, _f, _f, _f, _f, _f, _ll, _i, _f], _i),
+    "cvb_powerspherical_rsample_kl_head": ([_f, _f, _ll, _fl, _fl, _f, _f, _ull, _ull, _f, _f, _f, _f, _f, _ll, _i, _f], _i),
+    "cvb_powerspherical_rsample_backward_head": ([_f, _f, _f, _ll, _fl, _fl, _f, _f, _f, _ull, _ull, _f, _f, _ll, _i, _f], _i),
+    "cvb_vmf_rsample_kl_head": ([_f, _f, _ll, _fl, _fl, _f, _f, _i, _f, _ull, _ull, _f, _f, _f, _f, _f, _f, _f, _ll, _i, _f], _i),
+    "cvb_vmf_rsample_backward_head": ([_f, _f, _f, _ll, _fl, _fl, _f, _f, _ull, _ull, _f, _f, _ll, _i, _f], _i),
     "cvb_set_rng_device_counter": ([_f], _i),
     "cvb_ps_halfangle_icdf_table": ([_f, _ll, _f, _f, _f], _i),
     "cvb_philox_fill": ([_f, _ll, _ull, _ull, _f], _i),

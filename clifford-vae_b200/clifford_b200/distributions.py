@@ -20,6 +20,13 @@ from . import ops, testing
 _LOG_2PI = math.log(2 * math.pi)
 
 
+def head_concentration(raw_scale, floor, kmax):
+    """The reference models' concentration head as torch ops (mnist/mlp_vae.py:69-71, cnn/models.py:96,99) -- what the
+    ``from_head`` constructors fold into the sampling kernels; used only when a head-built distribution is asked for its
+    ``concentration`` / ``scale`` attribute or for a method outside the fused training path."""
+    return torch.clamp(torch.nn.functional.softplus(raw_scale) + floor, max=kmax)
+
+
 def _numel(shape) -> int:
     n = 1
     for s in shape:
@@ -73,7 +80,33 @@ class PowerSpherical(Distribution):
         self.loc, self.scale = loc, scale
         self.dim = loc.shape[-1]
         self._fused_entropy = None
+        self._head = None
         super().__init__(batch_shape=scale.shape, event_shape=torch.Size([self.dim]), validate_args=False)
+
+    @classmethod
+    def from_head(cls, loc, raw_scale, floor=0.8, max=10.0):
+        """Extension: PowerSpherical(loc, clamp(softplus(raw_scale) + floor, max=max)) with the
+        softplus + floor + clamp of the models' concentration head (mnist/mlp_vae.py:69-71: floor 0.8; cnn/models.py:96:
+        floor 0.5) evaluated INSIDE the sampling kernel and its backward, so rsample() + kl_divergence stay one launch
+        from the raw `fc_scale` output.  raw_scale: batch_shape or batch_shape + (1,).  `.scale` is materialised (torch
+        ops) only if something asks for it."""
+        self = cls.__new__(cls)
+        if raw_scale.dim() == loc.dim() and raw_scale.shape[-1] == 1:
+            raw_scale = raw_scale.squeeze(-1)
+        self.loc = loc
+        self.dim = loc.shape[-1]
+        self._fused_entropy = None
+        self._head = (float(floor), float(max))
+        self._raw_scale = raw_scale
+        Distribution.__init__(self, batch_shape=raw_scale.shape, event_shape=torch.Size([self.dim]), validate_args=False)
+        return self
+
+    def __getattr__(self, name):
+        # head-built instances: the concentration as a tensor, evaluated lazily (and differentiably) on first use
+        if name == "scale" and self.__dict__.get("_head") is not None:
+            self.__dict__["scale"] = head_concentration(self._raw_scale, *self._head)
+            return self.__dict__["scale"]
+        raise AttributeError(name)
 
     def _flat(self):
         D = self.dim
@@ -82,13 +115,20 @@ class PowerSpherical(Distribution):
 
     def rsample(self, sample_shape=torch.Size(), _base_draws=None):
         sample_shape = torch.Size(sample_shape)
-        loc2, kap = self._flat()
         n = _numel(sample_shape)
         if _base_draws is None:
             _base_draws = testing.take()
-        z, ent, dent = ops.PowerSphericalRsample.apply(loc2, kap, n, _base_draws)
+        if self._head is not None:
+            D = self.dim
+            loc2 = self.loc.expand(tuple(self.batch_shape) + (D,)).reshape(-1, D)
+            param = self._raw_scale
+            z, ent, dent = ops.PowerSphericalRsample.apply(loc2, param.reshape(-1), n, _base_draws, self._head)
+        else:
+            loc2, kap = self._flat()
+            param = self.scale
+            z, ent, dent = ops.PowerSphericalRsample.apply(loc2, kap, n, _base_draws)
         if ent.numel():                                             # same launch; entropy() / kl_divergence reuse it
-            self._fused_entropy = ops.row_scalar(self.scale, ent, dent).reshape(self.scale.shape)
+            self._fused_entropy = ops.row_scalar(param, ent, dent).reshape(param.shape)
         return z.reshape(tuple(sample_shape) + tuple(self.batch_shape) + (self.dim,)).to(self.loc.dtype)
 
     def sample(self, sample_shape=torch.Size()):
@@ -110,7 +150,8 @@ class PowerSpherical(Distribution):
     def entropy(self):
         cached = self._fused_entropy
         if cached is not None:
-            stale = (torch.is_grad_enabled() and torch.is_tensor(self.scale) and self.scale.requires_grad
+            param = self._raw_scale if self._head is not None else self.scale
+            stale = (torch.is_grad_enabled() and torch.is_tensor(param) and param.requires_grad
                      and cached.grad_fn is None and not cached.requires_grad)
             if not stale:
                 return cached.to(self.loc.dtype)
@@ -204,6 +245,7 @@ class CliffordPowerSphericalDistribution(CliffordTorusDistribution):
         self.dtype = loc.dtype
         self._fused_entropy = None
         self._sample_log_prob = None      # (weakref to the last no-grad sample, its version, its log_prob)
+        self._head = None
         d = self.orig_dim
         conc = self.concentration
         # one concentration per row (every reference driver) vs a full (.., d) tensor
@@ -215,18 +257,58 @@ class CliffordPowerSphericalDistribution(CliffordTorusDistribution):
         else:
             self._kappa = conc
 
+    @classmethod
+    def from_head(cls, loc, raw_scale, floor=0.03, max=10.0, normalize_ifft: bool = False):
+        """Extension: CliffordPowerSphericalDistribution(loc, clamp(softplus(raw_scale) + floor,
+        max=max)) with the concentration head of the reference models (mnist/mlp_vae.py:69-71: floor 0.03;
+        cnn/models.py:99: floor = concentration_floor) evaluated INSIDE the fused sampling kernel and its backward:
+        rsample() + kl_divergence stay ONE launch from the raw `fc_scale` / `fc_concentration` output and the gradient
+        arrives at that raw tensor with the softplus / clamp chain already applied.  raw_scale: batch_shape + (1,).
+        `.concentration` is materialised (torch ops) only if something asks for it."""
+        self = cls.__new__(cls)
+        d = loc.shape[-1]
+        if raw_scale.shape[-1] != 1:
+            raise ValueError("from_head needs one raw concentration per row: raw_scale of shape batch_shape + (1,)")
+        Distribution.__init__(self, batch_shape=loc.shape[:-1], event_shape=torch.Size([2 * d]), validate_args=False)
+        self.loc = loc
+        self.orig_dim = d
+        self.normalize_ifft = normalize_ifft
+        self.dtype = loc.dtype
+        self._fused_entropy = None
+        self._sample_log_prob = None
+        self._head = (float(floor), float(max))
+        self._raw_scale = raw_scale.expand(tuple(self.batch_shape) + (1,))
+        return self
+
+    def __getattr__(self, name):
+        # head-built instances: the concentration tensors, evaluated lazily (and differentiably) on first use
+        if name in ("_kappa", "concentration", "_raw_concentration") and self.__dict__.get("_head") is not None:
+            kap = head_concentration(self._raw_scale, *self._head)
+            self.__dict__["_kappa"] = kap
+            self.__dict__["_raw_concentration"] = kap
+            self.__dict__["concentration"] = kap.expand_as(self.loc)
+            return self.__dict__[name]
+        raise AttributeError(name)
+
     def _flat(self):
         d = self.orig_dim
         return self.loc.reshape(-1, d), self._kappa.reshape(-1, self._kappa.shape[-1])
 
     def rsample(self, sample_shape=torch.Size(), _base_draws=None) -> torch.Tensor:
         sample_shape = torch.Size(sample_shape)
-        loc2, kap2 = self._flat()
         n = _numel(sample_shape)
         d = self.orig_dim
         out_shape = tuple(sample_shape) + tuple(self.batch_shape) + (2 * d,)
         if _base_draws is None:
             _base_draws = testing.take()
+        if self._head is not None and torch.is_grad_enabled() and (self.loc.requires_grad or self._raw_scale.requires_grad):
+            # training path from the raw head output: softplus + floor + clamp inside the kernel
+            raw2 = self._raw_scale.reshape(-1, 1)
+            z, ent, dent = ops.CliffordPSRsample.apply(self.loc.reshape(-1, d), raw2, n, _base_draws, True, self._head)
+            if ent.numel():
+                self._fused_entropy = ops.row_scalar(raw2, ent, dent).reshape(self.batch_shape)
+            return z.reshape(out_shape).to(self.dtype)
+        loc2, kap2 = self._flat()
         no_grad = not (torch.is_grad_enabled() and (loc2.requires_grad or kap2.requires_grad))
         if (no_grad and len(sample_shape) > 0 and kap2.shape[-1] == 1 and 16 <= d <= 8192 and (d & (d - 1)) == 0
                 and loc2.shape[0] > 0 and n > 0):
@@ -287,7 +369,8 @@ class CliffordPowerSphericalDistribution(CliffordTorusDistribution):
         if cached is not None:
             # a value cached by a no-grad rsample (evaluation path) carries no graph: recompute when the caller now
             # wants d entropy / d kappa
-            stale = (torch.is_grad_enabled() and self._kappa.requires_grad and cached.grad_fn is None
+            param = self._raw_scale if self._head is not None else self._kappa
+            stale = (torch.is_grad_enabled() and param.requires_grad and cached.grad_fn is None
                      and not cached.requires_grad)
             if not stale:
                 return cached.to(self.dtype)

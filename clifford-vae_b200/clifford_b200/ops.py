@@ -99,15 +99,21 @@ class CliffordPSRsample(torch.autograd.Function):
     draws: None (device Philox) or (tprime, g) each (n_samples*B, d) -- parity mode.
     Returns (z (rows, 2d), entropy (B,), d entropy / d kappa (B,)); the last two are plain values (empty when kappa is per
     element or n_samples > 1) that the distribution re-attaches to kappa with row_scalar().
+
+    head = (floor, kmax): `kappa` is the RAW (B, 1) output of the concentration layer and the kernels evaluate
+    kappa = min(softplus(raw) + floor, kmax) themselves (mnist/mlp_vae.py:69-71, cnn/models.py:96,99); every
+    kappa-gradient returned is then the gradient with respect to that raw tensor.
     """
 
     @staticmethod
-    def forward(ctx, loc, kappa, n_samples, draws, want_entropy):
+    def forward(ctx, loc, kappa, n_samples, draws, want_entropy, head=None):
         lib, dev = _prep(loc, kappa)
         B, d = loc.shape
         rows = B * n_samples
         loc_c = _f32c(loc)
         kap_c, krs, kes = _kappa_layout(kappa, d)
+        if head is not None and kes != 0:
+            raise NotImplementedError("the folded concentration head needs one raw value per row, shape (B, 1)")
         z = torch.empty(rows, 2 * d, device=dev, dtype=torch.float32)
         need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
         fused_ent = bool(want_entropy) and kes == 0 and n_samples == 1
@@ -121,9 +127,14 @@ class CliffordPSRsample(torch.autograd.Function):
             tp, g = (_f32c(t.reshape(rows, d)) for t in draws)
             tp_signed = None
             seed, off = 0, 0
-        _launch("cvb_clifford_ps_rsample", dev, ptr(loc_c), ptr(kap_c), krs, kes, B, ptr(tp), ptr(g), seed, off, ptr(z),
-                ptr(tp_signed), ptr(ent), None, ptr(dent), rows, d, skip=rows == 0 or d == 0)
+        if head is None:
+            _launch("cvb_clifford_ps_rsample", dev, ptr(loc_c), ptr(kap_c), krs, kes, B, ptr(tp), ptr(g), seed, off, ptr(z),
+                    ptr(tp_signed), ptr(ent), None, ptr(dent), rows, d, skip=rows == 0 or d == 0)
+        else:
+            _launch("cvb_clifford_ps_rsample_head", dev, ptr(loc_c), ptr(kap_c), B, float(head[0]), float(head[1]), ptr(tp),
+                    ptr(g), seed, off, ptr(z), ptr(tp_signed), ptr(ent), None, ptr(dent), rows, d, skip=rows == 0 or d == 0)
         ctx.save_for_backward(loc_c, kap_c, tp, g, tp_signed)
+        ctx.head = head
         ctx.meta = (B, d, rows, n_samples, krs, kes, tuple(kappa.shape))
         if ent is None:
             ent, dent = z.new_empty(0), z.new_empty(0)
@@ -139,8 +150,13 @@ class CliffordPSRsample(torch.autograd.Function):
             gz = _f32c(grad_z)
             dloc_rows = torch.empty(rows, d, device=gz.device, dtype=torch.float32)
             dk_rows = torch.empty((rows,) if kes == 0 else (rows, d), device=gz.device, dtype=torch.float32)
-            _launch("cvb_clifford_ps_rsample_backward", gz.device, ptr(gz), ptr(loc_c), ptr(kap_c), krs, kes, B, ptr(tp),
-                    ptr(g), ptr(tp_signed), ptr(dloc_rows), ptr(dk_rows), rows, d, skip=rows == 0 or d == 0)
+            if ctx.head is None:
+                _launch("cvb_clifford_ps_rsample_backward", gz.device, ptr(gz), ptr(loc_c), ptr(kap_c), krs, kes, B, ptr(tp),
+                        ptr(g), ptr(tp_signed), ptr(dloc_rows), ptr(dk_rows), rows, d, skip=rows == 0 or d == 0)
+            else:
+                _launch("cvb_clifford_ps_rsample_backward_head", gz.device, ptr(gz), ptr(loc_c), ptr(kap_c), B,
+                        float(ctx.head[0]), float(ctx.head[1]), ptr(tp), ptr(g), ptr(tp_signed), ptr(dloc_rows),
+                        ptr(dk_rows), rows, d, skip=rows == 0 or d == 0)
             if n_samples > 1:
                 dloc_rows = dloc_rows.view(n_samples, B, d).sum(0)
                 dk_rows = dk_rows.view(n_samples, B, -1).sum(0) if kes else dk_rows.view(n_samples, B).sum(0)
@@ -148,7 +164,7 @@ class CliffordPSRsample(torch.autograd.Function):
             dkap = dk_rows.reshape(kshape)
         if dloc is None and ctx.needs_input_grad[0]:
             dloc = torch.zeros_like(loc_c)
-        return dloc, dkap, None, None, None
+        return dloc, dkap, None, None, None, None
 
 
 def clifford_rsample_bind(loc, kappa, other, n_samples=1, draws=None, want_sample=True):
@@ -546,7 +562,7 @@ class PowerSphericalRsample(torch.autograd.Function):
     values re-attached to kappa by row_scalar().  draws None or (tprime (rows,), g (rows, D-1))."""
 
     @staticmethod
-    def forward(ctx, loc, kappa, n_samples, draws):
+    def forward(ctx, loc, kappa, n_samples, draws, head=None):
         lib, dev = _prep(loc, kappa)
         B, D = loc.shape
         rows = B * n_samples
@@ -554,6 +570,8 @@ class PowerSphericalRsample(torch.autograd.Function):
         z = torch.empty(rows, D, device=dev, dtype=torch.float32)
         ent = torch.empty(B, device=dev, dtype=torch.float32)
         dent = torch.empty(B, device=dev, dtype=torch.float32)
+        hd = () if head is None else (float(head[0]), float(head[1]))      # head: kappa is the raw layer output
+        sfx = "" if head is None else "_head"
         if draws is None:
             tp = g = None
             save = torch.empty(rows, 2, device=dev, dtype=torch.float32)
@@ -562,9 +580,10 @@ class PowerSphericalRsample(torch.autograd.Function):
             tp = _f32c(draws[0].reshape(rows))
             g = _f32c(draws[1].reshape(rows, D - 1))
             save, seed, off = None, 0, 0
-        _launch("cvb_powerspherical_rsample_kl", dev, ptr(loc_c), ptr(kap_c), B, ptr(tp), ptr(g), seed, off, ptr(z),
+        _launch("cvb_powerspherical_rsample_kl" + sfx, dev, ptr(loc_c), ptr(kap_c), B, *hd, ptr(tp), ptr(g), seed, off, ptr(z),
                 ptr(save), ptr(ent), None, ptr(dent), rows, D, skip=z.numel() == 0)
         ctx.save_for_backward(loc_c, kap_c, tp, g, save)
+        ctx.head = (sfx, hd)
         ctx.meta = (B, D, rows, n_samples, seed, off, tuple(kappa.shape))
         ctx.mark_non_differentiable(ent, dent)
         return z, ent, dent
@@ -578,14 +597,15 @@ class PowerSphericalRsample(torch.autograd.Function):
             gz = _f32c(grad_z).reshape(rows, D)
             dloc = torch.empty(rows, D, device=gz.device, dtype=torch.float32)
             dk = torch.empty(rows, device=gz.device, dtype=torch.float32)
-            _launch("cvb_powerspherical_rsample_backward", gz.device, ptr(gz), ptr(loc_c), ptr(kap_c), B, ptr(tp), ptr(g),
-                    ptr(save), seed, off, ptr(dloc), ptr(dk), rows, D, skip=gz.numel() == 0)
+            sfx, hd = ctx.head
+            _launch("cvb_powerspherical_rsample_backward" + sfx, gz.device, ptr(gz), ptr(loc_c), ptr(kap_c), B, *hd, ptr(tp),
+                    ptr(g), ptr(save), seed, off, ptr(dloc), ptr(dk), rows, D, skip=gz.numel() == 0)
             if n_samples > 1:
                 dloc = dloc.view(n_samples, B, D).sum(0)
                 dk = dk.view(n_samples, B).sum(0)
         if dloc is None and ctx.needs_input_grad[0]:
             dloc = torch.zeros_like(loc_c)
-        return dloc, (None if dk is None else dk.reshape(kshape)), None, None
+        return dloc, (None if dk is None else dk.reshape(kshape)), None, None, None
 
 
 class PowerSphericalLogProb(torch.autograd.Function):
@@ -642,11 +662,13 @@ class VMFRsample(torch.autograd.Function):
     draws: None or (e_rounds (R, rows) f64 | None for D == 3, u_rounds (R, rows) f64, g (rows, D))."""
 
     @staticmethod
-    def forward(ctx, loc, kappa, n_samples, draws):
+    def forward(ctx, loc, kappa, n_samples, draws, head=None):
         lib, dev = _prep(loc, kappa)
         B, D = loc.shape
         rows = B * n_samples
         loc_c, kap_c = _f32c(loc), _f32c(kappa.reshape(-1))
+        hd = () if head is None else (float(head[0]), float(head[1]))      # head: kappa is the raw layer output
+        sfx = "" if head is None else "_head"
         z = torch.empty(rows, D, device=dev, dtype=torch.float32)
         save = torch.empty(rows, 2, device=dev, dtype=torch.float32)
         ent, ln, dent, dln = (torch.empty(B, device=dev, dtype=torch.float32) for _ in range(4))
@@ -661,9 +683,10 @@ class VMFRsample(torch.autograd.Function):
             R = u.shape[0]
             g = _f32c(g.reshape(rows, D))
             seed, off = 0, 0
-        _launch("cvb_vmf_rsample_kl", dev, ptr(loc_c), ptr(kap_c), B, ptr(e), ptr(u), R, ptr(g), seed, off, ptr(z), ptr(save),
-                ptr(ent), None, ptr(dent), ptr(ln), ptr(dln), rows, D, skip=z.numel() == 0)
+        _launch("cvb_vmf_rsample_kl" + sfx, dev, ptr(loc_c), ptr(kap_c), B, *hd, ptr(e), ptr(u), R, ptr(g), seed, off, ptr(z),
+                ptr(save), ptr(ent), None, ptr(dent), ptr(ln), ptr(dln), rows, D, skip=z.numel() == 0)
         ctx.save_for_backward(loc_c, kap_c, g, save)
+        ctx.head = (sfx, hd)
         ctx.meta = (B, D, rows, n_samples, seed, off, tuple(kappa.shape))
         ctx.mark_non_differentiable(ent, ln, dent, dln)
         return z, ent, ln, dent, dln
@@ -677,14 +700,15 @@ class VMFRsample(torch.autograd.Function):
             gz = _f32c(grad_z).reshape(rows, D)
             dloc = torch.empty(rows, D, device=gz.device, dtype=torch.float32)
             dk = torch.empty(rows, device=gz.device, dtype=torch.float32)
-            _launch("cvb_vmf_rsample_backward", gz.device, ptr(gz), ptr(loc_c), ptr(kap_c), B, ptr(g), ptr(save), seed, off,
-                    ptr(dloc), ptr(dk), rows, D, skip=gz.numel() == 0)
+            sfx, hd = ctx.head
+            _launch("cvb_vmf_rsample_backward" + sfx, gz.device, ptr(gz), ptr(loc_c), ptr(kap_c), B, *hd, ptr(g), ptr(save),
+                    seed, off, ptr(dloc), ptr(dk), rows, D, skip=gz.numel() == 0)
             if n_samples > 1:
                 dloc = dloc.view(n_samples, B, D).sum(0)
                 dk = dk.view(n_samples, B).sum(0)
         if dloc is None and ctx.needs_input_grad[0]:
             dloc = torch.zeros_like(loc_c)
-        return dloc, (None if dk is None else dk.reshape(kshape)), None, None
+        return dloc, (None if dk is None else dk.reshape(kshape)), None, None, None
 
 
 class VMFEntropyLogNorm(torch.autograd.Function):

@@ -77,7 +77,33 @@ class VonMisesFisher(torch.distributions.Distribution):
         self._m = loc.shape[-1]
         self.k = k
         self._fused = None
+        self._head = None
         super().__init__(self.loc.size(), validate_args=validate_args)   # batch_shape quirk kept (:44)
+
+    @classmethod
+    def from_head(cls, loc, raw_scale, floor=0.8, max=10.0, k=1):
+        """Extension: VonMisesFisher(loc, clamp(softplus(raw_scale) + floor, max=max)) with the
+        concentration head of mnist/mlp_vae.py:69-71 evaluated INSIDE the sampling kernel and its backward (one launch
+        from the raw `fc_scale` output; gradients arrive at raw_scale).  raw_scale: loc.shape[:-1] + (1,).  `.scale` is
+        materialised (torch ops) only if something asks for it."""
+        self = cls.__new__(cls)
+        self.dtype = loc.dtype
+        self.loc = loc
+        self.device = loc.device
+        self._m = loc.shape[-1]
+        self.k = k
+        self._fused = None
+        self._head = (float(floor), float(max))
+        self._raw_scale = raw_scale
+        torch.distributions.Distribution.__init__(self, self.loc.size(), validate_args=False)
+        return self
+
+    def __getattr__(self, name):
+        if name == "scale" and self.__dict__.get("_head") is not None:
+            from .distributions import head_concentration
+            self.__dict__["scale"] = head_concentration(self._raw_scale, *self._head)
+            return self.__dict__["scale"]
+        raise AttributeError(name)
 
     @property
     def mean(self):
@@ -97,22 +123,24 @@ class VonMisesFisher(torch.distributions.Distribution):
         shape = shape if isinstance(shape, torch.Size) else torch.Size([shape])
         m = self._m
         loc2 = self.loc.reshape(-1, m)
-        kap = self.scale.expand(tuple(self.loc.shape[:-1]) + (1,)).reshape(-1, 1)
+        param = self._raw_scale if self._head is not None else self.scale       # head: the kernels apply softplus/floor/clamp
+        kap = param.expand(tuple(self.loc.shape[:-1]) + (1,)).reshape(-1, 1)
         n = 1
         for s in shape:
             n *= int(s)
         if _base_draws is None:
             _base_draws = testing.take()
-        z, ent, ln, dent, dln = ops.VMFRsample.apply(loc2, kap, n, _base_draws)
-        if ent.numel() and tuple(self.scale.shape) == tuple(self.loc.shape[:-1]) + (1,):
-            shp = self.scale.shape[:-1]                     # same launch: entropy() / KL / log_prob reuse the row scalars
-            self._fused = (ops.row_scalar(self.scale, ent, dent).reshape(shp), ops.row_scalar(self.scale, ln, dln).reshape(shp))
+        z, ent, ln, dent, dln = ops.VMFRsample.apply(loc2, kap, n, _base_draws, self._head)
+        if ent.numel() and tuple(param.shape) == tuple(self.loc.shape[:-1]) + (1,):
+            shp = param.shape[:-1]                          # same launch: entropy() / KL / log_prob reuse the row scalars
+            self._fused = (ops.row_scalar(param, ent, dent).reshape(shp), ops.row_scalar(param, ln, dln).reshape(shp))
         return z.reshape(tuple(shape) + tuple(self.loc.shape)).type(self.dtype)
 
     def _ent_ln(self):
         cached = self._fused
         if cached is not None:
-            stale = (torch.is_grad_enabled() and self.scale.requires_grad and cached[0].grad_fn is None
+            param = self._raw_scale if self._head is not None else self.scale
+            stale = (torch.is_grad_enabled() and param.requires_grad and cached[0].grad_fn is None
                      and not cached[0].requires_grad)
             if not stale:
                 return cached

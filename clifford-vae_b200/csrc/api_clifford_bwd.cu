@@ -55,19 +55,36 @@ int dispatch_bwd(const CliffordBwdParams& p_in, cudaStream_t st) {
 
 extern "C" {
 
-int cvb_clifford_ps_rsample_backward(const float* grad_z, const float* loc, const float* kappa,
-                                     long long kappa_row_stride, int kappa_el_stride, long long loc_rows,
-                                     const float* tprime, const float* gnoise, const float* tp_signed, float* dloc,
-                                     float* dkappa, long long rows, int d, void* stream) {
+static int clifford_ps_rsample_backward_impl(const float* grad_z, const float* loc, const float* kappa,
+                                             long long kappa_row_stride, int kappa_el_stride, long long loc_rows,
+                                             const float* tprime, const float* gnoise, const float* tp_signed, float* dloc,
+                                             float* dkappa, long long rows, int d, KappaHead head, void* stream) {
   CVB_REQUIRE(grad_z && loc && kappa && dloc && dkappa, kBadArgument, "cvb_clifford_ps_rsample_backward: null pointer");
   CVB_REQUIRE(rows > 0 && d >= 1 && loc_rows > 0, kBadArgument, "cvb_clifford_ps_rsample_backward: bad sizes");
   CVB_REQUIRE(tp_signed || (tprime && gnoise), kBadArgument, "cvb_clifford_ps_rsample_backward: need tp_signed or (tprime, gnoise)");
   CliffordBwdParams p{};
   p.grad_z = grad_z; p.loc = loc; p.kappa = kappa; p.kappa_row_stride = kappa_row_stride;
   p.kappa_el_stride = kappa_el_stride; p.loc_rows = (int)loc_rows; p.tprime = tprime; p.gnoise = gnoise;
-  p.tp_signed = tp_signed; p.dloc = dloc; p.dkappa = dkappa; p.rows = rows; p.d = d;
+  p.tp_signed = tp_signed; p.dloc = dloc; p.dkappa = dkappa; p.rows = rows; p.d = d; p.head = head;
   cudaStream_t st = (cudaStream_t)stream;
   return kappa_el_stride == 0 ? dispatch_bwd<true>(p, st) : dispatch_bwd<false>(p, st);
+}
+
+int cvb_clifford_ps_rsample_backward(const float* grad_z, const float* loc, const float* kappa,
+                                     long long kappa_row_stride, int kappa_el_stride, long long loc_rows,
+                                     const float* tprime, const float* gnoise, const float* tp_signed, float* dloc,
+                                     float* dkappa, long long rows, int d, void* stream) {
+  return clifford_ps_rsample_backward_impl(grad_z, loc, kappa, kappa_row_stride, kappa_el_stride, loc_rows, tprime, gnoise,
+                                           tp_signed, dloc, dkappa, rows, d, KappaHead{0, 0.f, 0.f}, stream);
+}
+
+// backward of cvb_clifford_ps_rsample_head: draw_scale (rows) = d L / d raw_scale (softplus and clamp chain applied)
+int cvb_clifford_ps_rsample_backward_head(const float* grad_z, const float* loc, const float* raw_scale, long long loc_rows,
+                                          float floor, float kmax, const float* tprime, const float* gnoise,
+                                          const float* tp_signed, float* dloc, float* draw_scale, long long rows, int d,
+                                          void* stream) {
+  return clifford_ps_rsample_backward_impl(grad_z, loc, raw_scale, 1, 0, loc_rows, tprime, gnoise, tp_signed, dloc,
+                                           draw_scale, rows, d, KappaHead{1, floor, kmax}, stream);
 }
 
 int cvb_ps_entropy_kl(const float* kappa, long long kappa_row_stride, int kappa_el_stride, long long rows, int d,

@@ -34,7 +34,7 @@ int launch_fwd_fast(const CliffordFwdParams& p, cudaStream_t st) {
   const bool dynamic = !static_sched && work > grid;                         // dynamic rows only when CTAs loop
   if constexpr (MODE == kPsRng && ROWK && !LEAN) {
     // plain forward sampling: the specialised variant (no optional outputs, staged inputs)
-    if (!p.tp_signed && !p.log_prob && p.staged) return launch_fwd_fast<LOG2N, MODE, ROWK, true>(p, st);
+    if (!p.tp_signed && !p.log_prob && p.staged && !p.head.on) return launch_fwd_fast<LOG2N, MODE, ROWK, true>(p, st);
   }
   CliffordFwdParams q = p;
   q.sched = dynamic ? next_sched_slot() : nullptr;
@@ -102,10 +102,10 @@ int dispatch_fwd(const CliffordFwdParams& p_in, cudaStream_t st) {
 
 extern "C" {
 
-int cvb_clifford_ps_rsample(const float* loc, const float* kappa, long long kappa_row_stride, int kappa_el_stride,
-                            long long loc_rows, const float* tprime, const float* gnoise, unsigned long long seed,
-                            unsigned long long offset, float* z, float* tp_signed, float* entropy, float* kl,
-                            float* dentropy, long long rows, int d, void* stream) {
+static int clifford_ps_rsample_impl(const float* loc, const float* kappa, long long kappa_row_stride, int kappa_el_stride,
+                                    long long loc_rows, const float* tprime, const float* gnoise, unsigned long long seed,
+                                    unsigned long long offset, float* z, float* tp_signed, float* entropy, float* kl,
+                                    float* dentropy, long long rows, int d, KappaHead head, void* stream) {
   CVB_REQUIRE(loc && kappa && z, kBadArgument, "cvb_clifford_ps_rsample: null pointer");
   CVB_REQUIRE(rows > 0 && d >= 1 && loc_rows > 0, kBadArgument, "cvb_clifford_ps_rsample: rows=%lld d=%d loc_rows=%lld", rows, d, loc_rows);
   CVB_REQUIRE((tprime == nullptr) == (gnoise == nullptr), kBadArgument, "cvb_clifford_ps_rsample: give both tprime and gnoise or neither");
@@ -116,10 +116,30 @@ int cvb_clifford_ps_rsample(const float* loc, const float* kappa, long long kapp
   p.loc_rows = (int)loc_rows; p.tprime = tprime; p.gnoise = gnoise; p.z = z; p.tp_signed = tp_signed;
   p.entropy = entropy; p.kl = kl; p.dentropy = dentropy; p.rows = rows; p.d = d; p.n = 2 * d;
   p.key = make_key(seed, offset, 0);
+  p.head = head;
   cudaStream_t st = (cudaStream_t)stream;
   const bool rowk = kappa_el_stride == 0;
   if (tprime) return rowk ? dispatch_fwd<kPsInjected, true>(p, st) : dispatch_fwd<kPsInjected, false>(p, st);
   return rowk ? dispatch_fwd<kPsRng, true>(p, st) : dispatch_fwd<kPsRng, false>(p, st);
+}
+
+int cvb_clifford_ps_rsample(const float* loc, const float* kappa, long long kappa_row_stride, int kappa_el_stride,
+                            long long loc_rows, const float* tprime, const float* gnoise, unsigned long long seed,
+                            unsigned long long offset, float* z, float* tp_signed, float* entropy, float* kl,
+                            float* dentropy, long long rows, int d, void* stream) {
+  return clifford_ps_rsample_impl(loc, kappa, kappa_row_stride, kappa_el_stride, loc_rows, tprime, gnoise, seed, offset, z,
+                                  tp_signed, entropy, kl, dentropy, rows, d, KappaHead{0, 0.f, 0.f}, stream);
+}
+
+// the same launch with the concentration head folded in: kappa = min(softplus(raw_scale) + floor, kmax) per row
+// (mnist/mlp_vae.py:69-71, cnn/models.py:96,99); dentropy_draw = d entropy / d raw_scale
+int cvb_clifford_ps_rsample_head(const float* loc, const float* raw_scale, long long loc_rows, float floor, float kmax,
+                                 const float* tprime, const float* gnoise, unsigned long long seed,
+                                 unsigned long long offset, float* z, float* tp_signed, float* entropy, float* kl,
+                                 float* dentropy_draw, long long rows, int d, void* stream) {
+  CVB_REQUIRE(kmax > floor && floor >= 0.f, kBadArgument, "cvb_clifford_ps_rsample_head: need 0 <= floor < kmax (floor=%g kmax=%g)", (double)floor, (double)kmax);
+  return clifford_ps_rsample_impl(loc, raw_scale, 1, 0, loc_rows, tprime, gnoise, seed, offset, z, tp_signed, entropy, kl,
+                                  dentropy_draw, rows, d, KappaHead{1, floor, kmax}, stream);
 }
 
 // rsample + log q(z) of the drawn sample in one pass (IWAE / evaluation path, mnist/mlp_vae.py:146-190)

@@ -55,26 +55,26 @@ int cvb_powerspherical_rsample(const float* loc, const float* kappa, long long l
 
 // rsample fused with entropy() / KL to the uniform prior (dists/clifford.py:204-212, :335-337): one launch for the
 // training step's latent terms.  entropy / kl / dentropy: (loc_rows), each optional.
-int cvb_powerspherical_rsample_kl(const float* loc, const float* kappa, long long loc_rows, const float* tprime,
+static int powerspherical_rsample_kl_impl(const float* loc, const float* kappa, long long loc_rows, const float* tprime,
                                   const float* gnoise, unsigned long long seed, unsigned long long offset, float* z,
                                   float* save, float* entropy, float* kl, float* dentropy, long long rows, int D,
-                                  void* stream) {
+                                  KappaHead head, void* stream) {
   CVB_REQUIRE(loc && kappa && z && rows > 0 && loc_rows > 0 && D >= 2, kBadArgument, "cvb_powerspherical_rsample_kl: bad arguments");
   CVB_REQUIRE((tprime == nullptr) == (gnoise == nullptr), kBadArgument, "cvb_powerspherical_rsample_kl: give both tprime and gnoise or neither");
   SphereParams p{};
   p.loc = loc; p.kappa = kappa; p.loc_rows = loc_rows; p.tprime = tprime; p.gnoise = gnoise; p.g_pitch = D - 1;
   p.g_off = 0; p.z = z; p.save = save; p.rows = rows; p.D = D; p.norm_eps = 1e-7f; p.clamp_eps = 1e-7f;
   p.house_eps = 1e-7f; p.key = make_key(seed, offset, 0);
-  p.entropy = entropy; p.kl = kl; p.dentropy = dentropy;
+  p.entropy = entropy; p.kl = kl; p.dentropy = dentropy; p.head = head;
   // HypersphericalUniform.entropy (dists/clifford.py:109-121): ln 2 + (D/2) ln pi - lgamma(D/2)
   p.prior_entropy = 0.69314718055994530942 + 0.5 * (double)D * 1.14472988584940017414 - lgamma(0.5 * (double)D);
   return launch_sphere_rsample<kFamilyPS>(p, (cudaStream_t)stream, "sphere_rsample_kernel<PS,kl>");
 }
 
-int cvb_powerspherical_rsample_backward(const float* grad_z, const float* loc, const float* kappa, long long loc_rows,
+static int powerspherical_rsample_backward_impl(const float* grad_z, const float* loc, const float* kappa, long long loc_rows,
                                         const float* tprime, const float* gnoise, const float* save,
                                         unsigned long long seed, unsigned long long offset, float* dloc, float* dkappa,
-                                        long long rows, int D, void* stream) {
+                                        long long rows, int D, KappaHead head, void* stream) {
   CVB_REQUIRE(grad_z && loc && kappa && dloc && dkappa && rows > 0 && loc_rows > 0 && D >= 2, kBadArgument,
               "cvb_powerspherical_rsample_backward: bad arguments");
   CVB_REQUIRE((tprime && gnoise) || (save && !tprime && !gnoise), kBadArgument,
@@ -82,7 +82,7 @@ int cvb_powerspherical_rsample_backward(const float* grad_z, const float* loc, c
   SphereParams p{};
   p.loc = loc; p.kappa = kappa; p.loc_rows = loc_rows; p.tprime = tprime; p.gnoise = gnoise; p.g_pitch = D - 1;
   p.g_off = 0; p.save = const_cast<float*>(save); p.grad_z = grad_z; p.dloc = dloc; p.dkappa = dkappa; p.rows = rows;
-  p.D = D; p.norm_eps = 1e-7f; p.clamp_eps = 1e-7f; p.house_eps = 1e-7f; p.key = make_key(seed, offset, 0);
+  p.D = D; p.norm_eps = 1e-7f; p.clamp_eps = 1e-7f; p.house_eps = 1e-7f; p.key = make_key(seed, offset, 0); p.head = head;
   return launch_sphere_rsample_bwd<kFamilyPS>(p, (cudaStream_t)stream, "sphere_rsample_bwd_kernel<PS>");
 }
 
@@ -133,10 +133,10 @@ int cvb_vmf_rsample(const float* loc, const float* kappa, long long loc_rows, co
 }
 
 // rsample fused with entropy / KL to the uniform prior / log-normaliser (von_mises_fisher.py:183-217): one launch.
-int cvb_vmf_rsample_kl(const float* loc, const float* kappa, long long loc_rows, const double* e_rounds,
+static int vmf_rsample_kl_impl(const float* loc, const float* kappa, long long loc_rows, const double* e_rounds,
                        const double* u_rounds, int n_rounds, const float* gnoise, unsigned long long seed,
                        unsigned long long offset, float* z, float* save, float* entropy, float* kl, float* dentropy,
-                       float* log_norm, float* dlog_norm, long long rows, int D, void* stream) {
+                       float* log_norm, float* dlog_norm, long long rows, int D, KappaHead head, void* stream) {
   CVB_REQUIRE(loc && kappa && z && rows > 0 && loc_rows > 0 && D >= 2, kBadArgument, "cvb_vmf_rsample_kl: bad arguments");
   const bool injected = gnoise != nullptr;
   if (injected) {
@@ -148,21 +148,21 @@ int cvb_vmf_rsample_kl(const float* loc, const float* kappa, long long loc_rows,
   p.loc = loc; p.kappa = kappa; p.loc_rows = loc_rows; p.e_rounds = e_rounds; p.u_rounds = u_rounds;
   p.n_rounds = n_rounds; p.gnoise = gnoise; p.g_pitch = D; p.g_off = 1; p.z = z; p.save = save; p.rows = rows; p.D = D;
   p.norm_eps = 0.0f; p.clamp_eps = 1e-10f; p.house_eps = 1e-5f; p.key = make_key(seed, offset, 0);
-  p.entropy = entropy; p.kl = kl; p.dentropy = dentropy; p.log_norm = log_norm; p.dlog_norm = dlog_norm;
+  p.entropy = entropy; p.kl = kl; p.dentropy = dentropy; p.log_norm = log_norm; p.dlog_norm = dlog_norm; p.head = head;
   // vMF HypersphericalUniform.entropy (hyperspherical_uniform.py:48-54) in fp32 like the reference's tensor
   p.prior_entropy = (double)(float)(0.69314718055994530942 + 0.5 * (double)D * 1.14472988584940017414 - lgamma(0.5 * (double)D));
   return launch_sphere_rsample<kFamilyVMF>(p, (cudaStream_t)stream, "sphere_rsample_kernel<VMF,kl>");
 }
 
-int cvb_vmf_rsample_backward(const float* grad_z, const float* loc, const float* kappa, long long loc_rows,
+static int vmf_rsample_backward_impl(const float* grad_z, const float* loc, const float* kappa, long long loc_rows,
                              const float* gnoise, const float* save, unsigned long long seed, unsigned long long offset,
-                             float* dloc, float* dkappa, long long rows, int D, void* stream) {
+                             float* dloc, float* dkappa, long long rows, int D, KappaHead head, void* stream) {
   CVB_REQUIRE(grad_z && loc && kappa && save && dloc && dkappa && rows > 0 && loc_rows > 0 && D >= 2, kBadArgument,
               "cvb_vmf_rsample_backward: bad arguments");
   SphereParams p{};
   p.loc = loc; p.kappa = kappa; p.loc_rows = loc_rows; p.gnoise = gnoise; p.g_pitch = D; p.g_off = 1;
   p.save = const_cast<float*>(save); p.grad_z = grad_z; p.dloc = dloc; p.dkappa = dkappa; p.rows = rows; p.D = D;
-  p.norm_eps = 0.0f; p.clamp_eps = 1e-10f; p.house_eps = 1e-5f; p.key = make_key(seed, offset, 0);
+  p.norm_eps = 0.0f; p.clamp_eps = 1e-10f; p.house_eps = 1e-5f; p.key = make_key(seed, offset, 0); p.head = head;
   return launch_sphere_rsample_bwd<kFamilyVMF>(p, (cudaStream_t)stream, "sphere_rsample_bwd_kernel<VMF>");
 }
 
@@ -173,6 +173,67 @@ int cvb_vmf_entropy_lognorm(const float* kappa, long long rows, int D, float* en
   if (blocks > sm_count() * 8) blocks = sm_count() * 8;
   vmf_entropy_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(kappa, rows, D, entropy, log_norm, dentropy, dlog_norm);
   return check_launch("vmf_entropy_kernel");
+}
+
+// ---- public entry points over the implementations above: plain concentration, or the concentration head folded in
+// (kappa = min(softplus(raw_scale) + floor, kmax), mnist/mlp_vae.py:69-71; every kappa-derivative is then d / d raw_scale)
+int cvb_powerspherical_rsample_kl(const float* loc, const float* kappa, long long loc_rows, const float* tprime,
+                                  const float* gnoise, unsigned long long seed, unsigned long long offset, float* z,
+                                  float* save, float* entropy, float* kl, float* dentropy, long long rows, int D,
+                                  void* stream) {
+  return powerspherical_rsample_kl_impl(loc, kappa, loc_rows, tprime, gnoise, seed, offset, z, save, entropy, kl, dentropy, rows, D,
+                                        KappaHead{0, 0.f, 0.f}, stream);
+}
+int cvb_powerspherical_rsample_kl_head(const float* loc, const float* raw_scale, long long loc_rows, float floor, float kmax,
+                                       const float* tprime, const float* gnoise, unsigned long long seed,
+                                       unsigned long long offset, float* z, float* save, float* entropy, float* kl,
+                                       float* dentropy_draw, long long rows, int D, void* stream) {
+  CVB_REQUIRE(kmax > floor && floor >= 0.f, kBadArgument, "cvb_powerspherical_rsample_kl_head: need 0 <= floor < kmax");
+  return powerspherical_rsample_kl_impl(loc, raw_scale, loc_rows, tprime, gnoise, seed, offset, z, save, entropy, kl, dentropy_draw,
+                                        rows, D, KappaHead{1, floor, kmax}, stream);
+}
+int cvb_powerspherical_rsample_backward(const float* grad_z, const float* loc, const float* kappa, long long loc_rows,
+                                        const float* tprime, const float* gnoise, const float* save,
+                                        unsigned long long seed, unsigned long long offset, float* dloc, float* dkappa,
+                                        long long rows, int D, void* stream) {
+  return powerspherical_rsample_backward_impl(grad_z, loc, kappa, loc_rows, tprime, gnoise, save, seed, offset, dloc, dkappa, rows, D,
+                                              KappaHead{0, 0.f, 0.f}, stream);
+}
+int cvb_powerspherical_rsample_backward_head(const float* grad_z, const float* loc, const float* raw_scale, long long loc_rows,
+                                             float floor, float kmax, const float* tprime, const float* gnoise,
+                                             const float* save, unsigned long long seed, unsigned long long offset,
+                                             float* dloc, float* draw_scale, long long rows, int D, void* stream) {
+  return powerspherical_rsample_backward_impl(grad_z, loc, raw_scale, loc_rows, tprime, gnoise, save, seed, offset, dloc, draw_scale,
+                                              rows, D, KappaHead{1, floor, kmax}, stream);
+}
+int cvb_vmf_rsample_kl(const float* loc, const float* kappa, long long loc_rows, const double* e_rounds,
+                       const double* u_rounds, int n_rounds, const float* gnoise, unsigned long long seed,
+                       unsigned long long offset, float* z, float* save, float* entropy, float* kl, float* dentropy,
+                       float* log_norm, float* dlog_norm, long long rows, int D, void* stream) {
+  return vmf_rsample_kl_impl(loc, kappa, loc_rows, e_rounds, u_rounds, n_rounds, gnoise, seed, offset, z, save, entropy, kl, dentropy,
+                             log_norm, dlog_norm, rows, D, KappaHead{0, 0.f, 0.f}, stream);
+}
+int cvb_vmf_rsample_kl_head(const float* loc, const float* raw_scale, long long loc_rows, float floor, float kmax,
+                            const double* e_rounds, const double* u_rounds, int n_rounds, const float* gnoise,
+                            unsigned long long seed, unsigned long long offset, float* z, float* save, float* entropy,
+                            float* kl, float* dentropy_draw, float* log_norm, float* dlog_norm_draw, long long rows, int D,
+                            void* stream) {
+  CVB_REQUIRE(kmax > floor && floor >= 0.f, kBadArgument, "cvb_vmf_rsample_kl_head: need 0 <= floor < kmax");
+  return vmf_rsample_kl_impl(loc, raw_scale, loc_rows, e_rounds, u_rounds, n_rounds, gnoise, seed, offset, z, save, entropy, kl,
+                             dentropy_draw, log_norm, dlog_norm_draw, rows, D, KappaHead{1, floor, kmax}, stream);
+}
+int cvb_vmf_rsample_backward(const float* grad_z, const float* loc, const float* kappa, long long loc_rows,
+                             const float* gnoise, const float* save, unsigned long long seed, unsigned long long offset,
+                             float* dloc, float* dkappa, long long rows, int D, void* stream) {
+  return vmf_rsample_backward_impl(grad_z, loc, kappa, loc_rows, gnoise, save, seed, offset, dloc, dkappa, rows, D,
+                                   KappaHead{0, 0.f, 0.f}, stream);
+}
+int cvb_vmf_rsample_backward_head(const float* grad_z, const float* loc, const float* raw_scale, long long loc_rows,
+                                  float floor, float kmax, const float* gnoise, const float* save, unsigned long long seed,
+                                  unsigned long long offset, float* dloc, float* draw_scale, long long rows, int D,
+                                  void* stream) {
+  return vmf_rsample_backward_impl(grad_z, loc, raw_scale, loc_rows, gnoise, save, seed, offset, dloc, draw_scale, rows, D,
+                                   KappaHead{1, floor, kmax}, stream);
 }
 
 }  // extern "C"

@@ -71,8 +71,16 @@ struct CliffordFwdParams {
   const float* bind_b;     // fused bind tail: rows of length 2d to bind each sample with (row r uses r % bind_b_rows), or null
   long long bind_b_rows;
   float* bind_out;         // (rows, 2d): irfft(S * rfft(bind_b)) = bind(z, b) without re-transforming z (its spectrum S is known)
+  KappaHead head;          // on: `kappa` holds the raw head output (row scalar only); dentropy is then d entropy / d raw
   PhiloxKey key;
 };
+// the row's concentration (row-scalar layouts): through the folded head when one is given
+// (NOHEAD: the launcher guarantees head.on == 0 -- the register-capped LEAN variant compiles the head out)
+template <bool NOHEAD = false>
+__device__ __forceinline__ float fwd_row_kappa(const CliffordFwdParams& p, long long prow) {
+  const float raw = __ldg(p.kappa + prow * p.kappa_row_stride);
+  return NOHEAD ? raw : head_kappa(p.head, raw);
+}
 
 constexpr float kEps = 1e-7f;
 
@@ -247,7 +255,10 @@ __device__ __forceinline__ void clifford_row_entropy(const CliffordFwdParams& p,
   const double ent = (double)(p.d - 1) * c.entropy;
   if (p.entropy) p.entropy[row] = (float)ent;
   if (p.kl) p.kl[row] = (float)((double)(p.d - 1) * 1.83787706640934548356 - ent);
-  if (p.dentropy) p.dentropy[row] = (float)((double)(p.d - 1) * c.dentropy);
+  if (p.dentropy) {
+    const float chain = p.head.on ? head_dkappa(p.head, __ldg(p.kappa + (row % p.loc_rows) * p.kappa_row_stride)) : 1.0f;
+    p.dentropy[row] = (float)((double)(p.d - 1) * c.dentropy) * chain;
+  }
   if (p.log_prob) {
     // the sample-independent part of log q(z): d log C + kappa ((d-1) ln 2 + log1p(clamp(cos loc_0)))  (bin 0 has angle 0);
     // the row loop adds kappa * sum_k ln t'_k.  Two commutative adds onto zero: order-independent.
@@ -333,7 +344,7 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw, cons
   // here, those of every later row right after the previous row's sampling phase (their loads overlap its FFT)
   auto icdf_row_ok = [&](float kap) { return kap + kEps <= kIcdfKappaMax; };
   if (ICDF && first_row < p.rows) {
-    const float k0 = __ldg(p.kappa + (first_row % p.loc_rows) * p.kappa_row_stride);
+    const float k0 = fwd_row_kappa<LEAN>(p, first_row % p.loc_rows);
     if (icdf_row_ok(k0)) icdf_build_row(cells, k0 + kEps, icdf, t, T);
   }
 
@@ -342,7 +353,7 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw, cons
   const bool want_lp = !LEAN && PS && ROWK && p.log_prob != nullptr;
   if (PS && ROWK && (p.entropy || p.kl || p.dentropy || p.log_prob)) {
     for (long long row = first_row + (long long)t * stride; row < p.rows; row += (long long)T * stride)
-      clifford_row_entropy(p, row, __ldg(p.kappa + (row % p.loc_rows) * p.kappa_row_stride));
+      clifford_row_entropy(p, row, fwd_row_kappa<LEAN>(p, row % p.loc_rows));
   }
 
   // Row schedule.  Static: group g of CTA b takes rows b*G + g + i*stride.  Dynamic (sched != null, groups of
@@ -356,7 +367,7 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw, cons
     const bool valid = row < p.rows;
     const long long prow = valid ? (row % p.loc_rows) : 0;
     float kap_row = 1.0f;
-    if (PS && valid) kap_row = __ldg(p.kappa + prow * p.kappa_row_stride);
+    if (PS && valid) kap_row = fwd_row_kappa<LEAN>(p, prow);
     HalfAngle gm(kap_row + kEps);
     if (dynamic && t == 0) qcount[1] = atomicAdd(p.sched, 1);              // broadcast through smem after the barrier
     RowSrc src;
@@ -549,7 +560,7 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw, cons
     if (staged && t == 0 && next_row < p.rows) issue(next_row);
     if (ICDF && next_row < p.rows) {
       // ... and with this row's cells: build the next row's (the loop-top barrier orders them before its sampling)
-      const float kn = __ldg(p.kappa + (next_row % p.loc_rows) * p.kappa_row_stride);
+      const float kn = fwd_row_kappa<LEAN>(p, next_row % p.loc_rows);
       if (icdf_row_ok(kn)) icdf_build_row(cells, kn + kEps, icdf, t, T);
     }
     // phase 2: Hermitian half spectrum -> packed complex spectrum -> inverse FFT -> real row
@@ -639,6 +650,7 @@ struct CliffordBwdParams {
   long long rows;
   int d;
   int staged;              // 1: element-input rows are 16-byte aligned -> stage them with cp.async.bulk
+  KappaHead head;          // on: `kappa` holds the raw head output (row scalar only) and dkappa receives d L / d raw
 };
 
 // Per-row inputs of the backward, indexed by the bin k (global rows or their TMA-staged copies in smem).
@@ -746,7 +758,8 @@ clifford_bwd_kernel(const CliffordBwdParams p, const cplx* __restrict__ tw) {
     for (int e = 0; e < E; ++e) v[e] = valid ? ldg_stream2(gz + t + e * T) : make_float2(0.f, 0.f);
     // the row's Beta-gradient constants, built once by the first lanes of the group while grad_z is in flight
     // (published by the barriers of the FFT below; double-buffered against the previous row's readers)
-    const float kap_row = valid ? __ldg(p.kappa + prow * p.kappa_row_stride) : 1.0f;
+    const float kap_raw = valid ? __ldg(p.kappa + prow * p.kappa_row_stride) : 1.0f;
+    const float kap_row = head_kappa(p.head, kap_raw);
     float* rc = rowconst + (parity ? kBetaRowFloats : 0);
     if (ROWK) beta_row_build<T>(rc, 0.5f + (kap_row + kEps), 0.5f, t);
     fft_run<LOG2N, false>(v, xch, t, tw);
@@ -791,7 +804,7 @@ clifford_bwd_kernel(const CliffordBwdParams p, const cplx* __restrict__ tw) {
     }
     if (ROWK) {
       const float tot = group_sum<LOG2N>(dk_sum, scratch, t);
-      if (valid && t == 0) p.dkappa[row] = tot;
+      if (valid && t == 0) p.dkappa[row] = tot * head_dkappa(p.head, kap_raw);
     }
   }
 }
@@ -976,7 +989,7 @@ clifford_fwd_generic_kernel(const CliffordFwdParams p) {
   for (long long row = blockIdx.x; row < p.rows; row += gridDim.x) {
     const long long prow = row % p.loc_rows;
     float kap_row = 1.0f;
-    if (PS) kap_row = __ldg(p.kappa + prow * p.kappa_row_stride);
+    if (PS) kap_row = fwd_row_kappa(p, prow);
     HalfAngle gm(kap_row + kEps);
     __syncthreads();
     const RowSrc src = global_row_src(p, row, prow);
@@ -1025,7 +1038,8 @@ clifford_bwd_generic_kernel(const CliffordBwdParams p) {
     __syncthreads();
     for (int j = threadIdx.x; j < n; j += blockDim.x) g[j] = p.grad_z[row * n + j];
     __syncthreads();
-    const float kap_row = __ldg(p.kappa + prow * p.kappa_row_stride);
+    const float kap_raw = __ldg(p.kappa + prow * p.kappa_row_stride);
+    const float kap_row = head_kappa(p.head, kap_raw);
     BetaGradRow bc(0.5f + (kap_row + kEps), 0.5f);
     BwdRowSrc gsrc;
     gsrc.loc = p.loc + prow * d;
@@ -1054,7 +1068,7 @@ clifford_bwd_generic_kernel(const CliffordBwdParams p) {
     }
     if (ROWK) {
       const float tot = block_sum_256(dk_sum, scratch);
-      if (threadIdx.x == 0) p.dkappa[row] = tot;
+      if (threadIdx.x == 0) p.dkappa[row] = tot * head_dkappa(p.head, kap_raw);
     }
   }
 }

@@ -91,6 +91,28 @@ __device__ __forceinline__ float fast_sqrt(float x) {
   return r;
 }
 
+// Concentration head folded into the samplers (reference mnist/mlp_vae.py:69-71, cnn/models.py:96,99):
+//     kappa = min(softplus(raw) + floor, kmax)
+// evaluated by the kernel from the raw output of the `fc_scale` / `fc_concentration` layer, with the chain factor
+// d kappa / d raw applied to every kappa-gradient the kernel writes.  on == 0: the input already is kappa.
+// softplus as torch (beta 1, threshold 20: softplus(x) = x for x > 20); clamp(max=) passes the gradient where x <= max.
+struct KappaHead {
+  int on;
+  float floor, kmax;
+};
+__device__ __forceinline__ float head_kappa(const KappaHead& h, float raw) {
+  if (!h.on) return raw;
+  const float sp = raw > 20.0f ? raw : log1pf(expf(raw));
+  return fminf(sp + h.floor, h.kmax);
+}
+__device__ __forceinline__ float head_dkappa(const KappaHead& h, float raw) {
+  if (!h.on) return 1.0f;
+  const float e = expf(raw);
+  const float sp = raw > 20.0f ? raw : log1pf(e);
+  if (!(sp + h.floor <= h.kmax)) return 0.0f;
+  return raw > 20.0f ? 1.0f : e / (e + 1.0f);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

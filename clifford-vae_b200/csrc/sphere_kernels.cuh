@@ -40,6 +40,7 @@ struct SphereParams {
   float* log_norm;           // (loc_rows)  vMF only
   float* dlog_norm;          // (loc_rows)  vMF only
   double prior_entropy;
+  KappaHead head;            // on: `kappa` holds the raw head output; every kappa-derivative written is then d / d raw
   PhiloxKey key;
 };
 
@@ -187,19 +188,21 @@ __device__ __forceinline__ VmfRowScalars vmf_row_scalars(double k, int D) {
 // Fused row scalars (entropy / KL / their kappa-derivatives) of parameter row `prow`, written by ONE lane.
 template <int FAMILY>
 __device__ __forceinline__ void sphere_row_scalars(const SphereParams& p, long long prow) {
-  const double kap = (double)__ldg(p.kappa + prow);
+  const float raw = __ldg(p.kappa + prow);
+  const double kap = (double)head_kappa(p.head, raw);
+  const float chain = head_dkappa(p.head, raw);
   if (FAMILY == kFamilyVMF) {
     const VmfRowScalars r = vmf_row_scalars(kap, p.D);
     if (p.entropy) p.entropy[prow] = r.entropy;
     if (p.kl) p.kl[prow] = (float)(p.prior_entropy - (double)r.entropy);
-    if (p.dentropy) p.dentropy[prow] = r.dentropy;
+    if (p.dentropy) p.dentropy[prow] = r.dentropy * chain;
     if (p.log_norm) p.log_norm[prow] = r.log_norm;
-    if (p.dlog_norm) p.dlog_norm[prow] = r.dlog_norm;
+    if (p.dlog_norm) p.dlog_norm[prow] = r.dlog_norm * chain;
   } else {
     const PsConsts c = ps_consts(kap, 0.5 * (double)(p.D - 1));
     if (p.entropy) p.entropy[prow] = (float)c.entropy;
     if (p.kl) p.kl[prow] = (float)(p.prior_entropy - c.entropy);
-    if (p.dentropy) p.dentropy[prow] = (float)c.dentropy;
+    if (p.dentropy) p.dentropy[prow] = (float)c.dentropy * chain;
   }
 }
 
@@ -238,7 +241,7 @@ sphere_rsample_kernel(const SphereParams p) {
     }
     const long long prow = row % p.loc_rows;
     const float* lr = p.loc + prow * D;
-    const float kap = __ldg(p.kappa + prow);
+    const float kap = head_kappa(p.head, __ldg(p.kappa + prow));
     // scalar coordinate t
     float t, save0, save1 = 0.f;
     if (FAMILY == kFamilyPS) {
@@ -332,7 +335,7 @@ sphere_rsample_reg_kernel(const SphereParams p) {
   {
     const long long rj = base + (long long)lane * nwarps;
     if (rj < p.rows) {
-      const float kapj = __ldg(p.kappa + rj % p.loc_rows);
+      const float kapj = head_kappa(p.head, __ldg(p.kappa + rj % p.loc_rows));
       if (FAMILY == kFamilyVMF) {
         const WoodDraw wd = vmf_draw_w(p, rj, kapj);
         w_l = wd.w;
@@ -428,7 +431,8 @@ sphere_rsample_bwd_kernel(const SphereParams p) {
     const float* lr = p.loc + prow * D;
     const float* gz = p.grad_z + row * D;
     float* dl = p.dloc + row * D;
-    const float kap = __ldg(p.kappa + prow);
+    const float kap_raw = __ldg(p.kappa + prow);
+    const float kap = head_kappa(p.head, kap_raw);
     float t, tp = 0.f, dt_dk_direct = 0.f;
     if (FAMILY == kFamilyPS) {
       tp = p.tprime ? p.tprime[row] : p.save[2 * row];
@@ -496,7 +500,7 @@ sphere_rsample_bwd_kernel(const SphereParams p) {
       } else {
         dk = gt * dt_dk_direct;
       }
-      p.dkappa[row] = dk;
+      p.dkappa[row] = dk * head_dkappa(p.head, kap_raw);
     }
   }
 }
@@ -597,14 +601,15 @@ sphere_rsample_bwd_reg_kernel(const SphereParams p) {
     // scalar tails of the batch, one row per lane
     if (rj < p.rows) {
       float dk;
+      const float kap_raw = __ldg(p.kappa + rj % p.loc_rows);
       if (FAMILY == kFamilyPS) {
         const float half = 0.5f * (float)(D - 1);
-        const BetaGradConsts bc(half + (__ldg(p.kappa + rj % p.loc_rows) + 1e-7f), half);
+        const BetaGradConsts bc(half + (head_kappa(p.head, kap_raw) + 1e-7f), half);
         dk = 2.0f * gt_l * dirichlet_grad_one(s0_l, bc) * (1.0f - s0_l);
       } else {
         dk = gt_l * s1_l;
       }
-      p.dkappa[rj] = dk;
+      p.dkappa[rj] = dk * head_dkappa(p.head, kap_raw);
     }
   }
 }

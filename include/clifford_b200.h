@@ -212,6 +212,42 @@ CVB_API int cvb_vmf_rsample_backward(const float* grad_z, const float* loc, cons
 CVB_API int cvb_vmf_entropy_lognorm(const float* kappa, long long rows, int D, float* entropy, float* log_norm,
                                     float* dentropy, float* dlog_norm, void* stream);
 
+/* ---- Concentration head folded into the samplers ------------------------------------------
+ * Every reference model computes the concentration as  kappa = clamp(softplus(fc_scale(h)) + floor, max=kmax)
+ * (mnist/mlp_vae.py:69-71 floor 0.8 | 0.03, max 10; cnn/models.py:96,99 floor 0.5 | concentration_floor) right before
+ * it builds the distribution.  The *_head entry points take the RAW output of that linear layer, raw_scale (loc_rows),
+ * one value per row, and evaluate softplus + floor + clamp inside the sampling kernel; the backward entry points and
+ * every kappa-derivative output (dentropy_draw, dlog_norm_draw, draw_scale) carry the chain factor
+ * d kappa / d raw = sigmoid(raw) * [softplus(raw) + floor <= kmax], i.e. they are derivatives with respect to raw_scale.
+ * All other arguments are those of the entry point without the suffix. */
+CVB_API int cvb_clifford_ps_rsample_head(const float* loc, const float* raw_scale, long long loc_rows, float floor, float kmax,
+                                         const float* tprime, const float* gnoise, unsigned long long seed,
+                                         unsigned long long offset, float* z, float* tp_signed, float* entropy, float* kl,
+                                         float* dentropy_draw, long long rows, int d, void* stream);
+CVB_API int cvb_clifford_ps_rsample_backward_head(const float* grad_z, const float* loc, const float* raw_scale,
+                                                  long long loc_rows, float floor, float kmax, const float* tprime,
+                                                  const float* gnoise, const float* tp_signed, float* dloc,
+                                                  float* draw_scale, long long rows, int d, void* stream);
+CVB_API int cvb_powerspherical_rsample_kl_head(const float* loc, const float* raw_scale, long long loc_rows, float floor,
+                                               float kmax, const float* tprime, const float* gnoise,
+                                               unsigned long long seed, unsigned long long offset, float* z, float* save,
+                                               float* entropy, float* kl, float* dentropy_draw, long long rows, int D,
+                                               void* stream);
+CVB_API int cvb_powerspherical_rsample_backward_head(const float* grad_z, const float* loc, const float* raw_scale,
+                                                     long long loc_rows, float floor, float kmax, const float* tprime,
+                                                     const float* gnoise, const float* save, unsigned long long seed,
+                                                     unsigned long long offset, float* dloc, float* draw_scale,
+                                                     long long rows, int D, void* stream);
+CVB_API int cvb_vmf_rsample_kl_head(const float* loc, const float* raw_scale, long long loc_rows, float floor, float kmax,
+                                    const double* e_rounds, const double* u_rounds, int n_rounds, const float* gnoise,
+                                    unsigned long long seed, unsigned long long offset, float* z, float* save,
+                                    float* entropy, float* kl, float* dentropy_draw, float* log_norm,
+                                    float* dlog_norm_draw, long long rows, int D, void* stream);
+CVB_API int cvb_vmf_rsample_backward_head(const float* grad_z, const float* loc, const float* raw_scale, long long loc_rows,
+                                          float floor, float kmax, const float* gnoise, const float* save,
+                                          unsigned long long seed, unsigned long long offset, float* dloc,
+                                          float* draw_scale, long long rows, int D, void* stream);
+
 /* ---- CUDA-graph capture of the samplers.  (seed, offset) are kernel arguments chosen on the host, so a captured graph
  * would replay the same draws.  Register a device-resident 64-bit counter for the current device (NULL clears it): every
  * sampling kernel launched afterwards mixes it into its Philox offset.  The library only READS it; the caller bumps it
