@@ -2,6 +2,7 @@
 #include <cstdlib>
 #include "launch.cuh"
 #include "clifford_kernels.cuh"
+#include "clifford_small.cuh"
 #include "../../include/clifford_b200.h"
 
 using namespace cvb;
@@ -40,6 +41,16 @@ int dispatch_bwd(const CliffordBwdParams& p_in, cudaStream_t st) {
       CVB_CASE(13)
 #undef CVB_CASE
     }
+  }
+  static const bool no_small = getenv("CVB_NO_SMALL_ROWS") != nullptr;
+  if (2 * p.d <= kSmallMaxN && !no_small) {
+    const int rt = small_rows_per_tile(p.rows, sm_count());
+    const size_t smem_s = clifford_bwd_small_smem(p.d, rt);
+    auto kern_s = clifford_bwd_small_kernel<ROWK>;
+    int grid_s = 0;
+    if (int rc = persistent_grid(kern_s, kSmallThreads, smem_s, (p.rows + rt - 1) / rt, &grid_s)) return rc;
+    kern_s<<<grid_s, kSmallThreads, smem_s, st>>>(p, rt);
+    return check_launch("clifford_bwd_small_kernel");
   }
   const int n = 2 * p.d;
   const size_t smem = sizeof(cplx) * n + sizeof(float) * (n + 32);

@@ -2,6 +2,7 @@
 #include <cstdlib>
 #include "launch.cuh"
 #include "clifford_kernels.cuh"
+#include "clifford_small.cuh"
 #include "../../include/clifford_b200.h"
 
 using namespace cvb;
@@ -87,6 +88,17 @@ int dispatch_fwd(const CliffordFwdParams& p_in, cudaStream_t st) {
       CVB_CASE(13)
 #undef CVB_CASE
     }
+  }
+  static const bool no_small = getenv("CVB_NO_SMALL_ROWS") != nullptr;    // A/B switch: the one-CTA-per-row direct DFT
+  if (p.n <= kSmallMaxN && !no_small) {
+    // short rows (the reference's default MNIST latents, per-token latents): a tile of rows per CTA
+    const int rt = small_rows_per_tile(p.rows, sm_count());
+    const size_t smem_s = clifford_fwd_small_smem(p.n, rt);
+    auto kern_s = clifford_fwd_small_kernel<MODE, ROWK>;
+    int grid_s = 0;
+    if (int rc = persistent_grid(kern_s, kSmallThreads, smem_s, (p.rows + rt - 1) / rt, &grid_s)) return rc;
+    kern_s<<<grid_s, kSmallThreads, smem_s, st>>>(p, rt);
+    return check_launch("clifford_fwd_small_kernel");
   }
   const int nph = (p.n - 1) / 2;
   const size_t smem = sizeof(cplx) * ((size_t)p.n + nph + 1);

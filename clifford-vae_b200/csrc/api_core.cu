@@ -19,12 +19,21 @@ static int g_sms[64] = {0};
 static int* g_sched[64] = {nullptr};
 static std::atomic<unsigned> g_sched_seq{0};
 constexpr int kSchedSlots = 64;
-static std::unordered_map<unsigned long long, int> g_occ;   // (device, kernel) -> resident CTAs per SM
-static unsigned long long occ_key(const void* kernel) {
+// The dynamic-smem opt-in (cudaFuncSetAttribute) is per (device, kernel) and must only ever be RAISED (kernels with a
+// run-time shared-memory size -- the direct-DFT and short-row kernels -- are launched with different sizes); the
+// occupancy answer additionally depends on the launch's threads and shared memory.
+static std::unordered_map<unsigned long long, size_t> g_smem_optin;   // (device, kernel) -> largest opt-in applied
+static std::unordered_map<unsigned long long, int> g_occ;             // (device, kernel, threads, smem) -> resident CTAs per SM
+static unsigned long long func_key(const void* kernel) {
   int dev = 0;
   cudaGetDevice(&dev);
-  // the dynamic-smem opt-in (cudaFuncSetAttribute) and the occupancy answer are per device: key them so
   return (unsigned long long)reinterpret_cast<uintptr_t>(kernel) * 64ull + (unsigned long long)(dev & 63);
+}
+static unsigned long long occ_key(const void* kernel, int threads, size_t smem) {
+  unsigned long long h = func_key(kernel);
+  h ^= ((unsigned long long)smem + 0x9E3779B97F4A7C15ull) * 0xBF58476D1CE4E5B9ull;
+  h ^= ((unsigned long long)threads + 0x94D049BB133111EBull) * 0xD6E8FEB86659FD93ull;
+  return h;
 }
 static const float2* g_icdf[64] = {nullptr};
 static const unsigned long long* g_rng_ctr[64] = {nullptr};
@@ -162,15 +171,25 @@ int sm_count() {
   return n;
 }
 
-int cached_ctas_per_sm(const void* kernel, int, size_t, bool* found) {
+int cached_ctas_per_sm(const void* kernel, int threads, size_t smem, bool* found) {
   std::lock_guard<std::mutex> lk(g_mu);
-  auto it = g_occ.find(occ_key(kernel));
+  auto it = g_occ.find(occ_key(kernel, threads, smem));
   *found = it != g_occ.end();
   return *found ? it->second : 0;
 }
-void store_ctas_per_sm(const void* kernel, int per_sm) {
+void store_ctas_per_sm(const void* kernel, int threads, size_t smem, int per_sm) {
   std::lock_guard<std::mutex> lk(g_mu);
-  g_occ[occ_key(kernel)] = per_sm;
+  g_occ[occ_key(kernel, threads, smem)] = per_sm;
+}
+int ensure_smem_optin(const void* kernel, size_t smem) {
+  if (smem <= 48 * 1024) return kOk;
+  std::lock_guard<std::mutex> lk(g_mu);
+  size_t& cur = g_smem_optin[func_key(kernel)];
+  if (smem > cur) {
+    CVB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cur = smem;
+  }
+  return kOk;
 }
 
 __global__ void philox_fill_kernel(uint4* out, long long n, PhiloxKey key) {

@@ -250,13 +250,14 @@ __device__ __forceinline__ float circle_log_half_1pt(float tp) {
   return FAST ? __logf(c) : logf(c);
 }
 
+template <bool NOHEAD = false>
 __device__ __forceinline__ void clifford_row_entropy(const CliffordFwdParams& p, long long row, float kap_row) {
   const PsConsts c = ps_consts((double)kap_row, 0.5);
   const double ent = (double)(p.d - 1) * c.entropy;
   if (p.entropy) p.entropy[row] = (float)ent;
   if (p.kl) p.kl[row] = (float)((double)(p.d - 1) * 1.83787706640934548356 - ent);
   if (p.dentropy) {
-    const float chain = p.head.on ? head_dkappa(p.head, __ldg(p.kappa + (row % p.loc_rows) * p.kappa_row_stride)) : 1.0f;
+    const float chain = (!NOHEAD && p.head.on) ? head_dkappa(p.head, __ldg(p.kappa + (row % p.loc_rows) * p.kappa_row_stride)) : 1.0f;
     p.dentropy[row] = (float)((double)(p.d - 1) * c.dentropy) * chain;
   }
   if (p.log_prob) {
@@ -344,7 +345,7 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw, cons
   // here, those of every later row right after the previous row's sampling phase (their loads overlap its FFT)
   auto icdf_row_ok = [&](float kap) { return kap + kEps <= kIcdfKappaMax; };
   if (ICDF && first_row < p.rows) {
-    const float k0 = fwd_row_kappa<LEAN>(p, first_row % p.loc_rows);
+    const float k0 = fwd_row_kappa<LEAN || BIND>(p, first_row % p.loc_rows);
     if (icdf_row_ok(k0)) icdf_build_row(cells, k0 + kEps, icdf, t, T);
   }
 
@@ -353,7 +354,7 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw, cons
   const bool want_lp = !LEAN && PS && ROWK && p.log_prob != nullptr;
   if (PS && ROWK && (p.entropy || p.kl || p.dentropy || p.log_prob)) {
     for (long long row = first_row + (long long)t * stride; row < p.rows; row += (long long)T * stride)
-      clifford_row_entropy(p, row, fwd_row_kappa<LEAN>(p, row % p.loc_rows));
+      clifford_row_entropy<LEAN || BIND>(p, row, fwd_row_kappa<LEAN || BIND>(p, row % p.loc_rows));
   }
 
   // Row schedule.  Static: group g of CTA b takes rows b*G + g + i*stride.  Dynamic (sched != null, groups of
@@ -367,7 +368,7 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw, cons
     const bool valid = row < p.rows;
     const long long prow = valid ? (row % p.loc_rows) : 0;
     float kap_row = 1.0f;
-    if (PS && valid) kap_row = fwd_row_kappa<LEAN>(p, prow);
+    if (PS && valid) kap_row = fwd_row_kappa<LEAN || BIND>(p, prow);
     HalfAngle gm(kap_row + kEps);
     if (dynamic && t == 0) qcount[1] = atomicAdd(p.sched, 1);              // broadcast through smem after the barrier
     RowSrc src;
@@ -560,7 +561,7 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw, cons
     if (staged && t == 0 && next_row < p.rows) issue(next_row);
     if (ICDF && next_row < p.rows) {
       // ... and with this row's cells: build the next row's (the loop-top barrier orders them before its sampling)
-      const float kn = fwd_row_kappa<LEAN>(p, next_row % p.loc_rows);
+      const float kn = fwd_row_kappa<LEAN || BIND>(p, next_row % p.loc_rows);
       if (icdf_row_ok(kn)) icdf_build_row(cells, kn + kEps, icdf, t, T);
     }
     // phase 2: Hermitian half spectrum -> packed complex spectrum -> inverse FFT -> real row

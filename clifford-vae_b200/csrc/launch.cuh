@@ -46,20 +46,20 @@ inline int check_launch(const char* what) {
 }
 
 // Persistent grid: min(work CTAs, SMs x resident CTAs per SM).  Opts in to > 48 KB dynamic smem.
-// The occupancy answer and the > 48 KB opt-in are cached per (device, kernel): a second device in the same process
-// gets its own cudaFuncSetAttribute call.
+// The > 48 KB opt-in is tracked per (device, kernel) and only ever raised; the occupancy answer is cached per
+// (device, kernel, threads, smem) -- kernels with a run-time shared-memory size are launched with several sizes.
 int cached_ctas_per_sm(const void* kernel, int threads, size_t smem, bool* found);
-void store_ctas_per_sm(const void* kernel, int per_sm);
+void store_ctas_per_sm(const void* kernel, int threads, size_t smem, int per_sm);
+int ensure_smem_optin(const void* kernel, size_t smem);
 
 template <typename Kernel>
 inline int persistent_grid(Kernel kernel, int threads, size_t smem, long long work_ctas, int* grid_out) {
   bool found = false;
   int per_sm = cached_ctas_per_sm(reinterpret_cast<const void*>(kernel), threads, smem, &found);
   if (!found) {
-    if (smem > 48 * 1024)
-      CVB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (int rc = ensure_smem_optin(reinterpret_cast<const void*>(kernel), smem)) return rc;
     CVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
-    store_ctas_per_sm(reinterpret_cast<const void*>(kernel), per_sm);
+    store_ctas_per_sm(reinterpret_cast<const void*>(kernel), threads, smem, per_sm);
   }
   if (per_sm < 1) {
     set_last_error("kernel does not fit on an SM (threads=%d smem=%zu)", threads, smem);

@@ -315,3 +315,18 @@ def test_full_size_c4_streamed_2p20_vectors_vs_fp64_fft(d):
             assert float((rec - a[:sub]).abs().max() / a[:sub].abs().max()) < 2e-5
         del a, b, out
     assert worst < 1e-5, worst
+
+
+def test_direct_dft_shared_memory_optin_grows():
+    """The direct-DFT kernels size their shared memory at run time: a short length first (< 48 KB, no opt-in) and a long
+    one afterwards (> 48 KB) must both launch (the opt-in is tracked per kernel and raised on demand), and so must the
+    short one again."""
+    from utils import vsa
+    torch.manual_seed(3)
+    for d in (21, 3000, 21, 6000, 3000):
+        a = torch.randn(3, d, device=DEV)
+        b = torch.randn(3, d, device=DEV)
+        ab = vsa.bind(a, b)
+        got = vsa.unbind(ab, b, method="deconv")
+        ref = torch.fft.ifft(torch.fft.fft(ab.double()) / (torch.fft.fft(b.double()) + 1e-12)).real
+        assert rel_err(got.cpu(), ref.cpu()) < 5e-3, d
