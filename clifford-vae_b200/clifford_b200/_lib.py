@@ -66,6 +66,9 @@ _SIGNATURES = {
     "cvb_powerspherical_rsample_backward_head": ([_f, _f, _f, _ll, _fl, _fl, _f, _f, _f, _ull, _ull, _f, _f, _ll, _i, _f], _i),
     "cvb_vmf_rsample_kl_head": ([_f, _f, _ll, _fl, _fl, _f, _f, _i, _f, _ull, _ull, _f, _f, _f, _f, _f, _f, _f, _ll, _i, _f], _i),
     "cvb_vmf_rsample_backward_head": ([_f, _f, _f, _ll, _fl, _fl, _f, _f, _ull, _ull, _f, _f, _ll, _i, _f], _i),
+    "cvb_clifford_vm_entropy": ([_f, _ll, _i, _ll, _i, _f, _f, _f], _i),
+    "cvb_vmf_log_prob": ([_f, _f, _f, _f, _ll, _f, _f, _ll, _i, _f], _i),
+    "cvb_sphere_logprob_backward": ([_f, _f, _f, _ll, _f, _f, _ll, _i, _f], _i),
     "cvb_set_rng_device_counter": ([_f], _i),
     "cvb_ps_halfangle_icdf_table": ([_f, _ll, _f, _f, _f], _i),
     "cvb_philox_fill": ([_f, _ll, _ull, _ull, _f], _i),

@@ -192,7 +192,8 @@ class CliffordTorusDistribution(Distribution):
     (no gradient reaches loc / concentration).  The reference's own method never gets that far: its Hermitian-symmetry
     assert (:274) compares against the wrong flip and raises for generic angles, so no driver uses it
     (scripts/sample_viz.py:55-64 restates the sampler inline); this is the working version of what it computes.
-    ``entropy`` is evaluated with torch.special.i0e/i1e exactly as the reference does (off the hot path).
+    ``entropy`` is one kernel (`cvb_clifford_vm_entropy`: the reference's eps-regularised i0e/i1e expression, evaluated
+    from the fp64 log I_v of csrc/special.cuh, with its kappa-derivative).
     """
 
     arg_constraints: Dict[str, constraints.Constraint] = {}
@@ -218,12 +219,15 @@ class CliffordTorusDistribution(Distribution):
         return z.reshape(tuple(sample_shape) + tuple(self.batch_shape) + (2 * d,)).to(self.loc.dtype)
 
     def entropy(self):
-        k = self.concentration
-        eps = 1e-7
-        log_i0 = torch.log(torch.special.i0e(k) + eps) + k
-        log_i1 = torch.log(torch.special.i1e(k) + eps) + k
-        ent = _LOG_2PI + log_i0 - k * torch.exp(log_i1 - log_i0)
-        return ent[..., 1:].sum(-1)
+        # one kernel: sum over circles k >= 1 of ln 2 pi + ln(i0e + eps) + kappa - kappa (i1e + eps) / (i0e + eps)
+        d = self.orig_dim
+        raw = self._raw_concentration
+        if torch.is_tensor(raw) and raw.dim() >= 1 and raw.shape[-1] == 1 and d != 1:
+            kap = raw.expand(tuple(self.batch_shape) + (1,)).reshape(-1, 1)
+        else:
+            kap = self.concentration.reshape(-1, d)
+        ent = ops.VMTorusEntropy.apply(kap, d)
+        return ent.reshape(self.batch_shape).to(self.loc.dtype)
 
 
 class CliffordPowerSphericalDistribution(CliffordTorusDistribution):

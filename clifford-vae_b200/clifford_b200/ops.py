@@ -630,11 +630,81 @@ class PowerSphericalLogProb(torch.autograd.Function):
         val_c, loc_c, coef, dk = ctx.saved_tensors
         B, D, rows, kshape = ctx.meta
         S = rows // B
-        w = (grad.reshape(rows) * coef)[:, None]
-        dval = w * loc_c.repeat(S, 1) if ctx.needs_input_grad[0] else None
-        dloc = (w * val_c).view(S, B, D).sum(0) if ctx.needs_input_grad[1] else None
-        dkap = (grad.reshape(rows) * dk).view(S, B).sum(0).reshape(kshape) if ctx.needs_input_grad[2] else None
+        g = _f32c(grad).reshape(rows)
+        dval, dloc = _logprob_backward(g * coef, val_c, loc_c, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        dkap = (g * dk).view(S, B).sum(0).reshape(kshape) if ctx.needs_input_grad[2] else None
         return dval, dloc, dkap
+
+
+def _logprob_backward(w, val_c, loc_c, want_dval, want_dloc):
+    """d lp / d value = w loc and d lp / d loc = sum over samples of w value for a row log-density lp = f(<loc, value>),
+    w (rows) = upstream gradient times f'.  One kernel (the sample-dimension sum included)."""
+    rows, D = val_c.shape
+    B = loc_c.shape[0]
+    dval = torch.empty(rows, D, device=val_c.device, dtype=torch.float32) if want_dval else None
+    dloc = torch.empty(B, D, device=val_c.device, dtype=torch.float32) if want_dloc else None
+    if want_dval or want_dloc:
+        w = _f32c(w)
+        _launch("cvb_sphere_logprob_backward", val_c.device, ptr(w), ptr(val_c), ptr(loc_c), B, ptr(dval), ptr(dloc), rows, D,
+                skip=val_c.numel() == 0)
+    return dval, dloc
+
+
+class VMFLogProb(torch.autograd.Function):
+    """VonMisesFisher.log_prob (von_mises_fisher.py:193-212): lp (rows,) = kappa <loc, value> - log_norm for value
+    (rows, D), loc (B, D), kappa (B,), log_norm (B,) (the fused / cached `_log_normalization`, itself a function of kappa
+    in the autograd graph); rows = S * B."""
+
+    @staticmethod
+    def forward(ctx, value, loc, kappa, log_norm):
+        lib, dev = _prep(value, loc, kappa, log_norm)
+        B, D = loc.shape
+        rows = value.shape[0]
+        val_c, loc_c, kap_c, ln_c = _f32c(value), _f32c(loc), _f32c(kappa.reshape(-1)), _f32c(log_norm.reshape(-1))
+        lp = torch.empty(rows, device=dev, dtype=torch.float32)
+        dot = torch.empty(rows, device=dev, dtype=torch.float32) if ctx.needs_input_grad[2] else None
+        _launch("cvb_vmf_log_prob", dev, ptr(val_c), ptr(loc_c), ptr(kap_c), ptr(ln_c), B, ptr(lp), ptr(dot), rows, D,
+                skip=val_c.numel() == 0)
+        ctx.save_for_backward(val_c, loc_c, kap_c, dot)
+        ctx.meta = (B, D, rows, tuple(kappa.shape), tuple(log_norm.shape))
+        return lp
+
+    @staticmethod
+    def backward(ctx, grad):
+        val_c, loc_c, kap_c, dot = ctx.saved_tensors
+        B, D, rows, kshape, lshape = ctx.meta
+        S = rows // B
+        g = _f32c(grad).reshape(rows)
+        w = (g.view(S, B) * kap_c).reshape(rows)
+        dval, dloc = _logprob_backward(w, val_c, loc_c, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        dkap = (g * dot).view(S, B).sum(0).reshape(kshape) if ctx.needs_input_grad[2] else None
+        dln = (-g.view(S, B).sum(0)).reshape(lshape) if ctx.needs_input_grad[3] else None
+        return dval, dloc, dkap, dln
+
+
+class VMTorusEntropy(torch.autograd.Function):
+    """CliffordTorusDistribution.entropy (dists/clifford.py:21-31, :277-278) per row of kappa (B,1)|(B,d): the sum over
+    circles k >= 1 of the (eps-regularised) von Mises entropy, with its kappa-derivative for the backward."""
+
+    @staticmethod
+    def forward(ctx, kappa, d):
+        lib, dev = _prep(kappa)
+        kap_c, krs, kes = _kappa_layout(kappa, d)
+        B = kap_c.shape[0]
+        ent = torch.empty(B, device=dev, dtype=torch.float32)
+        dent = torch.empty((B,) if kes == 0 else (B, d), device=dev, dtype=torch.float32) if ctx.needs_input_grad[0] else None
+        _launch("cvb_clifford_vm_entropy", dev, ptr(kap_c), krs, kes, B, d, ptr(ent), ptr(dent), skip=B == 0)
+        ctx.save_for_backward(dent)
+        ctx.kshape = tuple(kappa.shape)
+        ctx.kes = kes
+        return ent
+
+    @staticmethod
+    def backward(ctx, grad):
+        (dent,) = ctx.saved_tensors
+        g = grad.reshape(-1)
+        dk = g * dent if ctx.kes == 0 else g[:, None] * dent
+        return dk.reshape(ctx.kshape), None
 
 
 class PSLogNormalizer(torch.autograd.Function):

@@ -152,7 +152,14 @@ class VonMisesFisher(torch.distributions.Distribution):
         return self._ent_ln()[0].type(self.dtype)
 
     def log_prob(self, x):
-        return self._log_unnormalized_prob(x) - self._log_normalization()
+        # one kernel: kappa <loc, x> - log_norm per row (von_mises_fisher.py:193-212)
+        m = self._m
+        lead = tuple(self.loc.shape[:-1])
+        if tuple(self.scale.shape) != lead + (1,) or tuple(x.shape[-len(lead) - 1:]) != lead + (m,):
+            return self._log_unnormalized_prob(x) - self._log_normalization()       # exotic broadcasting: torch ops
+        lp = ops.VMFLogProb.apply(x.reshape(-1, m), self.loc.reshape(-1, m), self.scale.reshape(-1),
+                                  self._log_normalization().reshape(-1))
+        return lp.reshape(x.shape[:-1]).type(self.dtype)
 
     def _log_unnormalized_prob(self, x):
         # kappa * <loc, x>: a row dot product -- the cosine kernel's numerator; use the PS log-prob

@@ -114,4 +114,18 @@ int cvb_ps_entropy_kl(const float* kappa, long long kappa_row_stride, int kappa_
   return check_launch("ps_entropy_kernel");
 }
 
+// CliffordTorusDistribution.entropy (dists/clifford.py:21-31, :277-278): sum over circles k >= 1 of the von Mises entropy
+int cvb_clifford_vm_entropy(const float* kappa, long long kappa_row_stride, int kappa_el_stride, long long rows, int d,
+                            float* entropy, float* dentropy, void* stream) {
+  CVB_REQUIRE(kappa && rows > 0 && d >= 1 && (entropy || dentropy), kBadArgument, "cvb_clifford_vm_entropy: bad arguments");
+  EntropyParams p{};
+  p.kappa = kappa; p.kappa_row_stride = kappa_row_stride; p.kappa_el_stride = kappa_el_stride; p.entropy = entropy;
+  p.dentropy = dentropy; p.rows = rows; p.d = d;
+  int blocks = (int)((rows * 32 + 255) / 256);
+  const int cap = sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  vm_entropy_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p);
+  return check_launch("vm_entropy_kernel");
+}
+
 }  // extern "C"

@@ -175,6 +175,29 @@ int cvb_vmf_entropy_lognorm(const float* kappa, long long rows, int D, float* en
   return check_launch("vmf_entropy_kernel");
 }
 
+// VonMisesFisher.log_prob (von_mises_fisher.py:193-212): kappa <loc, x> - log_norm; dot (rows) optional
+int cvb_vmf_log_prob(const float* value, const float* loc, const float* kappa, const float* log_norm, long long loc_rows,
+                     float* log_prob, float* dot, long long rows, int D, void* stream) {
+  CVB_REQUIRE(value && loc && kappa && log_norm && log_prob && rows > 0 && loc_rows > 0 && D >= 1, kBadArgument,
+              "cvb_vmf_log_prob: bad arguments");
+  VmfLogProbParams p{value, loc, kappa, log_norm, loc_rows, log_prob, dot, rows, D};
+  vmf_log_prob_kernel<<<row_warp_grid(rows), 256, 0, (cudaStream_t)stream>>>(p);
+  return check_launch("vmf_log_prob_kernel");
+}
+
+// backward helper of the row log-densities: dvalue = w (x) loc, dloc = sum over samples of w (x) value
+int cvb_sphere_logprob_backward(const float* w, const float* value, const float* loc, long long loc_rows, float* dvalue,
+                                float* dloc, long long rows, int D, void* stream) {
+  CVB_REQUIRE(w && value && loc && rows > 0 && loc_rows > 0 && D >= 1 && rows % loc_rows == 0 && (dvalue || dloc), kBadArgument,
+              "cvb_sphere_logprob_backward: bad arguments");
+  RowScaleParams p{w, value, loc, loc_rows, rows, D, dvalue, dloc};
+  long long blocks = (loc_rows * (long long)D + 255) / 256;
+  const long long cap = (long long)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  row_scale_pair_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+  return check_launch("row_scale_pair_kernel");
+}
+
 // ---- public entry points over the implementations above: plain concentration, or the concentration head folded in
 // (kappa = min(softplus(raw_scale) + floor, kmax), mnist/mlp_vae.py:69-71; every kappa-derivative is then d / d raw_scale)
 int cvb_powerspherical_rsample_kl(const float* loc, const float* kappa, long long loc_rows, const float* tprime,

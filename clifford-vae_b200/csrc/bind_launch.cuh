@@ -69,6 +69,19 @@ int dispatch_bind(const BindParams& p, int d, cudaStream_t st) {
   // any other length: the bilinear modes fold a zero-padded power-of-two convolution (bind_pad_kernel) once the
   // O(d^2) direct DFT would cost more (d > 48); the quotient modes need the true length-d spectrum (direct DFT)
   static const bool no_pad = getenv("CVB_BIND_NO_PAD") != nullptr;      // A/B switch for tools/bench_small_dims.py
+  static const bool no_small = getenv("CVB_NO_SMALL_ROWS") != nullptr;  // A/B switch: one CTA per pair at short lengths
+  constexpr bool kBilinear = (MODE == kBindMul || MODE == kBindMulConj || MODE == kBindNegMulConj);
+  if (d <= kBindSmallMaxD && !no_small && (!kBilinear || d <= 48 || no_pad)) {
+    // short vectors: a tile of pairs per CTA (rows per tile sized so that small batches stay spread over the SMs)
+    int rt = 32;
+    while (rt > 4 && (p.rows + rt - 1) / rt < 2LL * sm_count()) rt >>= 1;
+    const size_t smem_s = bind_small_smem(d, rt);
+    auto kern_s = bind_small_kernel<MODE>;
+    int grid_s = 0;
+    if (int rc = persistent_grid(kern_s, kBindSmallThreads, smem_s, (p.rows + rt - 1) / rt, &grid_s)) return rc;
+    kern_s<<<grid_s, kBindSmallThreads, smem_s, st>>>(p, d, rt);
+    return check_launch("bind_small_kernel");
+  }
   if constexpr (MODE == kBindMul || MODE == kBindMulConj || MODE == kBindNegMulConj) {
     if (d > 48 && d <= 8192 && !no_pad) {
       int log2m = 1;

@@ -668,4 +668,53 @@ static __global__ void vmf_entropy_kernel(const float* kappa, long long rows, in
   }
 }
 
+// VonMisesFisher.log_prob (von_mises_fisher.py:193-212): lp = kappa <loc, x> - log_norm(kappa), log_norm = the
+// reference's `_log_normalization` (passed in per parameter row, from the sampler launch or vmf_entropy_kernel).
+// Optional `dot` (rows) = <loc, x> for the backward.  One warp per row.
+struct VmfLogProbParams {
+  const float* value; const float* loc; const float* kappa; const float* log_norm; long long loc_rows;
+  float* log_prob; float* dot; long long rows; int D;
+};
+static __global__ void __launch_bounds__(256) vmf_log_prob_kernel(const VmfLogProbParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long row = warp; row < p.rows; row += nwarps) {
+    const long long prow = row % p.loc_rows;
+    const float* lr = p.loc + prow * p.D;
+    const float* vr = p.value + row * p.D;
+    float dot = 0.f;
+    for (int i = lane; i < p.D; i += 32) dot = fmaf(__ldg(lr + i), ldg_stream1(vr + i), dot);
+    dot = warp_sum(dot);
+    if (lane == 0) {
+      p.log_prob[row] = p.kappa[prow] * dot - p.log_norm[prow];
+      if (p.dot) p.dot[row] = dot;
+    }
+  }
+}
+
+// Backward helper of the row log-densities lp = f(<loc, x>): with w (rows) = upstream * d lp / d <loc, x>,
+//   dvalue[r, :] = w[r] loc[r % loc_rows, :]   and   dloc[q, :] = sum_{s} w[s loc_rows + q] value[s loc_rows + q, :]
+// (the sum over the sample dimension is done here, fixed order: deterministic).  Either output may be null.
+struct RowScaleParams {
+  const float* w; const float* value; const float* loc; long long loc_rows; long long rows; int D;
+  float* dvalue; float* dloc;
+};
+static __global__ void __launch_bounds__(256) row_scale_pair_kernel(const RowScaleParams p) {
+  const long long total = p.loc_rows * (long long)p.D;
+  const long long S = p.rows / p.loc_rows;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long q = i / p.D;
+    const float l = p.dvalue ? __ldg(p.loc + i) : 0.f;
+    float acc = 0.f;
+    for (long long s = 0; s < S; ++s) {
+      const long long r = s * p.loc_rows + q;
+      const float w = __ldg(p.w + r);
+      if (p.dvalue) p.dvalue[s * total + i] = w * l;
+      if (p.dloc) acc = fmaf(w, ldg_stream1(p.value + s * total + i), acc);
+    }
+    if (p.dloc) p.dloc[i] = acc;
+  }
+}
+
 }  // namespace cvb

@@ -401,6 +401,105 @@ bind_generic_kernel(const BindParams p, int d) {
   }
 }
 
+// ---- short vectors of any length (d <= 128): a TILE of RT pairs per CTA ----------------------------------------------
+// The reference's default MNIST latents are bound / unbound at d = 2 z_dim (Clifford: 4 .. 80) or z_dim + 1 (vMF:
+// 3 .. 41) (mnist/mnist_clifpws.py:235-236,713-719); one 256-thread CTA per pair (bind_generic_kernel) idles most of its
+// threads there.  Same scheme as clifford_small.cuh: operands parked as g[j][r], one (4 pairs, bin k) item per thread
+// for the two forward real DFTs (packed FMAs, exact index-reduced twiddles, 128-bit broadcast loads), the pointwise op,
+// then one (4 pairs, output j) item per thread for the inverse, outputs j and d - j together (shared cos, negated sin).
+// fp32 accumulation (<= 128 terms).
+constexpr int kBindSmallMaxD = 128;
+constexpr int kBindSmallThreads = 128;
+inline size_t bind_small_smem(int d, int rt) {
+  return sizeof(cplx) * (size_t)((d + 1) & ~1) + 2 * sizeof(float) * (size_t)d * (rt + 4) + sizeof(cplx) * (size_t)(d / 2 + 1) * (rt + 2);
+}
+template <int MODE>
+__global__ void __launch_bounds__(kBindSmallThreads)
+bind_small_kernel(const BindParams p, const int d, const int RT) {
+  extern __shared__ __align__(16) unsigned char smem_bs[];
+  const int GP = RT + 4, XP = RT + 2, nh = d / 2, kmax = (d - 1) / 2;
+  cplx* tw = reinterpret_cast<cplx*>(smem_bs);
+  float* ga = reinterpret_cast<float*>(tw + ((d + 1) & ~1));
+  float* gb = ga + (size_t)d * GP;
+  cplx* P = reinterpret_cast<cplx*>(gb + (size_t)d * GP);
+  for (int m = threadIdx.x; m < d; m += blockDim.x) {
+    double sn, cs;
+    sincospi(2.0 * (double)m / (double)d, &sn, &cs);
+    tw[m] = make_float2((float)cs, (float)sn);
+  }
+  const long long tiles = (p.rows + RT - 1) / RT;
+  const float inv_d = 1.0f / (float)d;
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const long long row0 = tile * RT;
+    __syncthreads();
+    for (int i = threadIdx.x; i < RT * d; i += kBindSmallThreads) {
+      const int r = i / d, j = i - r * d;
+      const long long row = row0 + r;
+      const bool in = row < p.rows;
+      ga[j * GP + r] = in ? __ldg(p.a + (row % p.a_rows) * (long long)d + j) : 0.0f;
+      gb[j * GP + r] = in ? __ldg(p.b + (row % p.b_rows) * (long long)d + j) : 0.0f;
+    }
+    __syncthreads();
+    // forward: A_k, B_k = sum_j x_j e^{-2 pi i jk/d}, k = 0 .. d/2, then the pointwise op
+    for (int i = threadIdx.x; i < (RT / 4) * (nh + 1); i += kBindSmallThreads) {
+      const int q = i / (nh + 1), k = i - q * (nh + 1);
+      float2 aa[4], bb[4];
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) { aa[rr] = make_float2(0.f, 0.f); bb[rr] = make_float2(0.f, 0.f); }
+      int m = 0;
+      for (int j = 0; j < d; ++j) {
+        const cplx w = make_float2(tw[m].x, -tw[m].y);
+        const float4 a4 = *reinterpret_cast<const float4*>(ga + j * GP + 4 * q);
+        const float4 b4 = *reinterpret_cast<const float4*>(gb + j * GP + 4 * q);
+        aa[0] = __ffma2_rn(make_float2(a4.x, a4.x), w, aa[0]); bb[0] = __ffma2_rn(make_float2(b4.x, b4.x), w, bb[0]);
+        aa[1] = __ffma2_rn(make_float2(a4.y, a4.y), w, aa[1]); bb[1] = __ffma2_rn(make_float2(b4.y, b4.y), w, bb[1]);
+        aa[2] = __ffma2_rn(make_float2(a4.z, a4.z), w, aa[2]); bb[2] = __ffma2_rn(make_float2(b4.z, b4.z), w, bb[2]);
+        aa[3] = __ffma2_rn(make_float2(a4.w, a4.w), w, aa[3]); bb[3] = __ffma2_rn(make_float2(b4.w, b4.w), w, bb[3]);
+        m += k;
+        if (m >= d) m -= d;
+      }
+      const bool real_bin = (k == 0) || (2 * k == d);
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        if (real_bin) { aa[rr].y = 0.f; bb[rr].y = 0.f; }
+        P[k * XP + 4 * q + rr] = bind_op(MODE, aa[rr], bb[rr]);
+      }
+    }
+    __syncthreads();
+    // inverse: out_j = (1/d) (P_0 + (-1)^j P_{d/2} + 2 sum_k (Re P_k cos(2 pi jk/d) - Im P_k sin(2 pi jk/d))); out_{d-j}: + Im P_k sin
+    for (int i = threadIdx.x; i < (RT / 4) * (nh + 1); i += kBindSmallThreads) {
+      const int q = i / (nh + 1), j = i - q * (nh + 1);
+      float2 acc[4];
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) acc[rr] = make_float2(0.f, 0.f);
+      int m = 0;
+      const cplx* pq = P + 4 * q;
+      for (int k = 1; k <= kmax; ++k) {
+        m += j;
+        if (m >= d) m -= d;
+        const cplx w = tw[m];
+        const float4 x01 = *reinterpret_cast<const float4*>(pq + k * XP);
+        const float4 x23 = *reinterpret_cast<const float4*>(pq + k * XP + 2);
+        acc[0] = __ffma2_rn(make_float2(x01.x, x01.y), w, acc[0]);
+        acc[1] = __ffma2_rn(make_float2(x01.z, x01.w), w, acc[1]);
+        acc[2] = __ffma2_rn(make_float2(x23.x, x23.y), w, acc[2]);
+        acc[3] = __ffma2_rn(make_float2(x23.z, x23.w), w, acc[3]);
+      }
+      const bool mirror = (j != 0) && (2 * j != d);
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        const long long row = row0 + 4 * q + rr;
+        if (row < p.rows) {
+          float base = pq[rr].x;
+          if ((d & 1) == 0) base += (j & 1) ? -pq[nh * XP + rr].x : pq[nh * XP + rr].x;
+          p.out[row * (long long)d + j] = inv_d * (base + 2.0f * (acc[rr].x - acc[rr].y));
+          if (mirror) p.out[row * (long long)d + (d - j)] = inv_d * (base + 2.0f * (acc[rr].x + acc[rr].y));
+        }
+      }
+    }
+  }
+}
+
 // ---- elementwise / reduction VSA helpers --------------------------------------------------------
 // invert (vsa.py:49-53): out[r, j] = a[r, (d - j) mod d]
 // one warp per row: no per-element 64-bit division

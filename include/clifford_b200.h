@@ -212,6 +212,21 @@ CVB_API int cvb_vmf_rsample_backward(const float* grad_z, const float* loc, cons
 CVB_API int cvb_vmf_entropy_lognorm(const float* kappa, long long rows, int D, float* entropy, float* log_norm,
                                     float* dentropy, float* dlog_norm, void* stream);
 
+/* CliffordTorusDistribution.entropy (dists/clifford.py:21-31 `_von_mises_entropy`, :277-278): sum over circles k >= 1 of
+ * ln 2 pi + ln(i0e(kappa) + 1e-7) + kappa - kappa (i1e(kappa) + 1e-7) / (i0e(kappa) + 1e-7).  kappa addressed like
+ * cvb_clifford_ps_rsample's.  entropy (rows); dentropy optional: (rows) when kappa_el_stride == 0, else (rows, d). */
+CVB_API int cvb_clifford_vm_entropy(const float* kappa, long long kappa_row_stride, int kappa_el_stride, long long rows,
+                                    int d, float* entropy, float* dentropy, void* stream);
+/* VonMisesFisher.log_prob (von_mises_fisher.py:193-212): log_prob (rows) = kappa <loc, value> - log_norm, with log_norm
+ * (loc_rows) from cvb_vmf_rsample_kl / cvb_vmf_entropy_lognorm; dot (rows) = <loc, value>, optional (for the backward). */
+CVB_API int cvb_vmf_log_prob(const float* value, const float* loc, const float* kappa, const float* log_norm,
+                             long long loc_rows, float* log_prob, float* dot, long long rows, int D, void* stream);
+/* Backward of the row log-densities lp = f(<loc, value>) (PowerSpherical.log_prob, VonMisesFisher.log_prob): with
+ * w (rows) = upstream * d lp / d <loc, value>:  dvalue (rows, D) = w loc,  dloc (loc_rows, D) = sum over the samples
+ * sharing a parameter row of w value.  Either output may be NULL. */
+CVB_API int cvb_sphere_logprob_backward(const float* w, const float* value, const float* loc, long long loc_rows,
+                                        float* dvalue, float* dloc, long long rows, int D, void* stream);
+
 /* ---- Concentration head folded into the samplers ------------------------------------------
  * Every reference model computes the concentration as  kappa = clamp(softplus(fc_scale(h)) + floor, max=kmax)
  * (mnist/mlp_vae.py:69-71 floor 0.8 | 0.03, max 10; cnn/models.py:96,99 floor 0.5 | concentration_floor) right before

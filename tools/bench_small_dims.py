@@ -68,7 +68,7 @@ for d in (32, 64, 128, 256, 512):
     del a, b, o
 # non-power-of-two VSA lengths: heat-map dims 144 / 484 (scripts/binding_depth_heatmap.py:101), d+1 latents 41 / 129 / 513
 # (mnist/mnist_clifpws.py:235-236), odd sizes
-for d in (21, 41, 100, 129, 144, 484, 513, 1000, 3000):
+for d in (4, 10, 21, 41, 80, 100, 129, 144, 484, 513, 1000, 3000):
     N = max(4096, (1 << 26) // (12 * d))
     a = torch.randn(N, d, device=dev); b = torch.randn(N, d, device=dev); o = torch.empty(N, d, device=dev)
     for name, mode in (("bind", 0), ("unbind inv", 1), ("unbind deconv", 2)):
