@@ -846,7 +846,10 @@ __device__ __forceinline__ void clifford_lp_element(const CliffordLogProbParams&
     sa = Fk.y * ri;
   }
   float sl, cl;
-  sincosf(loc_k, &sl, &cl);
+  // evaluation (no gradient outputs): Cody-Waite reduction + MUFU (abs error 4e-7 on the dot product, against the
+  // 1.2e-7 rounding the clamp bounds already carry); the gradient variants keep the accurate routine
+  if (FWD_ONLY) sincos_any<true>(loc_k, sl, cl);
+  else sincosf(loc_k, &sl, &cl);
   const float dot_raw = fmaf(cl, ca, sl * sa);
   const float dot = fminf(fmaxf(dot_raw, -1.0f + kEps), 1.0f - kEps);
   const float l1p = log1pf(dot);

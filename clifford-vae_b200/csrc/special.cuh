@@ -72,13 +72,21 @@ __device__ __forceinline__ void gamma_family(double x, double& lg, double& psi, 
   psi = lx - 0.5 * r - z * (1.0 / 12 + z * (-1.0 / 120 + z * (1.0 / 252 + z * (-1.0 / 240 + z * (1.0 / 132 + z * (-691.0 / 32760 + z / 12)))))) - s1;
   psi1 = r * (1.0 + 0.5 * r + z * (1.0 / 6 + z * (-1.0 / 30 + z * (1.0 / 42 + z * (-1.0 / 30 + z * (5.0 / 66 + z * (-691.0 / 2730 + z * (7.0 / 6)))))))) + s2;
 }
+// from the gamma families of a = half_dm1 + kappa + 1e-7 and of a + b (b = half_dm1), evaluated by the caller
+__device__ __forceinline__ PsConsts ps_consts_from(double kappa, double half_dm1, double lga, double psa, double p1a, double lgt,
+                                                   double pst, double p1t);
 __device__ __forceinline__ PsConsts ps_consts(double kappa, double half_dm1) {
-  const double LOG2 = 0.69314718055994530942, LOGPI = 1.14472988584940017414;
-  const double s = kappa + 1e-7;
-  const double a = half_dm1 + s, b = half_dm1;
+  const double a = half_dm1 + (kappa + 1e-7), b = half_dm1;
   double lga, psa, p1a, lgt, pst, p1t;
   gamma_family(a, lga, psa, p1a);
   gamma_family(a + b, lgt, pst, p1t);
+  return ps_consts_from(kappa, half_dm1, lga, psa, p1a, lgt, pst, p1t);
+}
+__device__ __forceinline__ PsConsts ps_consts_from(double kappa, double half_dm1, double lga, double psa, double p1a, double lgt,
+                                                   double pst, double p1t) {
+  const double LOG2 = 0.69314718055994530942, LOGPI = 1.14472988584940017414;
+  const double s = kappa + 1e-7;
+  const double a = half_dm1 + s, b = half_dm1;
   PsConsts c;
   c.log_norm = -((a + b) * LOG2 + lga - lgt + b * LOGPI);
   const double dpsi = psa - pst;

@@ -158,24 +158,36 @@ __device__ __forceinline__ void bessel_ratio_bound(double v, double z, double a,
   dB = (den - z * (ddelta + dS)) / (den * den);
 }
 struct VmfRowScalars { float entropy, log_norm, dentropy, dlog_norm; };
+// The four independent fp64 chains behind the row scalars: ive(v, k), ive(v - 1, k) and the two Bessel-ratio bounds.
+// One lane can run them back to back (vmf_row_scalars), or four lanes one each (sphere_row_scalars with few rows per
+// warp: the serial chain -- two Bessel series with their lgamma -- was 6 us of the 14 us C2 vMF step).
+__device__ __forceinline__ double vmf_piece_ive(double k, int D) { return exp(log_ive(0.5 * (double)D - 1.0, k)); }
+__device__ __forceinline__ double vmf_piece_ive_m1(double k, int D) {
+  const double v = 0.5 * (double)D - 1.0;
+  // ive(v - 1, k); orders below zero only occur for m = 2 (I_{-1} = I_1) and m = 3 (closed form)
+  if (v >= 1.0) return exp(log_ive(v - 1.0, k));
+  if (v == 0.0) return exp(log_ive(1.0, k));
+  return sqrt(2.0 / (3.14159265358979323846 * k)) * 0.5 * (1.0 + exp(-2.0 * k));
+}
+__device__ __forceinline__ VmfRowScalars vmf_row_scalars_combine(double k, int D, double ive, double im1, double B0, double dB0,
+                                                                  double B2, double dB2);
 __device__ __forceinline__ VmfRowScalars vmf_row_scalars(double k, int D) {
+  const double m2 = 0.5 * (double)D;
+  double B0, dB0, B2, dB2;
+  bessel_ratio_bound(m2, k, 0.0, B0, dB0);
+  bessel_ratio_bound(m2, k, 2.0, B2, dB2);
+  return vmf_row_scalars_combine(k, D, vmf_piece_ive(k, D), vmf_piece_ive_m1(k, D), B0, dB0, B2, dB2);
+}
+__device__ __forceinline__ VmfRowScalars vmf_row_scalars_combine(double k, int D, double ive, double im1, double B0, double dB0,
+                                                                  double B2, double dB2) {
   const double m2 = 0.5 * (double)D, v = m2 - 1.0;
-  const double live = log_ive(v, k);
-  const double ive = exp(live);
   const double lval = log(ive + 1e-20);
   const double ln = -(v * log(k) - m2 * 1.83787706640934548356 - (k + lval));
   // d ive/dk = ive(v-1) - ive(v) (v + k)/k   (ops/ive.py:29-34)
-  double im1;   // ive(v - 1, k); orders below zero only occur for m = 2 (I_{-1} = I_1) and m = 3 (closed form)
-  if (v >= 1.0) im1 = exp(log_ive(v - 1.0, k));
-  else if (v == 0.0) im1 = exp(log_ive(1.0, k));
-  else im1 = sqrt(2.0 / (3.14159265358979323846 * k)) * 0.5 * (1.0 + exp(-2.0 * k));
   const double dive = im1 - ive * (v + k) / k;
   const double dlval = dive / (ive + 1e-20);
   const double dln = -(v / k - (1.0 + dlval));
   const float ln_f = (float)ln;
-  double B0, dB0, B2, dB2;
-  bessel_ratio_bound(m2, k, 0.0, B0, dB0);
-  bessel_ratio_bound(m2, k, 2.0, B2, dB2);
   const double frac = 0.5 * (B0 + B2), dfrac = 0.5 * (dB0 + dB2);
   VmfRowScalars r;
   r.log_norm = ln_f;
@@ -314,6 +326,66 @@ sphere_rsample_kernel(const SphereParams p) {
 // loc row is loaded ONCE with all loads in flight together (the two-pass kernel above re-reads it and stashes the normals
 // in the output row: `long_scoreboard` 52 % of its stalls), the normals stay in registers, z is written once, and the
 // compile-time trip counts remove most of the per-element index arithmetic (IMAD/IADD3/LEA were 35 % of its instructions).
+__device__ __forceinline__ double shfl_double(double v, int src) {
+  return __hiloint2double(__shfl_sync(0xffffffffu, __double2hiint(v), src), __shfl_sync(0xffffffffu, __double2loint(v), src));
+}
+// The same row scalars with the independent fp64 chains of one row spread over a QUAD of lanes: lane 16 + 4 j + part
+// serves row j (j < 4) of the warp's batch.  Two steps, so that the (divergent) chains can interleave with the scalar
+// draws the first lanes run in between: `pieces` (no convergence point) and `combine` (shuffles inside the quad; all
+// 32 lanes must call it).  Used when a warp has at most 4 rows to serve.
+struct RowScalarPieces { double r0, r1, r2; float raw; bool mine; long long prow; };
+template <int FAMILY>
+__device__ __forceinline__ RowScalarPieces sphere_row_scalar_pieces(const SphereParams& p, long long base, long long nwarps, int lane) {
+  RowScalarPieces o;
+  o.r0 = o.r1 = o.r2 = 0.0; o.raw = 1.0f; o.mine = false; o.prow = 0;
+  if (lane < 16) return o;
+  const int jr = (lane - 16) >> 2, part = lane & 3;
+  o.prow = base + (long long)jr * nwarps;
+  o.mine = o.prow < p.rows && o.prow < p.loc_rows;
+  if (!o.mine) return o;
+  o.raw = __ldg(p.kappa + o.prow);
+  const double kap = (double)head_kappa(p.head, o.raw);
+  if (FAMILY == kFamilyVMF) {
+    // lanes of a quad must run the SAME instruction stream to run side by side (divergent paths of one warp are
+    // serialised): the two Bessel series differ only in their order, the two ratio bounds only in `a`
+    const double v = 0.5 * (double)p.D - 1.0;
+    if (part < 2) {
+      if (part == 1 && v < 1.0 && v != 0.0) o.r0 = vmf_piece_ive_m1(kap, p.D);                  // m = 3: closed form
+      else o.r0 = exp(log_ive(part == 0 ? v : (v >= 1.0 ? v - 1.0 : 1.0), kap));
+    } else {
+      bessel_ratio_bound(0.5 * (double)p.D, kap, part == 2 ? 0.0 : 2.0, o.r0, o.r1);
+    }
+  } else if (part < 2) {
+    // lgamma / digamma / trigamma of a (lane 0 of the quad) and of a + b (lane 1)
+    const double half = 0.5 * (double)(p.D - 1);
+    gamma_family(part == 0 ? half + (kap + 1e-7) : half + (kap + 1e-7) + half, o.r0, o.r1, o.r2);
+  }
+  return o;
+}
+template <int FAMILY>
+__device__ __forceinline__ void sphere_row_scalar_combine(const SphereParams& p, const RowScalarPieces& o, int lane) {
+  const int qb = lane & ~3;
+  const double a0 = shfl_double(o.r0, qb + 1), a1 = shfl_double(o.r1, qb + 1), a2 = shfl_double(o.r2, qb + 1);
+  const double b0 = shfl_double(o.r0, qb + 2), b1 = shfl_double(o.r1, qb + 2);
+  const double c0 = shfl_double(o.r0, qb + 3), c1 = shfl_double(o.r1, qb + 3);
+  if (!o.mine || (lane & 3) != 0) return;
+  const double kap = (double)head_kappa(p.head, o.raw);
+  const float chain = head_dkappa(p.head, o.raw);
+  if (FAMILY == kFamilyVMF) {
+    const VmfRowScalars r = vmf_row_scalars_combine(kap, p.D, o.r0, a0, b0, b1, c0, c1);
+    if (p.entropy) p.entropy[o.prow] = r.entropy;
+    if (p.kl) p.kl[o.prow] = (float)(p.prior_entropy - (double)r.entropy);
+    if (p.dentropy) p.dentropy[o.prow] = r.dentropy * chain;
+    if (p.log_norm) p.log_norm[o.prow] = r.log_norm;
+    if (p.dlog_norm) p.dlog_norm[o.prow] = r.dlog_norm * chain;
+  } else {
+    const PsConsts c = ps_consts_from(kap, 0.5 * (double)(p.D - 1), o.r0, o.r1, o.r2, a0, a1, a2);
+    if (p.entropy) p.entropy[o.prow] = (float)c.entropy;
+    if (p.kl) p.kl[o.prow] = (float)(p.prior_entropy - c.entropy);
+    if (p.dentropy) p.dentropy[o.prow] = (float)c.dentropy * chain;
+  }
+}
+
 template <int FAMILY, int K>
 __global__ void __launch_bounds__(256)
 sphere_rsample_reg_kernel(const SphereParams p) {
@@ -326,11 +398,19 @@ sphere_rsample_reg_kernel(const SphereParams p) {
   // lane for one row (that was 37 % of the vMF kernel).  With fewer than 32 rows per warp the idle lanes simply skip.
   for (long long base = warp; base < p.rows; base += 32 * nwarps) {
   float w_l = 0.f, dw_l = 0.f;      // lane j: scalar draw of the batch's j-th row (vMF: w, dw/dkappa; PS: t')
-  if (FAMILY != kFamilyUniform && (p.entropy || p.kl || p.dentropy || p.log_norm)) {
-    // fused entropy / KL of the batch's rows: lane (j + 16) % 32 takes row j, so that with a single row per warp (small
-    // batches) the fp64 chain runs on lane 16 while lane 0 draws -- the two divergent paths interleave
-    const long long re = base + (long long)((lane + 16) & 31) * nwarps;
-    if (re < p.rows && re < p.loc_rows) sphere_row_scalars<FAMILY>(p, re);
+  const bool want_scalars = FAMILY != kFamilyUniform && (p.entropy || p.kl || p.dentropy || p.log_norm);
+  // at most 4 rows in this batch (small batches: C2 has one row per warp): each row's independent fp64 chains run on
+  // four lanes side by side (lanes 16 .. 31), interleaved with the draws on lanes 0 .. 3; combined after the draws
+  const bool quad_scalars = want_scalars && (base + 4 * nwarps >= p.rows);
+  RowScalarPieces pieces{};
+  if (quad_scalars) pieces = sphere_row_scalar_pieces<FAMILY>(p, base, nwarps, lane);
+  if (want_scalars) {
+    if (!quad_scalars) {
+      // fused entropy / KL of the batch's rows: lane (j + 16) % 32 takes row j, so that the fp64 chains interleave with
+      // the draws of the first lanes
+      const long long re = base + (long long)((lane + 16) & 31) * nwarps;
+      if (re < p.rows && re < p.loc_rows) sphere_row_scalars<FAMILY>(p, re);
+    }
   }
   {
     const long long rj = base + (long long)lane * nwarps;
@@ -353,6 +433,7 @@ sphere_rsample_reg_kernel(const SphereParams p) {
       }
     }
   }
+  if (quad_scalars) sphere_row_scalar_combine<FAMILY>(p, pieces, lane);
   for (int jr = 0; jr < 32; ++jr) {
     const long long row = base + (long long)jr * nwarps;
     if (row >= p.rows) break;
