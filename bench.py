@@ -614,25 +614,22 @@ def config_legs(torch, lib, dev, st, world):
                             "launches_per_step": 1, "note": "4 MB per step: launch-latency bound at this batch"}, ms))
 
     # the same C1 / C2 steps captured once in a CUDA graph and replayed (device-resident Philox launch counter, so every
-    # replay draws a fresh stream: cvb_set_rng_device_counter)
+    # replay draws a fresh stream: cvb_set_rng_device_counter_autobump -- the sampling kernel bumps the counter itself)
     ctr = torch.zeros(1, dtype=torch.int64, device=dev)
-    lib.cvb_set_rng_device_counter(ctr.data_ptr())
+    lib.cvb_set_rng_device_counter_autobump(ctr.data_ptr())   # self-bumping: no counter-increment kernel between the steps
 
     def cur():
         return torch.cuda.current_stream().cuda_stream
 
     def g_c1():
-        ctr.add_(1)
         lib.cvb_clifford_ps_rsample(loc1.data_ptr(), kap1.data_ptr(), 1, 0, B1, None, None, 7, 0, z1.data_ptr(), None, None,
                                     kl1.data_ptr(), None, B1, d1, cur())
 
     def g_ps():
-        ctr.add_(1)
         lib.cvb_powerspherical_rsample_kl(loc.data_ptr(), kap2.data_ptr(), B2, None, None, 3, 0, z.data_ptr(), save.data_ptr(),
                                           ent.data_ptr(), kl.data_ptr(), None, B2, D2, cur())
 
     def g_vmf():
-        ctr.add_(1)
         lib.cvb_vmf_rsample_kl(loc.data_ptr(), kap2.data_ptr(), B2, None, None, 0, None, 3, 0, z.data_ptr(), save.data_ptr(),
                                ent.data_ptr(), kl.data_ptr(), None, None, None, B2, D2, cur())
 
@@ -651,7 +648,8 @@ def config_legs(torch, lib, dev, st, world):
         ms = timeit(graph.replay, reps=20) / 10
         legs.append((name, {"rows": rows, "unit": "samples/s", "units": rows, "bytes_per_unit": bpu,
                             "note": "CUDA graph of 10 steps replayed; fresh draws per replay"}, ms))
-    lib.cvb_set_rng_device_counter(None)
+    lib.cvb_set_rng_device_counter_autobump(None)
+    assert int(ctr.item()) > 0                 # the kernels really bumped it
 
     # ---- C5: depth 1..32 at d = 8192, 512 trials per depth per GPU, whole chain + cosine in one kernel per depth
     d5, T5, depths = 8192, 512, list(range(1, 33))

@@ -70,6 +70,7 @@ _SIGNATURES = {
     "cvb_vmf_log_prob": ([_f, _f, _f, _f, _ll, _f, _f, _ll, _i, _f], _i),
     "cvb_sphere_logprob_backward": ([_f, _f, _f, _ll, _f, _f, _ll, _i, _f], _i),
     "cvb_set_rng_device_counter": ([_f], _i),
+    "cvb_set_rng_device_counter_autobump": ([_f], _i),
     "cvb_ps_halfangle_icdf_table": ([_f, _ll, _f, _f, _f], _i),
     "cvb_philox_fill": ([_f, _ll, _ull, _ull, _f], _i),
 }
@@ -172,9 +173,9 @@ def next_rng(device=None):
     tests of the host logic) a process-local call counter stands in for the offset.
 
     Under CUDA-graph capture the host values are frozen into the graph, so a device-resident launch counter is
-    registered with the library (cvb_set_rng_device_counter) and bumped by a captured `counter += 1` right here --
-    i.e. once per sampling launch, before it -- which gives every replay of the graph a fresh stream.  Outside capture
-    the counter is cleared again (host offsets only).
+    registered with the library in self-bumping mode (cvb_set_rng_device_counter_autobump): every sampling kernel adds 1
+    to it when its last CTA retires, which gives every replay of the graph a fresh stream without a counter-increment
+    kernel between the sampling launches.  Outside capture the counter is cleared again (host offsets only).
     """
     global _rng_seed, _rng_offset
     if device is not None and torch.device(device).type == "cuda":
@@ -188,8 +189,7 @@ def next_rng(device=None):
                     "sampling inside CUDA-graph capture needs clifford_b200._lib.enable_graph_rng(device) to be called "
                     "BEFORE the capture starts (it allocates the device-resident launch counter)")
             with torch.cuda.device(idx):
-                lib.cvb_set_rng_device_counter(ctr.data_ptr())
-            ctr.add_(1)                                     # captured: runs on every replay
+                lib.cvb_set_rng_device_counter_autobump(ctr.data_ptr())     # the sampling kernel bumps it itself
             _graph_counters[-idx - 1] = ctr                 # mark: registered, clear it at the next eager call
             seed = _rank_mix(torch.initial_seed())
             # a per-capture host constant keeps distinct captured launches apart; torch's generator state cannot be
@@ -210,6 +210,44 @@ def next_rng(device=None):
     off = _rng_offset
     _rng_offset += 1
     return seed, off
+
+
+def graph_counter_snapshot(device):
+    """Under CUDA-graph capture: a (captured) copy of the launch counter as the NEXT sampling launch will read it, for a
+    backward that replays that launch's draws (the sphere samplers regenerate their tangent normals from the counter-
+    based generator instead of storing them).  None outside capture (host offsets identify the launch there)."""
+    if not _capturing():
+        return None
+    dev = torch.device(device)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    ctr = _graph_counters.get(idx)
+    return None if ctr is None else ctr.clone()
+
+
+class replay_counter:
+    """with replay_counter(device, snapshot): launches inside read `snapshot` as the device launch counter (no bumping);
+    the capture-mode registration is restored afterwards.  snapshot None: no-op."""
+
+    def __init__(self, device, snapshot):
+        dev = torch.device(device)
+        self.idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        self.snap = snapshot
+
+    def __enter__(self):
+        if self.snap is not None:
+            with torch.cuda.device(self.idx):
+                load().cvb_set_rng_device_counter(self.snap.data_ptr())
+        return self
+
+    def __exit__(self, *exc):
+        if self.snap is not None:
+            ctr = _graph_counters.get(self.idx)
+            with torch.cuda.device(self.idx):
+                if _capturing() and ctr is not None:
+                    load().cvb_set_rng_device_counter_autobump(ctr.data_ptr())
+                else:
+                    load().cvb_set_rng_device_counter(None)
+        return False
 
 
 def enable_graph_rng(device) -> torch.Tensor:

@@ -572,10 +572,13 @@ class PowerSphericalRsample(torch.autograd.Function):
         dent = torch.empty(B, device=dev, dtype=torch.float32)
         hd = () if head is None else (float(head[0]), float(head[1]))      # head: kappa is the raw layer output
         sfx = "" if head is None else "_head"
+        snap = None
         if draws is None:
             tp = g = None
             save = torch.empty(rows, 2, device=dev, dtype=torch.float32)
             seed, off = _lib.next_rng(dev)
+            if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+                snap = _lib.graph_counter_snapshot(dev)     # the backward replays this launch's normals
         else:
             tp = _f32c(draws[0].reshape(rows))
             g = _f32c(draws[1].reshape(rows, D - 1))
@@ -584,6 +587,7 @@ class PowerSphericalRsample(torch.autograd.Function):
                 ptr(save), ptr(ent), None, ptr(dent), rows, D, skip=z.numel() == 0)
         ctx.save_for_backward(loc_c, kap_c, tp, g, save)
         ctx.head = (sfx, hd)
+        ctx.snap = snap
         ctx.meta = (B, D, rows, n_samples, seed, off, tuple(kappa.shape))
         ctx.mark_non_differentiable(ent, dent)
         return z, ent, dent
@@ -598,8 +602,9 @@ class PowerSphericalRsample(torch.autograd.Function):
             dloc = torch.empty(rows, D, device=gz.device, dtype=torch.float32)
             dk = torch.empty(rows, device=gz.device, dtype=torch.float32)
             sfx, hd = ctx.head
-            _launch("cvb_powerspherical_rsample_backward" + sfx, gz.device, ptr(gz), ptr(loc_c), ptr(kap_c), B, *hd, ptr(tp),
-                    ptr(g), ptr(save), seed, off, ptr(dloc), ptr(dk), rows, D, skip=gz.numel() == 0)
+            with _lib.replay_counter(gz.device, ctx.snap):
+                _launch("cvb_powerspherical_rsample_backward" + sfx, gz.device, ptr(gz), ptr(loc_c), ptr(kap_c), B, *hd, ptr(tp),
+                        ptr(g), ptr(save), seed, off, ptr(dloc), ptr(dk), rows, D, skip=gz.numel() == 0)
             if n_samples > 1:
                 dloc = dloc.view(n_samples, B, D).sum(0)
                 dk = dk.view(n_samples, B).sum(0)
@@ -742,10 +747,13 @@ class VMFRsample(torch.autograd.Function):
         z = torch.empty(rows, D, device=dev, dtype=torch.float32)
         save = torch.empty(rows, 2, device=dev, dtype=torch.float32)
         ent, ln, dent, dln = (torch.empty(B, device=dev, dtype=torch.float32) for _ in range(4))
+        snap = None
         if draws is None:
             e = u = g = None
             R = 0
             seed, off = _lib.next_rng(dev)
+            if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+                snap = _lib.graph_counter_snapshot(dev)     # the backward replays this launch's normals
         else:
             e, u, g = draws
             u = u.to(torch.float64).reshape(-1, rows).contiguous()
@@ -757,6 +765,7 @@ class VMFRsample(torch.autograd.Function):
                 ptr(save), ptr(ent), None, ptr(dent), ptr(ln), ptr(dln), rows, D, skip=z.numel() == 0)
         ctx.save_for_backward(loc_c, kap_c, g, save)
         ctx.head = (sfx, hd)
+        ctx.snap = snap
         ctx.meta = (B, D, rows, n_samples, seed, off, tuple(kappa.shape))
         ctx.mark_non_differentiable(ent, ln, dent, dln)
         return z, ent, ln, dent, dln
@@ -771,8 +780,9 @@ class VMFRsample(torch.autograd.Function):
             dloc = torch.empty(rows, D, device=gz.device, dtype=torch.float32)
             dk = torch.empty(rows, device=gz.device, dtype=torch.float32)
             sfx, hd = ctx.head
-            _launch("cvb_vmf_rsample_backward" + sfx, gz.device, ptr(gz), ptr(loc_c), ptr(kap_c), B, *hd, ptr(g), ptr(save),
-                    seed, off, ptr(dloc), ptr(dk), rows, D, skip=gz.numel() == 0)
+            with _lib.replay_counter(gz.device, ctx.snap):
+                _launch("cvb_vmf_rsample_backward" + sfx, gz.device, ptr(gz), ptr(loc_c), ptr(kap_c), B, *hd, ptr(g), ptr(save),
+                        seed, off, ptr(dloc), ptr(dk), rows, D, skip=gz.numel() == 0)
             if n_samples > 1:
                 dloc = dloc.view(n_samples, B, D).sum(0)
                 dk = dk.view(n_samples, B).sum(0)

@@ -37,6 +37,8 @@ static unsigned long long occ_key(const void* kernel, int threads, size_t smem) 
 }
 static const float2* g_icdf[64] = {nullptr};
 static const unsigned long long* g_rng_ctr[64] = {nullptr};
+static unsigned int* g_rng_arrive[64] = {nullptr};      // per-device arrival word (allocated by cvb_init, self re-arming)
+static bool g_rng_autobump[64] = {false};
 static std::vector<float2> g_icdf_host;
 
 // ---- host construction of the half-angle inverse-CDF table (icdf_table.cuh), double precision ----------------
@@ -155,6 +157,12 @@ const unsigned long long* rng_device_counter() {
   return g_rng_ctr[dev];
 }
 
+unsigned int* rng_arrive_word() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || !g_rng_autobump[dev]) return nullptr;
+  return g_rng_arrive[dev];
+}
+
 int* next_sched_slot() {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || !g_sched[dev]) return nullptr;
@@ -241,6 +249,10 @@ int cvb_init(void) {
   }
   g_icdf[dev] = icdf;
   g_sched[dev] = sched;
+  unsigned int* arrive = nullptr;
+  CVB_CUDA(cudaMalloc(&arrive, sizeof(unsigned int)));
+  CVB_CUDA(cudaMemset(arrive, 0, sizeof(unsigned int)));
+  g_rng_arrive[dev] = arrive;
   g_tw[dev] = dptr;
   g_sms[dev] = prop.multiProcessorCount;
   return kOk;
@@ -255,6 +267,22 @@ int cvb_set_rng_device_counter(const unsigned long long* counter) {
   CVB_CUDA(cudaGetDevice(&dev));
   CVB_REQUIRE(dev >= 0 && dev < 64, kUnsupported, "device ordinal %d out of range", dev);
   g_rng_ctr[dev] = counter;
+  g_rng_autobump[dev] = false;
+  return kOk;
+}
+
+// The same registration in self-bumping mode: every launch that draws from the device generator adds 1 to *counter when
+// its last CTA retires (rng_launch_done), so a captured graph needs no `counter += 1` kernel of its own.  Launches in this
+// mode must be serialised on one stream (one arrival word per device).  Backward launches that REPLAY draws (the sphere
+// samplers regenerate their tangent normals) must see the forward's counter value: snapshot it before the forward and
+// register the snapshot with cvb_set_rng_device_counter around the backward launch (clifford_b200/ops.py does).
+int cvb_set_rng_device_counter_autobump(unsigned long long* counter) {
+  int dev = 0;
+  CVB_CUDA(cudaGetDevice(&dev));
+  CVB_REQUIRE(dev >= 0 && dev < 64, kUnsupported, "device ordinal %d out of range", dev);
+  CVB_REQUIRE(counter == nullptr || g_rng_arrive[dev] != nullptr, kBadArgument, "cvb_set_rng_device_counter_autobump: call cvb_init() first");
+  g_rng_ctr[dev] = counter;
+  g_rng_autobump[dev] = counter != nullptr;
   return kOk;
 }
 
@@ -281,6 +309,7 @@ int cvb_philox_fill(unsigned int* out, long long n_vec4, unsigned long long seed
   PhiloxKey key = make_key(seed, 0, 0);
   key.offset = (uint32_t)offset;
   key.dev_counter = nullptr;          // the known-answer test hook is addressed by (seed, offset) alone
+  key.arrive = nullptr;
   philox_fill_kernel<<<148, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<uint4*>(out), n_vec4, key);
   return check_launch("philox_fill_kernel");
 }

@@ -37,6 +37,7 @@ __global__ void normal_fill_kernel(float* out, long long total, float scale, Phi
     for (int j = 0; j < 4; ++j)
       if (4 * i + j < total) out[4 * i + j] = v[j];
   }
+  rng_launch_done(key);
 }
 
 inline int ew_grid(long long total, int threads) {

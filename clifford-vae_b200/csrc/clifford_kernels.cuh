@@ -633,6 +633,7 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw, cons
     // the last group to finish re-arms the counters for the next launch that uses this slot
     if (atomicAdd(p.sched + 1, 1) == (int)stride - 1) { p.sched[0] = 0; p.sched[1] = 0; }
   }
+  if (MODE == kPsRng || MODE == kUniformRng || MODE == kUnitaryRng || MODE == kVonMisesRng) rng_launch_done(p.key);
 }
 
 // ---- backward of rsample ---------------------------------------------------------------------
@@ -1025,6 +1026,7 @@ clifford_fwd_generic_kernel(const CliffordFwdParams p) {
     }
     if (PS && ROWK && threadIdx.x == 0 && (p.entropy || p.kl || p.dentropy)) clifford_row_entropy(p, row, kap_row);
   }
+  if (MODE == kPsRng || MODE == kUniformRng || MODE == kUnitaryRng || MODE == kVonMisesRng) rng_launch_done(p.key);
 }
 
 // smem: tw[n] cplx, g[n] float, scratch[32] float

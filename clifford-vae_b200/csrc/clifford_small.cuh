@@ -112,6 +112,7 @@ clifford_fwd_small_kernel(const CliffordFwdParams p, const int RT) {
       }
     }
   }
+  if (MODE == kPsRng || MODE == kUniformRng || MODE == kUnitaryRng || MODE == kVonMisesRng) rng_launch_done(p.key);
 }
 
 // ---- backward ----------------------------------------------------------------------------------------------------

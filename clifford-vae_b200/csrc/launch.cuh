@@ -76,10 +76,13 @@ inline int persistent_grid(Kernel kernel, int threads, size_t smem, long long wo
 
 // device launch counter registered for the current device (nullptr when none), see cvb_set_rng_device_counter
 const unsigned long long* rng_device_counter();
+// arrival word of the self-bumping mode for the current device (nullptr unless cvb_set_rng_device_counter_autobump is active)
+unsigned int* rng_arrive_word();
 
 inline PhiloxKey make_key(unsigned long long seed, unsigned long long offset, uint32_t stream_id) {
   PhiloxKey k;
   k.dev_counter = rng_device_counter();
+  k.arrive = k.dev_counter ? rng_arrive_word() : nullptr;
   k.k0 = (uint32_t)seed;
   k.k1 = (uint32_t)(seed >> 32);
   k.offset = (uint32_t)offset ^ (uint32_t)((offset >> 32) * 0x9E3779B9u);

@@ -14,6 +14,10 @@ struct PhiloxKey {
   // the host-chosen offset is frozen into the graph, so the caller keeps a counter in device memory and bumps it with a
   // captured kernel after every sampling launch -- each replay then draws a fresh stream.  nullptr: host offset only.
   const unsigned long long* dev_counter;
+  // Self-bumping mode (cvb_set_rng_device_counter_autobump): a zero-initialised arrival word; the last CTA of every
+  // sampling launch to retire adds 1 to *dev_counter and re-arms the word (rng_launch_done), so a captured graph needs
+  // no separate `counter += 1` kernel between sampling launches.  nullptr: the caller bumps the counter.
+  unsigned int* arrive;
 };
 
 __host__ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
@@ -37,6 +41,22 @@ __device__ __forceinline__ uint4 philox_draw(const PhiloxKey& key, uint64_t elem
   if (key.dev_counter) off += (uint32_t)__ldg(key.dev_counter) * 0x9E3779B9u;   // uniform branch on a kernel parameter
   return philox4x32_10(make_uint4((uint32_t)elem, (uint32_t)(elem >> 32), attempt | (key.stream << 24), off),
                        key.k0, key.k1);
+}
+
+// Last statement of every kernel that draws from the device generator; reached by ALL threads of the CTA.  Every CTA has
+// read the counter for the last time before it arrives, the last arrival bumps it; the next launch on the stream (also
+// one that was admitted early by programmatic dependent launch: it reads nothing before griddepcontrol.wait) sees the new
+// value.  One arrival word per device: launches in this mode must be serialised on one stream.
+__device__ __forceinline__ void rng_launch_done(const PhiloxKey& key) {
+  if (!key.arrive) return;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(key.arrive, 1u) == gridDim.x - 1) {
+      *key.arrive = 0u;
+      atomicAdd(const_cast<unsigned long long*>(key.dev_counter), 1ULL);
+    }
+  }
 }
 
 // uniform in (0, 1]: never 0, so logs are finite

@@ -318,6 +318,7 @@ sphere_rsample_kernel(const SphereParams p) {
     }
     if (p.save && lane == 0) { p.save[2 * row] = save0; p.save[2 * row + 1] = save1; }
   }
+  if (!p.gnoise) rng_launch_done(p.key);      // device RNG: this launch consumed a counter value
 }
 
 // Backward: grad_z -> dloc (rows, D), dkappa (rows).
@@ -498,6 +499,7 @@ sphere_rsample_reg_kernel(const SphereParams p) {
     if (p.save && lane == 0) { p.save[2 * row] = save0; p.save[2 * row + 1] = save1; }
   }
   }
+  if (!p.gnoise) rng_launch_done(p.key);      // device RNG: this launch consumed a counter value
 }
 
 template <int FAMILY>

@@ -268,6 +268,12 @@ CVB_API int cvb_vmf_rsample_backward_head(const float* grad_z, const float* loc,
  * sampling kernel launched afterwards mixes it into its Philox offset.  The library only READS it; the caller bumps it
  * on the stream after each sampling launch (inside the capture), so every replay draws a fresh stream. */
 CVB_API int cvb_set_rng_device_counter(const unsigned long long* counter);
+/* The same registration in self-bumping mode: every launch that draws from the device generator adds 1 to *counter itself
+ * when its last CTA retires, so a captured graph needs no counter-increment kernel between sampling launches.  Launches in
+ * this mode must be serialised on one stream.  A backward launch that replays draws (cvb_powerspherical_rsample_backward,
+ * cvb_vmf_rsample_backward) must read the value its forward read: snapshot the counter before the forward and register
+ * the snapshot with cvb_set_rng_device_counter around the backward.  NULL leaves the mode. */
+CVB_API int cvb_set_rng_device_counter_autobump(unsigned long long* counter);
 
 /* ---- host-only: the inverse-CDF table behind the device sampler of dists/clifford.py:124-134's Beta(1/2 + kappa, 1/2)
  * draw for row-scalar concentrations <= *kappa_max (csrc/icdf_table.cuh).  Layout: [n_kappa][n_nodes][2] floats =

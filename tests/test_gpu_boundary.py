@@ -229,3 +229,56 @@ def test_samplers_inside_a_cuda_graph_draw_fresh_streams_on_every_replay():
     # eager sampling afterwards still works and differs from the graph's draws
     z2 = CliffordPowerSphericalDistribution(loc, kap, validate_args=False).rsample()
     assert float((z2 - outs[-1][0]).abs().max()) > 1e-2
+
+
+def test_captured_training_step_replays_the_right_draws_in_backward():
+    """Inside a captured graph the sphere samplers' backward regenerates the forward's tangent normals from the counter-
+    based generator, so it must read the launch-counter value its OWN forward read -- also when other sampling launches
+    (which bump the counter) sit between the two.  Check through ||z|| = 1: with consistent draws d(z . z)/d loc = 0
+    (J^T z = 0); with any other draws it is O(1).  Two samplers forward, then both backward, captured once, replayed."""
+    from clifford_b200 import _lib
+    from dists.clifford import PowerSpherical
+    from hyperspherical_vae.distributions import VonMisesFisher
+    torch.manual_seed(1)
+    B, D = 64, 129
+    loc1 = torch.nn.functional.normalize(torch.randn(B, D, device=DEV), dim=-1).requires_grad_()
+    loc2 = torch.nn.functional.normalize(torch.randn(B, D, device=DEV), dim=-1).requires_grad_()
+    k1 = torch.full((B,), 4.0, device=DEV, requires_grad=True)
+    k2 = torch.full((B, 1), 6.0, device=DEV, requires_grad=True)
+    w = torch.randn(B, D, device=DEV)
+    _lib.enable_graph_rng(DEV)
+
+    def step():
+        z1 = PowerSpherical(loc1, k1).rsample()
+        z2 = VonMisesFisher(loc2, k2, validate_args=False).rsample()       # (argument validation syncs: not capturable)
+        z3 = PowerSpherical(loc1, k1).rsample()                    # one more bump before any backward runs
+        g_unit = torch.autograd.grad((z1 * z1.detach()).sum() + (z2 * z2.detach()).sum() + (z3 * z3.detach()).sum(),
+                                     [loc1, loc2], retain_graph=True)
+        g_w = torch.autograd.grad((z1 * w).sum() + (z2 * w).sum(), [loc1, loc2])
+        return z1, z2, z3, g_unit, g_w
+
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(2):
+            step()
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        z1, z2, z3, g_unit, g_w = step()
+    prev = None
+    for _ in range(3):
+        g.replay()
+        torch.cuda.synchronize()
+        for z in (z1, z2, z3):
+            assert float((z.norm(dim=-1) - 1).abs().max()) < 2e-5
+        assert float(g_unit[0].abs().max()) < 5e-5 and float(g_unit[1].abs().max()) < 5e-5     # the draws were replayed
+        assert float(g_w[0].abs().max()) > 1e-2 and float(g_w[1].abs().max()) > 1e-2            # and the test is not vacuous
+        assert float((z1 - z3).abs().max()) > 1e-2                                               # distinct launches differ
+        if prev is not None:
+            assert float((z1 - prev).abs().max()) > 1e-2                                         # fresh draws per replay
+        prev = z1.clone()
+    # eager mode afterwards: same identity (host offsets identify the launch there)
+    z = PowerSpherical(loc1, k1).rsample()
+    (gl,) = torch.autograd.grad((z * z.detach()).sum(), [loc1])
+    assert float(gl.abs().max()) < 5e-5
