@@ -18,13 +18,14 @@ int launch_bwd_fast(const CliffordBwdParams& p, cudaStream_t st) {
   }
   using Pl = FftPlan<LOG2N>;
   const cplx* tw = device_twiddles();
-  if (!tw) return kCudaError;
-  const size_t smem = clifford_bwd_smem_bytes<LOG2N>();
+  const float2* icdf = device_icdf_table();
+  if (!tw || !icdf) return kCudaError;
+  const size_t smem = clifford_bwd_smem_bytes<LOG2N, ROWK, FAST>();
   auto kern = clifford_bwd_kernel<LOG2N, ROWK, FAST>;
   int grid = 0;
   const long long work = (p.rows + Pl::GROUPS - 1) / Pl::GROUPS;
   if (int rc = persistent_grid(kern, Pl::THREADS, smem, work, &grid)) return rc;
-  launch_pdl(kern, grid, Pl::THREADS, smem, st, p, tw);
+  launch_pdl(kern, grid, Pl::THREADS, smem, st, p, tw, icdf);
   return check_launch("clifford_bwd_kernel");
 }
 

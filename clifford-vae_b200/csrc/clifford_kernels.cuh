@@ -83,6 +83,12 @@ __device__ __forceinline__ float fwd_row_kappa(const CliffordFwdParams& p, long 
 }
 
 constexpr float kEps = 1e-7f;
+// the reference's atan2(s sqrt(max(1 - t^2, eps)), t) (clifford.py:44-48) never returns a phase below sqrt(eps) or above
+// pi - sqrt(eps): the table sampler clamps |phi| to that range
+constexpr float kIcdfPhiMin = 3.16227766e-4f, kIcdfPhiMax = 3.14127642f;
+// which row lengths save the table coordinate instead of t' on table-sampled rows (see clifford_bwd_smem_bytes)
+template <int LOG2N>
+constexpr bool clifford_saves_table_coord() { return LOG2N >= 10; }
 
 __device__ __forceinline__ float sign_from_normal(float g) { return g / (fabsf(g) + kEps); }
 
@@ -415,15 +421,18 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw, cons
           // phi = s max(|phi|, sqrt(eps)): the reference's atan2(s sqrt(max(1 - t^2, eps)), t) (clifford.py:44-48) never
           // returns a phase below sqrt(eps); theta = loc + phi needs ONE sincos instead of sincos(loc), cos/sin(phi)
           // and a complex multiply
-          const float aphi = fminf(fmaxf(icdf_sample_phi(cells, inv_p, w[j]), 3.16227766e-4f), 3.14127642f);   // [sqrt(eps), pi - sqrt(eps)]
+          float xs;                                       // table coordinate of this draw (> 0)
+          const float aphi = fminf(fmaxf(icdf_sample_phi(cells, inv_p, w[j], xs), kIcdfPhiMin), kIcdfPhiMax);   // [sqrt(eps), pi - sqrt(eps)]
           const float phi = __uint_as_float(__float_as_uint(aphi) | (w[j] & 0x80000000u));
           cplx x = make_float2(1.0f, 0.0f);
           if (valid && k != 0) {
-            if ((!LEAN && p.tp_signed) || want_lp) {
-              const float tpj = icdf_tprime(aphi);
-              if (!LEAN && p.tp_signed) stg_stream1(p.tp_signed + row * d + k, __uint_as_float(__float_as_uint(tpj) | (w[j] & 0x80000000u)));
-              if (want_lp) lp_acc += circle_log_half_1pt<true>(tpj);
+            // saved for the backward: the signed table coordinate (NOT t'): clifford_bwd_kernel re-evaluates the phase and
+            // its pathwise kappa-derivative from the row's cells (table rows only; exact-sampler rows save copysign(t', s))
+            if (!LEAN && p.tp_signed) {
+              const float keep = clifford_saves_table_coord<LOG2N>() ? xs : icdf_tprime(aphi);
+              stg_stream1(p.tp_signed + row * d + k, __uint_as_float(__float_as_uint(keep) | (w[j] & 0x80000000u)));
             }
+            if (want_lp) lp_acc += circle_log_half_1pt<true>(icdf_tprime(aphi));
             sincos_any<true>(src.loc[k] + phi, x.y, x.x);
           }
           xch[pad16(k)] = x;
@@ -699,28 +708,41 @@ __device__ __forceinline__ float clifford_bwd_element(const CliffordBwdParams& p
   return dth;
 }
 
-// smem per group: exchange buffer | 32 floats reduction scratch | 3 staged rows (loc, tp_signed | tprime, gnoise) | mbarrier
-template <int LOG2N>
+// Rows the forward sampled through the inverse-CDF table (device RNG, one concentration <= kIcdfKappaMax per row) save
+// the signed TABLE COORDINATE of every draw instead of copysign(t', s) when d >= 1024, and the backward differentiates
+// the table map itself: phase and d phase / d kappa from the row's cells (icdf_phi_and_dkappa) -- the exact pathwise
+// derivative of what the sampler evaluated (accurate to 2.5e-5 of the analytic implicit gradient, tests/
+// test_icdf_table.py) for ~45 instructions per circle, where ATen's piecewise approximation of the implicit Beta
+// gradient (the reference's backward; still used for injected draws and exact-sampler rows) costs ~190 in three
+// divergent branches.  (d = 512 keeps t': two more 4 KB cell tables per row would cost its kernel two resident CTAs.)
+// smem per group: staged rows (loc, tp_signed | tprime, gnoise; FAST: two) | value + derivative cells (table rows) |
+// exchange buffer | 32 floats reduction scratch + row constants | mbarrier
+template <int LOG2N, bool ROWK = true, bool FAST = false>
 constexpr size_t clifford_bwd_smem_bytes() {
   using Pl = FftPlan<LOG2N>;
-  return (sizeof(cplx) * Pl::XCH + sizeof(float) * (32 + 2 * kBetaRowFloats) + sizeof(float) * 3 * Pl::N + sizeof(uint64_t)) *
-         Pl::GROUPS;
+  return (sizeof(cplx) * Pl::XCH + sizeof(float) * (32 + 2 * kBetaRowFloats) + sizeof(float) * (FAST ? 2 : 3) * Pl::N +
+          ((ROWK && clifford_saves_table_coord<LOG2N>()) ? 2 * sizeof(float4) * kIcdfCells : 0) + sizeof(uint64_t)) * Pl::GROUPS;
 }
 
 // FAST: saved draws + TMA-staged element inputs (the training path: backward of a device-RNG rsample with 16-byte
 // aligned rows); the injected-draw and unstaged paths are compiled out.
 template <int LOG2N, bool ROWK, bool FAST = false>
 __global__ void __launch_bounds__(FftPlan<LOG2N>::THREADS, (FftPlan<LOG2N>::THREADS <= 128 ? clifford_bwd_min_blocks<LOG2N>() : 1))
-clifford_bwd_kernel(const CliffordBwdParams p, const cplx* __restrict__ tw) {
+clifford_bwd_kernel(const CliffordBwdParams p, const cplx* __restrict__ tw, const float2* __restrict__ icdf) {
   pdl_wait_and_release();
   using Pl = FftPlan<LOG2N>;
   constexpr int d = Pl::N, T = Pl::T, E = Pl::E, G = Pl::GROUPS;
   constexpr uint32_t kRowBytes = d * sizeof(float);
+  constexpr bool TABLE = ROWK && clifford_saves_table_coord<LOG2N>();
+  constexpr int NSTAGE = FAST ? 2 : 3;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int group = threadIdx.x / T, t = threadIdx.x % T;
-  // layout: [G x 3 staged rows][G x xch][G x scratch][G x mbarrier]
-  float* stage = reinterpret_cast<float*>(smem_raw) + (size_t)group * 3 * d;
-  unsigned char* after_stage = smem_raw + sizeof(float) * (size_t)G * 3 * d;
+  // layout: [G x staged rows][G x (value cells | derivative cells)][G x xch][G x scratch][G x mbarrier]
+  float* stage = reinterpret_cast<float*>(smem_raw) + (size_t)group * NSTAGE * d;
+  unsigned char* after_rows = smem_raw + sizeof(float) * (size_t)G * NSTAGE * d;
+  float4* cells = reinterpret_cast<float4*>(after_rows) + (size_t)group * 2 * kIcdfCells;      // TABLE only
+  float4* dcells = cells + kIcdfCells;
+  unsigned char* after_stage = after_rows + (TABLE ? sizeof(float4) * 2 * kIcdfCells * (size_t)G : 0);
   cplx* xch = reinterpret_cast<cplx*>(after_stage) + (size_t)group * Pl::XCH;
   constexpr int kScratch = 32 + 2 * kBetaRowFloats;   // reduction scratch | two (double-buffered) row-constant blocks
   float* scratch = reinterpret_cast<float*>(after_stage + sizeof(cplx) * (size_t)G * Pl::XCH) + group * kScratch;
@@ -763,7 +785,15 @@ clifford_bwd_kernel(const CliffordBwdParams p, const cplx* __restrict__ tw) {
     const float kap_raw = valid ? __ldg(p.kappa + prow * p.kappa_row_stride) : 1.0f;
     const float kap_row = head_kappa(p.head, kap_raw);
     float* rc = rowconst + (parity ? kBetaRowFloats : 0);
-    if (ROWK) beta_row_build<T>(rc, 0.5f + (kap_row + kEps), 0.5f, t);
+    // a row the forward sampled through the table (same predicate as clifford_fwd_kernel; uniform over the group)
+    const bool table_row = TABLE && saved && valid && (kap_row + kEps <= kIcdfKappaMax);
+    if (TABLE && table_row) {
+      // every thread left the previous row's element loop (its closing barriers) before these are overwritten
+      icdf_build_row<false>(cells, kap_row + kEps, icdf, t, T);
+      icdf_build_row<true>(dcells, kap_row + kEps, icdf, t, T);
+    } else if (ROWK) {
+      beta_row_build<T>(rc, 0.5f + (kap_row + kEps), 0.5f, t);
+    }
     fft_run<LOG2N, false>(v, xch, t, tw);
     r2c_untangle<LOG2N>(v, xch, t, tw);        // v[e] = G[k]
 
@@ -788,17 +818,44 @@ clifford_bwd_kernel(const CliffordBwdParams p, const cplx* __restrict__ tw) {
       src.gnoise = p.gnoise ? p.gnoise + r0 * d : nullptr;
     }
     float dk_sum = 0.f;
-#pragma unroll 2
-    for (int e = 0; e < E; ++e) {
-      const int k = t + e * T;
-      float dk = 0.f;
-      if (valid && k != 0) {
-        clifford_bwd_element<ROWK, BetaGradRowShared, FAST>(p, src, row, prow, k, xch[pad16(k)], bc, 1.0f / (float)d, dk);
-      } else if (valid) {
-        stg_stream1(p.dloc + row * d, 0.0f);
-        if (!ROWK) stg_stream1(p.dkappa + row * d, 0.0f);
+    if (TABLE && table_row) {
+      // table-sampled row: phase and its pathwise kappa-derivative straight from the row's cells
+      const float inv_p = __frcp_rn(fmaf(2.0f, kap_row + kEps, 1.0f));       // as the forward
+      constexpr float inv_d = 1.0f / (float)d;
+#pragma unroll 4
+      for (int e = 0; e < E; ++e) {
+        const int k = t + e * T;
+        if (k != 0) {
+          const float sv = src.tps[k];
+          float dmag;
+          const float mag = icdf_phi_and_dkappa(cells, dcells, inv_p, fabsf(sv), dmag);
+          const bool clamped = (mag < kIcdfPhiMin) || (mag > kIcdfPhiMax);
+          const float aphi = fminf(fmaxf(mag, kIcdfPhiMin), kIcdfPhiMax);
+          const float phi = __uint_as_float(__float_as_uint(aphi) | (__float_as_uint(sv) & 0x80000000u));
+          cplx x;
+          sincos_any<true>(src.loc[k] + phi, x.y, x.x);
+          const cplx Gk = xch[pad16(k)];
+          const float dth = -inv_d * (x.y * Gk.x - x.x * Gk.y);          // dL/dtheta_k = -(2/n) Im(X_k conj(G_k))
+          stg_stream1(p.dloc + row * d + k, dth);
+          const float dsigned = __uint_as_float(__float_as_uint(dmag) ^ (__float_as_uint(sv) & 0x80000000u));
+          dk_sum = fmaf(dth, clamped ? 0.0f : dsigned, dk_sum);
+        } else {
+          stg_stream1(p.dloc + row * d, 0.0f);
+        }
       }
-      dk_sum += dk;
+    } else {
+#pragma unroll 2
+      for (int e = 0; e < E; ++e) {
+        const int k = t + e * T;
+        float dk = 0.f;
+        if (valid && k != 0) {
+          clifford_bwd_element<ROWK, BetaGradRowShared, FAST>(p, src, row, prow, k, xch[pad16(k)], bc, 1.0f / (float)d, dk);
+        } else if (valid) {
+          stg_stream1(p.dloc + row * d, 0.0f);
+          if (!ROWK) stg_stream1(p.dkappa + row * d, 0.0f);
+        }
+        dk_sum += dk;
+      }
     }
     if (staged) {
       group_sync<LOG2N>();                       // every thread is done with the staged rows

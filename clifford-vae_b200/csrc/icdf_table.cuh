@@ -29,15 +29,30 @@ const float2* device_icdf_table();
 #ifdef __CUDACC__
 // Build one row's cell polynomials psi(tau) = c.x + tau (c.y + tau (c.z + tau c.w)) in shared memory (kIcdfCells
 // float4); called by the T threads of a group (t = 0..T-1), followed by the caller's group barrier.
+// DERIV: the cells of d phase / d kappa at fixed s instead -- the kappa-derivative of the same interpolant (the Lagrange
+// weights differentiated, times d log1p(kappa) / d kappa), i.e. the exact pathwise derivative of what the sampler
+// evaluates; against the analytic d/dkappa of G_k^{-1}(1 - s^p) it is accurate to 1e-5 relative (max over s and
+// k in [0.03, 31]), tests/test_icdf_table.py.
+template <bool DERIV = false>
 __device__ __forceinline__ void icdf_build_row(float4* cell, float kappa, const float2* __restrict__ table, int t, int T) {
   const float x = log1pf(kappa) * ((float)(kIcdfKappaNodes - 1) / kIcdfQMax);
   int i = (int)x;
   i = i < 1 ? 1 : (i > kIcdfKappaNodes - 3 ? kIcdfKappaNodes - 3 : i);
   const float u = x - (float)i;                        // in [-1, 2] at the ends of the node range
-  const float w0 = -u * (u - 1.0f) * (u - 2.0f) * (1.0f / 6.0f);
-  const float w1 = (u + 1.0f) * (u - 1.0f) * (u - 2.0f) * 0.5f;
-  const float w2 = -(u + 1.0f) * u * (u - 2.0f) * 0.5f;
-  const float w3 = (u + 1.0f) * u * (u - 1.0f) * (1.0f / 6.0f);
+  float w0, w1, w2, w3;
+  if (DERIV) {
+    const float a = u + 1.0f, b = u, c = u - 1.0f, e = u - 2.0f;
+    const float dx = ((float)(kIcdfKappaNodes - 1) / kIcdfQMax) / (1.0f + kappa);     // d x / d kappa
+    w0 = -(c * e + b * e + b * c) * (1.0f / 6.0f) * dx;
+    w1 = (c * e + a * e + a * c) * 0.5f * dx;
+    w2 = -(b * e + a * e + a * b) * 0.5f * dx;
+    w3 = (b * c + a * c + a * b) * (1.0f / 6.0f) * dx;
+  } else {
+    w0 = -u * (u - 1.0f) * (u - 2.0f) * (1.0f / 6.0f);
+    w1 = (u + 1.0f) * (u - 1.0f) * (u - 2.0f) * 0.5f;
+    w2 = -(u + 1.0f) * u * (u - 2.0f) * 0.5f;
+    w3 = (u + 1.0f) * u * (u - 1.0f) * (1.0f / 6.0f);
+  }
   // thread t builds cells 2t', 2t'+1 from nodes 2t' .. 2t'+2: one 128-bit + one 64-bit load per concentration row
   const float2* r0 = table + (size_t)(i - 1) * kIcdfRowStride;
   for (int j = 2 * t; j < kIcdfCells; j += 2 * T) {
@@ -71,14 +86,36 @@ __device__ __forceinline__ float fast_log2(float x) {
 
 // One circle from one 32-bit word: bits 7..30 -> v in (0, 1]; returns the phase magnitude |phi| = 2 |psi| in [0, pi]
 // (the device table stores 2 H).  inv_p = 1 / (2k + 1).  Bit 31 of the word is the circle's sign draw.
-__device__ __forceinline__ float icdf_sample_phi(const float4* cell, float inv_p, uint32_t w) {
+// x_out: the table coordinate x = cells * s, s = v^(1/p) in (0, 1] -- what the training path saves for the backward.
+__device__ __forceinline__ float icdf_sample_phi(const float4* cell, float inv_p, uint32_t w, float& x_out) {
   const float v = (float)(((w >> 7) & 0xFFFFFFu) + 1u) * 0x1p-24f;
   const float x = fast_exp2(fast_log2(v) * inv_p) * (float)kIcdfCells;
+  x_out = x;
   int j = (int)x;
   j = j > kIcdfCells - 1 ? kIcdfCells - 1 : j;
   const float tau = x - (float)j;
   const float4 c = cell[j];
   return fmaf(fmaf(fmaf(c.w, tau, c.z), tau, c.y), tau, c.x);
+}
+__device__ __forceinline__ float icdf_sample_phi(const float4* cell, float inv_p, uint32_t w) {
+  float x_unused;
+  return icdf_sample_phi(cell, inv_p, w, x_unused);
+}
+// Backward of a table-sampled circle from its saved coordinate x (> 0): the same phase magnitude, bit for bit, and its
+// pathwise derivative with respect to the concentration at fixed uniform draw v:
+//   d|phi|/dkappa = D(s) + (d|phi|/dx) (dx/dkappa),   x = cells v^(1/p)  =>  dx/dkappa = -2 x ln(s) / p,  p = 2 kappa + 1
+// with D = d|phi|/dkappa at fixed s from the derivative cells (icdf_build_row<true>).
+__device__ __forceinline__ float icdf_phi_and_dkappa(const float4* cell, const float4* dcell, float inv_p, float x, float& dphi_dkappa) {
+  int j = (int)x;
+  j = j > kIcdfCells - 1 ? kIcdfCells - 1 : j;
+  const float tau = x - (float)j;
+  const float4 c = cell[j], g = dcell[j];
+  const float phi = fmaf(fmaf(fmaf(c.w, tau, c.z), tau, c.y), tau, c.x);
+  const float dphi_dx = fmaf(fmaf(3.0f * c.w, tau, 2.0f * c.z), tau, c.y);
+  const float dfix = fmaf(fmaf(fmaf(g.w, tau, g.z), tau, g.y), tau, g.x);
+  const float ln_s = __logf(x) - 5.545177444479562f;               // ln(x / 256)
+  dphi_dkappa = fmaf(dphi_dx, -2.0f * x * ln_s * inv_p, dfix);
+  return phi;
 }
 // t' = cos^2(psi) = (1 + cos phi) / 2 in torch's Beta clamp range, like the exact sampler
 __device__ __forceinline__ float icdf_tprime(float phi) {

@@ -52,8 +52,10 @@ CVB_API long long cvb_launch_count(void);
 /* CliffordPowerSphericalDistribution.rsample (dists/clifford.py:295-308) fused with entropy()/KL
  * (:318-327, :241-242).  loc (loc_rows, d).  Base draws: pass tprime and gnoise (rows, d) to inject
  * t' ~ Beta(1/2 + kappa + 1e-7, 1/2) and g ~ N(0,1) (parity mode), or both NULL to draw on the device
- * with Philox4x32-10 keyed by (seed, offset).  Outputs: z (rows, 2d); optional tp_signed (rows, d)
- * = copysign(t', sign) saved for the backward in RNG mode; optional entropy / kl / dentropy (rows)
+ * with Philox4x32-10 keyed by (seed, offset).  Outputs: z (rows, 2d); optional tp_signed (rows, d):
+ * the draws saved for cvb_clifford_ps_rsample_backward in RNG mode -- OPAQUE to the caller: copysign(t', sign), or, on
+ * rows sampled through the inverse-CDF table (one concentration <= 32 per row, power-of-two d >= 1024), the signed table
+ * coordinate of the draw; element 0 of every row is left unwritten; optional entropy / kl / dentropy (rows)
  * (dentropy = d entropy / d kappa), written only when kappa_el_stride == 0 (otherwise call
  * cvb_ps_entropy_kl). */
 CVB_API int cvb_clifford_ps_rsample(const float* loc, const float* kappa, long long kappa_row_stride, int kappa_el_stride,
@@ -62,8 +64,10 @@ CVB_API int cvb_clifford_ps_rsample(const float* loc, const float* kappa, long l
                             float* entropy, float* kl, float* dentropy, long long rows, int d, void* stream);
 
 /* Backward of the above (autograd through ifft / exp / atan2 / _Dirichlet_backward in the reference).
- * Give either (tprime, gnoise) or tp_signed.  dloc (rows, d); dkappa (rows) when kappa_el_stride == 0,
- * else (rows, d). */
+ * Give either (tprime, gnoise) [injected draws: ATen's piecewise implicit Beta gradient, like the reference] or the
+ * tp_signed buffer the forward wrote for the SAME (loc, kappa, rows, d) [table-sampled rows: the pathwise derivative of the
+ * table map itself, i.e. the same implicit reparameterisation gradient evaluated to 2.5e-5 instead of ATen's
+ * approximation of it].  dloc (rows, d); dkappa (rows) when kappa_el_stride == 0, else (rows, d). */
 CVB_API int cvb_clifford_ps_rsample_backward(const float* grad_z, const float* loc, const float* kappa,
                                      long long kappa_row_stride, int kappa_el_stride, long long loc_rows,
                                      const float* tprime, const float* gnoise, const float* tp_signed, float* dloc,
