@@ -22,9 +22,11 @@
 template <int LOG2N>
 constexpr int clifford_bwd_min_blocks() { return LOG2N == 10 ? 4 : 5; }
 #ifndef CVB_FWD_BIND_MINB
-#define CVB_FWD_BIND_MINB 3
+#define CVB_FWD_BIND_MINB 4
 #endif
-// the fused-bind variant carries a second set of transforms: it needs ~150 registers (it spilled at 4-5 CTAs / SM)
+// the fused-bind variant carries a second set of transforms; since its pair stage forms each (k, N-k) pair once it fits 124
+// registers without spilling: 4 resident CTAs / SM measured 0.1166 -> 0.1069 ms at the headline shape (3 before; 5 does not
+// fit the shared memory)
 #ifndef CVB_FWD_LEAN_MINB
 #define CVB_FWD_LEAN_MINB 7
 #endif
@@ -86,9 +88,12 @@ constexpr float kEps = 1e-7f;
 // the reference's atan2(s sqrt(max(1 - t^2, eps)), t) (clifford.py:44-48) never returns a phase below sqrt(eps) or above
 // pi - sqrt(eps): the table sampler clamps |phi| to that range
 constexpr float kIcdfPhiMin = 3.16227766e-4f, kIcdfPhiMax = 3.14127642f;
+#ifndef CVB_TABLE_COORD_MIN_LOG2N
+#define CVB_TABLE_COORD_MIN_LOG2N 9
+#endif
 // which row lengths save the table coordinate instead of t' on table-sampled rows (see clifford_bwd_smem_bytes)
 template <int LOG2N>
-constexpr bool clifford_saves_table_coord() { return LOG2N >= 10; }
+constexpr bool clifford_saves_table_coord() { return LOG2N >= CVB_TABLE_COORD_MIN_LOG2N; }
 
 __device__ __forceinline__ float sign_from_normal(float g) { return g / (fabsf(g) + kEps); }
 
@@ -708,13 +713,14 @@ __device__ __forceinline__ float clifford_bwd_element(const CliffordBwdParams& p
   return dth;
 }
 
-// Rows the forward sampled through the inverse-CDF table (device RNG, one concentration <= kIcdfKappaMax per row) save
-// the signed TABLE COORDINATE of every draw instead of copysign(t', s) when d >= 1024, and the backward differentiates
+// Rows the forward sampled through the inverse-CDF table (device RNG, one concentration <= kIcdfKappaMax per row, d >= 512)
+// save the signed TABLE COORDINATE of every draw instead of copysign(t', s), and the backward differentiates
 // the table map itself: phase and d phase / d kappa from the row's cells (icdf_phi_and_dkappa) -- the exact pathwise
 // derivative of what the sampler evaluated (accurate to 2.5e-5 of the analytic implicit gradient, tests/
 // test_icdf_table.py) for ~45 instructions per circle, where ATen's piecewise approximation of the implicit Beta
 // gradient (the reference's backward; still used for injected draws and exact-sampler rows) costs ~190 in three
-// divergent branches.  (d = 512 keeps t': two more 4 KB cell tables per row would cost its kernel two resident CTAs.)
+// divergent branches.  (At d = 512 the two 4 KB cell tables per row cost the kernel two of its five resident CTAs and it
+// still gains: 25.0 -> 31.9 % of the roofline; d = 2048: 27.6 -> 38.2 %.)
 // smem per group: staged rows (loc, tp_signed | tprime, gnoise; FAST: two) | value + derivative cells (table rows) |
 // exchange buffer | 32 floats reduction scratch + row constants | mbarrier
 template <int LOG2N, bool ROWK = true, bool FAST = false>

@@ -54,7 +54,7 @@ CVB_API long long cvb_launch_count(void);
  * t' ~ Beta(1/2 + kappa + 1e-7, 1/2) and g ~ N(0,1) (parity mode), or both NULL to draw on the device
  * with Philox4x32-10 keyed by (seed, offset).  Outputs: z (rows, 2d); optional tp_signed (rows, d):
  * the draws saved for cvb_clifford_ps_rsample_backward in RNG mode -- OPAQUE to the caller: copysign(t', sign), or, on
- * rows sampled through the inverse-CDF table (one concentration <= 32 per row, power-of-two d >= 1024), the signed table
+ * rows sampled through the inverse-CDF table (one concentration <= 32 per row, power-of-two d >= 512), the signed table
  * coordinate of the draw; element 0 of every row is left unwritten; optional entropy / kl / dentropy (rows)
  * (dentropy = d entropy / d kappa), written only when kappa_el_stride == 0 (otherwise call
  * cvb_ps_entropy_kl). */
