@@ -916,7 +916,8 @@ __device__ __forceinline__ void clifford_lp_element(const CliffordLogProbParams&
   else sincosf(loc_k, &sl, &cl);
   const float dot_raw = fmaf(cl, ca, sl * sa);
   const float dot = fminf(fmaxf(dot_raw, -1.0f + kEps), 1.0f - kEps);
-  const float l1p = log1pf(dot);
+  // evaluation: ln(1 + dot) through MUFU (abs error 3e-7 per circle on terms that sum to O(d)); gradient variants keep log1pf
+  const float l1p = FWD_ONLY ? __logf(1.0f + dot) : log1pf(dot);
   acc += logc + kap * l1p;
   if (!FWD_ONLY && p.dlp_dF) {
     // d/dF of kappa log1p(u_hat(F) . m), m = (cos loc, sin loc): kappa / (1 + dot) * (m - dot u_hat) / |F|
