@@ -45,7 +45,7 @@ int dispatch_bwd(const CliffordBwdParams& p_in, cudaStream_t st) {
   }
   static const bool no_small = getenv("CVB_NO_SMALL_ROWS") != nullptr;
   if (2 * p.d <= kSmallMaxN && !no_small) {
-    const int rt = small_rows_per_tile(p.rows, sm_count());
+    const int rt = small_rows_per_tile(p.rows, sm_count(), [&](int r) { return clifford_bwd_small_smem(p.d, r); });
     const size_t smem_s = clifford_bwd_small_smem(p.d, rt);
     auto kern_s = clifford_bwd_small_kernel<ROWK>;
     int grid_s = 0;

@@ -92,7 +92,7 @@ int dispatch_fwd(const CliffordFwdParams& p_in, cudaStream_t st) {
   static const bool no_small = getenv("CVB_NO_SMALL_ROWS") != nullptr;    // A/B switch: the one-CTA-per-row direct DFT
   if (p.n <= kSmallMaxN && !no_small) {
     // short rows (the reference's default MNIST latents, per-token latents): a tile of rows per CTA
-    const int rt = small_rows_per_tile(p.rows, sm_count());
+    const int rt = small_rows_per_tile(p.rows, sm_count(), [&](int r) { return clifford_fwd_small_smem(p.n, r); });
     const size_t smem_s = clifford_fwd_small_smem(p.n, rt);
     auto kern_s = clifford_fwd_small_kernel<MODE, ROWK>;
     int grid_s = 0;

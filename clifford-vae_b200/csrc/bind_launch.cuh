@@ -74,7 +74,7 @@ int dispatch_bind(const BindParams& p, int d, cudaStream_t st) {
   if (d <= kBindSmallMaxD && !no_small && (!kBilinear || d <= 48 || no_pad)) {
     // short vectors: a tile of pairs per CTA (rows per tile sized so that small batches stay spread over the SMs)
     int rt = 32;
-    while (rt > 4 && (p.rows + rt - 1) / rt < 2LL * sm_count()) rt >>= 1;
+    while (rt > 4 && ((p.rows + rt - 1) / rt < 2LL * sm_count() || bind_small_smem(d, rt) > 48 * 1024)) rt >>= 1;
     const size_t smem_s = bind_small_smem(d, rt);
     auto kern_s = bind_small_kernel<MODE>;
     int grid_s = 0;

@@ -1,4 +1,4 @@
-// Clifford-torus kernels for SHORT rows of any length: n = output length <= 128 (d <= 64 circles), power of two or not.
+// Clifford-torus kernels for SHORT rows of any length: n = output length <= 512 (d <= 256 circles), power of two or not.
 // This is where the reference's default MNIST latents live (d in {2, 5, 10, 20, 40}, mnist/mnist_clifpws.py:713-719)
 // and the per-token latents of cnn/cliffordar_model.py (D = 16).  At these sizes an FFT has nothing to factor and one
 // row cannot fill a CTA, so the direct-DFT kernels of clifford_kernels.cuh (one 256-thread CTA per row) idle most of
@@ -12,23 +12,26 @@
 //   backward  G_k = sum_j g_j e^{-2 pi i jk/n} the same way (4 rows per item), then the shared element routine
 //   log_prob  F_k likewise, then the shared element routine.
 //
-// fp32 accumulation: the sums have <= 127 terms (the long-row direct-DFT kernels keep fp64).
+// fp32 accumulation: the sums have <= 511 terms (the long-row direct-DFT kernels keep fp64).  Power-of-two d >= 16 never
+// comes here (the FFT engine is faster from d = 16 up); the tile shrinks with n so that a CTA stays within 48 KB.
 #pragma once
 #include "clifford_kernels.cuh"
 
 namespace cvb {
 
-constexpr int kSmallMaxN = 128;
+constexpr int kSmallMaxN = 512;
 constexpr int kSmallThreads = 128;
 constexpr int kSmallMaxRows = 32;
 
 __host__ __device__ __forceinline__ constexpr int small_pitch_c(int rt) { return rt + 2; }   // complex pitch: 16-byte aligned rows of 4
 __host__ __device__ __forceinline__ constexpr int small_pitch_f(int rt) { return rt + 4; }   // float pitch:   16-byte aligned rows of 4
 
-// rows per tile: as large as keeps >= 2 tiles per SM in flight (small batches stay spread over the SMs)
-inline int small_rows_per_tile(long long rows, int sms) {
+// rows per tile: as large as keeps >= 2 tiles per SM in flight (small batches stay spread over the SMs) and the tile's
+// shared memory (smem_of(rt)) within 48 KB
+template <class SmemOf>
+inline int small_rows_per_tile(long long rows, int sms, SmemOf smem_of) {
   int rt = kSmallMaxRows;
-  while (rt > 4 && (rows + rt - 1) / rt < 2LL * sms) rt >>= 1;
+  while (rt > 4 && ((rows + rt - 1) / rt < 2LL * sms || smem_of(rt) > 48 * 1024)) rt >>= 1;
   return rt;
 }
 

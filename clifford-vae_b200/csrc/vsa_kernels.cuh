@@ -401,14 +401,14 @@ bind_generic_kernel(const BindParams p, int d) {
   }
 }
 
-// ---- short vectors of any length (d <= 128): a TILE of RT pairs per CTA ----------------------------------------------
+// ---- short vectors of any length (d <= 256): a TILE of RT pairs per CTA ----------------------------------------------
 // The reference's default MNIST latents are bound / unbound at d = 2 z_dim (Clifford: 4 .. 80) or z_dim + 1 (vMF:
 // 3 .. 41) (mnist/mnist_clifpws.py:235-236,713-719); one 256-thread CTA per pair (bind_generic_kernel) idles most of its
 // threads there.  Same scheme as clifford_small.cuh: operands parked as g[j][r], one (4 pairs, bin k) item per thread
 // for the two forward real DFTs (packed FMAs, exact index-reduced twiddles, 128-bit broadcast loads), the pointwise op,
 // then one (4 pairs, output j) item per thread for the inverse, outputs j and d - j together (shared cos, negated sin).
-// fp32 accumulation (<= 128 terms).
-constexpr int kBindSmallMaxD = 128;
+// fp32 accumulation (<= 256 terms).
+constexpr int kBindSmallMaxD = 256;
 constexpr int kBindSmallThreads = 128;
 inline size_t bind_small_smem(int d, int rt) {
   return sizeof(cplx) * (size_t)((d + 1) & ~1) + 2 * sizeof(float) * (size_t)d * (rt + 4) + sizeof(cplx) * (size_t)(d / 2 + 1) * (rt + 2);

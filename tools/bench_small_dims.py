@@ -41,13 +41,13 @@ for d in (16, 32, 64, 128, 256):
     print(f"clifford fwd rng      d={d:5d} B={B:8d} {ms:8.3f} ms {B/ms*1e3:.3e} rows/s {gb:7.1f} GB/s {100*gb/PEAK:5.1f}%")
     del loc, z
 # the reference's default MNIST dims (mnist/mnist_clifpws.py:713-719): n = 2d is not a power of two -> direct-DFT kernels
-for d in (2, 5, 10, 20, 40, 64, 100):
+for d in (2, 5, 10, 20, 40, 64, 100, 200, 300):
     B = 1 << 16
     loc = torch.randn(B, d, device=dev); kap = torch.rand(B, device=dev) * 9 + 0.1; z = torch.empty(B, 2 * d, device=dev); kl = torch.empty(B, device=dev)
     ms = timeit(lambda: lib.cvb_clifford_ps_rsample(loc.data_ptr(), kap.data_ptr(), 1, 0, B, None, None, 7, 0, z.data_ptr(), None, None, kl.data_ptr(), None, B, d, st))
     gb = B * (12 * d + 8) / ms / 1e6
-    print(f"clifford fwd rng      d={d:5d} B={B:8d} {ms:8.3f} ms {B/ms*1e3:.3e} rows/s {gb:7.1f} GB/s {100*gb/PEAK:5.1f}%  (direct DFT, n={2*d}, {small if 2 * d <= 128 else "one CTA per row"})")
-    if d <= 64:
+    print(f"clifford fwd rng      d={d:5d} B={B:8d} {ms:8.3f} ms {B/ms*1e3:.3e} rows/s {gb:7.1f} GB/s {100*gb/PEAK:5.1f}%  (direct DFT, n={2*d}, {small if 2 * d <= 512 else "one CTA per row"})")
+    if d <= 256:
         # backward and log_prob of the same rows
         gz = torch.randn(B, 2 * d, device=dev); tps = torch.rand(B, d, device=dev) * 0.98 + 0.01; dl = torch.empty(B, d, device=dev); dk = torch.empty(B, device=dev)
         ms = timeit(lambda: lib.cvb_clifford_ps_rsample_backward(gz.data_ptr(), loc.data_ptr(), kap.data_ptr(), 1, 0, B, None, None, tps.data_ptr(), dl.data_ptr(), dk.data_ptr(), B, d, st))

@@ -17,7 +17,11 @@ $BENCH > $O/r2f_bench_short.json 2> /dev/null && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r2f_launches_bench.csv $BENCH > $O/r2f_ncu_list.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"clifford_fwd_kernel|bind_v3_kernel" -s 6 -c 3 -f -o $O/r2f_bench_kernels $BENCH > $O/r2f_ncu_full.log 2>&1
 python tools/prof_small.py > /dev/null 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:"small_kernel" -s 5 -c 7 -f -o $O/r2f_small_kernels python tools/prof_small.py > $O/r2f_ncu_small.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"small_kernel" -s 3 -c 7 -f -o $O/r2f_small_kernels python tools/prof_small.py > $O/r2f_ncu_small.log 2>&1
+python tools/prof_bwd.py > /dev/null 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:"clifford_bwd_kernel|clifford_log_prob_kernel" -s 2 -c 2 -f -o $O/r2f_bwd_lp python tools/prof_bwd.py > $O/r2f_ncu_bwd.log 2>&1
+python profiles/ncu_summarize.py $O/r2f_bwd_lp.ncu-rep > $O/r2f_ncu_summary_bwd_lp.txt 2>&1
+rm -f $O/r2f_bwd_lp.ncu-rep
 python profiles/ncu_summarize.py $O/r2f_bench_kernels.ncu-rep > $O/r2f_ncu_summary_bench.txt 2>&1
 python profiles/ncu_summarize.py $O/r2f_small_kernels.ncu-rep > $O/r2f_ncu_summary_small.txt 2>&1
 rm -f $O/r2f_small_kernels.ncu-rep
