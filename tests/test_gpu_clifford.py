@@ -218,6 +218,38 @@ def test_table_row_backward_matches_the_numpy_restatement(B, d):
     assert rel_err(dkap.cpu().numpy().reshape(-1), want_dk) < 1e-4
 
 
+def test_mixed_table_and_exact_rows_backward_vs_oracle():
+    """One launch with rows on both sides of the table's concentration range (kappa <= 32: table-sampled, signed table
+    coordinate saved, table-map backward; kappa > 32: exact rejection sampler, copysign(t', s) saved, ATen-form backward):
+    the per-row choice must be the same in forward and backward.  Sample and gradients vs the oracle on the kernel's own
+    draws, row by row."""
+    from clifford_b200 import ops
+    from oracle import latent_oracle as O
+    torch.manual_seed(11)
+    B, d = 10, 1024
+    kap0 = torch.tensor([0.5, 50.0, 5.0, 100.0, 31.9, 32.5, 0.03, 64.0, 10.0, 40.0]).reshape(B, 1)
+    loc = (torch.randn(B, d, device=DEV) * 2).requires_grad_()
+    kap = kap0.to(DEV).requires_grad_()
+    z, _, _ = ops.CliffordPSRsample.apply(loc, kap, 1, None, True)
+    saved = z.grad_fn.saved_tensors[4].clone()
+    saved[:, 0] = 0.5
+    gz = torch.randn_like(z)
+    dloc, dkap = torch.autograd.grad((z * gz).sum(), [loc, kap])
+    table = (kap0.reshape(-1) + 1e-7 <= 32.0)
+    tprime = saved.abs().cpu()
+    tprime[table] = _tprime_from_table_coordinate(saved.abs().cpu().numpy()[table.numpy()], kap0.numpy()[table.numpy()])
+    assert float(tprime.max()) <= 1.0 and float(saved.abs().cpu()[table][:, 1:].max()) > 1.5     # coordinates really are in (0, 256]
+    lo = loc.detach().cpu().requires_grad_()
+    ka = kap.detach().cpu().requires_grad_()
+    zo = O.clifford_ps_rsample(lo, ka, tprime, torch.sign(saved).cpu())
+    assert rel_err(zo.detach(), z.detach().cpu()) < 2e-5
+    dlo, dka = torch.autograd.grad((zo * gz.cpu()).sum(), [lo, ka])
+    assert rel_err(dloc.cpu()[:, 1:], dlo[:, 1:]) < 3e-4
+    # row by row (the high-concentration rows have small gradients that a max-norm over the batch would hide)
+    for r in range(B):
+        assert abs(float(dkap[r, 0]) - float(dka[r, 0])) < 3e-3 * max(abs(float(dka[r, 0])), 1e-3), (r, float(dkap[r, 0]), float(dka[r, 0]))
+
+
 def _tprime_from_table_coordinate(x, kappa):
     """numpy restatement of csrc/icdf_table.cuh (icdf_build_row + icdf_sample_phi): the saved coordinate x = 256 s of a
     table-sampled circle -> phase magnitude (the device table holds 2 H) -> t' = cos^2(phase / 2)."""
