@@ -218,6 +218,34 @@ def test_table_row_backward_matches_the_numpy_restatement(B, d):
     assert rel_err(dkap.cpu().numpy().reshape(-1), want_dk) < 1e-4
 
 
+def test_table_row_backward_is_the_derivative_of_the_forward_map():
+    """The forward is a deterministic function of (loc, kappa) for a fixed Philox (seed, offset) and, on table-sampled
+    rows, smooth in kappa at fixed uniform draws (no rejection decisions).  So the reparameterisation gradient can be
+    checked against the forward itself: central differences of L(kappa) = sum(z(kappa) * grad_z) with the SAME draws
+    (fp64 accumulation of the fp32 samples) against the backward's d L / d kappa, per row."""
+    from clifford_b200 import ops
+    B, d = 16, 2048
+    gen = torch.Generator().manual_seed(5)
+    loc = (torch.randn(B, d, generator=gen) * 2).to(DEV)
+    kap0 = torch.cat([torch.tensor([0.05, 0.3, 1.0, 3.0, 9.0, 20.0, 31.0]), torch.rand(B - 7, generator=gen) * 9.9 + 0.05]).reshape(B, 1).to(DEV)
+    gz = torch.randn(B, 2 * d, generator=gen).to(DEV)
+
+    def forward(kappa, need_grad):
+        torch.manual_seed(99)                                      # same Philox (seed, offset) on every call
+        k = kappa.clone().requires_grad_(need_grad)
+        z, _, _ = ops.CliffordPSRsample.apply(loc, k, 1, None, True)
+        return z, k
+
+    z, k = forward(kap0, True)
+    (dk,) = torch.autograd.grad((z * gz).sum(), [k])
+    h = 4e-3 * kap0.clamp_min(0.5)                                 # fp32 samples: the difference quotient carries ~1e-5 / h of noise
+    zp, _ = forward(kap0 + h, False)
+    zm, _ = forward(kap0 - h, False)
+    fd = (((zp.double() - zm.double()) * gz.double()).sum(-1, keepdim=True) / (2 * h.double()))
+    err = (dk.double() - fd).abs()
+    assert bool((err <= 1e-2 * fd.abs() + 2e-3 * float(fd.abs().max())).all()), (dk.reshape(-1), fd.reshape(-1))
+
+
 def test_mixed_table_and_exact_rows_backward_vs_oracle():
     """One launch with rows on both sides of the table's concentration range (kappa <= 32: table-sampled, signed table
     coordinate saved, table-map backward; kappa > 32: exact rejection sampler, copysign(t', s) saved, ATen-form backward):
