@@ -262,8 +262,13 @@ __device__ __forceinline__ float circle_log_half_1pt(float tp) {
 }
 
 template <bool NOHEAD = false>
+__device__ __forceinline__ void clifford_row_entropy(const CliffordFwdParams& p, long long row, float kap_row, const PsConsts& c);
+template <bool NOHEAD = false>
 __device__ __forceinline__ void clifford_row_entropy(const CliffordFwdParams& p, long long row, float kap_row) {
-  const PsConsts c = ps_consts((double)kap_row, 0.5);
+  clifford_row_entropy<NOHEAD>(p, row, kap_row, ps_consts((double)kap_row, 0.5));
+}
+template <bool NOHEAD>
+__device__ __forceinline__ void clifford_row_entropy(const CliffordFwdParams& p, long long row, float kap_row, const PsConsts& c) {
   const double ent = (double)(p.d - 1) * c.entropy;
   if (p.entropy) p.entropy[row] = (float)ent;
   if (p.kl) p.kl[row] = (float)((double)(p.d - 1) * 1.83787706640934548356 - ent);
@@ -364,8 +369,27 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw, cons
   // group will process, one row per thread, so the per-row loop carries no serial fp64 chain.
   const bool want_lp = !LEAN && PS && ROWK && p.log_prob != nullptr;
   if (PS && ROWK && (p.entropy || p.kl || p.dentropy || p.log_prob)) {
-    for (long long row = first_row + (long long)t * stride; row < p.rows; row += (long long)T * stride)
-      clifford_row_entropy<LEAN || BIND>(p, row, fwd_row_kappa<LEAN || BIND>(p, row % p.loc_rows));
+    if constexpr (T >= 32) {
+      // A PAIR of lanes per row: the even lane evaluates lgamma / digamma / trigamma of a = 1/2 + kappa + eps, the odd lane
+      // those of a + 1/2 -- one instruction stream, so the two chains run side by side and the serial fp64 chain ahead of
+      // the group's first row is halved (a group rarely has more than T/2 rows: 4096 rows over 888 groups = 5 each).
+      const int part = t & 1;
+      for (long long jb = 0; first_row + jb * stride < p.rows; jb += T / 2) {      // uniform over the group's warps
+        const long long row = first_row + (jb + (t >> 1)) * stride;
+        const bool mine = row < p.rows;
+        const float kap = mine ? fwd_row_kappa<LEAN || BIND>(p, row % p.loc_rows) : 1.0f;
+        const double a = 0.5 + ((double)kap + 1e-7);
+        double lg, ps, p1;
+        gamma_family(part ? a + 0.5 : a, lg, ps, p1);
+        const double lgt = __shfl_xor_sync(0xffffffffu, lg, 1), pst = __shfl_xor_sync(0xffffffffu, ps, 1),
+                     p1t = __shfl_xor_sync(0xffffffffu, p1, 1);
+        if (mine && !part)
+          clifford_row_entropy<LEAN || BIND>(p, row, kap, ps_consts_from((double)kap, 0.5, lg, ps, p1, lgt, pst, p1t));
+      }
+    } else {
+      for (long long row = first_row + (long long)t * stride; row < p.rows; row += (long long)T * stride)
+        clifford_row_entropy<LEAN || BIND>(p, row, fwd_row_kappa<LEAN || BIND>(p, row % p.loc_rows));
+    }
   }
 
   // Row schedule.  Static: group g of CTA b takes rows b*G + g + i*stride.  Dynamic (sched != null, groups of
