@@ -362,7 +362,7 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw, cons
   auto icdf_row_ok = [&](float kap) { return kap + kEps <= kIcdfKappaMax; };
   if (ICDF && first_row < p.rows) {
     const float k0 = fwd_row_kappa<LEAN || BIND>(p, first_row % p.loc_rows);
-    if (icdf_row_ok(k0)) icdf_build_row(cells, k0 + kEps, icdf, t, T);
+    if (icdf_row_ok(k0)) icdf_build_row<false, 4>(cells, k0 + kEps, icdf, t, T);
   }
 
   // Prologue: the closed-form row entropy / KL / dH/dkappa (fp64 special functions) of every row this

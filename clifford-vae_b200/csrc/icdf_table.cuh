@@ -33,7 +33,11 @@ const float2* device_icdf_table();
 // weights differentiated, times d log1p(kappa) / d kappa), i.e. the exact pathwise derivative of what the sampler
 // evaluates; against the analytic d/dkappa of G_k^{-1}(1 - s^p) it is accurate to 1e-5 relative (max over s and
 // k in [0.03, 31]), tests/test_icdf_table.py.
-template <bool DERIV = false>
+// UNROLL: iterations kept in flight together.  With T = 32 threads per row (d = 512) a build is four iterations, i.e. four
+// serial L2 round trips; ahead of a group's FIRST row (nothing to overlap them with: the latency of a small batch) the
+// caller asks for 4, inside the row loop (where the build overlaps the previous row's transform and registers are
+// scarce) for 1.
+template <bool DERIV = false, int UNROLL = 1>
 __device__ __forceinline__ void icdf_build_row(float4* cell, float kappa, const float2* __restrict__ table, int t, int T) {
   const float x = log1pf(kappa) * ((float)(kIcdfKappaNodes - 1) / kIcdfQMax);
   int i = (int)x;
@@ -55,6 +59,7 @@ __device__ __forceinline__ void icdf_build_row(float4* cell, float kappa, const 
   }
   // thread t builds cells 2t', 2t'+1 from nodes 2t' .. 2t'+2: one 128-bit + one 64-bit load per concentration row
   const float2* r0 = table + (size_t)(i - 1) * kIcdfRowStride;
+#pragma unroll UNROLL
   for (int j = 2 * t; j < kIcdfCells; j += 2 * T) {
     float2 n0 = make_float2(0.f, 0.f), n1 = n0, n2 = n0;
 #pragma unroll
