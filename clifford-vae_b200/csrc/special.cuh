@@ -415,9 +415,12 @@ struct BetaGradRowShared {
 
 // ---- log(I_v(x) e^{-x}), v >= 0, x > 0, fp64 ------------------------------------------------
 // Ascending series (A&S 9.6.10) when it converges fast, the uniform Debye expansion in v
-// (A&S 9.7.7) for v >= 12, otherwise Hankel's large-argument expansion (A&S 9.7.1).
+// (A&S 9.7.7) for v >= 12, otherwise Hankel's large-argument expansion (A&S 9.7.1).  For v >= 100 (the reference's
+// 512 / 513-dimensional vMF latents: v = 255, 255.5) the four-term Debye expansion is uniformly accurate to 2e-12
+// (checked against SciPy's ive over x in [1e-3, 1e3]) and is used for every x: no series loop with an fp64 division per
+// term and no lgamma on the serial chain of the row scalars.
 __device__ inline double log_ive(double v, double x) {
-  if (x * x <= 80.0 * (v + 1.0) || (v < 12.0 && x <= 30.0)) {
+  if (v < 100.0 && (x * x <= 80.0 * (v + 1.0) || (v < 12.0 && x <= 30.0))) {
     const double q = 0.25 * x * x;
     double term = 1.0, sum = 1.0;
     for (int k = 1; k < 2000; ++k) {
