@@ -161,11 +161,21 @@ struct VmfRowScalars { float entropy, log_norm, dentropy, dlog_norm; };
 // The four independent fp64 chains behind the row scalars: ive(v, k), ive(v - 1, k) and the two Bessel-ratio bounds.
 // One lane can run them back to back (vmf_row_scalars), or four lanes one each (sphere_row_scalars with few rows per
 // warp: the serial chain -- two Bessel series with their lgamma -- was 6 us of the 14 us C2 vMF step).
-__device__ __forceinline__ double vmf_piece_ive(double k, int D) { return exp(log_ive(0.5 * (double)D - 1.0, k)); }
+// ive(v, k) as the row scalars consume it.  The reference evaluates log(ive + 1e-20) and d ive / (ive + 1e-20) in float64
+// (von_mises_fisher.py:200-212, ops/ive.py:29-34): once ive < e^-110 = 1.7e-48 both are bit-identical to their values at
+// ive = 0, and at the reference's 512 / 513-dimensional latents with kappa <= 10 ive is ~e^-750.  From the series,
+// ive(v, k) <= (k/2)^v e^{k^2 / (4 (v + 1)) - k} / Gamma(v + 1) and Gamma(v + 1) >= (v / e)^v, so
+//   log ive <= v (log(k / (2 v)) + 1) + k^2 / (4 (v + 1)) - k:
+// one log and one division decide it, and the Bessel evaluation drops out of the serial chain ahead of the row.
+__device__ __forceinline__ double vmf_ive_or_zero(double v, double k) {
+  if (v >= 1.0 && v * (log(k / (2.0 * v)) + 1.0) + k * k / (4.0 * (v + 1.0)) - k < -110.0) return 0.0;
+  return exp(log_ive(v, k));
+}
+__device__ __forceinline__ double vmf_piece_ive(double k, int D) { return vmf_ive_or_zero(0.5 * (double)D - 1.0, k); }
 __device__ __forceinline__ double vmf_piece_ive_m1(double k, int D) {
   const double v = 0.5 * (double)D - 1.0;
   // ive(v - 1, k); orders below zero only occur for m = 2 (I_{-1} = I_1) and m = 3 (closed form)
-  if (v >= 1.0) return exp(log_ive(v - 1.0, k));
+  if (v >= 1.0) return vmf_ive_or_zero(v - 1.0, k);
   if (v == 0.0) return exp(log_ive(1.0, k));
   return sqrt(2.0 / (3.14159265358979323846 * k)) * 0.5 * (1.0 + exp(-2.0 * k));
 }
@@ -352,7 +362,7 @@ __device__ __forceinline__ RowScalarPieces sphere_row_scalar_pieces(const Sphere
     const double v = 0.5 * (double)p.D - 1.0;
     if (part < 2) {
       if (part == 1 && v < 1.0 && v != 0.0) o.r0 = vmf_piece_ive_m1(kap, p.D);                  // m = 3: closed form
-      else o.r0 = exp(log_ive(part == 0 ? v : (v >= 1.0 ? v - 1.0 : 1.0), kap));
+      else o.r0 = vmf_ive_or_zero(part == 0 ? v : (v >= 1.0 ? v - 1.0 : 1.0), kap);
     } else {
       bessel_ratio_bound(0.5 * (double)p.D, kap, part == 2 ? 0.0 : 2.0, o.r0, o.r1);
     }
