@@ -202,3 +202,31 @@ def test_fused_row_scalars_one_launch_and_separate_backward_passes(family, golde
     q4, _ = make()
     (g4,) = torch.autograd.grad((q4.rsample() * w).sum(), [kap])
     assert rel_err(g3.cpu(), (g4 + g2_ref).cpu()) < 1e-5
+
+
+@pytest.mark.parametrize("D", [41, 130, 202, 256, 513, 1024, 2050])
+def test_vmf_row_scalars_order_and_concentration_sweep(D):
+    """Entropy / log-normaliser and their kappa-derivatives over four decades of kappa at small and large orders against
+    the float64 restatement of the reference (von_mises_fisher.py:183-212, ops/ive.py:29-34, SciPy's ive).  Orders
+    v = D/2 - 1 >= 100 run through the four-term Debye expansion for every kappa; where ive(v, kappa) sits far below the
+    reference's 1e-20 regulariser (small kappa at large D) the kernel skips the Bessel evaluation altogether; large kappa at
+    the same D does not underflow and crosses that switch inside one launch."""
+    from clifford_b200 import ops
+    from oracle import latent_oracle as O
+    kap = torch.logspace(-2, 3.5, 97, dtype=torch.float32).reshape(-1, 1)
+    k_ref = kap.clone().to(torch.float64).requires_grad_()
+    ent_ref = O.vmf_entropy(k_ref, D)
+    ln_ref = O.vmf_log_normalization(k_ref, D)
+    (dent_ref,) = torch.autograd.grad(ent_ref.sum(), k_ref, retain_graph=True)
+    (dln_ref,) = torch.autograd.grad(ln_ref.sum(), k_ref)
+    k_dev = kap.to(DEV).requires_grad_()
+    ent, ln = ops.VMFEntropyLogNorm.apply(k_dev, D)
+    (dent,) = torch.autograd.grad(ent.sum(), k_dev, retain_graph=True)
+    (dln,) = torch.autograd.grad(ln.sum(), k_dev)
+    scale = max(1.0, float(ln_ref.detach().abs().max()))
+    assert float((ln.detach().cpu().double() - ln_ref.detach()).abs().max()) < 1e-5 * scale
+    assert float((ent.detach().cpu().double() - ent_ref.detach()).abs().max()) < 1e-5 * scale
+    # element-wise: derivative error relative to max(1, |value|) per element
+    for got, ref in ((dln, dln_ref), (dent, dent_ref)):
+        err = (got.cpu().double().reshape(-1) - ref.reshape(-1)).abs() / ref.reshape(-1).abs().clamp_min(1.0)
+        assert float(err.max()) < 2e-5, float(err.max())
