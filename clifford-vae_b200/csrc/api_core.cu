@@ -202,7 +202,7 @@ int ensure_smem_optin(const void* kernel, size_t smem) {
 
 __global__ void philox_fill_kernel(uint4* out, long long n, PhiloxKey key) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    out[i] = philox4x32_10(make_uint4((uint32_t)i, (uint32_t)(i >> 32), 0u, key.offset), key.k0, key.k1);
+    out[i] = philox4x32_10_rk(make_uint4((uint32_t)i, (uint32_t)(i >> 32), 0u, key.offset), key);   // the kernels' form (round keys from the host)
 }
 
 }  // namespace cvb

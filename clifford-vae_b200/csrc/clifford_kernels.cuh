@@ -437,12 +437,11 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw, cons
     if (ICDF && table_row) {
       // device RNG through the row's inverse-CDF cells: one Philox call per FOUR circles, no rejection, no queue
       const uint64_t quad_base = (uint64_t)row * (uint64_t)(d / 4) + (uint64_t)t * (E / 4);
-      PhiloxKey pkey = p.key;
-      pkey.stream = 10;
+      const uint32_t call_off = philox_call_offset(p.key);      // once per row, not once per Philox call
       const float inv_p = __frcp_rn(fmaf(2.0f, kap_row + kEps, 1.0f));
 #pragma unroll 2
       for (int e = 0; e < E; e += 4) {
-        const uint4 r = philox_draw(pkey, quad_base + (e >> 2), 0);
+        const uint4 r = philox_draw_at(p.key, 10u, call_off, quad_base + (e >> 2));
         const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -453,20 +452,23 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw, cons
           float xs;                                       // table coordinate of this draw (> 0)
           const float aphi = fminf(fmaxf(icdf_sample_phi(cells, inv_p, w[j], xs), kIcdfPhiMin), kIcdfPhiMax);   // [sqrt(eps), pi - sqrt(eps)]
           const float phi = __uint_as_float(__float_as_uint(aphi) | (w[j] & 0x80000000u));
-          cplx x = make_float2(1.0f, 0.0f);
-          if (valid && k != 0) {
+          if (!LEAN && valid && k != 0) {
             // saved for the backward: the signed table coordinate (NOT t'): clifford_bwd_kernel re-evaluates the phase and
             // its pathwise kappa-derivative from the row's cells (table rows only; exact-sampler rows save copysign(t', s))
-            if (!LEAN && p.tp_signed) {
+            if (p.tp_signed) {
               const float keep = clifford_saves_table_coord<LOG2N>() ? xs : icdf_tprime(aphi);
               stg_stream1(p.tp_signed + row * d + k, __uint_as_float(__float_as_uint(keep) | (w[j] & 0x80000000u)));
             }
             if (want_lp) lp_acc += circle_log_half_1pt<true>(icdf_tprime(aphi));
-            sincos_any<true>(src.loc[k] + phi, x.y, x.x);
           }
+          // unconditional (no per-circle branch): bin 0 is overwritten with 1 after the loop, and the phasors of an invalid
+          // row (static schedule padding; finite garbage from the staged buffer) are never stored
+          cplx x;
+          sincos_any<true>(src.loc[k] + phi, x.y, x.x);
           xch[pad16(k)] = x;
         }
       }
+      if (t == 0) xch[pad16(0)] = make_float2(1.0f, 0.0f);      // same thread wrote bin 0 above: program order suffices
     } else if (MODE == kPsRng) {
       // device RNG: one Philox call + one Box-Muller per PAIR of bins (one envelope proposal each);
       // rejected proposals are queued and finished in phase 1b

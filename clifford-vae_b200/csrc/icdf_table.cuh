@@ -89,11 +89,13 @@ __device__ __forceinline__ float fast_log2(float x) {
   return r;
 }
 
-// One circle from one 32-bit word: bits 7..30 -> v in (0, 1]; returns the phase magnitude |phi| = 2 |psi| in [0, pi]
+// One circle from one 32-bit word: bits 0..22 -> v in (0, 1), midpoints of 2^23 equal bins; returns the phase magnitude |phi| = 2 |psi| in [0, pi]
 // (the device table stores 2 H).  inv_p = 1 / (2k + 1).  Bit 31 of the word is the circle's sign draw.
 // x_out: the table coordinate x = cells * s, s = v^(1/p) in (0, 1] -- what the training path saves for the backward.
 __device__ __forceinline__ float icdf_sample_phi(const float4* cell, float inv_p, uint32_t w, float& x_out) {
-  const float v = (float)(((w >> 7) & 0xFFFFFFu) + 1u) * 0x1p-24f;
+  // v = (2 m + 1) / 2^24 from the word's low 23 bits m, built in the mantissa of a float in [1, 2): two instructions
+  // (mask-or, subtract; 1 - 2^-24 is exact) instead of shift / mask / add / convert / scale
+  const float v = __uint_as_float((w & 0x007FFFFFu) | 0x3F800000u) - 0.99999994f;
   const float x = fast_exp2(fast_log2(v) * inv_p) * (float)kIcdfCells;
   x_out = x;
   int j = (int)x;

@@ -87,6 +87,7 @@ inline PhiloxKey make_key(unsigned long long seed, unsigned long long offset, ui
   k.k1 = (uint32_t)(seed >> 32);
   k.offset = (uint32_t)offset ^ (uint32_t)((offset >> 32) * 0x9E3779B9u);
   k.stream = stream_id;
+  philox_fill_round_keys(k);
   return k;
 }
 

@@ -18,6 +18,10 @@ struct PhiloxKey {
   // sampling launch to retire adds 1 to *dev_counter and re-arms the word (rng_launch_done), so a captured graph needs
   // no separate `counter += 1` kernel between sampling launches.  nullptr: the caller bumps the counter.
   unsigned int* arrive;
+  // Round keys k + r W of the ten rounds, filled by make_key on the host: the kernels' XORs read them straight from the
+  // constant bank (kernel parameters) instead of bumping both key words with two integer adds in every round -- 18 of
+  // the ~66 instructions of one Philox call.
+  uint32_t rk0[10], rk1[10];
 };
 
 __host__ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
@@ -35,12 +39,37 @@ __host__ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, ui
   return c;
 }
 
-// counter layout: (element lo, element hi, attempt | stream << 24, call offset)
-__device__ __forceinline__ uint4 philox_draw(const PhiloxKey& key, uint64_t elem, uint32_t attempt) {
+// the same rounds with the precomputed round keys of a PhiloxKey (bit-identical to philox4x32_10(c, key.k0, key.k1))
+__device__ __forceinline__ uint4 philox4x32_10_rk(uint4 c, const PhiloxKey& key) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)M0 * c.x, p1 = (uint64_t)M1 * c.z;
+    const uint32_t hi0 = (uint32_t)(p0 >> 32), hi1 = (uint32_t)(p1 >> 32);
+    const uint32_t lo0 = (uint32_t)p0, lo1 = (uint32_t)p1;
+    c = make_uint4(hi1 ^ c.y ^ key.rk0[r], lo1, hi0 ^ c.w ^ key.rk1[r], lo0);
+  }
+  return c;
+}
+inline void philox_fill_round_keys(PhiloxKey& key) {
+  uint32_t k0 = key.k0, k1 = key.k1;
+  for (int r = 0; r < 10; ++r) { key.rk0[r] = k0; key.rk1[r] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+}
+
+// the call offset of this launch: the host-chosen offset plus the device launch counter when one is registered
+__device__ __forceinline__ uint32_t philox_call_offset(const PhiloxKey& key) {
   uint32_t off = key.offset;
   if (key.dev_counter) off += (uint32_t)__ldg(key.dev_counter) * 0x9E3779B9u;   // uniform branch on a kernel parameter
-  return philox4x32_10(make_uint4((uint32_t)elem, (uint32_t)(elem >> 32), attempt | (key.stream << 24), off),
-                       key.k0, key.k1);
+  return off;
+}
+// hot loops: stream and call offset resolved once by the caller (philox_call_offset), the key read in place (round keys
+// from the constant bank)
+__device__ __forceinline__ uint4 philox_draw_at(const PhiloxKey& key, uint32_t stream, uint32_t call_offset, uint64_t elem) {
+  return philox4x32_10_rk(make_uint4((uint32_t)elem, (uint32_t)(elem >> 32), stream << 24, call_offset), key);
+}
+// counter layout: (element lo, element hi, attempt | stream << 24, call offset)
+__device__ __forceinline__ uint4 philox_draw(const PhiloxKey& key, uint64_t elem, uint32_t attempt) {
+  return philox4x32_10_rk(make_uint4((uint32_t)elem, (uint32_t)(elem >> 32), attempt | (key.stream << 24), philox_call_offset(key)), key);
 }
 
 // Last statement of every kernel that draws from the device generator; reached by ALL threads of the CTA.  Every CTA has
