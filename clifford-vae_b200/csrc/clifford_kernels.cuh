@@ -27,6 +27,9 @@ constexpr int clifford_bwd_min_blocks() { return LOG2N == 10 ? 4 : 5; }
 // the fused-bind variant carries a second set of transforms; since its pair stage forms each (k, N-k) pair once it fits 124
 // registers without spilling: 4 resident CTAs / SM measured 0.1166 -> 0.1069 ms at the headline shape (3 before; 5 does not
 // fit the shared memory)
+#ifndef CVB_ICDF_LOOP_UNROLL
+#define CVB_ICDF_LOOP_UNROLL 4
+#endif
 #ifndef CVB_FWD_LEAN_MINB
 #define CVB_FWD_LEAN_MINB 7
 #endif
@@ -85,6 +88,9 @@ __device__ __forceinline__ float fwd_row_kappa(const CliffordFwdParams& p, long 
 }
 
 constexpr float kEps = 1e-7f;
+// the forward sampler's table carries the padding cell of icdf_build_row<.., PAD> (index = floor(x) unclamped)
+constexpr int kFwdIcdfCells = kIcdfCells + 1;
+constexpr int kIcdfLoopUnroll = CVB_ICDF_LOOP_UNROLL;   // Philox calls (4 circles each) of the table sampling loop unrolled together
 // the reference's atan2(s sqrt(max(1 - t^2, eps)), t) (clifford.py:44-48) never returns a phase below sqrt(eps) or above
 // pi - sqrt(eps): the table sampler clamps |phi| to that range
 constexpr float kIcdfPhiMin = 3.16227766e-4f, kIcdfPhiMax = 3.14127642f;
@@ -123,7 +129,8 @@ __device__ __forceinline__ CirclePhase circle_phase(float tp, float sgn) {
 template <bool FAST>
 __device__ __forceinline__ void sincos_any(float x, float& s, float& c) {
   if (FAST) {
-    const float n = rintf(x * 0.15915494309189535f);
+    // n = rint(x / 2 pi) by the 1.5 * 2^23 trick (|x| < 2^22 * 2 pi): two FP-pipe instructions, no FRND on the MUFU unit
+    const float n = fmaf(x, 0.15915494309189535f, 12582912.0f) - 12582912.0f;
     float r = fmaf(-n, 6.28318548202514648f, x);        // 2 pi rounded to fp32 ...
     r = fmaf(-n, -1.74845553146951715e-7f, r);          // ... and its remainder
     __sincosf(r, &s, &c);
@@ -299,7 +306,7 @@ template <int LOG2N, int MODE, bool BIND = false>
 constexpr size_t clifford_fwd_smem_bytes() {
   using Pl = FftPlan<LOG2N>;
   return (sizeof(cplx) * Pl::XCH + sizeof(QueueIndex) * Pl::N + sizeof(float) * Pl::N * clifford_fwd_stages(MODE) +
-          (BIND ? sizeof(cplx) * Pl::N : 0) + (clifford_fwd_has_icdf<LOG2N, MODE>() ? sizeof(float4) * kIcdfCells : 0)) * Pl::GROUPS +
+          (BIND ? sizeof(cplx) * Pl::N : 0) + (clifford_fwd_has_icdf<LOG2N, MODE>() ? sizeof(float4) * kFwdIcdfCells : 0)) * Pl::GROUPS +
          (sizeof(uint64_t) + sizeof(int) * 2 + sizeof(float) * kLpSlots) * Pl::GROUPS;
 }
 
@@ -330,7 +337,7 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw, cons
   float* lps = reinterpret_cast<float*>(after_stage + (sizeof(cplx) * Pl::XCH + sizeof(QueueIndex) * d + sizeof(uint64_t) + 2 * sizeof(int)) * (size_t)G) + kLpSlots * group;
   cplx* spec = reinterpret_cast<cplx*>(after_stage + (sizeof(cplx) * Pl::XCH + sizeof(QueueIndex) * d + sizeof(uint64_t) + 2 * sizeof(int) + kLpSlots * sizeof(float)) * (size_t)G) + (size_t)group * d;   // BIND only
   // row inverse-CDF cells (16-byte aligned: every block before it is a multiple of 16 bytes per CTA)
-  float4* cells = reinterpret_cast<float4*>(after_stage + (sizeof(cplx) * Pl::XCH + sizeof(QueueIndex) * d + sizeof(uint64_t) + 2 * sizeof(int) + kLpSlots * sizeof(float) + (BIND ? sizeof(cplx) * d : 0)) * (size_t)G) + (size_t)group * kIcdfCells;
+  float4* cells = reinterpret_cast<float4*>(after_stage + (sizeof(cplx) * Pl::XCH + sizeof(QueueIndex) * d + sizeof(uint64_t) + 2 * sizeof(int) + kLpSlots * sizeof(float) + (BIND ? sizeof(cplx) * d : 0)) * (size_t)G) + (size_t)group * kFwdIcdfCells;
   constexpr bool PS = (MODE == kPsInjected || MODE == kPsRng);
   const long long stride = (long long)gridDim.x * G;
   const bool staged = LEAN ? true : (NST > 0 && p.staged);   // LEAN implies TMA-staged inputs (16-byte aligned rows)
@@ -362,7 +369,7 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw, cons
   auto icdf_row_ok = [&](float kap) { return kap + kEps <= kIcdfKappaMax; };
   if (ICDF && first_row < p.rows) {
     const float k0 = fwd_row_kappa<LEAN || BIND>(p, first_row % p.loc_rows);
-    if (icdf_row_ok(k0)) icdf_build_row<false, 4>(cells, k0 + kEps, icdf, t, T);
+    if (icdf_row_ok(k0)) icdf_build_row<false, 4, true>(cells, k0 + kEps, icdf, t, T);
   }
 
   // Prologue: the closed-form row entropy / KL / dH/dkappa (fp64 special functions) of every row this
@@ -439,7 +446,7 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw, cons
       const uint64_t quad_base = (uint64_t)row * (uint64_t)(d / 4) + (uint64_t)t * (E / 4);
       const uint32_t call_off = philox_call_offset(p.key);      // once per row, not once per Philox call
       const float inv_p = __frcp_rn(fmaf(2.0f, kap_row + kEps, 1.0f));
-#pragma unroll 2
+#pragma unroll kIcdfLoopUnroll
       for (int e = 0; e < E; e += 4) {
         const uint4 r = philox_draw_at(p.key, 10u, call_off, quad_base + (e >> 2));
         const uint32_t w[4] = {r.x, r.y, r.z, r.w};
@@ -450,7 +457,7 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw, cons
           // returns a phase below sqrt(eps); theta = loc + phi needs ONE sincos instead of sincos(loc), cos/sin(phi)
           // and a complex multiply
           float xs;                                       // table coordinate of this draw (> 0)
-          const float aphi = fminf(fmaxf(icdf_sample_phi(cells, inv_p, w[j], xs), kIcdfPhiMin), kIcdfPhiMax);   // [sqrt(eps), pi - sqrt(eps)]
+          const float aphi = fminf(fmaxf(icdf_sample_phi_t<true>(cells, inv_p, w[j], xs), kIcdfPhiMin), kIcdfPhiMax);   // [sqrt(eps), pi - sqrt(eps)]
           const float phi = __uint_as_float(__float_as_uint(aphi) | (w[j] & 0x80000000u));
           if (!LEAN && valid && k != 0) {
             // saved for the backward: the signed table coordinate (NOT t'): clifford_bwd_kernel re-evaluates the phase and
@@ -602,7 +609,7 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw, cons
     if (ICDF && next_row < p.rows) {
       // ... and with this row's cells: build the next row's (the loop-top barrier orders them before its sampling)
       const float kn = fwd_row_kappa<LEAN || BIND>(p, next_row % p.loc_rows);
-      if (icdf_row_ok(kn)) icdf_build_row(cells, kn + kEps, icdf, t, T);
+      if (icdf_row_ok(kn)) icdf_build_row<false, 1, true>(cells, kn + kEps, icdf, t, T);
     }
     // phase 2: Hermitian half spectrum -> packed complex spectrum -> inverse FFT -> real row
     cplx v[E];

@@ -37,7 +37,9 @@ const float2* device_icdf_table();
 // serial L2 round trips; ahead of a group's FIRST row (nothing to overlap them with: the latency of a small batch) the
 // caller asks for 4, inside the row loop (where the build overlaps the previous row's transform and registers are
 // scarce) for 1.
-template <bool DERIV = false, int UNROLL = 1>
+// PAD: also write cell[kIcdfCells] = the constant H(1) (the table must then hold kIcdfCells + 1 cells), so that a sampler
+// may index it with floor(x) for x = cells * s up to and including cells (s = 1) without clamping.
+template <bool DERIV = false, int UNROLL = 1, bool PAD = false>
 __device__ __forceinline__ void icdf_build_row(float4* cell, float kappa, const float2* __restrict__ table, int t, int T) {
   const float x = log1pf(kappa) * ((float)(kIcdfKappaNodes - 1) / kIcdfQMax);
   int i = (int)x;
@@ -74,6 +76,7 @@ __device__ __forceinline__ void icdf_build_row(float4* cell, float kappa, const 
     const float d0 = n1.x - n0.x, d1 = n2.x - n1.x;
     cell[j] = make_float4(n0.x, n0.y, 3.0f * d0 - 2.0f * n0.y - n1.y, -2.0f * d0 + n0.y + n1.y);
     cell[j + 1] = make_float4(n1.x, n1.y, 3.0f * d1 - 2.0f * n1.y - n2.y, -2.0f * d1 + n1.y + n2.y);
+    if (PAD && j + 2 == kIcdfCells) cell[kIcdfCells] = make_float4(n2.x, 0.0f, 0.0f, 0.0f);
   }
 }
 
@@ -92,17 +95,33 @@ __device__ __forceinline__ float fast_log2(float x) {
 // One circle from one 32-bit word: bits 0..22 -> v in (0, 1), midpoints of 2^23 equal bins; returns the phase magnitude |phi| = 2 |psi| in [0, pi]
 // (the device table stores 2 H).  inv_p = 1 / (2k + 1).  Bit 31 of the word is the circle's sign draw.
 // x_out: the table coordinate x = cells * s, s = v^(1/p) in (0, 1] -- what the training path saves for the backward.
-__device__ __forceinline__ float icdf_sample_phi(const float4* cell, float inv_p, uint32_t w, float& x_out) {
-  // v = (2 m + 1) / 2^24 from the word's low 23 bits m, built in the mantissa of a float in [1, 2): two instructions
-  // (mask-or, subtract; 1 - 2^-24 is exact) instead of shift / mask / add / convert / scale
-  const float v = __uint_as_float((w & 0x007FFFFFu) | 0x3F800000u) - 0.99999994f;
-  const float x = fast_exp2(fast_log2(v) * inv_p) * (float)kIcdfCells;
+// PADDED (the table has the extra cell of icdf_build_row<.., PAD>): floor(x) from a round-toward-zero add of 2^23 -- the
+// cell index sits in the low mantissa bits, no float <-> int conversions (they share the MUFU unit with the four
+// transcendentals of a circle) and no clamp.
+template <bool PADDED>
+__device__ __forceinline__ float icdf_sample_phi_t(const float4* cell, float inv_p, uint32_t w, float& x_out) {
+  uint32_t vb;
+  asm("lop3.b32 %0, %1, 0x007FFFFF, 0x3F800000, 0xEA;" : "=r"(vb) : "r"(w));      // (w & mask) | one, one instruction
+  const float v = __uint_as_float(vb) - 0.99999994f;
+  static_assert(kIcdfCells == 256, "the table coordinate below is 2^8 s");
+  const float x = fast_exp2(fmaf(fast_log2(v), inv_p, 8.0f));                      // cells * v^(1/p), in (0, 256]
   x_out = x;
-  int j = (int)x;
-  j = j > kIcdfCells - 1 ? kIcdfCells - 1 : j;
-  const float tau = x - (float)j;
-  const float4 c = cell[j];
+  float tau;
+  float4 c;
+  if (PADDED) {
+    const float y = __fadd_rz(x, 8388608.0f);
+    tau = x - (y - 8388608.0f);
+    c = cell[__float_as_uint(y) & 0x1FFu];
+  } else {
+    int j = (int)x;
+    j = j > kIcdfCells - 1 ? kIcdfCells - 1 : j;
+    tau = x - (float)j;
+    c = cell[j];
+  }
   return fmaf(fmaf(fmaf(c.w, tau, c.z), tau, c.y), tau, c.x);
+}
+__device__ __forceinline__ float icdf_sample_phi(const float4* cell, float inv_p, uint32_t w, float& x_out) {
+  return icdf_sample_phi_t<false>(cell, inv_p, w, x_out);
 }
 __device__ __forceinline__ float icdf_sample_phi(const float4* cell, float inv_p, uint32_t w) {
   float x_unused;
