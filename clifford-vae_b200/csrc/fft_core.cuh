@@ -263,7 +263,25 @@ __device__ __forceinline__ void apply_twiddle_powers(cplx (&u)[R], cplx w1) {
   for (int i = 1; i < R; ++i) u[i] = cmul(u[i], w[i]);
 }
 
-template <class Pl, int P, bool INV>
+// This thread's points {t + e T} of a padded exchange buffer.  pad16(t + e T) = pad16(t) + e (T + T/16) whenever T is a
+// multiple of 16 (adding a multiple of 16 never carries out of the low four bits), so one base address and compile-time
+// offsets replace a shift / add / scale per point.
+template <class Pl>
+__device__ __forceinline__ void load_own_points(cplx (&v)[Pl::E], const cplx* xch, int t) {
+  if constexpr (Pl::T % 16 == 0) {
+    constexpr int S = Pl::T + Pl::T / 16;
+    const cplx* xr = xch + pad16(t);
+#pragma unroll
+    for (int e = 0; e < Pl::E; ++e) v[e] = xr[e * S];
+  } else {
+#pragma unroll
+    for (int e = 0; e < Pl::E; ++e) v[e] = xch[pad16(t + e * Pl::T)];
+  }
+}
+
+// BASEPTR: read the exchanged points through load_own_points (the Clifford kernels: fewer address instructions in their
+// issue-bound loops); the bind kernels keep the indexed form (measured: -0.8 % at d = 4096 with the base-pointer form).
+template <class Pl, int P, bool INV, bool BASEPTR = false>
 __device__ __forceinline__ void fft_pass_p(cplx (&v)[Pl::E], cplx* xch, const int t, const cplx* __restrict__ tw) {
   constexpr int LOG2N = Pl::LOG2N;
   constexpr int LOGNS = P * Pl::LOGE;
@@ -295,9 +313,13 @@ __device__ __forceinline__ void fft_pass_p(cplx (&v)[Pl::E], cplx* xch, const in
   }
   if constexpr (!LAST) {
     group_sync_p<Pl>();
+    if constexpr (BASEPTR) {
+      load_own_points<Pl>(v, xch, t);
+    } else {
 #pragma unroll
-    for (int e = 0; e < Pl::E; ++e) v[e] = xch[pad16(t + e * Pl::T)];
-    fft_pass_p<Pl, P + 1, INV>(v, xch, t, tw);
+      for (int e = 0; e < Pl::E; ++e) v[e] = xch[pad16(t + e * Pl::T)];
+    }
+    fft_pass_p<Pl, P + 1, INV, BASEPTR>(v, xch, t, tw);
   }
 }
 
@@ -309,7 +331,7 @@ __device__ __forceinline__ void fft_run_p(cplx (&v)[Pl::E], cplx* xch, int t, co
 template <int LOG2N, bool INV>
 __device__ __forceinline__ void fft_run(cplx (&v)[FftPlan<LOG2N>::E], cplx* xch, int t,
                                         const cplx* __restrict__ tw) {
-  fft_pass_p<FftPlan<LOG2N>, 0, INV>(v, xch, t, tw);
+  fft_pass_p<FftPlan<LOG2N>, 0, INV, true>(v, xch, t, tw);
 }
 
 // R2C untangle.  In: v = Z = FFT_N(z), z[m] = x[2m] + i x[2m+1] of a real row of length n = 2N.
@@ -372,6 +394,24 @@ __device__ __forceinline__ void c2r_pretangle_load(cplx (&v)[FftPlan<LOG2N>::E],
   using Pl = FftPlan<LOG2N>;
   constexpr int N = Pl::N;
   constexpr float scale = 1.0f / (2.0f * N);
+  if constexpr (Pl::T % 16 == 0) {
+    // bins k = t + e T and N - k from two base addresses with compile-time offsets (see load_own_points), the twiddles
+    // from one base pointer
+    constexpr int S = Pl::T + Pl::T / 16;
+    const cplx* xk = xch + pad16(t);
+    const cplx* xm = xch + pad16(N - t);
+    const cplx* twp = tw + twiddle_offset(LOG2N) + t;
+#pragma unroll
+    for (int e = 0; e < Pl::E; ++e) {
+      const cplx x = xk[e * S];
+      const cplx xp = cconj(xm[-e * S]);
+      const cplx w = cconj(__ldg(twp + e * Pl::T));               // exp(+2 pi i k / n)
+      const cplx s = cadd(x, xp), d = csub(x, xp);
+      const cplx wd = cmul_i(cmul(w, d));
+      v[e] = cadd_scaled(s, wd, scale);
+    }
+    return;
+  }
 #pragma unroll
   for (int e = 0; e < Pl::E; ++e) {
     const int k = t + e * Pl::T;
