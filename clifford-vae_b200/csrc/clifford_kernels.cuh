@@ -541,12 +541,11 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw, cons
     } else if (MODE == kUniformRng || MODE == kUnitaryRng) {
       // one uniform phase per circle: one Philox call serves four circles (one 32-bit word each; for the
       // unitary initialiser the top bit is the sign draw and the next 24 bits the magnitude draw)
-      PhiloxKey pkey = p.key;
-      pkey.stream = 9;
+      const uint32_t call_off = philox_call_offset(p.key);      // once per row, not once per Philox call
       const uint64_t quad_base = (uint64_t)row * (uint64_t)(d / 4) + (uint64_t)t * (E / 4);
 #pragma unroll 2
       for (int e = 0; e < E; e += 4) {
-        const uint4 r = philox_draw(pkey, quad_base + (e >> 2), 0);
+        const uint4 r = philox_draw_at(p.key, 9u, call_off, quad_base + (e >> 2));
         const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {

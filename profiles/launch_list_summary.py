@@ -30,6 +30,6 @@ if fwd and bnd:
     if len(sys.argv) > 2:
         d = json.load(open(sys.argv[2]))["kernels"]
         f2, b2 = d["rsample_kl"]["ms"], d["bind"]["ms"]
-        print(f"  bench.py's live CUDA-event split of the same command: rsample_kl {f2:.4f} ms / bind {b2:.4f} ms = "
+        print(f"  bench.py's live CUDA-event split (the bench JSON given: 20 timed steps of the default command on the same build): rsample_kl {f2:.4f} ms / bind {b2:.4f} ms = "
               f"{100 * f2 / (f2 + b2):.1f} % / {100 * b2 / (f2 + b2):.1f} %")
 print(f"\nother launches in the list ({len(seq) - len(ours)}): torch's fills of the synthetic inputs and the e2e leg's device copies")
