@@ -836,10 +836,14 @@ clifford_bwd_kernel(const CliffordBwdParams p, const cplx* __restrict__ tw, cons
     r2c_untangle<LOG2N>(v, xch, t, tw);        // v[e] = G[k]
 
     // G[k] goes back to this thread's own exchange slots so that the (large, divergent) element
-    // routine runs in a rolled loop: keeps the kernel inside the instruction cache
-    group_sync<LOG2N>();
+    // routine runs in a rolled loop: keeps the kernel inside the instruction cache.  (Table-sampled rows consume G[k]
+    // straight from the registers instead: their element is ~45 instructions and is unrolled.)
+    const bool table_elems = TABLE && table_row;
+    if (!table_elems) {
+      group_sync<LOG2N>();
 #pragma unroll
-    for (int e = 0; e < E; ++e) xch[pad16(t + e * T)] = v[e];
+      for (int e = 0; e < E; ++e) xch[pad16(t + e * T)] = v[e];
+    }
     BetaGradRowShared bc(rc);
     BwdRowSrc src;
     if (staged) {
@@ -860,26 +864,27 @@ clifford_bwd_kernel(const CliffordBwdParams p, const cplx* __restrict__ tw, cons
       // table-sampled row: phase and its pathwise kappa-derivative straight from the row's cells
       const float inv_p = __frcp_rn(fmaf(2.0f, kap_row + kEps, 1.0f));       // as the forward
       constexpr float inv_d = 1.0f / (float)d;
-#pragma unroll 4
+      float* dloc_row = p.dloc + row * d + t;
+#pragma unroll
       for (int e = 0; e < E; ++e) {
         const int k = t + e * T;
-        if (k != 0) {
-          const float sv = src.tps[k];
-          float dmag;
-          const float mag = icdf_phi_and_dkappa(cells, dcells, inv_p, fabsf(sv), dmag);
-          const bool clamped = (mag < kIcdfPhiMin) || (mag > kIcdfPhiMax);
-          const float aphi = fminf(fmaxf(mag, kIcdfPhiMin), kIcdfPhiMax);
-          const float phi = __uint_as_float(__float_as_uint(aphi) | (__float_as_uint(sv) & 0x80000000u));
-          cplx x;
-          sincos_any<true>(src.loc[k] + phi, x.y, x.x);
-          const cplx Gk = xch[pad16(k)];
-          const float dth = -inv_d * (x.y * Gk.x - x.x * Gk.y);          // dL/dtheta_k = -(2/n) Im(X_k conj(G_k))
-          stg_stream1(p.dloc + row * d + k, dth);
-          const float dsigned = __uint_as_float(__float_as_uint(dmag) ^ (__float_as_uint(sv) & 0x80000000u));
-          dk_sum = fmaf(dth, clamped ? 0.0f : dsigned, dk_sum);
-        } else {
-          stg_stream1(p.dloc + row * d, 0.0f);
-        }
+        // no branch per circle: bin 0 (only e == 0 of thread 0; the forward never writes its slot) is evaluated like the
+        // others on a harmless coordinate and its gradient is zeroed by a select -- two selects in one unrolled iteration
+        float sv = src.tps[k];
+        if (e == 0) sv = (t == 0) ? 1.0f : sv;
+        float dmag;
+        const float mag = icdf_phi_and_dkappa(cells, dcells, inv_p, fabsf(sv), dmag);
+        const bool clamped = (mag < kIcdfPhiMin) || (mag > kIcdfPhiMax);
+        const float aphi = fminf(fmaxf(mag, kIcdfPhiMin), kIcdfPhiMax);
+        const float phi = __uint_as_float(__float_as_uint(aphi) | (__float_as_uint(sv) & 0x80000000u));
+        cplx x;
+        sincos_any<true>(src.loc[k] + phi, x.y, x.x);
+        const cplx Gk = v[e];
+        float dth = -inv_d * (x.y * Gk.x - x.x * Gk.y);                  // dL/dtheta_k = -(2/n) Im(X_k conj(G_k))
+        if (e == 0) dth = (t == 0) ? 0.0f : dth;
+        stg_stream1(dloc_row + e * T, dth);
+        const float dsigned = __uint_as_float(__float_as_uint(dmag) ^ (__float_as_uint(sv) & 0x80000000u));
+        dk_sum = fmaf(dth, clamped ? 0.0f : dsigned, dk_sum);
       }
     } else {
 #pragma unroll 2
