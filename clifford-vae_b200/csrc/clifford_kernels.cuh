@@ -1032,6 +1032,26 @@ clifford_log_prob_kernel(const CliffordLogProbParams p, const cplx* __restrict__
         dlogc = (float)c.dlog_norm;
       }
     }
+    if constexpr (FWD_ONLY && ROWK) {
+      // Evaluation with one concentration per row: the element is ~20 instructions (MUFU sincos / rsqrt / lg2), so it is
+      // unrolled over the registers that already hold F[k] and loc[k] -- no round trip through shared memory, no barrier,
+      // no branch per bin (angle(0) = 0 by a select); sum_k (log C + kappa l_k) = d log C + kappa sum_k l_k per thread.
+      float lsum = 0.f;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const cplx Fk = v[e];
+        const float mag2 = fmaf(Fk.x, Fk.x, Fk.y * Fk.y);
+        const float ri = rsqrtf(mag2);
+        const float ca = (mag2 > 0.f) ? Fk.x * ri : 1.0f, sa = (mag2 > 0.f) ? Fk.y * ri : 0.0f;
+        float sl, cl;
+        sincos_any<true>(locv[e], sl, cl);
+        const float dot = fminf(fmaxf(fmaf(cl, ca, sl * sa), -1.0f + kEps), 1.0f - kEps);
+        lsum += __logf(1.0f + dot);
+      }
+      const float tot = group_sum<LOG2N>(fmaf(kap_row, lsum, (float)E * logc), scratch, t);
+      if (valid && t == 0) p.log_prob[row] = tot;
+      continue;
+    }
     // F[k] and loc[k] go to this thread's own shared-memory slots so that the (large: accurate sincos, log1p, optional
     // gradient outputs) element routine runs in a rolled loop and the kernel stays inside the instruction cache
     group_sync<LOG2N>();                         // the untangle's partner reads of the exchange buffer are done
