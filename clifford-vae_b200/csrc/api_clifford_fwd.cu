@@ -23,8 +23,9 @@ int launch_fwd_fast(const CliffordFwdParams& p, cudaStream_t st) {
   const long long work = (p.rows + Pl::GROUPS - 1) / Pl::GROUPS;
   if (int rc = persistent_grid(kern, Pl::THREADS, smem, work, &grid)) return rc;
   if constexpr (LEAN) {
-    // 7 resident CTAs / SM win 2-3 % once a CTA loops over >= 8 rows (and for single-row grids), but the longer row
-    // latency costs 1-2 % when a CTA only gets 3-5 rows (B = 4096 at d = 2048): fall back to 6 there (measured sweep)
+    // (only reachable when the kernel is built for 7 resident CTAs / SM, -DCVB_FWD_LEAN_MINB=7: they won 2-3 % once a CTA
+    // looped over >= 8 rows, but the longer row latency cost 1-2 % when a CTA only gets 3-5 rows (B = 4096 at d = 2048);
+    // the default build is capped for 6, see clifford_kernels.cuh)
     const int sms = sm_count();
     if (grid == sms * 7) {
       const double rows_per_cta = (double)work / (double)grid;

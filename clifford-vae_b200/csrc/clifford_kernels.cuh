@@ -27,11 +27,18 @@ constexpr int clifford_bwd_min_blocks() { return LOG2N == 10 ? 4 : 5; }
 // the fused-bind variant carries a second set of transforms; since its pair stage forms each (k, N-k) pair once it fits 124
 // registers without spilling: 4 resident CTAs / SM measured 0.1166 -> 0.1069 ms at the headline shape (3 before; 5 does not
 // fit the shared memory)
+#ifndef CVB_FWD_KEEP_OWN
+#define CVB_FWD_KEEP_OWN 1
+#endif
 #ifndef CVB_ICDF_LOOP_UNROLL
 #define CVB_ICDF_LOOP_UNROLL 4
 #endif
+// The lean forward sampler at d = 2048: its shared memory (33.9 KB per CTA) admits 6 resident CTAs, so the register cap
+// is set for 6 (85 registers) -- room to keep a table row's own phasors in registers between the sampling loop and the
+// C2R pre-tangle (CVB_FWD_KEEP_OWN: -16 shared-memory reads per thread and row, +3 %; at the 72-register cap of 7 CTAs
+// that spills 116 bytes and loses 10 %).
 #ifndef CVB_FWD_LEAN_MINB
-#define CVB_FWD_LEAN_MINB 7
+#define CVB_FWD_LEAN_MINB 6
 #endif
 template <int LOG2N, bool BIND = false, bool LEAN = false>
 constexpr int clifford_fwd_min_blocks() {
@@ -441,6 +448,8 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw, cons
     };
     // phase 1: phasors of the half spectrum into the exchange buffer (lightly unrolled: small code, some ILP)
     const bool table_row = ICDF && icdf_row_ok(kap_row);      // uniform over the group
+    constexpr bool KEEP_OWN = CVB_FWD_KEEP_OWN && ICDF && !BIND;    // table rows keep their own phasors in registers
+    cplx xown[KEEP_OWN ? E : 1];
     if (ICDF && table_row) {
       // device RNG through the row's inverse-CDF cells: one Philox call per FOUR circles, no rejection, no queue
       const uint64_t quad_base = (uint64_t)row * (uint64_t)(d / 4) + (uint64_t)t * (E / 4);
@@ -472,10 +481,14 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw, cons
           // row (static schedule padding; finite garbage from the staged buffer) are never stored
           cplx x;
           sincos_any<true>(src.loc[k] + phi, x.y, x.x);
+          if (KEEP_OWN) {
+            if (e + j == 0) x = (t == 0) ? make_float2(1.0f, 0.0f) : x;      // bin 0 (one select in the whole loop)
+            xown[KEEP_OWN ? e + j : 0] = x;
+          }
           xch[pad16(k)] = x;
         }
       }
-      if (t == 0) xch[pad16(0)] = make_float2(1.0f, 0.0f);      // same thread wrote bin 0 above: program order suffices
+      if (!KEEP_OWN && t == 0) xch[pad16(0)] = make_float2(1.0f, 0.0f);      // same thread wrote bin 0 above: program order suffices
     } else if (MODE == kPsRng) {
       // device RNG: one Philox call + one Box-Muller per PAIR of bins (one envelope proposal each);
       // rejected proposals are queued and finished in phase 1b
@@ -618,7 +631,17 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw, cons
       for (int e = 0; e < E; ++e) spec[t + e * T] = xch[pad16(t + e * T)];
     }
     if (!BIND || p.z) {
-      c2r_pretangle_load<LOG2N>(v, xch, t, tw);
+      if constexpr (KEEP_OWN) {
+        if (table_row) {
+#pragma unroll
+          for (int e = 0; e < E; ++e) v[e] = xown[KEEP_OWN ? e : 0];
+          c2r_pretangle_load<LOG2N, true>(v, xch, t, tw);
+        } else {
+          c2r_pretangle_load<LOG2N>(v, xch, t, tw);
+        }
+      } else {
+        c2r_pretangle_load<LOG2N>(v, xch, t, tw);
+      }
       fft_run<LOG2N, true>(v, xch, t, tw);
       if (valid) {
         float2* zr = reinterpret_cast<float2*>(p.z + row * (2LL * d));

@@ -388,7 +388,9 @@ __device__ __forceinline__ void c2r_pretangle(cplx (&v)[FftPlan<LOG2N>::E], floa
 
 // C2R pre-processing when the half spectrum X[0..N] already sits in the exchange buffer (written by
 // the caller, followed by a __syncthreads()).  Out: v = Z as in c2r_pretangle.
-template <int LOG2N>
+// OWN: on entry v[e] already holds this thread's own bins X[t + e T] (the caller kept what it wrote to the buffer in
+// registers): only the partner bins are read.
+template <int LOG2N, bool OWN = false>
 __device__ __forceinline__ void c2r_pretangle_load(cplx (&v)[FftPlan<LOG2N>::E], const cplx* xch, int t,
                                                    const cplx* __restrict__ tw) {
   using Pl = FftPlan<LOG2N>;
@@ -403,7 +405,7 @@ __device__ __forceinline__ void c2r_pretangle_load(cplx (&v)[FftPlan<LOG2N>::E],
     const cplx* twp = tw + twiddle_offset(LOG2N) + t;
 #pragma unroll
     for (int e = 0; e < Pl::E; ++e) {
-      const cplx x = xk[e * S];
+      const cplx x = OWN ? v[e] : xk[e * S];
       const cplx xp = cconj(xm[-e * S]);
       const cplx w = cconj(__ldg(twp + e * Pl::T));               // exp(+2 pi i k / n)
       const cplx s = cadd(x, xp), d = csub(x, xp);
@@ -415,7 +417,7 @@ __device__ __forceinline__ void c2r_pretangle_load(cplx (&v)[FftPlan<LOG2N>::E],
 #pragma unroll
   for (int e = 0; e < Pl::E; ++e) {
     const int k = t + e * Pl::T;
-    const cplx x = xch[pad16(k)];
+    const cplx x = OWN ? v[e] : xch[pad16(k)];
     const cplx xp = cconj(xch[pad16(N - k)]);
     const cplx w = cconj(__ldg(&tw[twiddle_offset(LOG2N) + k]));   // exp(+2 pi i k / n)
     const cplx s = cadd(x, xp), d = csub(x, xp);
