@@ -25,7 +25,10 @@ int launch_bwd_fast(const CliffordBwdParams& p, cudaStream_t st) {
   int grid = 0;
   const long long work = (p.rows + Pl::GROUPS - 1) / Pl::GROUPS;
   if (int rc = persistent_grid(kern, Pl::THREADS, smem, work, &grid)) return rc;
-  launch_pdl(kern, grid, Pl::THREADS, smem, st, p, tw, icdf);
+  CliffordBwdParams q = p;
+  static const bool static_sched = getenv("CVB_STATIC_SCHEDULE") != nullptr;
+  q.sched = (Pl::GROUPS == 1 && !static_sched && work > grid) ? next_sched_slot() : nullptr;   // dynamic rows when CTAs loop
+  launch_pdl(kern, grid, Pl::THREADS, smem, st, q, tw, icdf);
   return check_launch("clifford_bwd_kernel");
 }
 

@@ -722,6 +722,7 @@ struct CliffordBwdParams {
   int d;
   int staged;              // 1: element-input rows are 16-byte aligned -> stage them with cp.async.bulk
   KappaHead head;          // on: `kappa` holds the raw head output (row scalar only) and dkappa receives d L / d raw
+  int* sched;              // dynamic row schedule: {next-row counter, finished-CTA counter} (launcher), or null = static
 };
 
 // Per-row inputs of the backward, indexed by the bin k (global rows or their TMA-staged copies in smem).
@@ -832,11 +833,17 @@ clifford_bwd_kernel(const CliffordBwdParams p, const cplx* __restrict__ tw, cons
     if (t == 0 && first_row < p.rows) issue(first_row);
   }
 
+  // Row schedule.  Static: CTA b takes rows b*G + g + i*stride.  Dynamic (one row per CTA at a time, sched != null): after
+  // its first row a CTA fetches the next unprocessed row from a global counter, which removes the tail imbalance when
+  // rows / CTAs is small (4096 rows over 740 CTAs: 5 vs 6 rows each, i.e. 8 % of the launch idle).
+  const bool dynamic = (G == 1) && p.sched != nullptr;
+  int* next_slot = reinterpret_cast<int*>(scratch) + 31;     // group_sum uses scratch[0 .. T/32)
   uint32_t parity = 0;
-  for (long long base = (long long)blockIdx.x * G; base < p.rows; base += stride, parity ^= 1u) {
+  for (long long base = (long long)blockIdx.x * G, next_base = 0; base < p.rows; base = next_base, parity ^= 1u) {
     const long long row = base + group;
     const bool valid = row < p.rows;
     const long long prow = valid ? (row % p.loc_rows) : 0;
+    if (dynamic && t == 0) *next_slot = atomicAdd(p.sched, 1);     // published by the barriers of the FFT below
     cplx v[E];
     const float2* gz = reinterpret_cast<const float2*>(p.grad_z + (valid ? row : 0) * (2LL * d));
 #pragma unroll
@@ -857,6 +864,7 @@ clifford_bwd_kernel(const CliffordBwdParams p, const cplx* __restrict__ tw, cons
     }
     fft_run<LOG2N, false>(v, xch, t, tw);
     r2c_untangle<LOG2N>(v, xch, t, tw);        // v[e] = G[k]
+    if constexpr (G == 1) next_base = dynamic ? (long long)*next_slot + stride : base + stride;
 
     // G[k] goes back to this thread's own exchange slots so that the (large, divergent) element
     // routine runs in a rolled loop: keeps the kernel inside the instruction cache.  (Table-sampled rows consume G[k]
@@ -925,12 +933,19 @@ clifford_bwd_kernel(const CliffordBwdParams p, const cplx* __restrict__ tw, cons
     }
     if (staged) {
       group_sync<LOG2N>();                       // every thread is done with the staged rows
-      if (t == 0 && row + stride < p.rows) issue(row + stride);
+      if (t == 0 && (G == 1 ? next_base : base + stride) + group < p.rows) issue((G == 1 ? next_base : base + stride) + group);
     }
     if (ROWK) {
       const float tot = group_sum<LOG2N>(dk_sum, scratch, t);
       if (valid && t == 0) p.dkappa[row] = tot * head_dkappa(p.head, kap_raw);
+    } else if (dynamic) {
+      group_sync<LOG2N>();                       // next_slot is rewritten at the top of the next row
     }
+    if constexpr (G != 1) next_base = base + stride;      // static only: nothing extra kept live across the element loop
+  }
+  if (dynamic && t == 0) {
+    // the last CTA to finish re-arms the counters for the next launch that uses this slot
+    if (atomicAdd(p.sched + 1, 1) == (int)stride - 1) { p.sched[0] = 0; p.sched[1] = 0; }
   }
 }
 
