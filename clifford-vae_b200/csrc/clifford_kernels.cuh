@@ -857,8 +857,7 @@ clifford_bwd_kernel(const CliffordBwdParams p, const cplx* __restrict__ tw, cons
     const bool table_row = TABLE && saved && valid && (kap_row + kEps <= kIcdfKappaMax);
     if (TABLE && table_row) {
       // every thread left the previous row's element loop (its closing barriers) before these are overwritten
-      icdf_build_row<false>(cells, kap_row + kEps, icdf, t, T);
-      icdf_build_row<true>(dcells, kap_row + kEps, icdf, t, T);
+      icdf_build_row_both(cells, dcells, kap_row + kEps, icdf, t, T);
     } else if (ROWK) {
       beta_row_build<T>(rc, 0.5f + (kap_row + kEps), 0.5f, t);
     }

@@ -80,6 +80,43 @@ __device__ __forceinline__ void icdf_build_row(float4* cell, float kappa, const 
   }
 }
 
+// Value cells and d/dkappa cells of one row in ONE pass over the node rows (the backward needs both and they read the
+// same nodes: half the loads and address arithmetic of two icdf_build_row calls).  Same arithmetic, cell for cell.
+__device__ __forceinline__ void icdf_build_row_both(float4* cell, float4* dcell, float kappa, const float2* __restrict__ table,
+                                                    int t, int T) {
+  const float x = log1pf(kappa) * ((float)(kIcdfKappaNodes - 1) / kIcdfQMax);
+  int i = (int)x;
+  i = i < 1 ? 1 : (i > kIcdfKappaNodes - 3 ? kIcdfKappaNodes - 3 : i);
+  const float u = x - (float)i;
+  const float a1 = u + 1.0f, b1 = u, c1 = u - 1.0f, e1 = u - 2.0f;
+  const float dx = ((float)(kIcdfKappaNodes - 1) / kIcdfQMax) / (1.0f + kappa);
+  const float w[4] = {-u * (u - 1.0f) * (u - 2.0f) * (1.0f / 6.0f), (u + 1.0f) * (u - 1.0f) * (u - 2.0f) * 0.5f,
+                      -(u + 1.0f) * u * (u - 2.0f) * 0.5f, (u + 1.0f) * u * (u - 1.0f) * (1.0f / 6.0f)};
+  const float g[4] = {-(c1 * e1 + b1 * e1 + b1 * c1) * (1.0f / 6.0f) * dx, (c1 * e1 + a1 * e1 + a1 * c1) * 0.5f * dx,
+                      -(b1 * e1 + a1 * e1 + a1 * b1) * 0.5f * dx, (b1 * c1 + a1 * c1 + a1 * b1) * (1.0f / 6.0f) * dx};
+  const float2* r0 = table + (size_t)(i - 1) * kIcdfRowStride;
+  for (int j = 2 * t; j < kIcdfCells; j += 2 * T) {
+    float2 n0 = make_float2(0.f, 0.f), n1 = n0, n2 = n0, m0 = n0, m1 = n0, m2 = n0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(r0 + (size_t)q * kIcdfRowStride + j));
+      const float2 b = __ldg(r0 + (size_t)q * kIcdfRowStride + j + 2);
+      n0.x = fmaf(w[q], a.x, n0.x); n0.y = fmaf(w[q], a.y, n0.y);
+      n1.x = fmaf(w[q], a.z, n1.x); n1.y = fmaf(w[q], a.w, n1.y);
+      n2.x = fmaf(w[q], b.x, n2.x); n2.y = fmaf(w[q], b.y, n2.y);
+      m0.x = fmaf(g[q], a.x, m0.x); m0.y = fmaf(g[q], a.y, m0.y);
+      m1.x = fmaf(g[q], a.z, m1.x); m1.y = fmaf(g[q], a.w, m1.y);
+      m2.x = fmaf(g[q], b.x, m2.x); m2.y = fmaf(g[q], b.y, m2.y);
+    }
+    const float d0 = n1.x - n0.x, d1 = n2.x - n1.x;
+    cell[j] = make_float4(n0.x, n0.y, 3.0f * d0 - 2.0f * n0.y - n1.y, -2.0f * d0 + n0.y + n1.y);
+    cell[j + 1] = make_float4(n1.x, n1.y, 3.0f * d1 - 2.0f * n1.y - n2.y, -2.0f * d1 + n1.y + n2.y);
+    const float f0 = m1.x - m0.x, f1 = m2.x - m1.x;
+    dcell[j] = make_float4(m0.x, m0.y, 3.0f * f0 - 2.0f * m0.y - m1.y, -2.0f * f0 + m0.y + m1.y);
+    dcell[j + 1] = make_float4(m1.x, m1.y, 3.0f * f1 - 2.0f * m1.y - m2.y, -2.0f * f1 + m1.y + m2.y);
+  }
+}
+
 __device__ __forceinline__ float fast_exp2(float x) {
   float r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
