@@ -342,6 +342,30 @@ __device__ __forceinline__ float r2c_untangle(cplx (&v)[FftPlan<LOG2N>::E], cplx
                                               const cplx* __restrict__ tw) {
   using Pl = FftPlan<LOG2N>;
   constexpr int N = Pl::N;
+  if constexpr (Pl::T % 16 == 0) {
+    // base addresses with compile-time offsets (see load_own_points): own slots from pad16(t), partners N - k downwards from
+    // pad16(N - t); the one wrap-around (k = 0 pairs with itself) is a select in the first iteration of thread 0
+    constexpr int S = Pl::T + Pl::T / 16;
+    cplx* xk = xch + pad16(t);
+    const cplx* xm = xch + pad16(N - t);
+    const cplx* twp = tw + twiddle_offset(LOG2N) + t;
+    group_sync<LOG2N>();
+#pragma unroll
+    for (int e = 0; e < Pl::E; ++e) xk[e * S] = v[e];
+    group_sync<LOG2N>();
+    const float nyq0 = v[0].x - v[0].y;      // for t == 0: Re Z0 - Im Z0
+#pragma unroll
+    for (int e = 0; e < Pl::E; ++e) {
+      const cplx z = v[e];
+      const cplx* pp = (e == 0) ? ((t == 0) ? xch : xm) : xm - e * S;
+      const cplx zp = cconj(*pp);
+      const cplx w = __ldg(twp + e * Pl::T);                              // exp(-2 pi i k / n)
+      const cplx s = cadd(z, zp), d = csub(z, zp);
+      const cplx wd = cmul_mi(cmul(w, d));                                 // -i w (z - zp)
+      v[e] = cadd_scaled(s, wd, 0.5f);
+    }
+    return nyq0;
+  }
   group_sync<LOG2N>();
 #pragma unroll
   for (int e = 0; e < Pl::E; ++e) xch[pad16(t + e * Pl::T)] = v[e];
