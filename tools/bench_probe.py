@@ -1,3 +1,4 @@
+"""Short probe of the bench: headline value, kernel split and a few other_configs legs (python tools/bench_probe.py)."""
 import json,sys,subprocess
 out=subprocess.run([sys.executable,"bench.py","--steps","10","--warmup","3","--no-cpu-baseline","--no-vae-step"],capture_output=True,text=True).stdout
 d=json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
