@@ -1,6 +1,8 @@
 #!/bin/bash
 # Round-2 evidence run on the GPU box (one gpurun call): tests, smoke, bench (both arms), per-op benches, then the ncu passes
 # (launch list of the bench command, --set full of the headline kernels and of the short-row kernels).  Outputs -> gpurun_out/.
+# Afterwards, here: tools/publish_evidence.sh copies the outputs into profiles/ under the round's names and regenerates the
+# launch-list summary, the traffic file and the SASS evidence.
 set -u
 O=gpurun_out
 python -m pytest tests -m gpu -q 2>&1 | tail -3 > $O/r2f_pytest_gpu.log
