@@ -373,7 +373,9 @@ clifford_fwd_kernel(const CliffordFwdParams p, const cplx* __restrict__ tw, cons
   if (staged && t == 0 && first_row < p.rows) issue(first_row);
   // a row is table-sampled when its concentration is inside the table's range; the cells of the first row are built
   // here, those of every later row right after the previous row's sampling phase (their loads overlap its FFT)
-  auto icdf_row_ok = [&](float kap) { return kap + kEps <= kIcdfKappaMax; };
+  // (kap >= 0: the unclamped cell index floor(256 v^(1/(2 kap + 1))) stays inside the table only for a valid concentration;
+  // a negative or NaN one -- invalid input -- takes the exact sampler like before)
+  auto icdf_row_ok = [&](float kap) { return kap >= 0.0f && kap + kEps <= kIcdfKappaMax; };
   if (ICDF && first_row < p.rows) {
     const float k0 = fwd_row_kappa<LEAN || BIND>(p, first_row % p.loc_rows);
     if (icdf_row_ok(k0)) icdf_build_row<false, 4, true>(cells, k0 + kEps, icdf, t, T);
@@ -854,7 +856,7 @@ clifford_bwd_kernel(const CliffordBwdParams p, const cplx* __restrict__ tw, cons
     const float kap_row = head_kappa(p.head, kap_raw);
     float* rc = rowconst + (parity ? kBetaRowFloats : 0);
     // a row the forward sampled through the table (same predicate as clifford_fwd_kernel; uniform over the group)
-    const bool table_row = TABLE && saved && valid && (kap_row + kEps <= kIcdfKappaMax);
+    const bool table_row = TABLE && saved && valid && kap_row >= 0.0f && (kap_row + kEps <= kIcdfKappaMax);
     if (TABLE && table_row) {
       // every thread left the previous row's element loop (its closing barriers) before these are overwritten
       icdf_build_row_both(cells, dcells, kap_row + kEps, icdf, t, T);

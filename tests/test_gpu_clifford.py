@@ -638,3 +638,29 @@ def test_von_mises_torus_entropy_matches_reference_formula(d, rowk):
     assert rel_err(ent.detach().cpu()[ok], ref32.cpu()[ok]) < 5e-5
     kl = torch.distributions.kl.kl_divergence(q, CliffordTorusUniform(d, device=DEV))
     assert rel_err(kl.detach().cpu(), ((d - 1) * np.log(2 * np.pi) - ref).detach().cpu()) < 1e-4
+
+
+@pytest.mark.parametrize("d", [512, 2048])
+def test_invalid_concentration_rows_do_not_fault(d):
+    """A negative or NaN concentration is invalid input (the reference's arg validation rejects it), but a diverged model
+    can produce one: those rows must neither fault nor hang the launch (the table sampler indexes its cells without a
+    clamp, so it only takes rows with 0 <= kappa <= 32; everything else goes to the bounded exact sampler), and the valid
+    rows of the same launch stay exact unit vectors, forward and backward."""
+    from dists.clifford import CliffordPowerSphericalDistribution
+    torch.manual_seed(3)
+    B = 64
+    loc = torch.randn(B, d, device=DEV, requires_grad=True)
+    kap = (torch.rand(B, 1, device=DEV) * 9 + 0.1)
+    kap[3] = -0.7
+    kap[17] = float("nan")
+    kap[40] = -1e6
+    kap = kap.requires_grad_()
+    q = CliffordPowerSphericalDistribution(loc, kap, validate_args=False)
+    z = q.rsample()
+    ok = torch.ones(B, dtype=torch.bool, device=DEV)
+    ok[[3, 17, 40]] = False
+    torch.cuda.synchronize()
+    assert float((z.detach()[ok].norm(dim=-1) - 1).abs().max()) < 1e-5
+    (z[ok] * torch.randn_like(z[ok])).sum().backward()
+    torch.cuda.synchronize()
+    assert torch.isfinite(loc.grad[ok]).all() and torch.isfinite(kap.grad[ok]).all()
